@@ -1,0 +1,221 @@
+// Device-side CDF arithmetic shared by cdf_kernels.cu and exec.cu (see cdf_kernels.cu for the design notes).
+#pragma once
+#include "cz_common.cuh"
+
+namespace czk {
+
+__constant__ uint64_t c_exp2f_tab[32] = {
+    0x3ff0000000000000ull, 0x3fefd9b0d3158574ull, 0x3fefb5586cf9890full, 0x3fef9301d0125b51ull,
+    0x3fef72b83c7d517bull, 0x3fef54873168b9aaull, 0x3fef387a6e756238ull, 0x3fef1e9df51fdee1ull,
+    0x3fef06fe0a31b715ull, 0x3feef1a7373aa9cbull, 0x3feedea64c123422ull, 0x3feece086061892dull,
+    0x3feebfdad5362a27ull, 0x3feeb42b569d4f82ull, 0x3feeab07dd485429ull, 0x3feea47eb03a5585ull,
+    0x3feea09e667f3bcdull, 0x3fee9f75e8ec5f74ull, 0x3feea11473eb0187ull, 0x3feea589994cce13ull,
+    0x3feeace5422aa0dbull, 0x3feeb737b0cdc5e5ull, 0x3feec49182a3f090ull, 0x3feed503b23e255dull,
+    0x3feee89f995ad3adull, 0x3feeff76f2fb5e47ull, 0x3fef199bdd85529cull, 0x3fef3720dcef9069ull,
+    0x3fef5818dcfba487ull, 0x3fef7c97337b9b5full, 0x3fefa4afa2a490daull, 0x3fefd0765b6e4540ull,
+};
+
+// The 32-entry table is replicated per lane in shared memory ([entry][lane], lo and hi words separately) so a
+// warp's 32 data-dependent lookups never bank-conflict.
+struct ExpTab {
+  const uint32_t *lo;
+  const uint32_t *hi;
+  int lane;
+};
+
+__device__ __forceinline__ void exp_tab_init(uint32_t *s_lo, uint32_t *s_hi) {
+  for (int i = threadIdx.x; i < 32 * 32; i += blockDim.x) {
+    uint64_t t = c_exp2f_tab[i >> 5];
+    s_lo[i] = (uint32_t)t;
+    s_hi[i] = (uint32_t)(t >> 32);
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ float cz_expf(float x, const ExpTab &tab) {
+  const double inv_ln2_n = 0x1.71547652b82fep+0 * 32;
+  const double shift = 0x1.8p+52;
+  const double c0 = 0x1.c6af84b912394p-5 / 32 / 32 / 32;
+  const double c1 = 0x1.ebfce50fac4f3p-3 / 32 / 32;
+  const double c2 = 0x1.62e42ff0c52d6p-1 / 32;
+  if (x < -0x1.9fe368p6f) return 0.0f;
+  if (x > 0x1.62e42ep6f) return __int_as_float(0x7f800000);
+  double xd = (double)x;
+  double z = __dmul_rn(inv_ln2_n, xd);
+  double kd = __dadd_rn(z, shift);
+  uint64_t ki = (uint64_t)__double_as_longlong(kd);
+  kd = __dsub_rn(kd, shift);
+  double r = __fma_rn(inv_ln2_n, xd, -kd);
+  int idx = ((int)(ki & 31) << 5) + tab.lane;
+  uint64_t t = ((uint64_t)tab.hi[idx] << 32) | (uint64_t)tab.lo[idx];
+  t += ki << 47;
+  double s = __longlong_as_double((long long)t);
+  double p = __fma_rn(c0, r, c1);
+  double r2 = __dmul_rn(r, r);
+  double y = __fma_rn(c2, r, 1.0);
+  y = __fma_rn(p, r2, y);
+  y = __dmul_rn(y, s);
+  return __double2float_rn(y);
+}
+
+// floor(acc * 2^30) clamped to [0, 2^30]  (src/main.rs:813-815; NaN -> 0 like Rust's `as i64`)
+__device__ __forceinline__ uint32_t quant(double acc) {
+  double f = __dmul_rn(acc, 1073741824.0);
+  if (!(f == f)) return 0u;
+  if (f >= 1073741824.0) return CZ_AC_CDF_TOTAL;
+  if (f <= 0.0) return 0u;
+  return (uint32_t)__double2ll_rd(f);
+}
+
+enum { OP_BOUNDS = 0, OP_SEARCH = 1, OP_XE = 2 };
+
+#define CZ_P_FLOOR 0x1p-29 /* ac_p_min(): src/main.rs:235-238 */
+
+// status bits written to *err (OR-ed)
+#define CZ_DEVERR_NAN 1
+#define CZ_DEVERR_SYM 2
+
+// Column walker shared by the stand-alone CDF kernels (cdf_kernels.cu) and the fused decode step (exec.cu).
+// MUST be called by all 32 lanes of a warp (inactive lanes pass a clamped, valid column and active=false).
+// p points at logits[0][col]; element v of the column is p[v * ld].
+template <int MODE, int OP>
+__device__ __forceinline__ void cdf_col(const float *__restrict__ p, size_t ld, int V, uint32_t arg, bool active,
+                                        const ExpTab &tab, uint32_t &sym_out, uint32_t &lo_out, uint32_t &hi_out,
+                                        double &xe_out, int &errbits) {
+  const int n_sym = MODE == CZ_CDF_RWKV_LITERALS ? V + 256 : V;
+  sym_out = 0;
+  lo_out = 0;
+  hi_out = 0;
+  xe_out = 0.0;
+  // pass A: max (f32, NaN-ignoring exactly like `if v > max`)
+  float mx = __int_as_float(0xff800000);
+#pragma unroll 8
+  for (int v = 0; v < V; v++) {
+    float x = __ldg(p + (size_t)v * ld);
+    if (x > mx) mx = x;
+  }
+  // pass B: S = sum_i (f64)expf(l_i - max), sequential
+  double S = 0.0;
+#pragma unroll 4
+  for (int v = 0; v < V; v++) {
+    float x = __ldg(p + (size_t)v * ld);
+    S = __dadd_rn(S, (double)cz_expf(__fsub_rn(x, mx), tab));
+  }
+  if (!(S == S) && active) errbits |= CZ_DEVERR_NAN;
+
+  // element pdf before the final CDF accumulation
+  double norm = 1.0, sum2 = 1.0;
+  const double scale = 1.0 - 256.0 * CZ_P_FLOOR;
+  const bool uniform = (MODE == CZ_CDF_SMOLLM && OP != OP_XE) && (S <= 0.0);  // src/main.rs:794-798
+  const double uni = 1.0 / (double)V;
+
+  if (MODE == CZ_CDF_RWKV_LITERALS || OP == OP_XE) {
+    // softmax_pdf_floor: norm = sum_i max(e_i / S, floor)   (src/main.rs:763-764)
+    double acc = 0.0;
+#pragma unroll 4
+    for (int v = 0; v < V; v++) {
+      float x = __ldg(p + (size_t)v * ld);
+      double q = __ddiv_rn((double)cz_expf(__fsub_rn(x, mx), tab), S);
+      acc = __dadd_rn(acc, fmax(q, CZ_P_FLOOR));
+    }
+    norm = acc;
+  }
+  if (MODE == CZ_CDF_RWKV_LITERALS) {
+    // combined_pdf_with_literals: sum2 over V scaled entries + 256 literal entries (src/main.rs:773-779)
+    double acc = 0.0;
+#pragma unroll 4
+    for (int v = 0; v < V; v++) {
+      float x = __ldg(p + (size_t)v * ld);
+      double q = __ddiv_rn((double)cz_expf(__fsub_rn(x, mx), tab), S);
+      q = __ddiv_rn(fmax(q, CZ_P_FLOOR), norm);
+      acc = __dadd_rn(acc, __dmul_rn(q, scale));
+    }
+    for (int j = 0; j < 256; j++) acc = __dadd_rn(acc, CZ_P_FLOOR);
+    sum2 = acc;
+  }
+
+  auto pdf_at = [&](int v) -> double {  // final pdf entry v (v < n_sym)
+    if (MODE == CZ_CDF_RWKV_LITERALS) {
+      double q;
+      if (v < V) {
+        float x = __ldg(p + (size_t)v * ld);
+        q = __ddiv_rn((double)cz_expf(__fsub_rn(x, mx), tab), S);
+        q = __dmul_rn(__ddiv_rn(fmax(q, CZ_P_FLOOR), norm), scale);
+      } else {
+        q = CZ_P_FLOOR;
+      }
+      return sum2 > 0.0 ? __ddiv_rn(q, sum2) : q;
+    } else if (OP == OP_XE) {
+      float x = __ldg(p + (size_t)v * ld);
+      double q = __ddiv_rn((double)cz_expf(__fsub_rn(x, mx), tab), S);
+      return __ddiv_rn(fmax(q, CZ_P_FLOOR), norm);
+    } else {
+      if (uniform) return uni;
+      float x = __ldg(p + (size_t)v * ld);
+      return __ddiv_rn((double)cz_expf(__fsub_rn(x, mx), tab), S);
+    }
+  };
+
+  if (OP == OP_XE) {
+    double pr = (int)arg < n_sym ? pdf_at((int)arg) : CZ_P_FLOOR;  // pdf.get(sym).unwrap_or(ac_p_min())
+    pr = fmax(pr, 1e-300);
+    xe_out = -log2(pr);
+    return;
+  }
+
+  if (OP == OP_BOUNDS) {
+    uint32_t sym = arg;
+    bool sym_bad = false;
+    if ((int)sym >= n_sym) {
+      if (active) errbits |= CZ_DEVERR_SYM;
+      sym = 0;  // keep walking with the warp (shuffles below need every lane), result is discarded
+      sym_bad = true;
+    }
+    double acc = 0.0;
+    uint32_t lo = 0, hi = 0;
+    // the warp walks to the largest symbol among its lanes; each lane snapshots at its own sym-1 / sym
+    uint32_t wmax = sym;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) wmax = max(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
+    for (uint32_t v = 0; v <= wmax; v++) {
+      if (v <= sym) {
+        acc = __dadd_rn(acc, pdf_at((int)v));
+        if (v + 1 == sym) lo = quant(acc);
+        if (v == sym) hi = quant(acc);
+      }
+    }
+    if (hi < lo) hi = lo;                          // non-decreasing clamp (src/main.rs:818)
+    if ((int)sym == n_sym - 1) hi = CZ_AC_CDF_TOTAL;  // cdf[n] = total (src/main.rs:822)
+    lo_out = sym_bad ? 0u : lo;
+    hi_out = sym_bad ? 0u : hi;
+    return;
+  }
+
+  if (OP == OP_SEARCH) {
+    const uint32_t value = arg;
+    double acc = 0.0;
+    uint32_t prev = 0, found_sym = (uint32_t)(n_sym - 1), lo = 0, hi = CZ_AC_CDF_TOTAL;
+    bool done = false;
+    for (int v = 0; v < n_sym; v++) {
+      if (!done) {
+        acc = __dadd_rn(acc, pdf_at(v));
+        uint32_t cur = quant(acc);
+        if (cur < prev) cur = prev;
+        if (v == n_sym - 1) cur = CZ_AC_CDF_TOTAL;
+        if (value < cur) {
+          found_sym = (uint32_t)v;
+          lo = prev;
+          hi = cur;
+          done = true;
+        }
+        prev = cur;
+      }
+      if (__all_sync(0xffffffffu, done)) break;
+    }
+    sym_out = found_sym;
+    lo_out = lo;
+    hi_out = hi;
+  }
+}
+
+}  // namespace czk

@@ -1,0 +1,95 @@
+// Shared helpers for the candlezip_b200 CUDA sources (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <string>
+
+#include "../../include/candlezip_b200.h"
+
+namespace cz {
+
+void set_error(const std::string &msg);
+const char *get_error();
+
+#define CZ_CUDA_TRY(expr)                                                                              \
+  do {                                                                                                 \
+    cudaError_t _e = (expr);                                                                           \
+    if (_e != cudaSuccess) {                                                                           \
+      cz::set_error(std::string(#expr) + ": " + cudaGetErrorString(_e) + " @" + __FILE__ + ":" +       \
+                    std::to_string(__LINE__));                                                         \
+      return CZ_ERR_CUDA;                                                                              \
+    }                                                                                                  \
+  } while (0)
+
+#define CZ_TRY(expr)              \
+  do {                            \
+    int _rc = (expr);             \
+    if (_rc != CZ_OK) return _rc; \
+  } while (0)
+
+static inline size_t ceil_div(size_t a, size_t b) { return (a + b - 1) / b; }
+
+}  // namespace cz
+
+// One ctx == one GPU == one stream of work (plus a side stream for overlap).
+struct cz_ctx {
+  int device = -1;          // -1: host-only ctx (weight generation / container work without a GPU)
+  int sm_count = 0;
+  cudaStream_t stream = nullptr;
+  cudaStream_t stream2 = nullptr;
+  uint64_t launches = 0;
+  // per-family profiling
+  bool prof_on = false;
+  double prof_ms[CZ_K_FAMILIES] = {0};
+  uint64_t prof_launches[CZ_K_FAMILIES] = {0};
+  cudaEvent_t prof_ev0 = nullptr, prof_ev1 = nullptr;
+  // scratch for the small kernels' host entry points
+  void *scratch = nullptr;
+  size_t scratch_bytes = 0;
+  int *err_flag_dev = nullptr;  // device int set by kernels on zero-width intervals etc.
+};
+
+namespace cz {
+
+int ensure_scratch(cz_ctx *ctx, size_t bytes);
+
+// RAII-free launch accounting: CZ_LAUNCH(ctx, family, kernel<<<...>>>(...))
+struct LaunchScope {
+  cz_ctx *ctx;
+  int fam;
+  LaunchScope(cz_ctx *c, int f) : ctx(c), fam(f) {
+    if (ctx->prof_on) cudaEventRecord(ctx->prof_ev0, ctx->stream);
+  }
+  ~LaunchScope() {
+    ctx->launches++;
+    ctx->prof_launches[fam]++;
+    if (ctx->prof_on) {
+      cudaEventRecord(ctx->prof_ev1, ctx->stream);
+      cudaEventSynchronize(ctx->prof_ev1);
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, ctx->prof_ev0, ctx->prof_ev1);
+      ctx->prof_ms[fam] += ms;
+    }
+  }
+};
+
+#define CZ_LAUNCH(ctx, fam, ...)       \
+  do {                                 \
+    cz::LaunchScope _ls((ctx), (fam)); \
+    __VA_ARGS__;                       \
+  } while (0)
+
+#define CZ_CHECK_LAUNCH()                                                                          \
+  do {                                                                                             \
+    cudaError_t _e = cudaGetLastError();                                                           \
+    if (_e != cudaSuccess) {                                                                       \
+      cz::set_error(std::string("kernel launch: ") + cudaGetErrorString(_e) + " @" + __FILE__ +   \
+                    ":" + std::to_string(__LINE__));                                               \
+      return CZ_ERR_CUDA;                                                                          \
+    }                                                                                              \
+  } while (0)
+
+}  // namespace cz

@@ -1,0 +1,709 @@
+// Schedule executor: batched teacher-forced encode, lock-step batched decode, paired XE scan, and the
+// batch-of-1 LanguageModelSession shim.  Replaces the per-token loops of src/main.rs:1979-2355 (encode),
+// 2528-2653 (decode) and 1725-1751 (gate cross-entropy): logits never leave the GPU, the quantised CDF bounds
+// feed the on-device arithmetic-coder lanes directly, and the host only builds row metadata and launches kernels.
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "cdf_device.cuh"
+#include "coder.cuh"
+#include "model.h"
+#include "schedule.h"
+
+namespace cz {
+int launch_cdf_cols(cz_ctx *ctx, int op, int mode, const float *logits_dev, size_t V, size_t M, size_t ld,
+                    const uint32_t *arg_dev, uint32_t *sym_out_dev, uint32_t *c_lo_dev, uint32_t *c_hi_dev,
+                    double *xe_dev, cudaStream_t stream);
+int launch_ac_encode_lanes(cz_ctx *ctx, const uint32_t *c_lo_dev, const uint32_t *c_hi_dev, const uint64_t *lane_off_dev,
+                           size_t n_lanes, uint8_t *out_dev, const uint64_t *out_off_dev, uint64_t *out_len_dev,
+                           unsigned long long *err_index_dev, cudaStream_t stream);
+int require_device(cz_ctx *ctx);
+int fetch_device_status(cz_ctx *ctx, unsigned long long *err_index_dev, unsigned long long *err_index_out);
+}  // namespace cz
+
+namespace czk {
+
+// tok[r] = src[r] >= 0 ? ids[src[r]] : (src[r] == -1 ? bos : extra[-2 - src[r]])
+__global__ void gather_tokens_kernel(const long long *__restrict__ src, const uint32_t *__restrict__ ids,
+                                     const uint32_t *__restrict__ extra, uint32_t bos, uint32_t *__restrict__ tok, int n) {
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  long long s = src[r];
+  tok[r] = s >= 0 ? ids[s] : (s == -1 ? bos : extra[-2 - s]);
+}
+
+__global__ void compact_payload_kernel(const uint8_t *__restrict__ raw, const uint64_t *__restrict__ raw_off,
+                                       const uint64_t *__restrict__ dst_off, uint8_t *__restrict__ dst) {
+  const uint64_t a = raw_off[blockIdx.x], b = dst_off[blockIdx.x], n = dst_off[blockIdx.x + 1] - b;
+  for (uint64_t i = threadIdx.x; i < n; i += blockDim.x) dst[b + i] = raw[a + i];
+}
+
+// ---- decode ------------------------------------------------------------------------------------------------
+__global__ void ac_decoder_init_kernel(const uint8_t *__restrict__ payload, const uint64_t *__restrict__ seg_off, int n_lanes,
+                                       AcDecoderState *__restrict__ st) {
+  int lane = blockIdx.x * blockDim.x + threadIdx.x;
+  if (lane >= n_lanes) return;
+  AcDecoder d;
+  d.init(payload + seg_off[lane], seg_off[lane + 1] - seg_off[lane]);
+  st[lane] = d.s;
+}
+
+// One thread per stream: AC target value -> CDF search over its logits column -> symbol -> AC state update.
+// (src/main.rs:2622-2626: to_vec1 + softmax_pdf + quantize_pdf_to_cdf + decode_symbol_counts, fused, on device.)
+template <int MODE>
+__global__ void __launch_bounds__(128) decode_step_kernel(const float *__restrict__ logits, int V, size_t ld, int n_lanes,
+                                                          const uint8_t *__restrict__ payload, const uint64_t *__restrict__ seg_off,
+                                                          const uint64_t *__restrict__ seg_start, uint64_t coded_index,
+                                                          AcDecoderState *__restrict__ st, uint32_t *__restrict__ ids_out,
+                                                          uint32_t *__restrict__ next_tok, int *__restrict__ err) {
+  __shared__ uint32_t s_lo[32 * 32], s_hi[32 * 32];
+  exp_tab_init(s_lo, s_hi);
+  ExpTab tab{s_lo, s_hi, (int)(threadIdx.x & 31)};
+  int lane = blockIdx.x * blockDim.x + threadIdx.x;
+  bool active = lane < n_lanes;
+  if (!active) lane = n_lanes - 1;
+  const uint64_t seg_len = seg_start[lane + 1] - seg_start[lane];
+  const bool live = active && coded_index < seg_len;  // streams past their end idle (ragged last segment)
+  AcDecoder d;
+  d.resume(st[lane], payload + seg_off[lane], seg_off[lane + 1] - seg_off[lane]);
+  const uint32_t value = d.peek_value();
+  uint32_t sym, lo, hi;
+  double xe;
+  int errbits = 0;
+  cdf_col<MODE, OP_SEARCH>(logits + lane, ld, V, value, live, tab, sym, lo, hi, xe, errbits);
+  if (!live) return;
+  if (errbits) atomicOr(err, errbits);
+  d.consume(lo, hi);
+  st[lane] = d.s;
+  ids_out[seg_start[lane] + coded_index] = sym;
+  next_tok[lane] = sym;
+}
+
+__global__ void fill_int_kernel(int *__restrict__ p, int v, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+__global__ void sum_bits_kernel(const double *__restrict__ bits, const uint64_t *__restrict__ job_off, double *__restrict__ out, int n_jobs) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n_jobs) return;
+  double acc = 0.0;  // sequential f64, like `bits += ...` in src/main.rs:1747
+  for (uint64_t t = job_off[j]; t < job_off[j + 1]; t++) acc = __dadd_rn(acc, bits[t]);
+  out[j] = acc;
+}
+
+}  // namespace czk
+
+namespace cz {
+
+// -------------------------------------------------------------------------------------------------------------
+// Wave builder: rows of several chunks packed back to back (teacher-forced), each chunk its own sequence.
+// -------------------------------------------------------------------------------------------------------------
+struct Wave {
+  std::vector<long long> src;
+  std::vector<int> pos, kv_base, logit_rows;
+  size_t n_rows() const { return src.size(); }
+  size_t n_logit() const { return logit_rows.size(); }
+  void clear() {
+    src.clear();
+    pos.clear();
+    kv_base.clear();
+    logit_rows.clear();
+  }
+  // prime_src(k), coded_src(j): token source of prime position k / coded token j
+  template <class FP, class FC>
+  void add_chunk(uint32_t prime_len, uint32_t n_coded, FP prime_src, FC coded_src) {
+    const int base = (int)src.size();
+    int p = 0;
+    for (uint32_t k = 0; k < prime_len; k++, p++) {
+      src.push_back(prime_src(k));
+      pos.push_back(p);
+      kv_base.push_back(base);
+    }
+    for (uint32_t j = 0; j + 1 < n_coded; j++, p++) {  // the last coded token is never fed (its logits are unused)
+      src.push_back(coded_src(j));
+      pos.push_back(p);
+      kv_base.push_back(base);
+    }
+    for (uint32_t j = 0; j < n_coded; j++) logit_rows.push_back(base + (int)prime_len - 1 + (int)j);
+  }
+};
+
+struct DevBuf {
+  void *p = nullptr;
+  ~DevBuf() {
+    if (p) cudaFree(p);
+  }
+  int alloc(size_t bytes) {
+    if (p) cudaFree(p);
+    p = nullptr;
+    CZ_CUDA_TRY(cudaMalloc(&p, bytes ? bytes : 16));
+    return CZ_OK;
+  }
+  template <class T>
+  T *as() { return (T *)p; }
+};
+
+// Copies a wave's row metadata through the pinned staging buffer.  The buffer is reused by the next wave, so the
+// host waits for the PREVIOUS wave's copies (an event right after them) -- never for the kernels behind them.
+static int stage_and_upload(cz_model *m, const Wave &w, long long *src_dev, cudaStream_t st) {
+  Workspace &ws = m->ws;
+  const size_t R = w.n_rows(), NL = w.n_logit();
+  const size_t b_src = R * 8, b_i = R * 4, b_l = NL * 4;
+  if (!ws.stage_ev) CZ_CUDA_TRY(cudaEventCreateWithFlags(&ws.stage_ev, cudaEventDisableTiming));
+  else CZ_CUDA_TRY(cudaEventSynchronize(ws.stage_ev));
+  CZ_TRY(ensure_stage(m, b_src + 2 * b_i + b_l + 64));
+  char *h = (char *)ws.h_stage;
+  memcpy(h, w.src.data(), b_src);
+  memcpy(h + b_src, w.pos.data(), b_i);
+  memcpy(h + b_src + b_i, w.kv_base.data(), b_i);
+  memcpy(h + b_src + 2 * b_i, w.logit_rows.data(), b_l);
+  CZ_CUDA_TRY(cudaMemcpyAsync(src_dev, h, b_src, cudaMemcpyHostToDevice, st));
+  CZ_CUDA_TRY(cudaMemcpyAsync(ws.pos, h + b_src, b_i, cudaMemcpyHostToDevice, st));
+  CZ_CUDA_TRY(cudaMemcpyAsync(ws.kv_base, h + b_src + b_i, b_i, cudaMemcpyHostToDevice, st));
+  CZ_CUDA_TRY(cudaMemcpyAsync(ws.logit_rows, h + b_src + 2 * b_i, b_l, cudaMemcpyHostToDevice, st));
+  CZ_CUDA_TRY(cudaEventRecord(ws.stage_ev, st));
+  return CZ_OK;
+}
+
+// uploads a wave's metadata, gathers tokens, runs trunk + final norm.  On return ws.xn_logit holds n_logit rows.
+static int run_wave_trunk(cz_model *m, const Wave &w, const uint32_t *ids_dev, const uint32_t *extra_dev, uint32_t bos,
+                          long long *src_dev_scratch, cudaStream_t st) {
+  const size_t R = w.n_rows(), NL = w.n_logit();
+  CZ_TRY(ensure_workspace(m, R, NL));
+  Workspace &ws = m->ws;
+  CZ_TRY(stage_and_upload(m, w, src_dev_scratch, st));
+  CZ_LAUNCH(m->ctx, CZ_K_OTHER,
+            (czk::gather_tokens_kernel<<<(unsigned)ceil_div(R, 256), 256, 0, st>>>(src_dev_scratch, ids_dev, extra_dev, bos, ws.tok, (int)R)));
+  CZ_CHECK_LAUNCH();
+  KvView kv;
+  kv.k = ws.kpack;
+  kv.v = ws.vpack;
+  kv.layer_stride = 0;
+  CZ_TRY(forward_trunk(m, (int)R, kv, st));
+  CZ_TRY(final_norm_gather(m, (int)NL, st));
+  return CZ_OK;
+}
+
+// LM head + CDF op over the wave's logit columns, in sub-batches of ws.ld_sub columns.
+// syms_dev[j] is the symbol of column j; results go to lo_out/hi_out (OP_BOUNDS) or xe_out (OP_XE), indexed by column.
+static int run_wave_head(cz_model *m, size_t n_logit, int op, int mode, const uint32_t *syms_dev, uint32_t *lo_out, uint32_t *hi_out,
+                         double *xe_out, cudaStream_t st) {
+  Workspace &ws = m->ws;
+  int buf = 0;
+  for (size_t c0 = 0; c0 < n_logit; c0 += ws.ld_sub, buf ^= 1) {
+    const size_t nc = std::min(ws.ld_sub, n_logit - c0);
+    CZ_TRY(lm_head(m, (int)c0, (int)nc, ws.logits[buf], ws.ld_sub, st));
+    CZ_TRY(launch_cdf_cols(m->ctx, op, mode, ws.logits[buf], (size_t)m->cfg.vocab, nc, ws.ld_sub, syms_dev + c0, nullptr,
+                           lo_out ? lo_out + c0 : nullptr, hi_out ? hi_out + c0 : nullptr, xe_out ? xe_out + c0 : nullptr, st));
+  }
+  return CZ_OK;
+}
+
+static int check_schedule(const cz_schedule *s, size_t n_tokens) {
+  if (!s || s->n_segments == 0 || !s->seg_start || s->seg_start[0] != 0 || s->seg_start[s->n_segments] != n_tokens) {
+    set_error("schedule: need n_segments >= 1 and seg_start[0] = 0 .. seg_start[n] = n_tokens");
+    return CZ_ERR_INVALID;
+  }
+  for (uint32_t g = 0; g < s->n_segments; g++)
+    if (s->seg_start[g + 1] < s->seg_start[g]) {
+      set_error("schedule: seg_start must be non-decreasing");
+      return CZ_ERR_INVALID;
+    }
+  if (s->n_events && s->n_segments != 1) {
+    set_error("schedule: hint prime events need n_segments == 1");
+    return CZ_ERR_INVALID;
+  }
+  if (s->reprime_interval == 0 || s->context == 0) {
+    set_error("schedule: context and reprime_interval must be > 0");
+    return CZ_ERR_INVALID;
+  }
+  return CZ_OK;
+}
+
+static int coded_mode(const cz_model *m) { return m->cfg.arch == CZ_ARCH_RWKV7 ? CZ_CDF_RWKV_LITERALS : CZ_CDF_SMOLLM; }
+
+// Core of cz_encode / cz_encode_dev: ids already on the device.  Leaves the compacted payload in out_dev
+// (device) and the per-segment offsets in seg_off_host.
+static int encode_core(cz_model *m, const uint32_t *ids_dev, size_t n_tokens, const cz_schedule *sched, uint8_t *out_dev,
+                       size_t out_cap, uint64_t *seg_off_host) {
+  cz_ctx *ctx = m->ctx;
+  cudaStream_t st = ctx->stream;
+  const uint32_t S = sched->n_segments;
+  const size_t max_rows = sched->max_batch_tokens ? sched->max_batch_tokens : (size_t)262144;
+  DevBuf d_lo, d_hi, d_src, d_extra, d_lane, d_raw, d_misc;
+  CZ_TRY(d_lo.alloc(n_tokens * 4));
+  CZ_TRY(d_hi.alloc(n_tokens * 4));
+  // explicit prime token lists of the hint events
+  std::vector<uint32_t> extra;
+  std::vector<size_t> ev_off(sched->n_events + 1, 0);
+  for (uint32_t e = 0; e < sched->n_events; e++) {
+    ev_off[e] = extra.size();
+    extra.insert(extra.end(), sched->events[e].prime, sched->events[e].prime + sched->events[e].prime_len);
+  }
+  CZ_TRY(d_extra.alloc(extra.size() * 4));
+  if (!extra.empty()) CZ_CUDA_TRY(cudaMemcpyAsync(d_extra.p, extra.data(), extra.size() * 4, cudaMemcpyHostToDevice, st));
+
+  size_t src_cap = 0;
+  Wave w;
+  size_t wave_first = 0;  // global coded index of the wave's first logit column
+  size_t coded_done = 0;
+  auto flush = [&]() -> int {
+    if (w.n_rows() == 0) return CZ_OK;
+    if (w.n_rows() > src_cap) {
+      src_cap = w.n_rows() + w.n_rows() / 8 + 1024;
+      CZ_CUDA_TRY(cudaStreamSynchronize(st));
+      CZ_TRY(d_src.alloc(src_cap * 8));
+    }
+    CZ_TRY(run_wave_trunk(m, w, ids_dev, d_extra.as<uint32_t>(), sched->bos, d_src.as<long long>(), st));
+    CZ_TRY(run_wave_head(m, w.n_logit(), czk::OP_BOUNDS, coded_mode(m), ids_dev + wave_first, d_lo.as<uint32_t>() + wave_first,
+                         d_hi.as<uint32_t>() + wave_first, nullptr, st));
+    wave_first += w.n_logit();
+    w.clear();
+    return CZ_OK;
+  };
+  std::vector<Chunk> chunks;
+  for (uint32_t g = 0; g < S; g++) {
+    const uint64_t t0 = sched->seg_start[g], n = sched->seg_start[g + 1] - t0;
+    build_chunks(n, sched->context, sched->reprime_interval, sched->events, sched->n_events, chunks);
+    for (const Chunk &c : chunks) {
+      const size_t rows = (size_t)c.prime_len + c.n_coded - 1;
+      if (rows > 2000) {
+        set_error("schedule produces a sequence longer than the attention kernel supports (2000 positions)");
+        return CZ_ERR_UNSUPPORTED;
+      }
+      if (w.n_rows() + rows > max_rows && w.n_rows() > 0) CZ_TRY(flush());
+      // S[k] = k == 0 ? bos : ids[t0 + k - 1];  coded token j of the chunk = ids[t0 + first + j]
+      if (c.event >= 0) {
+        const long long e0 = (long long)ev_off[c.event];
+        w.add_chunk(c.prime_len, c.n_coded, [&](uint32_t k) { return (long long)(-2 - (e0 + k)); },
+                    [&](uint32_t j) { return (long long)(t0 + c.first + j); });
+      } else {
+        w.add_chunk(c.prime_len, c.n_coded,
+                    [&](uint32_t k) { uint64_t si = c.prime_start + k; return si == 0 ? -1ll : (long long)(t0 + si - 1); },
+                    [&](uint32_t j) { return (long long)(t0 + c.first + j); });
+      }
+      coded_done += c.n_coded;
+    }
+  }
+  CZ_TRY(flush());
+  if (coded_done != n_tokens || wave_first != n_tokens) {
+    set_error("internal: schedule did not cover every token");
+    return CZ_ERR_INVALID;
+  }
+  // ---- arithmetic-coder lanes: one per segment ----
+  std::vector<uint64_t> lane_off(sched->seg_start, sched->seg_start + S + 1), raw_off(S + 1);
+  for (uint32_t g = 0; g <= S; g++) raw_off[g] = 4 * lane_off[g] + 8 * (uint64_t)g;
+  CZ_TRY(d_lane.alloc((S + 1) * 8 * 4 + 64));
+  uint64_t *d_lane_off = d_lane.as<uint64_t>(), *d_raw_off = d_lane_off + (S + 1), *d_len = d_raw_off + (S + 1),
+           *d_dst_off = d_len + (S + 1);
+  unsigned long long *d_eidx = (unsigned long long *)(d_dst_off + (S + 1));
+  const unsigned long long none = ~0ull;
+  CZ_CUDA_TRY(cudaMemcpyAsync(d_lane_off, lane_off.data(), (S + 1) * 8, cudaMemcpyHostToDevice, st));
+  CZ_CUDA_TRY(cudaMemcpyAsync(d_raw_off, raw_off.data(), (S + 1) * 8, cudaMemcpyHostToDevice, st));
+  CZ_CUDA_TRY(cudaMemcpyAsync(d_eidx, &none, 8, cudaMemcpyHostToDevice, st));
+  CZ_TRY(d_raw.alloc(raw_off[S] + 16));
+  CZ_TRY(launch_ac_encode_lanes(ctx, d_lo.as<uint32_t>(), d_hi.as<uint32_t>(), d_lane_off, S, d_raw.as<uint8_t>(), d_raw_off, d_len,
+                                d_eidx, st));
+  std::vector<uint64_t> len(S);
+  CZ_CUDA_TRY(cudaMemcpyAsync(len.data(), d_len, S * 8, cudaMemcpyDeviceToHost, st));
+  CZ_TRY(fetch_device_status(ctx, d_eidx, nullptr));
+  seg_off_host[0] = 0;
+  for (uint32_t g = 0; g < S; g++) seg_off_host[g + 1] = seg_off_host[g] + len[g];
+  if (seg_off_host[S] > out_cap) {
+    set_error("output buffer too small: need " + std::to_string(seg_off_host[S]) + " bytes");
+    return CZ_ERR_NOMEM;
+  }
+  CZ_CUDA_TRY(cudaMemcpyAsync(d_dst_off, seg_off_host, (S + 1) * 8, cudaMemcpyHostToDevice, st));
+  CZ_LAUNCH(ctx, CZ_K_CODER, (czk::compact_payload_kernel<<<S, 128, 0, st>>>(d_raw.as<uint8_t>(), d_raw_off, d_dst_off, out_dev)));
+  CZ_CHECK_LAUNCH();
+  CZ_CUDA_TRY(cudaStreamSynchronize(st));
+  return CZ_OK;
+}
+
+}  // namespace cz
+
+using namespace cz;
+
+// =============================================================================================================
+struct cz_session {
+  cz_model *m = nullptr;
+  size_t index_pos = 0;
+  int max_pos = 1536;
+  __nv_bfloat16 *k = nullptr, *v = nullptr;  // [L][max_pos][kvd]
+  float *logits_dev = nullptr;               // [V][4]
+  long long *src_dev = nullptr;
+  uint32_t *hist_dev = nullptr;
+};
+
+static int session_forward(cz_session *s, const uint32_t *tok, size_t n, float *logits_out) {
+  cz_model *m = s->m;
+  cz_ctx *ctx = m->ctx;
+  cudaStream_t st = ctx->stream;
+  CZ_CUDA_TRY(cudaSetDevice(ctx->device));
+  if (s->index_pos + n > (size_t)s->max_pos) {
+    set_error("session: KV capacity exceeded");
+    return CZ_ERR_INVALID;
+  }
+  CZ_TRY(ensure_workspace(m, n, 1));
+  Workspace &ws = m->ws;
+  std::vector<int> pos(n), base(n, 0);
+  for (size_t i = 0; i < n; i++) pos[i] = (int)(s->index_pos + i);
+  const int lrow = (int)n - 1;
+  CZ_CUDA_TRY(cudaMemcpyAsync(ws.tok, tok, n * 4, cudaMemcpyHostToDevice, st));
+  CZ_CUDA_TRY(cudaMemcpyAsync(ws.pos, pos.data(), n * 4, cudaMemcpyHostToDevice, st));
+  CZ_CUDA_TRY(cudaMemcpyAsync(ws.kv_base, base.data(), n * 4, cudaMemcpyHostToDevice, st));
+  CZ_CUDA_TRY(cudaMemcpyAsync(ws.logit_rows, &lrow, 4, cudaMemcpyHostToDevice, st));
+  CZ_CUDA_TRY(cudaStreamSynchronize(st));  // pos/base are stack-owned
+  KvView kv;
+  kv.k = s->k;
+  kv.v = s->v;
+  kv.layer_stride = (size_t)s->max_pos * m->cfg.n_kv_heads * 64;
+  CZ_TRY(forward_trunk(m, (int)n, kv, st));
+  CZ_TRY(final_norm_gather(m, 1, st));
+  CZ_TRY(lm_head(m, 0, 1, s->logits_dev, 4, st));
+  CZ_CUDA_TRY(cudaMemcpy2DAsync(logits_out, 4, s->logits_dev, 16, 4, (size_t)m->cfg.vocab, cudaMemcpyDeviceToHost, st));
+  CZ_CUDA_TRY(cudaStreamSynchronize(st));
+  s->index_pos += n;
+  return CZ_OK;
+}
+
+extern "C" {
+
+int cz_session_new(cz_model *m, cz_session **out) {
+  if (!m || !out) return CZ_ERR_INVALID;
+  CZ_TRY(require_device(m->ctx));
+  CZ_TRY(model_finalize(m));
+  cz_session *s = new cz_session();
+  s->m = m;
+  const size_t kvd = (size_t)m->cfg.n_kv_heads * 64, L = m->cfg.n_layers;
+  CZ_CUDA_TRY(cudaSetDevice(m->ctx->device));
+  CZ_CUDA_TRY(cudaMalloc((void **)&s->k, L * s->max_pos * kvd * 2));
+  CZ_CUDA_TRY(cudaMalloc((void **)&s->v, L * s->max_pos * kvd * 2));
+  CZ_CUDA_TRY(cudaMalloc((void **)&s->logits_dev, (size_t)m->cfg.vocab * 16));
+  *out = s;
+  return CZ_OK;
+}
+void cz_session_free(cz_session *s) {
+  if (!s) return;
+  cudaSetDevice(s->m->ctx->device);
+  cudaDeviceSynchronize();
+  if (s->k) cudaFree(s->k);
+  if (s->v) cudaFree(s->v);
+  if (s->logits_dev) cudaFree(s->logits_dev);
+  delete s;
+}
+size_t cz_session_vocab_size(const cz_session *s) { return s ? (size_t)s->m->cfg.vocab : 0; }
+size_t cz_session_max_context_length(const cz_session *s) {
+  return s && s->m->cfg.arch == CZ_ARCH_SMOLLM ? 512 : (size_t)-1;  // src/models.rs:91, 150
+}
+size_t cz_session_index_pos(const cz_session *s) { return s ? s->index_pos : 0; }
+int cz_session_step_logits(cz_session *s, uint32_t token, float *logits_out) {  // src/models.rs:92-103
+  if (!s || !logits_out) return CZ_ERR_INVALID;
+  return session_forward(s, &token, 1, logits_out);
+}
+int cz_session_reprime(cz_session *s, const uint32_t *history, size_t n, float *logits_out) {  // src/models.rs:104-119
+  if (!s || !logits_out) return CZ_ERR_INVALID;
+  if (n == 0) {
+    set_error("reprime called with empty history");
+    return CZ_ERR_INVALID;
+  }
+  s->index_pos = 0;  // fresh KV cache
+  return session_forward(s, history, n, logits_out);
+}
+
+// -------------------------------------------------------------------------------------------------------------
+int cz_encode_dev(cz_model *m, const uint32_t *ids_dev, size_t n_tokens, const cz_schedule *sched, uint8_t *out_dev,
+                  size_t out_cap, uint64_t *seg_off_host) {
+  if (!m || !seg_off_host) return CZ_ERR_INVALID;
+  CZ_TRY(require_device(m->ctx));
+  CZ_TRY(check_schedule(sched, n_tokens));
+  CZ_TRY(model_finalize(m));
+  CZ_CUDA_TRY(cudaSetDevice(m->ctx->device));
+  if (n_tokens == 0) {
+    // every segment is an empty stream: finish() alone emits 0x40 (1 byte)
+  }
+  return encode_core(m, ids_dev, n_tokens, sched, out_dev, out_cap, seg_off_host);
+}
+
+int cz_encode(cz_model *m, const uint32_t *ids, size_t n_tokens, const cz_schedule *sched, cz_bitstreams *out) {
+  if (!m || !out || !out->data || !out->seg_off || (n_tokens && !ids)) return CZ_ERR_INVALID;
+  CZ_TRY(require_device(m->ctx));
+  CZ_TRY(check_schedule(sched, n_tokens));
+  CZ_TRY(model_finalize(m));
+  cz_ctx *ctx = m->ctx;
+  CZ_CUDA_TRY(cudaSetDevice(ctx->device));
+  DevBuf d_ids, d_out;
+  CZ_TRY(d_ids.alloc(n_tokens * 4));
+  if (n_tokens) CZ_CUDA_TRY(cudaMemcpyAsync(d_ids.p, ids, n_tokens * 4, cudaMemcpyHostToDevice, ctx->stream));
+  const size_t cap = 4 * n_tokens + 8 * (size_t)sched->n_segments + 16;
+  CZ_TRY(d_out.alloc(cap));
+  CZ_TRY(encode_core(m, d_ids.as<uint32_t>(), n_tokens, sched, d_out.as<uint8_t>(), cap, out->seg_off));
+  const uint64_t total = out->seg_off[sched->n_segments];
+  if (total > out->cap) {
+    set_error("cz_encode: output capacity " + std::to_string(out->cap) + " < payload " + std::to_string(total));
+    return CZ_ERR_NOMEM;
+  }
+  CZ_CUDA_TRY(cudaMemcpyAsync(out->data, d_out.p, total, cudaMemcpyDeviceToHost, ctx->stream));
+  CZ_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  return CZ_OK;
+}
+
+// -------------------------------------------------------------------------------------------------------------
+int cz_decode(cz_model *m, const uint8_t *payload, const uint64_t *seg_off, size_t n_tokens, const cz_schedule *sched,
+              uint32_t *ids_out) {
+  if (!m || !payload || !seg_off || (n_tokens && !ids_out)) return CZ_ERR_INVALID;
+  CZ_TRY(require_device(m->ctx));
+  CZ_TRY(check_schedule(sched, n_tokens));
+  CZ_TRY(model_finalize(m));
+  if (sched->n_events) {
+    set_error("cz_decode: hint prime events are not wired into the batched decoder yet (use the session shim)");
+    return CZ_ERR_UNSUPPORTED;
+  }
+  if (n_tokens == 0) return CZ_OK;
+  cz_ctx *ctx = m->ctx;
+  cudaStream_t st = ctx->stream;
+  CZ_CUDA_TRY(cudaSetDevice(ctx->device));
+  const cz_model_config &c = m->cfg;
+  const uint32_t S = sched->n_segments;
+  const size_t kvd = (size_t)c.n_kv_heads * 64, L = c.n_layers;
+  uint64_t max_len = 0;
+  for (uint32_t g = 0; g < S; g++) max_len = std::max<uint64_t>(max_len, sched->seg_start[g + 1] - sched->seg_start[g]);
+  std::vector<Chunk> chunks;  // master timeline = chunk structure of the longest segment
+  build_chunks(max_len, sched->context, sched->reprime_interval, nullptr, 0, chunks);
+  size_t max_pos = 0;
+  for (const Chunk &ch : chunks) max_pos = std::max<size_t>(max_pos, (size_t)ch.prime_len + ch.n_coded);
+  max_pos = (max_pos + 63) & ~(size_t)63;
+  if (max_pos > 2000) {
+    set_error("schedule produces a sequence longer than the attention kernel supports");
+    return CZ_ERR_UNSUPPORTED;
+  }
+  const size_t S_pad = (S + 3) & ~(size_t)3;
+  DevBuf d_pay, d_off, d_start, d_state, d_ids, d_k, d_v, d_logits, d_src, d_kvb;
+  const uint64_t pay_total = seg_off[S];
+  CZ_TRY(d_pay.alloc(pay_total + 16));
+  CZ_TRY(d_off.alloc((S + 1) * 8));
+  CZ_TRY(d_start.alloc((S + 1) * 8));
+  CZ_TRY(d_state.alloc(S * sizeof(czk::AcDecoderState)));
+  CZ_TRY(d_ids.alloc(n_tokens * 4));
+  CZ_TRY(d_k.alloc(L * S * max_pos * kvd * 2));
+  CZ_TRY(d_v.alloc(L * S * max_pos * kvd * 2));
+  CZ_TRY(d_logits.alloc((size_t)c.vocab * S_pad * 4));
+  CZ_CUDA_TRY(cudaMemcpyAsync(d_pay.p, payload, pay_total, cudaMemcpyHostToDevice, st));
+  CZ_CUDA_TRY(cudaMemcpyAsync(d_off.p, seg_off, (S + 1) * 8, cudaMemcpyHostToDevice, st));
+  CZ_CUDA_TRY(cudaMemcpyAsync(d_start.p, sched->seg_start, (S + 1) * 8, cudaMemcpyHostToDevice, st));
+  CZ_LAUNCH(ctx, CZ_K_CODER,
+            (czk::ac_decoder_init_kernel<<<(unsigned)ceil_div(S, 128), 128, 0, st>>>(d_pay.as<uint8_t>(), d_off.as<uint64_t>(), (int)S,
+                                                                                    d_state.as<czk::AcDecoderState>())));
+  CZ_CHECK_LAUNCH();
+  KvView kv;
+  kv.k = d_k.as<__nv_bfloat16>();
+  kv.v = d_v.as<__nv_bfloat16>();
+  kv.layer_stride = (size_t)S * max_pos * kvd;
+  size_t src_cap = 0;
+  Wave w;
+  // per-stream constant metadata for the single-token steps
+  std::vector<int> kvb(S), lrows(S);
+  for (uint32_t g = 0; g < S; g++) {
+    kvb[g] = (int)(g * max_pos);
+    lrows[g] = (int)g;
+  }
+  CZ_TRY(d_kvb.alloc(S * 8));
+  int *d_kvb_i = d_kvb.as<int>(), *d_lrows_i = d_kvb_i + S;
+  CZ_CUDA_TRY(cudaMemcpyAsync(d_kvb_i, kvb.data(), S * 4, cudaMemcpyHostToDevice, st));
+  CZ_CUDA_TRY(cudaMemcpyAsync(d_lrows_i, lrows.data(), S * 4, cudaMemcpyHostToDevice, st));
+  CZ_CUDA_TRY(cudaStreamSynchronize(st));
+
+  for (const Chunk &ch : chunks) {
+    // ---- prime every stream that is still live at this chunk (fresh cache: positions 0 .. prime_len-1) ----
+    std::vector<uint32_t> live;
+    for (uint32_t g = 0; g < S; g++)
+      if (sched->seg_start[g + 1] - sched->seg_start[g] > ch.first) live.push_back(g);
+    if (live.empty()) break;
+    // column g of the logits must be stream g: live streams have to be the prefix [0, n_live), i.e. segment
+    // lengths non-increasing (the host splitter puts the longer segments first)
+    for (size_t i = 0; i < live.size(); i++)
+      if (live[i] != i) {
+        set_error("cz_decode: segment lengths must be non-increasing (longest first) for the lock-step decoder");
+        return CZ_ERR_UNSUPPORTED;
+      }
+    w.clear();
+    for (uint32_t g : live) {
+      const uint64_t t0 = sched->seg_start[g];
+      const int base = (int)(g * max_pos);
+      for (uint32_t k = 0; k < ch.prime_len; k++) {
+        const uint64_t si = ch.prime_start + k;
+        w.src.push_back(si == 0 ? -1ll : (long long)(t0 + si - 1));
+        w.pos.push_back((int)k);
+        w.kv_base.push_back(base);
+      }
+      w.logit_rows.push_back((int)w.src.size() - 1);
+    }
+    {
+      const size_t R = w.n_rows(), NL = w.n_logit();
+      if (R > src_cap) {
+        src_cap = R + R / 8 + 1024;
+        CZ_CUDA_TRY(cudaStreamSynchronize(st));
+        CZ_TRY(d_src.alloc(src_cap * 8));
+      }
+      CZ_TRY(ensure_workspace(m, std::max<size_t>(R, S), std::max<size_t>(NL, S)));
+      Workspace &ws = m->ws;
+      const size_t b_src = R * 8, b_i = R * 4, b_l = NL * 4;
+      CZ_TRY(ensure_stage(m, b_src + 2 * b_i + b_l + 64));
+      char *h = (char *)ws.h_stage;
+      memcpy(h, w.src.data(), b_src);
+      memcpy(h + b_src, w.pos.data(), b_i);
+      memcpy(h + b_src + b_i, w.kv_base.data(), b_i);
+      memcpy(h + b_src + 2 * b_i, w.logit_rows.data(), b_l);
+      CZ_CUDA_TRY(cudaMemcpyAsync(d_src.p, h, b_src, cudaMemcpyHostToDevice, st));
+      CZ_CUDA_TRY(cudaMemcpyAsync(ws.pos, h + b_src, b_i, cudaMemcpyHostToDevice, st));
+      CZ_CUDA_TRY(cudaMemcpyAsync(ws.kv_base, h + b_src + b_i, b_i, cudaMemcpyHostToDevice, st));
+      CZ_CUDA_TRY(cudaMemcpyAsync(ws.logit_rows, h + b_src + 2 * b_i, b_l, cudaMemcpyHostToDevice, st));
+      CZ_LAUNCH(ctx, CZ_K_OTHER,
+                (czk::gather_tokens_kernel<<<(unsigned)ceil_div(R, 256), 256, 0, st>>>(d_src.as<long long>(), d_ids.as<uint32_t>(), nullptr,
+                                                                                      sched->bos, ws.tok, (int)R)));
+      CZ_CHECK_LAUNCH();
+      CZ_TRY(forward_trunk(m, (int)R, kv, st));
+      CZ_TRY(final_norm_gather(m, (int)NL, st));
+      CZ_TRY(lm_head(m, 0, (int)NL, d_logits.as<float>(), S_pad, st));
+    }
+    const int n_live = (int)live.size();
+    Workspace &ws = m->ws;
+    for (uint32_t j = 0; j < ch.n_coded; j++) {
+      const uint64_t i = ch.first + j;
+      if (coded_mode(m) == CZ_CDF_SMOLLM)
+        CZ_LAUNCH(ctx, CZ_K_CDF,
+                  (czk::decode_step_kernel<CZ_CDF_SMOLLM><<<(unsigned)ceil_div(n_live, 128), 128, 0, st>>>(
+                      d_logits.as<float>(), c.vocab, S_pad, n_live, d_pay.as<uint8_t>(), d_off.as<uint64_t>(), d_start.as<uint64_t>(), i,
+                      d_state.as<czk::AcDecoderState>(), d_ids.as<uint32_t>(), ws.tok, ctx->err_flag_dev)));
+      else
+        CZ_LAUNCH(ctx, CZ_K_CDF,
+                  (czk::decode_step_kernel<CZ_CDF_RWKV_LITERALS><<<(unsigned)ceil_div(n_live, 128), 128, 0, st>>>(
+                      d_logits.as<float>(), c.vocab, S_pad, n_live, d_pay.as<uint8_t>(), d_off.as<uint64_t>(), d_start.as<uint64_t>(), i,
+                      d_state.as<czk::AcDecoderState>(), d_ids.as<uint32_t>(), ws.tok, ctx->err_flag_dev)));
+      CZ_CHECK_LAUNCH();
+      if (j + 1 == ch.n_coded) break;  // the step after the chunk's last symbol is never used (next chunk re-primes)
+      // single-token step for every live stream: tok = symbol just decoded, position = prime_len + j
+      CZ_LAUNCH(ctx, CZ_K_OTHER,
+                (czk::fill_int_kernel<<<(unsigned)ceil_div(n_live, 256), 256, 0, st>>>(ws.pos, (int)(ch.prime_len + j), n_live)));
+      CZ_CHECK_LAUNCH();
+      CZ_CUDA_TRY(cudaMemcpyAsync(ws.kv_base, d_kvb_i, (size_t)n_live * 4, cudaMemcpyDeviceToDevice, st));
+      CZ_CUDA_TRY(cudaMemcpyAsync(ws.logit_rows, d_lrows_i, (size_t)n_live * 4, cudaMemcpyDeviceToDevice, st));
+      CZ_TRY(forward_trunk(m, n_live, kv, st));
+      CZ_TRY(final_norm_gather(m, n_live, st));
+      CZ_TRY(lm_head(m, 0, n_live, d_logits.as<float>(), S_pad, st));
+    }
+    CZ_TRY(fetch_device_status(ctx, nullptr, nullptr));
+  }
+  CZ_CUDA_TRY(cudaMemcpyAsync(ids_out, d_ids.p, n_tokens * 4, cudaMemcpyDeviceToHost, st));
+  CZ_CUDA_TRY(cudaStreamSynchronize(st));
+  return CZ_OK;
+}
+
+// -------------------------------------------------------------------------------------------------------------
+int cz_xe_bits(cz_model *m, const cz_xe_job *jobs, size_t n_jobs, double *bits_out) {
+  if (!m || (n_jobs && (!jobs || !bits_out))) return CZ_ERR_INVALID;
+  CZ_TRY(require_device(m->ctx));
+  CZ_TRY(model_finalize(m));
+  if (n_jobs == 0) return CZ_OK;
+  cz_ctx *ctx = m->ctx;
+  cudaStream_t st = ctx->stream;
+  CZ_CUDA_TRY(cudaSetDevice(ctx->device));
+  // all tokens go to the `extra` buffer: [prime_0 | targets_0 | prime_1 | targets_1 | ...]; a parallel buffer holds
+  // the targets contiguously in job order so that column j's symbol is tgt[j]
+  std::vector<uint32_t> extra, tgt;
+  std::vector<uint64_t> job_off(n_jobs + 1, 0);
+  std::vector<size_t> p_off(n_jobs), t_off(n_jobs);
+  for (size_t j = 0; j < n_jobs; j++) {
+    if (jobs[j].n_targets && jobs[j].prime_len == 0) {
+      set_error("xe job with targets needs a non-empty prime (the reference bails on an empty reprime)");
+      return CZ_ERR_INVALID;
+    }
+    p_off[j] = extra.size();
+    extra.insert(extra.end(), jobs[j].prime, jobs[j].prime + jobs[j].prime_len);
+    t_off[j] = extra.size();
+    extra.insert(extra.end(), jobs[j].targets, jobs[j].targets + jobs[j].n_targets);
+    tgt.insert(tgt.end(), jobs[j].targets, jobs[j].targets + jobs[j].n_targets);
+    job_off[j + 1] = job_off[j] + jobs[j].n_targets;
+  }
+  const size_t n_cols = tgt.size();
+  DevBuf d_extra, d_tgt, d_bits, d_src, d_joff, d_out;
+  CZ_TRY(d_extra.alloc(extra.size() * 4));
+  CZ_TRY(d_tgt.alloc(n_cols * 4));
+  CZ_TRY(d_bits.alloc(n_cols * 8));
+  CZ_TRY(d_joff.alloc((n_jobs + 1) * 8));
+  CZ_TRY(d_out.alloc(n_jobs * 8));
+  CZ_CUDA_TRY(cudaMemcpyAsync(d_extra.p, extra.data(), extra.size() * 4, cudaMemcpyHostToDevice, st));
+  if (n_cols) CZ_CUDA_TRY(cudaMemcpyAsync(d_tgt.p, tgt.data(), n_cols * 4, cudaMemcpyHostToDevice, st));
+  CZ_CUDA_TRY(cudaMemcpyAsync(d_joff.p, job_off.data(), (n_jobs + 1) * 8, cudaMemcpyHostToDevice, st));
+  const size_t max_rows = 262144;
+  size_t src_cap = 0, col_first = 0;
+  Wave w;
+  auto flush = [&]() -> int {
+    if (w.n_rows() == 0) return CZ_OK;
+    if (w.n_rows() > src_cap) {
+      src_cap = w.n_rows() + w.n_rows() / 8 + 1024;
+      CZ_CUDA_TRY(cudaStreamSynchronize(st));
+      CZ_TRY(d_src.alloc(src_cap * 8));
+    }
+    CZ_TRY(run_wave_trunk(m, w, nullptr, d_extra.as<uint32_t>(), 0, d_src.as<long long>(), st));
+    CZ_TRY(run_wave_head(m, w.n_logit(), czk::OP_XE, coded_mode(m), d_tgt.as<uint32_t>() + col_first, nullptr, nullptr,
+                         d_bits.as<double>() + col_first, st));
+    col_first += w.n_logit();
+    w.clear();
+    return CZ_OK;
+  };
+  for (size_t j = 0; j < n_jobs; j++) {
+    if (jobs[j].n_targets == 0) continue;
+    const size_t rows = (size_t)jobs[j].prime_len + jobs[j].n_targets - 1;
+    if (rows > 2000) {
+      set_error("xe job longer than the attention kernel supports");
+      return CZ_ERR_UNSUPPORTED;
+    }
+    if (w.n_rows() + rows > max_rows && w.n_rows() > 0) CZ_TRY(flush());
+    const long long p0 = (long long)p_off[j], t0 = (long long)t_off[j];
+    w.add_chunk(jobs[j].prime_len, jobs[j].n_targets, [&](uint32_t k) { return -2 - (p0 + k); }, [&](uint32_t q) { return -2 - (t0 + q); });
+  }
+  CZ_TRY(flush());
+  CZ_LAUNCH(ctx, CZ_K_OTHER,
+            (czk::sum_bits_kernel<<<(unsigned)ceil_div(n_jobs, 128), 128, 0, st>>>(d_bits.as<double>(), d_joff.as<uint64_t>(),
+                                                                                  d_out.as<double>(), (int)n_jobs)));
+  CZ_CHECK_LAUNCH();
+  CZ_CUDA_TRY(cudaMemcpyAsync(bits_out, d_out.p, n_jobs * 8, cudaMemcpyDeviceToHost, st));
+  return fetch_device_status(ctx, nullptr, nullptr);
+}
+
+int cz_chunk_logits(cz_model *m, const uint32_t *prime, size_t prime_len, const uint32_t *targets, size_t n_targets,
+                    float *logits_out) {
+  if (!m || !prime || !prime_len || !n_targets || !logits_out) return CZ_ERR_INVALID;
+  CZ_TRY(require_device(m->ctx));
+  CZ_TRY(model_finalize(m));
+  cz_ctx *ctx = m->ctx;
+  cudaStream_t st = ctx->stream;
+  CZ_CUDA_TRY(cudaSetDevice(ctx->device));
+  std::vector<uint32_t> extra(prime, prime + prime_len);
+  if (n_targets > 1) extra.insert(extra.end(), targets, targets + n_targets - 1);
+  DevBuf d_extra, d_src;
+  CZ_TRY(d_extra.alloc(extra.size() * 4));
+  CZ_CUDA_TRY(cudaMemcpyAsync(d_extra.p, extra.data(), extra.size() * 4, cudaMemcpyHostToDevice, st));
+  Wave w;
+  w.add_chunk((uint32_t)prime_len, (uint32_t)n_targets, [&](uint32_t k) { return -2 - (long long)k; },
+              [&](uint32_t q) { return -2 - (long long)(prime_len + q); });
+  CZ_TRY(d_src.alloc(w.n_rows() * 8));
+  CZ_TRY(run_wave_trunk(m, w, nullptr, d_extra.as<uint32_t>(), 0, d_src.as<long long>(), st));
+  Workspace &ws = m->ws;
+  const size_t V = m->cfg.vocab;
+  std::vector<float> tmp(V * ws.ld_sub);
+  for (size_t c0 = 0; c0 < n_targets; c0 += ws.ld_sub) {
+    const size_t nc = std::min(ws.ld_sub, n_targets - c0);
+    CZ_TRY(lm_head(m, (int)c0, (int)nc, ws.logits[0], ws.ld_sub, st));
+    CZ_CUDA_TRY(cudaMemcpyAsync(tmp.data(), ws.logits[0], V * ws.ld_sub * 4, cudaMemcpyDeviceToHost, st));
+    CZ_CUDA_TRY(cudaStreamSynchronize(st));
+    for (size_t j = 0; j < nc; j++)
+      for (size_t v = 0; v < V; v++) logits_out[(c0 + j) * V + v] = tmp[v * ws.ld_sub + j];
+  }
+  return CZ_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,31 @@
+// Dense-contraction interface shared by the tcgen05 and SIMT engines.
+#pragma once
+#include <cuda_runtime.h>
+
+struct cz_ctx;
+
+namespace cz {
+
+enum GemmEpilogue {
+  EPI_STORE_F32 = 0,    // C[M][ldc] f32  = A*B^T
+  EPI_ADD_F32 = 1,      // C[M][ldc] f32 += A*B^T          (residual add fused into o_proj / down_proj)
+  EPI_SWIGLU_BF16 = 2,  // C[M][ldc] bf16 = silu(gate)*up   (B rows packed per tile: BN/2 gate rows then BN/2 up rows; N = 2*ffn)
+  EPI_STORE_BF16 = 3,   // C[M][ldc] bf16 = A*B^T
+};
+
+struct GemmArgs {
+  const void *a;  // bf16 [M][lda], K-major
+  const void *b;  // bf16 [N][ldb], K-major (nn.Linear weight layout [out][in])
+  void *c;
+  int M, N, K;
+  int lda, ldb, ldc;
+  int epi;  // GemmEpilogue
+  int bn;   // tile width: 192 or 256 (also the gate/up packing granularity for EPI_SWIGLU_BF16)
+};
+
+int gemm_tcgen05(cz_ctx *ctx, const GemmArgs &g, cudaStream_t stream);
+int gemm_simt(cz_ctx *ctx, const GemmArgs &g, cudaStream_t stream);
+// engine: CZ_ENGINE_TCGEN05 / CZ_ENGINE_SIMT
+int gemm(cz_ctx *ctx, int engine, const GemmArgs &g, cudaStream_t stream);
+
+}  // namespace cz

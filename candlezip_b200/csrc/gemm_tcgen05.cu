@@ -1,0 +1,420 @@
+// K4: persistent, warp-specialised tcgen05 GEMM for sm_100a.
+//
+//   C[M,N] (+)= A[M,K] * B[N,K]^T        A, B bf16 K-major (row-major [rows][K]), fp32 accumulate in TMEM.
+//
+// Replaces the candle matmuls behind SmolLM's q/k/v/o/gate/up/down/lm_head projections (candle-transformers
+// llama.rs, called from src/models.rs:94,110) and RWKV-7's Linear layers (candle_rwkv7/src/models/rwkv7.rs:205-234,
+// 325, 426-427, 520).  Design:
+//   * one CTA per SM, persistent over output tiles of 128 x BN (tile index -> (m_blk, n_blk) with n fastest so
+//     the CTAs running at the same time share the A rows in L2);
+//   * warp 0: TMA producer (cp.async.bulk.tensor 2D, SWIZZLE_128B, BLOCK_K = 64 bf16 = one 128-byte swizzle row);
+//   * warp 1: TMEM allocator + single-thread tcgen05.mma issuer (UMMA 128 x BN x 16, cta_group::1);
+//   * warps 2-5: epilogue, one TMEM lane quadrant each (tcgen05.ld 32x32b), double-buffered accumulator so the
+//     epilogue of tile i overlaps the MMAs of tile i+1;
+//   * three mbarrier pipelines: smem full/empty (TMA <-> MMA), TMEM full/empty (MMA <-> epilogue).
+// ROW INVARIANCE (decode safety): an output element depends only on its A row, its B row and K; the K loop order
+// and the instruction shape are fixed per (BN, K), there is no split-K and no atomics, so the same activation
+// row gives bit-identical results whatever the batch size, tile position or GPU count.
+#include <cuda.h>
+
+#include "cz_common.cuh"
+#include "gemm.h"
+
+namespace czk {
+
+using cz::EPI_ADD_F32;
+using cz::EPI_STORE_BF16;
+using cz::EPI_STORE_F32;
+using cz::EPI_SWIGLU_BF16;
+
+constexpr int BM = 128;
+constexpr int BK = 64;  // bf16 elements: 128 bytes = one swizzle row
+constexpr int UMMA_K = 16;
+constexpr int GEMM_THREADS = 192;
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int kStages = BN <= 192 ? 5 : 4;
+  static constexpr int kABytes = BM * BK * 2;
+  static constexpr int kBBytes = BN * BK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kTmemCols = 512;  // 2 accumulator stages of BN columns, power of two >= 2*BN
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
+//   [0,14) start>>4 | [16,30) LBO>>4 (=1, unused for swizzled K-major) | [32,46) SBO>>4 (8 rows * 128 B = 1024)
+//   [46,48) version = 1 (sm_100) | [61,64) layout = 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+// Instruction descriptor, kind::f16 (cute::UMMA::InstrDescriptor): D=F32, A=B=BF16, both K-major, M=128, N=BN.
+template <int BN>
+__device__ __forceinline__ constexpr uint32_t make_idesc() {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
+__device__ __forceinline__ float silu_mul(float g, float u) { return g / (1.0f + __expf(-g)) * u; }
+
+template <int BN, int EPI>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+    gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, void *__restrict__ c_ptr,
+                   int M, int N, int K, int ldc) {
+  using Cfg = GemmCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t *smem_a = smem;
+  uint8_t *smem_b = smem + Cfg::kStages * Cfg::kABytes;
+  uint64_t *bars = (uint64_t *)(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint64_t *full_bar = bars;                       // [kStages]
+  uint64_t *empty_bar = bars + Cfg::kStages;       // [kStages]
+  uint64_t *tfull_bar = bars + 2 * Cfg::kStages;   // [2]
+  uint64_t *tempty_bar = tfull_bar + 2;            // [2]
+  uint32_t *tmem_slot = (uint32_t *)(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int m_tiles = (M + BM - 1) / BM;
+  const int n_tiles = (N + BN - 1) / BN;
+  const int num_tiles = m_tiles * n_tiles;
+  const int k_blocks = K / BK;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_b) : "memory");
+    for (int s = 0; s < Cfg::kStages; s++) {
+      mbar_init(smem_u32(&full_bar[s]), 1);
+      mbar_init(smem_u32(&empty_bar[s]), 1);
+    }
+    for (int s = 0; s < 2; s++) {
+      mbar_init(smem_u32(&tfull_bar[s]), 1);
+      mbar_init(smem_u32(&tempty_bar[s]), 4);  // one arrival per epilogue warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "n"(Cfg::kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+        for (int kb = 0; kb < k_blocks; kb++) {
+          mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+          const uint32_t fb = smem_u32(&full_bar[stage]);
+          mbar_expect_tx(fb, Cfg::kStageBytes);
+          tma_load_2d(smem_u32(smem_a + stage * Cfg::kABytes), &tm_a, fb, kb * BK, m_blk * BM);
+          tma_load_2d(smem_u32(smem_b + stage * Cfg::kBBytes), &tm_b, fb, kb * BK, n_blk * BN);
+          if (++stage == Cfg::kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (one thread) =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc<BN>();
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, it++) {
+        const int as = it & 1;
+        mbar_wait(smem_u32(&tempty_bar[as]), ((it >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
+        for (int kb = 0; kb < k_blocks; kb++) {
+          mbar_wait(smem_u32(&full_bar[stage]), phase);
+          tc_fence_after();
+          const uint64_t a_desc = make_kmajor_sw128_desc(smem_u32(smem_a + stage * Cfg::kABytes));
+          const uint64_t b_desc = make_kmajor_sw128_desc(smem_u32(smem_b + stage * Cfg::kBBytes));
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; k++) {
+            // advance 16 bf16 = 32 bytes inside the 128-byte swizzle row: +2 in the (addr >> 4) field
+            tc_mma_bf16(d_tmem, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          tc_commit(smem_u32(&empty_bar[stage]));  // frees the smem slot once these MMAs have read it
+          if (++stage == Cfg::kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        tc_commit(smem_u32(&tfull_bar[as]));  // accumulator complete -> epilogue
+      }
+    }
+  } else {
+    // ===================== epilogue warps (TMEM -> registers -> global) =====================
+    const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, it++) {
+      const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+      const int as = it & 1;
+      mbar_wait(smem_u32(&tfull_bar[as]), (it >> 1) & 1);
+      tc_fence_after();
+      const int row = m_blk * BM + quad * 32 + lane;
+      const bool row_ok = row < M;
+      const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BN);
+      if (EPI == EPI_SWIGLU_BF16) {
+        // tile columns [0, BN/2) are gate rows, [BN/2, BN) the matching up rows (weights are packed that way)
+        __nv_bfloat16 *out = (__nv_bfloat16 *)c_ptr;
+#pragma unroll 1
+        for (int c = 0; c < BN / 64; c++) {
+          uint32_t g[32], u[32];
+          tc_ld_32x32(t_row + (uint32_t)(c * 32), g);
+          tc_ld_32x32(t_row + (uint32_t)(BN / 2 + c * 32), u);
+          tc_ld_wait();
+          const int col0 = n_blk * (BN / 2) + c * 32;
+          if (row_ok && col0 < N / 2) {
+            uint32_t packed[16];
+#pragma unroll
+            for (int j = 0; j < 16; j++) {
+              float v0 = silu_mul(__uint_as_float(g[2 * j]), __uint_as_float(u[2 * j]));
+              float v1 = silu_mul(__uint_as_float(g[2 * j + 1]), __uint_as_float(u[2 * j + 1]));
+              __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
+              packed[j] = *reinterpret_cast<uint32_t *>(&h);
+            }
+            uint4 *dst = reinterpret_cast<uint4 *>(out + (size_t)row * ldc + col0);
+#pragma unroll
+            for (int j = 0; j < 4; j++) dst[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+          }
+        }
+      } else {
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; c++) {
+          uint32_t r[32];
+          tc_ld_32x32(t_row + (uint32_t)(c * 32), r);
+          tc_ld_wait();
+          const int col0 = n_blk * BN + c * 32;
+          if (!row_ok || col0 >= N) continue;
+          if (EPI == EPI_STORE_BF16) {
+            __nv_bfloat16 *out = (__nv_bfloat16 *)c_ptr + (size_t)row * ldc + col0;
+            if (col0 + 32 <= N) {
+              uint4 *dst = reinterpret_cast<uint4 *>(out);
+#pragma unroll
+              for (int j = 0; j < 4; j++) {
+                uint32_t pk[4];
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                  __nv_bfloat162 h = __floats2bfloat162_rn(__uint_as_float(r[8 * j + 2 * q]), __uint_as_float(r[8 * j + 2 * q + 1]));
+                  pk[q] = *reinterpret_cast<uint32_t *>(&h);
+                }
+                dst[j] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+              }
+            } else {
+              for (int j = 0; j < 32 && col0 + j < N; j++) out[j] = __float2bfloat16_rn(__uint_as_float(r[j]));
+            }
+          } else {
+            float *out = (float *)c_ptr + (size_t)row * ldc + col0;
+            if (col0 + 32 <= N) {
+              float4 *dst = reinterpret_cast<float4 *>(out);
+#pragma unroll
+              for (int j = 0; j < 8; j++) {
+                float4 v = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
+                                       __uint_as_float(r[4 * j + 3]));
+                if (EPI == EPI_ADD_F32) {
+                  float4 o = dst[j];
+                  v.x += o.x;
+                  v.y += o.y;
+                  v.z += o.z;
+                  v.w += o.w;
+                }
+                dst[j] = v;
+              }
+            } else {
+              for (int j = 0; j < 32 && col0 + j < N; j++) {
+                float v = __uint_as_float(r[j]);
+                if (EPI == EPI_ADD_F32) v += out[j];
+                out[j] = v;
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[as]));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(Cfg::kTmemCols) : "memory");
+  }
+}
+
+}  // namespace czk
+
+namespace cz {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+// 2D bf16 [rows][K] row-major, box = 64 x box_rows, 128-byte swizzle, OOB rows read as zero
+static int make_map(CUtensorMap *map, const void *ptr, int rows, int K, int ld_elems, int box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled entry point not available");
+    return CZ_ERR_CUDA;
+  }
+  cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)ld_elems * 2};
+  cuuint32_t box[2] = {(cuuint32_t)czk::BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(ptr), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
+    return CZ_ERR_CUDA;
+  }
+  return CZ_OK;
+}
+
+template <int BN, int EPI>
+static int launch_tc(cz_ctx *ctx, const CUtensorMap &ta, const CUtensorMap &tb, void *c, int M, int N, int K, int ldc,
+                     cudaStream_t stream) {
+  using Cfg = czk::GemmCfg<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CZ_CUDA_TRY(cudaFuncSetAttribute(czk::gemm_tc_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  const int tiles = (int)(ceil_div(M, czk::BM) * ceil_div(N, BN));
+  const int grid = tiles < ctx->sm_count ? tiles : ctx->sm_count;
+  CZ_LAUNCH(ctx, CZ_K_GEMM,
+            (czk::gemm_tc_kernel<BN, EPI><<<grid, czk::GEMM_THREADS, Cfg::kSmemBytes, stream>>>(ta, tb, c, M, N, K, ldc)));
+  CZ_CHECK_LAUNCH();
+  return CZ_OK;
+}
+
+int gemm_tcgen05(cz_ctx *ctx, const GemmArgs &g, cudaStream_t stream) {
+  if (g.M <= 0 || g.N <= 0) return CZ_OK;
+  if (g.K % czk::BK != 0 || g.lda < g.K || g.ldb < g.K || (g.lda % 8) || (g.ldb % 8) || ((uintptr_t)g.a % 16) ||
+      ((uintptr_t)g.b % 16) || ((uintptr_t)g.c % 16)) {
+    set_error("gemm_tcgen05: K must be a multiple of 64 and operands 16-byte aligned");
+    return CZ_ERR_INVALID;
+  }
+  if (g.epi == EPI_SWIGLU_BF16 && (g.N % g.bn)) {
+    set_error("gemm_tcgen05: swiglu needs N % BN == 0");
+    return CZ_ERR_INVALID;
+  }
+  if ((g.epi == EPI_STORE_F32 || g.epi == EPI_ADD_F32) && (g.ldc % 4)) {
+    set_error("gemm_tcgen05: f32 output needs ldc % 4 == 0");
+    return CZ_ERR_INVALID;
+  }
+  if ((g.epi == EPI_STORE_BF16 || g.epi == EPI_SWIGLU_BF16) && (g.ldc % 8)) {
+    set_error("gemm_tcgen05: bf16 output needs ldc % 8 == 0");
+    return CZ_ERR_INVALID;
+  }
+  CUtensorMap ta, tb;
+  CZ_TRY(make_map(&ta, g.a, g.M, g.K, g.lda, czk::BM));
+  CZ_TRY(make_map(&tb, g.b, g.N, g.K, g.ldb, g.bn));
+#define CZ_TC_CASE(BN_, EPI_) \
+  if (g.bn == BN_ && g.epi == EPI_) return launch_tc<BN_, EPI_>(ctx, ta, tb, g.c, g.M, g.N, g.K, g.ldc, stream)
+  CZ_TC_CASE(192, EPI_STORE_F32);
+  CZ_TC_CASE(192, EPI_ADD_F32);
+  CZ_TC_CASE(192, EPI_SWIGLU_BF16);
+  CZ_TC_CASE(192, EPI_STORE_BF16);
+  CZ_TC_CASE(256, EPI_STORE_F32);
+  CZ_TC_CASE(256, EPI_STORE_BF16);
+#undef CZ_TC_CASE
+  set_error("gemm_tcgen05: unsupported (BN, epilogue) combination");
+  return CZ_ERR_UNSUPPORTED;
+}
+
+}  // namespace cz

@@ -1,0 +1,15 @@
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+struct cz_ctx;
+namespace cz {
+int launch_embed(cz_ctx *ctx, const __nv_bfloat16 *table, const uint32_t *tok, float *x, int n_rows, int d, cudaStream_t st);
+int launch_rmsnorm(cz_ctx *ctx, const float *x, const float *w, const int *rows, __nv_bfloat16 *y, int n_out, int d, float eps,
+                   cudaStream_t st);
+int launch_rope_split(cz_ctx *ctx, const float *qkv, const int *pos, const int *kv_base, const float *cos_tab, const float *sin_tab,
+                      __nv_bfloat16 *q, __nv_bfloat16 *k_arena, __nv_bfloat16 *v_arena, int n_rows, int nh, int nkv,
+                      cudaStream_t st);
+int launch_attn_rows(cz_ctx *ctx, const __nv_bfloat16 *q, const __nv_bfloat16 *k_arena, const __nv_bfloat16 *v_arena, const int *pos,
+                     const int *kv_base, __nv_bfloat16 *out, int n_rows, int nh, int nkv, cudaStream_t st);
+}  // namespace cz

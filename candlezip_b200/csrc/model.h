@@ -1,0 +1,82 @@
+// Internal model representation (SmolLM / LLaMA architecture; RWKV-7 shares the tensor store).
+#pragma once
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "cz_common.cuh"
+
+struct TensorSlot {
+  std::string name;
+  size_t n = 0;
+  std::vector<uint16_t> host;        // bf16 bits; kept only on host-only ctxs (device ctxs read back on demand)
+  __nv_bfloat16 *dev = nullptr;
+  bool set = false;
+};
+
+struct Workspace {
+  size_t cap_rows = 0, cap_logit = 0;
+  float *x = nullptr;                 // [rows][D]   residual stream, fp32
+  __nv_bfloat16 *xn = nullptr;        // [rows][D]   normed activations (GEMM A operand)
+  float *qkv = nullptr;               // [rows][(nh+2nkv)*64]
+  __nv_bfloat16 *q = nullptr;         // [rows][D]
+  __nv_bfloat16 *attn = nullptr;      // [rows][D]
+  __nv_bfloat16 *act = nullptr;       // [rows][F]
+  __nv_bfloat16 *kpack = nullptr;     // packed-mode (teacher-forced) K rows of the current layer [rows][kvd]
+  __nv_bfloat16 *vpack = nullptr;
+  uint32_t *tok = nullptr;            // row metadata
+  int *pos = nullptr;
+  int *kv_base = nullptr;
+  int *logit_rows = nullptr;          // [cap_logit]
+  uint32_t *syms = nullptr;           // [cap_logit] symbol coded from each logit row
+  uint64_t *out_index = nullptr;      // [cap_logit] global coded index the result belongs to
+  __nv_bfloat16 *xn_logit = nullptr;  // [cap_logit][D]
+  uint32_t *lo_tmp = nullptr, *hi_tmp = nullptr;  // [sub] per-sub-batch CDF outputs before the scatter
+  double *xe_tmp = nullptr;
+  float *logits[2] = {nullptr, nullptr};  // [V][ld_sub] vocab-major, double-buffered
+  size_t ld_sub = 0;
+  // pinned host staging for row metadata
+  void *h_stage = nullptr;
+  size_t h_stage_bytes = 0;
+  cudaEvent_t stage_ev = nullptr;
+};
+
+struct cz_model {
+  cz_ctx *ctx = nullptr;
+  cz_model_config cfg;
+  std::vector<TensorSlot> tensors;
+  std::unordered_map<std::string, int> index;
+  bool finalized = false;
+  // packed device weights (SmolLM)
+  __nv_bfloat16 *w_qkv = nullptr;  // [L][(nh+2nkv)*64][D]
+  __nv_bfloat16 *w_o = nullptr;    // [L][D][D]
+  __nv_bfloat16 *w_gu = nullptr;   // [L][2F][D], gate/up interleaved in groups of gu_bn/2 rows
+  __nv_bfloat16 *w_d = nullptr;    // [L][D][F]
+  __nv_bfloat16 *embed = nullptr;  // alias of the embed_tokens slot
+  float *norms = nullptr;          // [L][2][D] + [D]
+  float *cos_tab = nullptr, *sin_tab = nullptr;  // [rope_max_pos][32]
+  int rope_max_pos = 2048;
+  int gu_bn = 192;
+  Workspace ws;
+};
+
+namespace cz {
+
+int model_finalize(cz_model *m);
+int ensure_workspace(cz_model *m, size_t rows, size_t n_logit);
+int ensure_stage(cz_model *m, size_t bytes);
+
+// KV arena view: element (layer l, slot s) lives at base + l*layer_stride + s*kvd
+struct KvView {
+  __nv_bfloat16 *k = nullptr, *v = nullptr;
+  size_t layer_stride = 0;  // elements
+};
+
+// embedding + all layers over n_rows rows whose metadata (tok/pos/kv_base) is already in m->ws; leaves the residual in ws.x
+int forward_trunk(cz_model *m, int n_rows, const KvView &kv, cudaStream_t st);
+// final RMSNorm of the n_logit rows listed in ws.logit_rows -> ws.xn_logit
+int final_norm_gather(cz_model *m, int n_logit, cudaStream_t st);
+// logits[V][ld] (vocab-major) for columns [col0, col0+n_cols) of ws.xn_logit
+int lm_head(cz_model *m, int col0, int n_cols, float *logits, size_t ld, cudaStream_t st);
+
+}  // namespace cz
