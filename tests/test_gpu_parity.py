@@ -1,0 +1,340 @@
+"""GPU suite (-m gpu): the CUDA path, through the C ABI, against the oracle on the same seeded inputs.
+Bit-exact for integer/byte work (CDF bounds, symbols, bitstreams, tokens); stated tolerances for logits."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import candlezip_b200 as cz
+import oracle
+from candlezip_b200 import _lib
+
+pytestmark = pytest.mark.gpu
+TOTAL = 1 << 30
+
+
+def _adversarial_logits(rng, v, m):
+    """columns that exercise ties, huge dynamic range, -inf, masses around 2^-30 and f64 rounding of tiny terms"""
+    cols = []
+    cols.append(np.zeros(v, np.float32))                                   # all equal
+    a = rng.normal(0, 1, v).astype(np.float32); a[v // 3] = 60.0; cols.append(a)   # one dominant symbol
+    a = rng.normal(0, 12, v).astype(np.float32); cols.append(a)           # many terms far below ulp(sum)
+    a = np.full(v, -np.inf, np.float32); a[5] = 0.0; a[v - 1] = -1.0; cols.append(a)  # -inf entries
+    a = np.linspace(-25, 0, v).astype(np.float32); cols.append(a)          # masses straddling 2^-30
+    a = np.full(v, -20.794415, np.float32); a[0] = 0.0; cols.append(a)      # e ~ 2^-30 each
+    a = np.repeat(rng.normal(0, 3, v // 2 + 1).astype(np.float32), 2)[:v]; cols.append(a)  # exact ties
+    a = (rng.normal(0, 40, v)).astype(np.float32); cols.append(a)          # underflow to exactly 0 for most entries
+    while len(cols) < m:
+        cols.append(rng.normal(0, rng.uniform(0.2, 8), v).astype(np.float32))
+    return np.stack(cols[:m], axis=1)  # [V, M]
+
+
+@pytest.mark.parametrize("v,m", [(1024, 8), (4099, 37), (49152, 40)])
+def test_k1_cdf_bounds_bit_exact(gpu_ctx, v, m):
+    rng = np.random.default_rng(v + m)
+    logits = _adversarial_logits(rng, v, m)
+    syms = rng.integers(0, v, m).astype(np.uint32)
+    syms[:4] = [0, v - 1, 1, v - 2]
+    lo, hi = gpu_ctx.cdf_bounds(logits, syms)
+    for j in range(m):
+        cdf = oracle.logits_to_cdf(logits[:, j], 0)
+        assert (int(lo[j]), int(hi[j])) == (int(cdf[syms[j]]), int(cdf[syms[j] + 1])), (j, syms[j])
+
+
+def test_k1_cdf_full_bit_exact(gpu_ctx):
+    rng = np.random.default_rng(0)
+    for v in (257, 5000):
+        logits = rng.normal(0, 6, v).astype(np.float32)
+        for mode in (0, 1):
+            assert np.array_equal(gpu_ctx.cdf_full(logits, mode), oracle.logits_to_cdf(logits, mode)), (v, mode)
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_k1_cdf_search_bit_exact(gpu_ctx, mode):
+    rng = np.random.default_rng(11 + mode)
+    v, m = 3000, 70
+    logits = _adversarial_logits(rng, v, m)
+    values = rng.integers(0, TOTAL, m).astype(np.uint32)
+    values[:3] = [0, TOTAL - 1, 1]
+    sym, lo, hi = gpu_ctx.cdf_search(logits, values, mode)
+    for j in range(m):
+        cdf = oracle.logits_to_cdf(logits[:, j], mode)
+        s = int(np.searchsorted(cdf, values[j], side="right") - 1)
+        assert (int(sym[j]), int(lo[j]), int(hi[j])) == (s, int(cdf[s]), int(cdf[s + 1])), j
+
+
+def test_k1_rwkv_literal_mode_bounds(gpu_ctx):
+    rng = np.random.default_rng(5)
+    v, m = 2048, 33
+    logits = _adversarial_logits(rng, v, m)
+    syms = rng.integers(0, v + 256, m).astype(np.uint32)
+    syms[:3] = [v, v + 255, v - 1]
+    lo, hi = gpu_ctx.cdf_bounds(logits, syms, mode=1)
+    for j in range(m):
+        cdf = oracle.logits_to_cdf(logits[:, j], 1)
+        assert (int(lo[j]), int(hi[j])) == (int(cdf[syms[j]]), int(cdf[syms[j] + 1])), j
+        assert hi[j] > lo[j]  # the floor guarantees a non-empty interval
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_k9_xe_bits(gpu_ctx, mode):
+    rng = np.random.default_rng(2)
+    v, m = 1500, 20
+    logits = rng.normal(0, 5, (v, m)).astype(np.float32)
+    syms = rng.integers(0, v, m).astype(np.uint32)
+    got = gpu_ctx.xe_bits_cols(logits, syms, mode)
+    for j in range(m):
+        pdf = oracle.combined_pdf_with_literals(logits[:, j]) if mode else oracle.softmax_pdf_floor(logits[:, j])
+        want = -np.log2(max(pdf[syms[j]], 1e-300))
+        assert abs(got[j] - want) <= 1e-12 * max(1.0, abs(want)), j  # f64; only log2's last ulp may differ
+
+
+def test_k2_encoder_lanes_bit_exact(gpu_ctx):
+    rng = np.random.default_rng(3)
+    lanes, bounds_all, off = [], [], [0]
+    for lane in range(41):
+        n = int(rng.integers(0, 400)) if lane else 0  # lane 0 is the empty stream -> 0x40
+        b = []
+        for _ in range(n):
+            kind = rng.integers(0, 4)
+            if kind == 0:
+                lo = int(rng.integers(0, TOTAL - 1)); hi = lo + 1          # narrowest interval: long carry runs
+            elif kind == 1:
+                lo = int(rng.integers(0, TOTAL // 2)); hi = int(rng.integers(lo + 1, TOTAL + 1))
+            elif kind == 2:
+                lo = (TOTAL // 2) - int(rng.integers(1, 5)); hi = (TOTAL // 2) + int(rng.integers(1, 5))  # straddles 1/2 (E3)
+            else:
+                lo, hi = 0, TOTAL                                         # probability-1 symbol: no bits
+            b.append((lo, hi))
+        lanes.append(b)
+        bounds_all += b
+        off.append(len(bounds_all))
+    lo = np.array([b[0] for b in bounds_all], np.uint32)
+    hi = np.array([b[1] for b in bounds_all], np.uint32)
+    got = gpu_ctx.ac_encode_lanes(lo, hi, off)
+    for lane, b in enumerate(lanes):
+        assert got[lane] == oracle.ac_encode(b), lane
+    assert got[0] == bytes([0x40])
+
+
+def test_k2_zero_width_is_an_error(gpu_ctx):
+    with pytest.raises(cz.CzError) as e:
+        gpu_ctx.ac_encode_lanes([1, 7], [2, 7], [0, 2])
+    assert e.value.code == _lib.CZ_ERR_ZERO_WIDTH
+
+
+def test_k3_decoder_lanes_roundtrip(gpu_ctx):
+    rng = np.random.default_rng(4)
+    w = rng.integers(1, 1000, 300).astype(np.float64)
+    cdf = np.concatenate([[0], np.floor(np.cumsum(w) / w.sum() * TOTAL)]).astype(np.uint32)
+    cdf[-1] = TOTAL
+    off, syms_all, pays = [0], [], []
+    for lane in range(23):
+        n = int(rng.integers(1, 500))
+        syms = rng.integers(0, 300, n)
+        pays.append(oracle.ac_encode([(int(cdf[s]), int(cdf[s + 1])) for s in syms]))
+        syms_all += list(syms)
+        off.append(len(syms_all))
+    got = gpu_ctx.ac_decode_lanes(pays, off, cdf)
+    assert np.array_equal(got, np.array(syms_all, np.uint32))
+
+
+# ------------------------------------------------------------------ dense contraction engines
+def _bf16(a):
+    a = np.ascontiguousarray(a, np.float32)
+    u = a.view(np.uint32).astype(np.uint64)
+    u = (u + 0x7FFF + ((u >> 16) & 1)) >> 16
+    return u.astype(np.uint16)
+
+
+def _bf16_to_f32(b):
+    return (b.astype(np.uint32) << 16).view(np.float32)
+
+
+def _run_gemm(ctx, engine, a16, b16, epi, bn, c_init, ldc):
+    M, K = a16.shape
+    N = b16.shape[0]
+    c = np.ascontiguousarray(c_init).copy()
+    _lib.check(_lib.lib.cz_test_gemm(ctx._h, engine, M, N, K, a16.ctypes.data_as(C.POINTER(C.c_uint16)),
+                                     b16.ctypes.data_as(C.POINTER(C.c_uint16)), epi, bn, c.ctypes.data_as(C.c_void_p), ldc))
+    return c
+
+
+@pytest.mark.parametrize("engine", [_lib.CZ_ENGINE_SIMT, _lib.CZ_ENGINE_TCGEN05], ids=["simt", "tc"])
+@pytest.mark.parametrize("M,N,K,bn", [(128, 192, 64, 192), (300, 960, 576, 192), (1000, 576, 1536, 192), (49152 // 8, 77, 576, 256),
+                                      (129, 200, 192, 192)])
+def test_gemm_store_f32(gpu_ctx, engine, M, N, K, bn):
+    rng = np.random.default_rng(M + N + K)
+    a16 = _bf16(rng.normal(0, 1, (M, K)))
+    b16 = _bf16(rng.normal(0, 1, (N, K)))
+    ldc = (N + 3) // 4 * 4
+    c = _run_gemm(gpu_ctx, engine, a16, b16, 0, bn, np.zeros((M, ldc), np.float32), ldc)
+    want = _bf16_to_f32(a16).astype(np.float64) @ _bf16_to_f32(b16).astype(np.float64).T
+    err = np.abs(c[:, :N] - want).max()
+    assert err < 2e-3 * np.sqrt(K / 64), (err,)
+    assert np.all(c[:, N:] == 0)
+
+
+@pytest.mark.parametrize("engine", [_lib.CZ_ENGINE_SIMT, _lib.CZ_ENGINE_TCGEN05], ids=["simt", "tc"])
+def test_gemm_epilogues(gpu_ctx, engine):
+    rng = np.random.default_rng(8)
+    M, K, F = 260, 192, 576
+    a16 = _bf16(rng.normal(0, 1, (M, K)))
+    # residual add
+    b16 = _bf16(rng.normal(0, 0.2, (192, K)))
+    base = rng.normal(0, 1, (M, 192)).astype(np.float32)
+    c = _run_gemm(gpu_ctx, engine, a16, b16, 1, 192, base, 192)
+    want = base + _bf16_to_f32(a16).astype(np.float64) @ _bf16_to_f32(b16).astype(np.float64).T
+    assert np.abs(c - want).max() < 5e-3
+    # swiglu over packed gate/up rows (groups of 96)
+    wg = _bf16(rng.normal(0, 0.1, (F, K)))
+    wu = _bf16(rng.normal(0, 0.1, (F, K)))
+    packed = np.empty((2 * F, K), np.uint16)
+    for g in range(F // 96):
+        packed[g * 192 : g * 192 + 96] = wg[g * 96 : (g + 1) * 96]
+        packed[g * 192 + 96 : (g + 1) * 192] = wu[g * 96 : (g + 1) * 96]
+    out16 = _run_gemm(gpu_ctx, engine, a16, packed, 2, 192, np.zeros((M, F), np.uint16), F)
+    A = _bf16_to_f32(a16).astype(np.float64)
+    gate = A @ _bf16_to_f32(wg).astype(np.float64).T
+    up = A @ _bf16_to_f32(wu).astype(np.float64).T
+    want = gate / (1 + np.exp(-gate)) * up
+    got = _bf16_to_f32(out16)
+    assert np.abs(got - want).max() < 0.02 * max(1.0, np.abs(want).max())
+    # bf16 store
+    o16 = _run_gemm(gpu_ctx, engine, a16, b16, 3, 192, np.zeros((M, 192), np.uint16), 192)
+    want = A @ _bf16_to_f32(b16).astype(np.float64).T
+    assert np.abs(_bf16_to_f32(o16) - want).max() < 0.02 * max(1.0, np.abs(want).max())
+
+
+def test_gemm_tcgen05_row_invariance(gpu_ctx):
+    """decode safety: a row's result must not depend on batch size or on its position in the tile grid."""
+    rng = np.random.default_rng(12)
+    K, N = 576, 960
+    b16 = _bf16(rng.normal(0, 1, (N, K)))
+    rows = _bf16(rng.normal(0, 1, (700, K)))
+    big = _run_gemm(gpu_ctx, _lib.CZ_ENGINE_TCGEN05, rows, b16, 0, 192, np.zeros((700, N), np.float32), N)
+    for sel in ([0], [5, 131, 699], list(range(257, 300))):
+        small = _run_gemm(gpu_ctx, _lib.CZ_ENGINE_TCGEN05, np.ascontiguousarray(rows[sel]), b16, 0, 192, np.zeros((len(sel), N), np.float32), N)
+        assert np.array_equal(small.view(np.uint32), big[sel].view(np.uint32)), sel
+
+
+# ------------------------------------------------------------------ SmolLM forward / encode / decode
+def _tiny(gpu_ctx, engine, seed=5, embed_std=0.05):
+    return cz.Model(gpu_ctx, cz.SMOLLM_TINY, engine=engine).random_init(seed, 0.05, embed_std)
+
+
+def _oracle_for(model, round_bf16):
+    cfg = dict(model.cfg)
+    cfg["rms_eps"] = cfg.pop("norm_eps")
+    return oracle.Session.llama(cfg, model.tensors(), round_bf16=round_bf16)
+
+
+@pytest.mark.parametrize("engine", [_lib.CZ_ENGINE_SIMT, _lib.CZ_ENGINE_TCGEN05], ids=["simt", "tc"])
+def test_tiny_logits_vs_oracle(gpu_ctx, engine):
+    model = _tiny(gpu_ctx, engine, embed_std=0.2)
+    rng = np.random.default_rng(1)
+    prime = rng.integers(0, 1024, 37).astype(np.uint32)
+    targets = rng.integers(0, 1024, 9).astype(np.uint32)
+    got = model.chunk_logits(prime, targets)
+    orc = _oracle_for(model, round_bf16=1)
+    ref = _oracle_for(model, round_bf16=0)
+    want = [orc.reprime(prime)] + [orc.step_logits(t) for t in targets[:-1]]
+    want32 = [ref.reprime(prime)] + [ref.step_logits(t) for t in targets[:-1]]
+    for j in range(len(targets)):
+        scale = max(1.0, np.abs(want32[j]).max())
+        # vs the oracle with the same bf16 rounding points: only accumulation order differs
+        assert np.abs(got[j] - want[j]).max() < 0.03 * scale, j
+        # vs the reference's pure-f32 CPU semantics: the stated logits tolerance of the bf16 path
+        assert np.abs(got[j] - want32[j]).max() < 0.06 * scale, j
+
+
+@pytest.mark.parametrize("engine", [_lib.CZ_ENGINE_SIMT, _lib.CZ_ENGINE_TCGEN05], ids=["simt", "tc"])
+def test_tiny_stepwise_equals_teacher_forced_bitwise(gpu_ctx, engine):
+    model = _tiny(gpu_ctx, engine, embed_std=0.2)
+    rng = np.random.default_rng(2)
+    prime = rng.integers(0, 1024, 150).astype(np.uint32)
+    targets = rng.integers(0, 1024, 140).astype(np.uint32)
+    tf = model.chunk_logits(prime, targets)
+    s = model.session()
+    step = [s.reprime_with_history_and_get_last_logits_tensor(prime)]
+    for t in targets[:-1]:
+        step.append(s.step_logits_tensor(t))
+    step = np.stack(step)
+    assert np.array_equal(tf.view(np.uint32), step.view(np.uint32)), "teacher-forced and stepwise logits differ bitwise"
+    assert s.index_pos() == len(prime) + len(targets) - 1
+
+
+@pytest.mark.parametrize("engine", [_lib.CZ_ENGINE_SIMT, _lib.CZ_ENGINE_TCGEN05], ids=["simt", "tc"])
+@pytest.mark.parametrize("n,n_seg", [(1, 1), (700, 1), (1700, 1), (2300, 3), (513, 5)])
+def test_tiny_roundtrip_and_oracle_bitstream(gpu_ctx, engine, n, n_seg):
+    model = _tiny(gpu_ctx, engine)
+    rng = np.random.default_rng(n + n_seg)
+    ids = rng.integers(0, 1024, n).astype(np.uint32)
+    pays, seg_start = model.encode(ids, n_segments=n_seg)
+    assert len(pays) == len(seg_start) - 1
+    # (1) bitstream parity: GPU logits -> ORACLE quantiser + ORACLE coder must reproduce the GPU payload bit for bit
+    g = 0
+    a, b = int(seg_start[g]), int(seg_start[g + 1])
+    seq = np.concatenate([[0], ids[a:b]]).astype(np.uint32)
+    first = min(512, b - a)
+    logits = model.chunk_logits([0], ids[a : a + first])
+    bounds = [tuple(int(x) for x in oracle.logits_to_cdf(logits[j], 0)[[ids[a + j], ids[a + j] + 1]]) for j in range(first)]
+    if b - a > 512:  # second chunk: prime = seq[2..513)
+        second = min(512, b - a - 512)
+        logits2 = model.chunk_logits(seq[2:513], ids[a + 512 : a + 512 + second])
+        bounds += [tuple(int(x) for x in oracle.logits_to_cdf(logits2[j], 0)[[ids[a + 512 + j], ids[a + 512 + j] + 1]]) for j in range(second)]
+    if len(bounds) == b - a:
+        assert oracle.ac_encode(bounds) == pays[g]
+    # (2) round trip through the batched lock-step decoder
+    out = model.decode(pays, seg_start)
+    assert np.array_equal(out, ids)
+    # (3) compressed size vs the CPU oracle on the same weights (bits/byte parity, <= 0.5 %)
+    if n >= 700 and n_seg == 1:
+        orc = _oracle_for(model, round_bf16=0)
+        ref_payload, _ = orc.encode_tokens(np.concatenate([[0], ids]).astype(np.uint32))
+        assert abs(len(pays[0]) - len(ref_payload)) <= 0.005 * len(ref_payload) + 2
+
+
+def test_tiny_segment_invariance(gpu_ctx):
+    """identical bytes whatever the wave size; per-segment streams equal single-stream encodes of the same tokens"""
+    model = _tiny(gpu_ctx, _lib.CZ_ENGINE_TCGEN05)
+    rng = np.random.default_rng(77)
+    ids = rng.integers(0, 1024, 3000).astype(np.uint32)
+    p1, s1 = model.encode(ids, n_segments=4)
+    p2, s2 = model.encode(ids, n_segments=4, max_batch_tokens=600)
+    assert p1 == p2 and np.array_equal(s1, s2)
+    for g in range(4):
+        solo, _ = model.encode(ids[int(s1[g]) : int(s1[g + 1])], n_segments=1)
+        assert solo[0] == p1[g]
+
+
+def test_tiny_xe_bits_vs_oracle(gpu_ctx):
+    model = _tiny(gpu_ctx, _lib.CZ_ENGINE_TCGEN05, embed_std=0.2)
+    rng = np.random.default_rng(6)
+    hist = rng.integers(0, 1024, 600).astype(np.uint32)
+    targets = rng.integers(0, 1024, 64).astype(np.uint32)
+    hint = rng.integers(0, 1024, 127).astype(np.uint32)
+    jobs = [(cz.xe_make_prime(hist, None), targets), (cz.xe_make_prime(hist, hint), targets), (cz.xe_make_prime(hist[:5], hint[:3]), targets[:7])]
+    got = model.xe_bits(jobs)
+    orc = _oracle_for(model, round_bf16=1)
+    want = [orc.xe_bits(hist, targets), orc.xe_bits(hist, targets, hint), orc.xe_bits(hist[:5], targets[:7], hint[:3])]
+    for a, b in zip(got, want):
+        assert abs(a - b) <= 0.01 * b, (a, b)
+
+
+def test_full_size_smollm_parity_and_roundtrip(gpu_ctx):
+    """SmolLM-135M shape (random-init): logits vs the oracle on a few positions, then a 2-segment round trip."""
+    model = cz.Model(gpu_ctx, cz.SMOLLM_135M).random_init(0, 0.02, 0.05)
+    rng = np.random.default_rng(0)
+    prime = rng.integers(0, 49152, 6).astype(np.uint32)
+    targets = rng.integers(0, 49152, 3).astype(np.uint32)
+    got = model.chunk_logits(prime, targets)
+    orc = _oracle_for(model, round_bf16=1)
+    want = [orc.reprime(prime)] + [orc.step_logits(t) for t in targets[:-1]]
+    for j in range(3):
+        assert np.abs(got[j] - want[j]).max() < 0.03 * max(1.0, np.abs(want[j]).max()), j
+    ids = rng.integers(0, 49152, 1200).astype(np.uint32)
+    pays, seg_start = model.encode(ids, n_segments=2)
+    out = model.decode(pays, seg_start)
+    assert np.array_equal(out, ids)
