@@ -90,6 +90,7 @@ SIGNATURES = {
     "cz_last_error": (C.c_char_p, []),
     "cz_launch_count": (C.c_uint64, [_vp]),
     "cz_profile_enable": (C.c_int, [_vp, C.c_int]),
+    "cz_ctx_stream": (_vp, [_vp]),
     "cz_profile_read": (C.c_int, [_vp, f64p, u64p, C.c_int]),
     "cz_cdf_bounds": (C.c_int, [_vp, f32p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int, u32p, u32p, u32p]),
     "cz_cdf_bounds_dev": (C.c_int, [_vp, _vp, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int, _vp, _vp, _vp]),

@@ -60,8 +60,12 @@ class Context:
     def launch_count(self):
         return int(lib.cz_launch_count(self._h))
 
-    def profile(self, on=True):
-        check(lib.cz_profile_enable(self._h, 1 if on else 0))
+    def profile(self, mode=1):
+        """0 off, 1 synchronous per-launch timing, 2 deferred event pairs (does not perturb a timed region)"""
+        check(lib.cz_profile_enable(self._h, int(mode)))
+
+    def stream_ptr(self):
+        return int(lib.cz_ctx_stream(self._h) or 0)
 
     def profile_read(self, reset=True):
         ms = (C.c_double * 6)()

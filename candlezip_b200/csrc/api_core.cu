@@ -139,13 +139,23 @@ void cz_shutdown(cz_ctx *ctx) {
 
 uint64_t cz_launch_count(const cz_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
-int cz_profile_enable(cz_ctx *ctx, int on) {
+int cz_profile_enable(cz_ctx *ctx, int mode) {
   CZ_TRY(require_device(ctx));
-  ctx->prof_on = on != 0;
+  ctx->prof_on = mode == 1;
+  ctx->prof_mode = mode;
   return CZ_OK;
 }
+void *cz_ctx_stream(cz_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
 int cz_profile_read(cz_ctx *ctx, double ms_out[CZ_K_FAMILIES], uint64_t launches_out[CZ_K_FAMILIES], int reset) {
   if (!ctx) return CZ_ERR_INVALID;
+  if (ctx->ev_used) {  // fold the deferred event pairs in
+    cudaStreamSynchronize(ctx->stream);
+    for (size_t i = 0; i < ctx->ev_used; i++) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, ctx->ev_pool[2 * i], ctx->ev_pool[2 * i + 1]) == cudaSuccess) ctx->prof_ms[ctx->ev_fam[i]] += ms;
+    }
+    ctx->ev_used = 0;
+  }
   for (int i = 0; i < CZ_K_FAMILIES; i++) {
     if (ms_out) ms_out[i] = ctx->prof_ms[i];
     if (launches_out) launches_out[i] = ctx->prof_launches[i];

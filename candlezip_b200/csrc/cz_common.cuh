@@ -6,6 +6,7 @@
 #include <stdio.h>
 
 #include <string>
+#include <vector>
 
 #include "../../include/candlezip_b200.h"
 
@@ -41,7 +42,12 @@ struct cz_ctx {
   cudaStream_t stream = nullptr;
   cudaStream_t stream2 = nullptr;
   uint64_t launches = 0;
-  // per-family profiling
+  // per-family profiling: mode 1 = synchronous (event pair + sync per launch), mode 2 = deferred (event pairs are
+  // pooled and only read in cz_profile_read, so the timed region is not perturbed by host syncs)
+  int prof_mode = 0;
+  std::vector<cudaEvent_t> ev_pool;       // [2*i], [2*i+1] = start/stop of pooled launch i
+  std::vector<int> ev_fam;
+  size_t ev_used = 0;
   bool prof_on = false;
   double prof_ms[CZ_K_FAMILIES] = {0};
   uint64_t prof_launches[CZ_K_FAMILIES] = {0};
@@ -60,13 +66,30 @@ int ensure_scratch(cz_ctx *ctx, size_t bytes);
 struct LaunchScope {
   cz_ctx *ctx;
   int fam;
+  size_t slot = 0;
   LaunchScope(cz_ctx *c, int f) : ctx(c), fam(f) {
-    if (ctx->prof_on) cudaEventRecord(ctx->prof_ev0, ctx->stream);
+    if (ctx->prof_mode == 2) {
+      slot = ctx->ev_used++;
+      if (ctx->ev_pool.size() < 2 * ctx->ev_used) {
+        cudaEvent_t a, b;
+        cudaEventCreate(&a);
+        cudaEventCreate(&b);
+        ctx->ev_pool.push_back(a);
+        ctx->ev_pool.push_back(b);
+        ctx->ev_fam.push_back(f);
+      }
+      ctx->ev_fam[slot] = f;
+      cudaEventRecord(ctx->ev_pool[2 * slot], ctx->stream);
+    } else if (ctx->prof_on) {
+      cudaEventRecord(ctx->prof_ev0, ctx->stream);
+    }
   }
   ~LaunchScope() {
     ctx->launches++;
     ctx->prof_launches[fam]++;
-    if (ctx->prof_on) {
+    if (ctx->prof_mode == 2) {
+      cudaEventRecord(ctx->ev_pool[2 * slot + 1], ctx->stream);
+    } else if (ctx->prof_on) {
       cudaEventRecord(ctx->prof_ev1, ctx->stream);
       cudaEventSynchronize(ctx->prof_ev1);
       float ms = 0.f;

@@ -60,7 +60,11 @@ uint64_t cz_launch_count(const cz_ctx *ctx);
 /* per-kernel-family device time accounting (CUDA events on the ctx stream); family ids below.
  * enable, run, then read accumulated milliseconds + launches. */
 enum { CZ_K_GEMM = 0, CZ_K_ATTN = 1, CZ_K_ELEMWISE = 2, CZ_K_CDF = 3, CZ_K_CODER = 4, CZ_K_OTHER = 5, CZ_K_FAMILIES = 6 };
-int cz_profile_enable(cz_ctx *ctx, int on);
+/* mode 0 off; 1 synchronous (sync after every launch: exact per-launch times, perturbs the step); 2 deferred
+ * (event pairs recorded around every launch, read back in cz_profile_read: does not perturb the timed region) */
+int cz_profile_enable(cz_ctx *ctx, int mode);
+/* the cudaStream_t every kernel of this ctx is launched on (so callers can bracket work with their own events) */
+void *cz_ctx_stream(cz_ctx *ctx);
 int cz_profile_read(cz_ctx *ctx, double ms_out[CZ_K_FAMILIES], uint64_t launches_out[CZ_K_FAMILIES], int reset);
 
 /* ---------------------------------------------------------------- K1: logits -> integer CDF */

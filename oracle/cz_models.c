@@ -132,6 +132,7 @@ static void linear(const float *x, size_t t, size_t kdim, const float *w, size_t
     for (size_t i = 0; i < t; i++) {
       const float *xr = x + i * kdim;
       float acc = 0.f;
+#pragma omp simd reduction(+ : acc)
       for (size_t k = 0; k < kdim; k++) acc += xr[k] * wr[k];
       y[i * n + j] = acc;
     }
@@ -203,6 +204,7 @@ static const float *llama_forward(czo_session *s, const uint32_t *tok, size_t t,
         for (size_t p = 0; p < n_keys; p++) {
           const float *kv = L->kcache + p * kvd + kvh * hd;
           float acc = 0.f;
+#pragma omp simd reduction(+ : acc)
           for (size_t j = 0; j < hd; j++) acc += qv[j] * kv[j];
           acc *= scale;
           sc[p] = acc;
