@@ -78,10 +78,17 @@ enum { OP_BOUNDS = 0, OP_SEARCH = 1, OP_XE = 2 };
 // Column walker shared by the stand-alone CDF kernels (cdf_kernels.cu) and the fused decode step (exec.cu).
 // MUST be called by all 32 lanes of a warp (inactive lanes pass a clamped, valid column and active=false).
 // p points at logits[0][col]; element v of the column is p[v * ld].
+// order-preserving int <-> float mapping used for the column max produced by the LM-head GEMM epilogue
+__device__ __forceinline__ float colmax_decode(int v) {
+  v ^= (v >> 31) & 0x7fffffff;
+  return __int_as_float(v);
+}
+
+// have_max: the column max was already computed (exactly) by the producer; otherwise pass A below finds it.
 template <int MODE, int OP>
 __device__ __forceinline__ void cdf_col(const float *__restrict__ p, size_t ld, int V, uint32_t arg, bool active,
                                         const ExpTab &tab, uint32_t &sym_out, uint32_t &lo_out, uint32_t &hi_out,
-                                        double &xe_out, int &errbits) {
+                                        double &xe_out, int &errbits, bool have_max = false, float known_max = 0.f) {
   const int n_sym = MODE == CZ_CDF_RWKV_LITERALS ? V + 256 : V;
   sym_out = 0;
   lo_out = 0;
@@ -89,10 +96,14 @@ __device__ __forceinline__ void cdf_col(const float *__restrict__ p, size_t ld, 
   xe_out = 0.0;
   // pass A: max (f32, NaN-ignoring exactly like `if v > max`)
   float mx = __int_as_float(0xff800000);
+  if (have_max) {
+    mx = known_max;
+  } else {
 #pragma unroll 8
-  for (int v = 0; v < V; v++) {
-    float x = __ldg(p + (size_t)v * ld);
-    if (x > mx) mx = x;
+    for (int v = 0; v < V; v++) {
+      float x = __ldg(p + (size_t)v * ld);
+      if (x > mx) mx = x;
+    }
   }
   // pass B: S = sum_i (f64)expf(l_i - max), sequential
   double S = 0.0;

@@ -22,7 +22,7 @@ __global__ void __launch_bounds__(128) cdf_cols_kernel(const float *__restrict__
                                                        const uint32_t *__restrict__ syms_or_values,
                                                        uint32_t *__restrict__ sym_out, uint32_t *__restrict__ c_lo_out,
                                                        uint32_t *__restrict__ c_hi_out, double *__restrict__ xe_out,
-                                                       int *__restrict__ err) {
+                                                       int *__restrict__ err, const int *__restrict__ colmax) {
   __shared__ uint32_t s_lo[32 * 32], s_hi[32 * 32];
   exp_tab_init(s_lo, s_hi);
   ExpTab tab{s_lo, s_hi, (int)(threadIdx.x & 31)};
@@ -32,7 +32,8 @@ __global__ void __launch_bounds__(128) cdf_cols_kernel(const float *__restrict__
   uint32_t sym, lo, hi;
   double xe;
   int errbits = 0;
-  cdf_col<MODE, OP>(logits + col, ld, V, syms_or_values[col], active, tab, sym, lo, hi, xe, errbits);
+  cdf_col<MODE, OP>(logits + col, ld, V, syms_or_values[col], active, tab, sym, lo, hi, xe, errbits, colmax != nullptr,
+                    colmax ? colmax_decode(colmax[col]) : 0.f);
   if (!active) return;
   if (errbits) atomicOr(err, errbits);
   if (OP == OP_XE) {
@@ -98,14 +99,26 @@ __global__ void cdf_full_kernel(const float *__restrict__ logits, int V, uint32_
   cdf[n_sym] = CZ_AC_CDF_TOTAL;
 }
 
+__global__ void fill_i32_kernel(int *__restrict__ p, int v, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
 }  // namespace czk
 
 namespace cz {
 
+int launch_fill_i32(cz_ctx *ctx, int *p, int v, size_t n, cudaStream_t stream) {
+  if (n == 0) return CZ_OK;
+  CZ_LAUNCH(ctx, CZ_K_OTHER, (czk::fill_i32_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, stream>>>(p, v, n)));
+  CZ_CHECK_LAUNCH();
+  return CZ_OK;
+}
+
 // Device-pointer launchers (used by the executor and by the host-buffer C-ABI wrappers in api.cu)
 int launch_cdf_cols(cz_ctx *ctx, int op, int mode, const float *logits_dev, size_t V, size_t M, size_t ld,
                     const uint32_t *arg_dev, uint32_t *sym_out_dev, uint32_t *c_lo_dev, uint32_t *c_hi_dev,
-                    double *xe_dev, cudaStream_t stream) {
+                    double *xe_dev, cudaStream_t stream, const int *colmax_dev) {
   if (M == 0) return CZ_OK;
   if (V == 0 || V > (1u << 24) || ld < M) {
     set_error("cdf: bad shape");
@@ -117,7 +130,7 @@ int launch_cdf_cols(cz_ctx *ctx, int op, int mode, const float *logits_dev, size
   CZ_LAUNCH(ctx, CZ_K_CDF,                                                                                    \
             (czk::cdf_cols_kernel<MODE, OP><<<grid, threads, 0, stream>>>(logits_dev, (int)V, M, ld, arg_dev, \
                                                                           sym_out_dev, c_lo_dev, c_hi_dev,    \
-                                                                          xe_dev, ctx->err_flag_dev)))
+                                                                          xe_dev, ctx->err_flag_dev, colmax_dev)))
   if (mode == CZ_CDF_SMOLLM) {
     if (op == czk::OP_BOUNDS) CZ_CDF_CASE(CZ_CDF_SMOLLM, czk::OP_BOUNDS);
     else if (op == czk::OP_SEARCH) CZ_CDF_CASE(CZ_CDF_SMOLLM, czk::OP_SEARCH);

@@ -8,10 +8,12 @@ namespace czk {
 
 struct AcEncoder {
   uint64_t low, high, carry_run;
-  uint8_t *out;      // lane's output region
-  uint64_t n_bytes;  // bytes_out
+  uint8_t *out;      // lane's output region (global)
+  uint64_t n_bytes;  // bytes_out, including bytes still in the staging buffer
   uint32_t bit_buffer;
   uint32_t bit_count;
+  uint8_t *stage;    // optional shared-memory staging buffer (nullptr: write straight to `out`)
+  uint32_t stage_cap, stage_n;
 
   __device__ __forceinline__ void init(uint8_t *o) {
     low = 0;
@@ -21,11 +23,25 @@ struct AcEncoder {
     n_bytes = 0;
     bit_buffer = 0;
     bit_count = 0;
+    stage = nullptr;
+    stage_cap = stage_n = 0;
+  }
+  // single-thread flush of the staging buffer (slow path: only when a carry burst overfills it)
+  __device__ __forceinline__ void flush_stage_serial() {
+    const uint64_t b0 = n_bytes - stage_n;
+    for (uint32_t i = 0; i < stage_n; i++) out[b0 + i] = stage[i];
+    stage_n = 0;
   }
   __device__ __forceinline__ void put_bit_internal(uint32_t bit) {
     bit_buffer = (bit_buffer << 1) | (bit & 1u);
     if (++bit_count == 8) {
-      out[n_bytes++] = (uint8_t)bit_buffer;
+      if (stage) {
+        if (stage_n == stage_cap) flush_stage_serial();
+        stage[stage_n++] = (uint8_t)bit_buffer;
+        n_bytes++;
+      } else {
+        out[n_bytes++] = (uint8_t)bit_buffer;
+      }
       bit_buffer = 0;
       bit_count = 0;
     }

@@ -8,28 +8,66 @@
 
 namespace czk {
 
-// err[0]: OR of status bits; err[1]: smallest interval index that had zero width (atomicMin)
-__global__ void ac_encode_lanes_kernel(const uint32_t *__restrict__ c_lo, const uint32_t *__restrict__ c_hi,
-                                       const uint64_t *__restrict__ lane_off, size_t n_lanes,
-                                       uint8_t *__restrict__ out, const uint64_t *__restrict__ out_off,
-                                       uint64_t *__restrict__ out_len, int *__restrict__ err,
-                                       unsigned long long *__restrict__ err_index) {
-  size_t lane = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+// One WARP per lane: the 32 threads prefetch the next AC_BATCH intervals into shared memory with coalesced loads and
+// flush the produced bytes with coalesced stores; thread 0 runs the (inherently sequential) coder out of shared memory.
+// A single thread reading (c_lo, c_hi) straight from global memory pays a full DRAM round trip per symbol.
+// err[0]: OR of status bits; err_index: smallest interval index that had zero width (atomicMin)
+constexpr int AC_BATCH = 512;
+constexpr int AC_STAGE = 4096;
+__global__ void __launch_bounds__(32) ac_encode_lanes_kernel(const uint32_t *__restrict__ c_lo, const uint32_t *__restrict__ c_hi,
+                                                             const uint64_t *__restrict__ lane_off, size_t n_lanes,
+                                                             uint8_t *__restrict__ out, const uint64_t *__restrict__ out_off,
+                                                             uint64_t *__restrict__ out_len, int *__restrict__ err,
+                                                             unsigned long long *__restrict__ err_index) {
+  __shared__ uint32_t s_lo[AC_BATCH], s_hi[AC_BATCH];
+  __shared__ uint8_t s_stage[AC_STAGE];
+  const size_t lane = blockIdx.x;
   if (lane >= n_lanes) return;
+  const int tid = threadIdx.x;
   AcEncoder enc;
   enc.init(out + out_off[lane]);
+  enc.stage = s_stage;
+  enc.stage_cap = AC_STAGE;
   const uint64_t t0 = lane_off[lane], t1 = lane_off[lane + 1];
-  for (uint64_t t = t0; t < t1; t++) {
-    const uint32_t lo = __ldg(c_lo + t), hi = __ldg(c_hi + t);
-    if (hi <= lo || hi > CZ_AC_CDF_TOTAL) {
-      atomicOr(err, 4);
-      atomicMin(err_index, (unsigned long long)t);
-      out_len[lane] = 0;
+  uint8_t *gout = out + out_off[lane];
+  for (uint64_t base = t0; base < t1; base += AC_BATCH) {
+    const int cnt = (int)((t1 - base) < (uint64_t)AC_BATCH ? (t1 - base) : (uint64_t)AC_BATCH);
+    for (int i = tid; i < cnt; i += 32) {
+      s_lo[i] = __ldg(c_lo + base + i);
+      s_hi[i] = __ldg(c_hi + base + i);
+    }
+    __syncwarp();
+    int bad = 0;
+    if (tid == 0) {
+      for (int i = 0; i < cnt; i++) {
+        const uint32_t lo = s_lo[i], hi = s_hi[i];
+        if (hi <= lo || hi > CZ_AC_CDF_TOTAL) {
+          atomicOr(err, 4);
+          atomicMin(err_index, (unsigned long long)(base + i));
+          bad = 1;
+          break;
+        }
+        enc.encode_counts(lo, hi);
+      }
+    }
+    bad = __shfl_sync(0xffffffffu, bad, 0);
+    if (bad) {
+      if (tid == 0) out_len[lane] = 0;
       return;
     }
-    enc.encode_counts(lo, hi);
+    // cooperative flush of the staged bytes
+    __syncwarp();  // thread 0's shared-memory writes -> visible to the warp
+    const uint32_t n_st = __shfl_sync(0xffffffffu, enc.stage_n, 0);
+    const uint64_t b0 = __shfl_sync(0xffffffffu, (unsigned long long)(enc.n_bytes - enc.stage_n), 0);
+    for (uint32_t i = tid; i < n_st; i += 32) gout[b0 + i] = s_stage[i];
+    __syncwarp();
+    if (tid == 0) enc.stage_n = 0;
   }
-  out_len[lane] = enc.finish();
+  if (tid == 0) {
+    const uint64_t total = enc.finish();
+    enc.flush_stage_serial();
+    out_len[lane] = total;
+  }
 }
 
 __global__ void ac_decode_lanes_static_kernel(const uint8_t *__restrict__ payload, const uint64_t *__restrict__ pay_off,
@@ -62,9 +100,8 @@ int launch_ac_encode_lanes(cz_ctx *ctx, const uint32_t *c_lo_dev, const uint32_t
                            size_t n_lanes, uint8_t *out_dev, const uint64_t *out_off_dev, uint64_t *out_len_dev,
                            unsigned long long *err_index_dev, cudaStream_t stream) {
   if (n_lanes == 0) return CZ_OK;
-  const int threads = 32;  // lanes diverge heavily; small blocks spread them over more SMs
   CZ_LAUNCH(ctx, CZ_K_CODER,
-            (czk::ac_encode_lanes_kernel<<<(unsigned)ceil_div(n_lanes, threads), threads, 0, stream>>>(
+            (czk::ac_encode_lanes_kernel<<<(unsigned)n_lanes, 32, 0, stream>>>(
                 c_lo_dev, c_hi_dev, lane_off_dev, n_lanes, out_dev, out_off_dev, out_len_dev, ctx->err_flag_dev,
                 err_index_dev)));
   CZ_CHECK_LAUNCH();

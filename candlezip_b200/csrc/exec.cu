@@ -15,7 +15,7 @@
 namespace cz {
 int launch_cdf_cols(cz_ctx *ctx, int op, int mode, const float *logits_dev, size_t V, size_t M, size_t ld,
                     const uint32_t *arg_dev, uint32_t *sym_out_dev, uint32_t *c_lo_dev, uint32_t *c_hi_dev,
-                    double *xe_dev, cudaStream_t stream);
+                    double *xe_dev, cudaStream_t stream, const int *colmax_dev = nullptr);
 int launch_ac_encode_lanes(cz_ctx *ctx, const uint32_t *c_lo_dev, const uint32_t *c_hi_dev, const uint64_t *lane_off_dev,
                            size_t n_lanes, uint8_t *out_dev, const uint64_t *out_off_dev, uint64_t *out_len_dev,
                            unsigned long long *err_index_dev, cudaStream_t stream);
@@ -57,7 +57,8 @@ __global__ void __launch_bounds__(128) decode_step_kernel(const float *__restric
                                                           const uint8_t *__restrict__ payload, const uint64_t *__restrict__ seg_off,
                                                           const uint64_t *__restrict__ seg_start, uint64_t coded_index,
                                                           AcDecoderState *__restrict__ st, uint32_t *__restrict__ ids_out,
-                                                          uint32_t *__restrict__ next_tok, int *__restrict__ err) {
+                                                          uint32_t *__restrict__ next_tok, int *__restrict__ err,
+                                                          const int *__restrict__ colmax) {
   __shared__ uint32_t s_lo[32 * 32], s_hi[32 * 32];
   exp_tab_init(s_lo, s_hi);
   ExpTab tab{s_lo, s_hi, (int)(threadIdx.x & 31)};
@@ -72,7 +73,8 @@ __global__ void __launch_bounds__(128) decode_step_kernel(const float *__restric
   uint32_t sym, lo, hi;
   double xe;
   int errbits = 0;
-  cdf_col<MODE, OP_SEARCH>(logits + lane, ld, V, value, live, tab, sym, lo, hi, xe, errbits);
+  cdf_col<MODE, OP_SEARCH>(logits + lane, ld, V, value, live, tab, sym, lo, hi, xe, errbits, colmax != nullptr,
+                           colmax ? colmax_decode(colmax[lane]) : 0.f);
   if (!live) return;
   if (errbits) atomicOr(err, errbits);
   d.consume(lo, hi);
@@ -102,14 +104,24 @@ namespace cz {
 // -------------------------------------------------------------------------------------------------------------
 struct Wave {
   std::vector<long long> src;
-  std::vector<int> pos, kv_base, logit_rows;
+  std::vector<int> pos, kv_base, logit_rows, tile_row0, tile_n;
   size_t n_rows() const { return src.size(); }
+  size_t n_tiles() const { return tile_row0.size(); }
   size_t n_logit() const { return logit_rows.size(); }
   void clear() {
     src.clear();
     pos.clear();
     kv_base.clear();
     logit_rows.clear();
+    tile_row0.clear();
+    tile_n.clear();
+  }
+  // attention tiles of one sequence occupying rows [base, base + rows): 64 positions each, anchored at position 0
+  void add_tiles(int base, int rows) {
+    for (int p = 0; p < rows; p += 64) {
+      tile_row0.push_back(base + p);
+      tile_n.push_back(rows - p < 64 ? rows - p : 64);
+    }
   }
   // prime_src(k), coded_src(j): token source of prime position k / coded token j
   template <class FP, class FC>
@@ -127,6 +139,7 @@ struct Wave {
       kv_base.push_back(base);
     }
     for (uint32_t j = 0; j < n_coded; j++) logit_rows.push_back(base + (int)prime_len - 1 + (int)j);
+    add_tiles(base, p);
   }
 };
 
@@ -149,20 +162,24 @@ struct DevBuf {
 // host waits for the PREVIOUS wave's copies (an event right after them) -- never for the kernels behind them.
 static int stage_and_upload(cz_model *m, const Wave &w, long long *src_dev, cudaStream_t st) {
   Workspace &ws = m->ws;
-  const size_t R = w.n_rows(), NL = w.n_logit();
-  const size_t b_src = R * 8, b_i = R * 4, b_l = NL * 4;
+  const size_t R = w.n_rows(), NL = w.n_logit(), NT = w.n_tiles();
+  const size_t b_src = R * 8, b_i = R * 4, b_l = NL * 4, b_t = NT * 4;
   if (!ws.stage_ev) CZ_CUDA_TRY(cudaEventCreateWithFlags(&ws.stage_ev, cudaEventDisableTiming));
   else CZ_CUDA_TRY(cudaEventSynchronize(ws.stage_ev));
-  CZ_TRY(ensure_stage(m, b_src + 2 * b_i + b_l + 64));
+  CZ_TRY(ensure_stage(m, b_src + 2 * b_i + b_l + 2 * b_t + 64));
   char *h = (char *)ws.h_stage;
   memcpy(h, w.src.data(), b_src);
   memcpy(h + b_src, w.pos.data(), b_i);
   memcpy(h + b_src + b_i, w.kv_base.data(), b_i);
   memcpy(h + b_src + 2 * b_i, w.logit_rows.data(), b_l);
+  memcpy(h + b_src + 2 * b_i + b_l, w.tile_row0.data(), b_t);
+  memcpy(h + b_src + 2 * b_i + b_l + b_t, w.tile_n.data(), b_t);
   CZ_CUDA_TRY(cudaMemcpyAsync(src_dev, h, b_src, cudaMemcpyHostToDevice, st));
   CZ_CUDA_TRY(cudaMemcpyAsync(ws.pos, h + b_src, b_i, cudaMemcpyHostToDevice, st));
   CZ_CUDA_TRY(cudaMemcpyAsync(ws.kv_base, h + b_src + b_i, b_i, cudaMemcpyHostToDevice, st));
   CZ_CUDA_TRY(cudaMemcpyAsync(ws.logit_rows, h + b_src + 2 * b_i, b_l, cudaMemcpyHostToDevice, st));
+  CZ_CUDA_TRY(cudaMemcpyAsync(ws.tile_row0, h + b_src + 2 * b_i + b_l, b_t, cudaMemcpyHostToDevice, st));
+  CZ_CUDA_TRY(cudaMemcpyAsync(ws.tile_n, h + b_src + 2 * b_i + b_l + b_t, b_t, cudaMemcpyHostToDevice, st));
   CZ_CUDA_TRY(cudaEventRecord(ws.stage_ev, st));
   return CZ_OK;
 }
@@ -171,7 +188,7 @@ static int stage_and_upload(cz_model *m, const Wave &w, long long *src_dev, cuda
 static int run_wave_trunk(cz_model *m, const Wave &w, const uint32_t *ids_dev, const uint32_t *extra_dev, uint32_t bos,
                           long long *src_dev_scratch, cudaStream_t st) {
   const size_t R = w.n_rows(), NL = w.n_logit();
-  CZ_TRY(ensure_workspace(m, R, NL));
+  CZ_TRY(ensure_workspace(m, R, NL, w.n_tiles()));
   Workspace &ws = m->ws;
   CZ_TRY(stage_and_upload(m, w, src_dev_scratch, st));
   CZ_LAUNCH(m->ctx, CZ_K_OTHER,
@@ -181,6 +198,9 @@ static int run_wave_trunk(cz_model *m, const Wave &w, const uint32_t *ids_dev, c
   kv.k = ws.kpack;
   kv.v = ws.vpack;
   kv.layer_stride = 0;
+  kv.tile_row0 = ws.tile_row0;
+  kv.tile_n = ws.tile_n;
+  kv.n_tiles = (int)w.n_tiles();
   CZ_TRY(forward_trunk(m, (int)R, kv, st));
   CZ_TRY(final_norm_gather(m, (int)NL, st));
   return CZ_OK;
@@ -194,9 +214,11 @@ static int run_wave_head(cz_model *m, size_t n_logit, int op, int mode, const ui
   int buf = 0;
   for (size_t c0 = 0; c0 < n_logit; c0 += ws.ld_sub, buf ^= 1) {
     const size_t nc = std::min(ws.ld_sub, n_logit - c0);
-    CZ_TRY(lm_head(m, (int)c0, (int)nc, ws.logits[buf], ws.ld_sub, st));
+    bool have_max = false;
+    CZ_TRY(lm_head(m, (int)c0, (int)nc, ws.logits[buf], ws.ld_sub, st, ws.colmax, &have_max));
     CZ_TRY(launch_cdf_cols(m->ctx, op, mode, ws.logits[buf], (size_t)m->cfg.vocab, nc, ws.ld_sub, syms_dev + c0, nullptr,
-                           lo_out ? lo_out + c0 : nullptr, hi_out ? hi_out + c0 : nullptr, xe_out ? xe_out + c0 : nullptr, st));
+                           lo_out ? lo_out + c0 : nullptr, hi_out ? hi_out + c0 : nullptr, xe_out ? xe_out + c0 : nullptr, st,
+                           have_max ? ws.colmax : nullptr));
   }
   return CZ_OK;
 }
@@ -346,20 +368,36 @@ static int session_forward(cz_session *s, const uint32_t *tok, size_t n, float *
     set_error("session: KV capacity exceeded");
     return CZ_ERR_INVALID;
   }
-  CZ_TRY(ensure_workspace(m, n, 1));
-  Workspace &ws = m->ws;
-  std::vector<int> pos(n), base(n, 0);
+  std::vector<int> pos(n), base(n, 0), trow, tn;
   for (size_t i = 0; i < n; i++) pos[i] = (int)(s->index_pos + i);
+  if (s->index_pos == 0) {
+    for (size_t p = 0; p < n; p += 64) {
+      trow.push_back((int)p);
+      tn.push_back((int)std::min<size_t>(64, n - p));
+    }
+  } else {  // continuing an existing sequence: one tile per new row (tiles must start at a multiple of 64 or be single rows)
+    for (size_t i = 0; i < n; i++) {
+      trow.push_back((int)i);
+      tn.push_back(1);
+    }
+  }
+  CZ_TRY(ensure_workspace(m, n, 1, trow.size()));
+  Workspace &ws = m->ws;
   const int lrow = (int)n - 1;
   CZ_CUDA_TRY(cudaMemcpyAsync(ws.tok, tok, n * 4, cudaMemcpyHostToDevice, st));
   CZ_CUDA_TRY(cudaMemcpyAsync(ws.pos, pos.data(), n * 4, cudaMemcpyHostToDevice, st));
   CZ_CUDA_TRY(cudaMemcpyAsync(ws.kv_base, base.data(), n * 4, cudaMemcpyHostToDevice, st));
   CZ_CUDA_TRY(cudaMemcpyAsync(ws.logit_rows, &lrow, 4, cudaMemcpyHostToDevice, st));
+  CZ_CUDA_TRY(cudaMemcpyAsync(ws.tile_row0, trow.data(), trow.size() * 4, cudaMemcpyHostToDevice, st));
+  CZ_CUDA_TRY(cudaMemcpyAsync(ws.tile_n, tn.data(), tn.size() * 4, cudaMemcpyHostToDevice, st));
   CZ_CUDA_TRY(cudaStreamSynchronize(st));  // pos/base are stack-owned
   KvView kv;
   kv.k = s->k;
   kv.v = s->v;
   kv.layer_stride = (size_t)s->max_pos * m->cfg.n_kv_heads * 64;
+  kv.tile_row0 = ws.tile_row0;
+  kv.tile_n = ws.tile_n;
+  kv.n_tiles = (int)trow.size();
   CZ_TRY(forward_trunk(m, (int)n, kv, st));
   CZ_TRY(final_norm_gather(m, 1, st));
   CZ_TRY(lm_head(m, 0, 1, s->logits_dev, 4, st));
@@ -509,12 +547,15 @@ int cz_decode(cz_model *m, const uint8_t *payload, const uint64_t *seg_off, size
     kvb[g] = (int)(g * max_pos);
     lrows[g] = (int)g;
   }
-  CZ_TRY(d_kvb.alloc(S * 8));
-  int *d_kvb_i = d_kvb.as<int>(), *d_lrows_i = d_kvb_i + S;
+  CZ_TRY(d_kvb.alloc(S * 12));
+  int *d_kvb_i = d_kvb.as<int>(), *d_lrows_i = d_kvb_i + S, *d_ones_i = d_lrows_i + S;  // step tiles: row0 = g, n = 1
+  std::vector<int> ones(S, 1);
   CZ_CUDA_TRY(cudaMemcpyAsync(d_kvb_i, kvb.data(), S * 4, cudaMemcpyHostToDevice, st));
   CZ_CUDA_TRY(cudaMemcpyAsync(d_lrows_i, lrows.data(), S * 4, cudaMemcpyHostToDevice, st));
+  CZ_CUDA_TRY(cudaMemcpyAsync(d_ones_i, ones.data(), S * 4, cudaMemcpyHostToDevice, st));
   CZ_CUDA_TRY(cudaStreamSynchronize(st));
 
+  bool have_max = false;
   for (const Chunk &ch : chunks) {
     // ---- prime every stream that is still live at this chunk (fresh cache: positions 0 .. prime_len-1) ----
     std::vector<uint32_t> live;
@@ -532,6 +573,7 @@ int cz_decode(cz_model *m, const uint8_t *payload, const uint64_t *seg_off, size
     for (uint32_t g : live) {
       const uint64_t t0 = sched->seg_start[g];
       const int base = (int)(g * max_pos);
+      const int r0 = (int)w.src.size();
       for (uint32_t k = 0; k < ch.prime_len; k++) {
         const uint64_t si = ch.prime_start + k;
         w.src.push_back(si == 0 ? -1ll : (long long)(t0 + si - 1));
@@ -539,6 +581,7 @@ int cz_decode(cz_model *m, const uint8_t *payload, const uint64_t *seg_off, size
         w.kv_base.push_back(base);
       }
       w.logit_rows.push_back((int)w.src.size() - 1);
+      w.add_tiles(r0, (int)ch.prime_len);
     }
     {
       const size_t R = w.n_rows(), NL = w.n_logit();
@@ -547,7 +590,7 @@ int cz_decode(cz_model *m, const uint8_t *payload, const uint64_t *seg_off, size
         CZ_CUDA_TRY(cudaStreamSynchronize(st));
         CZ_TRY(d_src.alloc(src_cap * 8));
       }
-      CZ_TRY(ensure_workspace(m, std::max<size_t>(R, S), std::max<size_t>(NL, S)));
+      CZ_TRY(ensure_workspace(m, std::max<size_t>(R, S), std::max<size_t>(NL, S), std::max<size_t>(w.n_tiles(), S)));
       Workspace &ws = m->ws;
       const size_t b_src = R * 8, b_i = R * 4, b_l = NL * 4;
       CZ_TRY(ensure_stage(m, b_src + 2 * b_i + b_l + 64));
@@ -564,9 +607,12 @@ int cz_decode(cz_model *m, const uint8_t *payload, const uint64_t *seg_off, size
                 (czk::gather_tokens_kernel<<<(unsigned)ceil_div(R, 256), 256, 0, st>>>(d_src.as<long long>(), d_ids.as<uint32_t>(), nullptr,
                                                                                       sched->bos, ws.tok, (int)R)));
       CZ_CHECK_LAUNCH();
+      kv.tile_row0 = ws.tile_row0;
+      kv.tile_n = ws.tile_n;
+      kv.n_tiles = (int)w.n_tiles();
       CZ_TRY(forward_trunk(m, (int)R, kv, st));
       CZ_TRY(final_norm_gather(m, (int)NL, st));
-      CZ_TRY(lm_head(m, 0, (int)NL, d_logits.as<float>(), S_pad, st));
+      CZ_TRY(lm_head(m, 0, (int)NL, d_logits.as<float>(), S_pad, st, ws.colmax, &have_max));
     }
     const int n_live = (int)live.size();
     Workspace &ws = m->ws;
@@ -576,12 +622,12 @@ int cz_decode(cz_model *m, const uint8_t *payload, const uint64_t *seg_off, size
         CZ_LAUNCH(ctx, CZ_K_CDF,
                   (czk::decode_step_kernel<CZ_CDF_SMOLLM><<<(unsigned)ceil_div(n_live, 128), 128, 0, st>>>(
                       d_logits.as<float>(), c.vocab, S_pad, n_live, d_pay.as<uint8_t>(), d_off.as<uint64_t>(), d_start.as<uint64_t>(), i,
-                      d_state.as<czk::AcDecoderState>(), d_ids.as<uint32_t>(), ws.tok, ctx->err_flag_dev)));
+                      d_state.as<czk::AcDecoderState>(), d_ids.as<uint32_t>(), ws.tok, ctx->err_flag_dev, have_max ? ws.colmax : nullptr)));
       else
         CZ_LAUNCH(ctx, CZ_K_CDF,
                   (czk::decode_step_kernel<CZ_CDF_RWKV_LITERALS><<<(unsigned)ceil_div(n_live, 128), 128, 0, st>>>(
                       d_logits.as<float>(), c.vocab, S_pad, n_live, d_pay.as<uint8_t>(), d_off.as<uint64_t>(), d_start.as<uint64_t>(), i,
-                      d_state.as<czk::AcDecoderState>(), d_ids.as<uint32_t>(), ws.tok, ctx->err_flag_dev)));
+                      d_state.as<czk::AcDecoderState>(), d_ids.as<uint32_t>(), ws.tok, ctx->err_flag_dev, have_max ? ws.colmax : nullptr)));
       CZ_CHECK_LAUNCH();
       if (j + 1 == ch.n_coded) break;  // the step after the chunk's last symbol is never used (next chunk re-primes)
       // single-token step for every live stream: tok = symbol just decoded, position = prime_len + j
@@ -590,9 +636,12 @@ int cz_decode(cz_model *m, const uint8_t *payload, const uint64_t *seg_off, size
       CZ_CHECK_LAUNCH();
       CZ_CUDA_TRY(cudaMemcpyAsync(ws.kv_base, d_kvb_i, (size_t)n_live * 4, cudaMemcpyDeviceToDevice, st));
       CZ_CUDA_TRY(cudaMemcpyAsync(ws.logit_rows, d_lrows_i, (size_t)n_live * 4, cudaMemcpyDeviceToDevice, st));
+      kv.tile_row0 = d_lrows_i;
+      kv.tile_n = d_ones_i;
+      kv.n_tiles = n_live;
       CZ_TRY(forward_trunk(m, n_live, kv, st));
       CZ_TRY(final_norm_gather(m, n_live, st));
-      CZ_TRY(lm_head(m, 0, n_live, d_logits.as<float>(), S_pad, st));
+      CZ_TRY(lm_head(m, 0, n_live, d_logits.as<float>(), S_pad, st, ws.colmax, &have_max));
     }
     CZ_TRY(fetch_device_status(ctx, nullptr, nullptr));
   }

@@ -11,6 +11,8 @@ enum GemmEpilogue {
   EPI_ADD_F32 = 1,      // C[M][ldc] f32 += A*B^T          (residual add fused into o_proj / down_proj)
   EPI_SWIGLU_BF16 = 2,  // C[M][ldc] bf16 = silu(gate)*up   (B rows packed per tile: BN/2 gate rows then BN/2 up rows; N = 2*ffn)
   EPI_STORE_BF16 = 3,   // C[M][ldc] bf16 = A*B^T
+  EPI_STORE_F32_COLMAX = 4,  // EPI_STORE_F32 + aux[n] = max over rows m of C[m][n], as an order-preserving int (atomicMax);
+                             // used by the vocab-major LM head so the CDF kernel does not need its own max pass
 };
 
 struct GemmArgs {
@@ -21,6 +23,7 @@ struct GemmArgs {
   int lda, ldb, ldc;
   int epi;  // GemmEpilogue
   int bn;   // tile width: 192 or 256 (also the gate/up packing granularity for EPI_SWIGLU_BF16)
+  int *aux = nullptr;  // EPI_STORE_F32_COLMAX: per-column running max, must be pre-filled with INT_MIN
 };
 
 int gemm_tcgen05(cz_ctx *ctx, const GemmArgs &g, cudaStream_t stream);

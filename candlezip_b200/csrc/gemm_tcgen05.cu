@@ -16,6 +16,7 @@
 // and the instruction shape are fixed per (BN, K), there is no split-K and no atomics, so the same activation
 // row gives bit-identical results whatever the batch size, tile position or GPU count.
 #include <cuda.h>
+#include <limits.h>
 
 #include "cz_common.cuh"
 #include "gemm.h"
@@ -25,6 +26,7 @@ namespace czk {
 using cz::EPI_ADD_F32;
 using cz::EPI_STORE_BF16;
 using cz::EPI_STORE_F32;
+using cz::EPI_STORE_F32_COLMAX;
 using cz::EPI_SWIGLU_BF16;
 
 constexpr int BM = 128;
@@ -125,7 +127,7 @@ __device__ __forceinline__ float silu_mul(float g, float u) { return g / (1.0f +
 template <int BN, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
     gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, void *__restrict__ c_ptr,
-                   int M, int N, int K, int ldc) {
+                   int M, int N, int K, int ldc, int *__restrict__ aux) {
   using Cfg = GemmCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -264,6 +266,20 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
           tc_ld_32x32(t_row + (uint32_t)(c * 32), r);
           tc_ld_wait();
           const int col0 = n_blk * BN + c * 32;
+          if (EPI == EPI_STORE_F32_COLMAX) {
+            // per-column max over this warp's 32 rows: floats mapped to order-preserving ints, one REDUX per column,
+            // lane j keeps column j, then one coalesced atomicMax per warp.  max is exact and order-independent.
+            int mine = INT_MIN;
+#pragma unroll
+            for (int j = 0; j < 32; j++) {
+              int v = (int)r[j];
+              v ^= (v >> 31) & 0x7fffffff;
+              if (!row_ok) v = INT_MIN;
+              const int mx = __reduce_max_sync(0xffffffffu, v);
+              if (lane == j) mine = mx;
+            }
+            if (col0 + lane < N) atomicMax(aux + col0 + lane, mine);
+          }
           if (!row_ok || col0 >= N) continue;
           if (EPI == EPI_STORE_BF16) {
             __nv_bfloat16 *out = (__nv_bfloat16 *)c_ptr + (size_t)row * ldc + col0;
@@ -366,7 +382,7 @@ static int make_map(CUtensorMap *map, const void *ptr, int rows, int K, int ld_e
 }
 
 template <int BN, int EPI>
-static int launch_tc(cz_ctx *ctx, const CUtensorMap &ta, const CUtensorMap &tb, void *c, int M, int N, int K, int ldc,
+static int launch_tc(cz_ctx *ctx, const CUtensorMap &ta, const CUtensorMap &tb, void *c, int M, int N, int K, int ldc, int *aux,
                      cudaStream_t stream) {
   using Cfg = czk::GemmCfg<BN>;
   static bool attr_set = false;
@@ -377,7 +393,7 @@ static int launch_tc(cz_ctx *ctx, const CUtensorMap &ta, const CUtensorMap &tb, 
   const int tiles = (int)(ceil_div(M, czk::BM) * ceil_div(N, BN));
   const int grid = tiles < ctx->sm_count ? tiles : ctx->sm_count;
   CZ_LAUNCH(ctx, CZ_K_GEMM,
-            (czk::gemm_tc_kernel<BN, EPI><<<grid, czk::GEMM_THREADS, Cfg::kSmemBytes, stream>>>(ta, tb, c, M, N, K, ldc)));
+            (czk::gemm_tc_kernel<BN, EPI><<<grid, czk::GEMM_THREADS, Cfg::kSmemBytes, stream>>>(ta, tb, c, M, N, K, ldc, aux)));
   CZ_CHECK_LAUNCH();
   return CZ_OK;
 }
@@ -393,7 +409,7 @@ int gemm_tcgen05(cz_ctx *ctx, const GemmArgs &g, cudaStream_t stream) {
     set_error("gemm_tcgen05: swiglu needs N % BN == 0");
     return CZ_ERR_INVALID;
   }
-  if ((g.epi == EPI_STORE_F32 || g.epi == EPI_ADD_F32) && (g.ldc % 4)) {
+  if ((g.epi == EPI_STORE_F32 || g.epi == EPI_ADD_F32 || g.epi == EPI_STORE_F32_COLMAX) && (g.ldc % 4)) {
     set_error("gemm_tcgen05: f32 output needs ldc % 4 == 0");
     return CZ_ERR_INVALID;
   }
@@ -405,13 +421,14 @@ int gemm_tcgen05(cz_ctx *ctx, const GemmArgs &g, cudaStream_t stream) {
   CZ_TRY(make_map(&ta, g.a, g.M, g.K, g.lda, czk::BM));
   CZ_TRY(make_map(&tb, g.b, g.N, g.K, g.ldb, g.bn));
 #define CZ_TC_CASE(BN_, EPI_) \
-  if (g.bn == BN_ && g.epi == EPI_) return launch_tc<BN_, EPI_>(ctx, ta, tb, g.c, g.M, g.N, g.K, g.ldc, stream)
+  if (g.bn == BN_ && g.epi == EPI_) return launch_tc<BN_, EPI_>(ctx, ta, tb, g.c, g.M, g.N, g.K, g.ldc, g.aux, stream)
   CZ_TC_CASE(192, EPI_STORE_F32);
   CZ_TC_CASE(192, EPI_ADD_F32);
   CZ_TC_CASE(192, EPI_SWIGLU_BF16);
   CZ_TC_CASE(192, EPI_STORE_BF16);
   CZ_TC_CASE(256, EPI_STORE_F32);
   CZ_TC_CASE(256, EPI_STORE_BF16);
+  CZ_TC_CASE(256, EPI_STORE_F32_COLMAX);
 #undef CZ_TC_CASE
   set_error("gemm_tcgen05: unsupported (BN, epilogue) combination");
   return CZ_ERR_UNSUPPORTED;

@@ -12,4 +12,7 @@ int launch_rope_split(cz_ctx *ctx, const float *qkv, const int *pos, const int *
                       cudaStream_t st);
 int launch_attn_rows(cz_ctx *ctx, const __nv_bfloat16 *q, const __nv_bfloat16 *k_arena, const __nv_bfloat16 *v_arena, const int *pos,
                      const int *kv_base, __nv_bfloat16 *out, int n_rows, int nh, int nkv, cudaStream_t st);
+int launch_attn_mma(cz_ctx *ctx, const __nv_bfloat16 *q, const __nv_bfloat16 *k_arena, const __nv_bfloat16 *v_arena, const int *pos,
+                    const int *kv_base, const int *tile_row0, const int *tile_n, int n_tiles, __nv_bfloat16 *out, int nh, int nkv,
+                    cudaStream_t st);
 }  // namespace cz

@@ -27,12 +27,16 @@ struct Workspace {
   uint32_t *tok = nullptr;            // row metadata
   int *pos = nullptr;
   int *kv_base = nullptr;
+  int *tile_row0 = nullptr;           // attention tiles: first row / number of valid positions (<= 64), [cap_rows/64 + ...]
+  int *tile_n = nullptr;
+  size_t cap_tiles = 0;
   int *logit_rows = nullptr;          // [cap_logit]
   uint32_t *syms = nullptr;           // [cap_logit] symbol coded from each logit row
   uint64_t *out_index = nullptr;      // [cap_logit] global coded index the result belongs to
   __nv_bfloat16 *xn_logit = nullptr;  // [cap_logit][D]
   uint32_t *lo_tmp = nullptr, *hi_tmp = nullptr;  // [sub] per-sub-batch CDF outputs before the scatter
   double *xe_tmp = nullptr;
+  int *colmax = nullptr;              // [ld_sub] per-column max of the current logits sub-batch
   float *logits[2] = {nullptr, nullptr};  // [V][ld_sub] vocab-major, double-buffered
   size_t ld_sub = 0;
   // pinned host staging for row metadata
@@ -63,13 +67,17 @@ struct cz_model {
 namespace cz {
 
 int model_finalize(cz_model *m);
-int ensure_workspace(cz_model *m, size_t rows, size_t n_logit);
+int ensure_workspace(cz_model *m, size_t rows, size_t n_logit, size_t n_tiles = 0);
 int ensure_stage(cz_model *m, size_t bytes);
 
 // KV arena view: element (layer l, slot s) lives at base + l*layer_stride + s*kvd
 struct KvView {
   __nv_bfloat16 *k = nullptr, *v = nullptr;
   size_t layer_stride = 0;  // elements
+  // attention tiles (device): tile t covers rows [tile_row0[t], +tile_n[t]) = consecutive positions of one sequence,
+  // starting at a position that is a multiple of 64 (or a single decode row)
+  const int *tile_row0 = nullptr, *tile_n = nullptr;
+  int n_tiles = 0;
 };
 
 // embedding + all layers over n_rows rows whose metadata (tok/pos/kv_base) is already in m->ws; leaves the residual in ws.x
@@ -77,6 +85,9 @@ int forward_trunk(cz_model *m, int n_rows, const KvView &kv, cudaStream_t st);
 // final RMSNorm of the n_logit rows listed in ws.logit_rows -> ws.xn_logit
 int final_norm_gather(cz_model *m, int n_logit, cudaStream_t st);
 // logits[V][ld] (vocab-major) for columns [col0, col0+n_cols) of ws.xn_logit
-int lm_head(cz_model *m, int col0, int n_cols, float *logits, size_t ld, cudaStream_t st);
+// colmax (optional, [>= n_cols] ints): receives the exact per-column max in the order-preserving int encoding; *colmax_valid
+// says whether this engine produced it
+int lm_head(cz_model *m, int col0, int n_cols, float *logits, size_t ld, cudaStream_t st, int *colmax = nullptr,
+            bool *colmax_valid = nullptr);
 
 }  // namespace cz

@@ -1,6 +1,7 @@
 // Model store, seeded random init, weight packing and the batched SmolLM forward (trunk + LM head).
 // Replaces SmolLmSession::load (src/models.rs:48-61) and the candle Llama::forward call behind
 // step_logits_tensor / reprime_with_history_and_get_last_logits_tensor (src/models.rs:92-119).
+#include <limits.h>
 #include <math.h>
 #include <string.h>
 
@@ -93,7 +94,7 @@ static int realloc_dev(T *&p, size_t n) {
   return CZ_OK;
 }
 
-int ensure_workspace(cz_model *m, size_t rows, size_t n_logit) {
+int ensure_workspace(cz_model *m, size_t rows, size_t n_logit, size_t n_tiles) {
   Workspace &w = m->ws;
   const cz_model_config &c = m->cfg;
   const size_t D = c.d_model, F = c.d_ffn, kvd = (size_t)c.n_kv_heads * 64, QKV = D + 2 * kvd;
@@ -114,6 +115,13 @@ int ensure_workspace(cz_model *m, size_t rows, size_t n_logit) {
     CZ_TRY(realloc_dev(w.kv_base, r));
     w.cap_rows = r;
   }
+  if (n_tiles > w.cap_tiles) {
+    CZ_CUDA_TRY(cudaStreamSynchronize(m->ctx->stream));
+    size_t r = n_tiles + n_tiles / 8 + 128;
+    CZ_TRY(realloc_dev(w.tile_row0, r));
+    CZ_TRY(realloc_dev(w.tile_n, r));
+    w.cap_tiles = r;
+  }
   if (n_logit > w.cap_logit) {
     CZ_CUDA_TRY(cudaStreamSynchronize(m->ctx->stream));
     size_t r = n_logit + n_logit / 8 + 128;
@@ -124,15 +132,17 @@ int ensure_workspace(cz_model *m, size_t rows, size_t n_logit) {
     w.cap_logit = r;
   }
   if (!w.logits[0]) {
-    // sub-batch of LM-head columns: 8192 columns x V x 4 B (1.6 GB for V = 49152), two buffers
-    size_t ld = 8192;
-    while (ld > 256 && ld * (size_t)c.vocab * 4 > ((size_t)2 << 30)) ld >>= 1;
+    // sub-batch of LM-head columns: 32768 columns x V x 4 B (6.4 GB for V = 49152), two buffers. The thread-per-column
+    // CDF kernel gets its parallelism from the column count, so the sub-batch must be tens of thousands of columns.
+    size_t ld = 32768;
+    while (ld > 256 && ld * (size_t)c.vocab * 4 > ((size_t)7 << 30)) ld >>= 1;
     w.ld_sub = ld;
     CZ_TRY(realloc_dev(w.logits[0], ld * (size_t)c.vocab));
     CZ_TRY(realloc_dev(w.logits[1], ld * (size_t)c.vocab));
     CZ_TRY(realloc_dev(w.lo_tmp, ld));
     CZ_TRY(realloc_dev(w.hi_tmp, ld));
     CZ_TRY(realloc_dev(w.xe_tmp, ld));
+    CZ_TRY(realloc_dev(w.colmax, ld));
   }
   return CZ_OK;
 }
@@ -236,7 +246,10 @@ int forward_trunk(cz_model *m, int n_rows, const KvView &kv, cudaStream_t st) {
     g.M = n_rows; g.N = QKV; g.K = D; g.epi = EPI_STORE_F32; g.bn = 192;
     CZ_TRY(gemm(ctx, c.engine, g, st));
     CZ_TRY(launch_rope_split(ctx, w.qkv, w.pos, w.kv_base, m->cos_tab, m->sin_tab, w.q, kl, vl, n_rows, nh, nkv, st));
-    CZ_TRY(launch_attn_rows(ctx, w.q, kl, vl, w.pos, w.kv_base, w.attn, n_rows, nh, nkv, st));
+    if (c.engine == CZ_ENGINE_TCGEN05)
+      CZ_TRY(launch_attn_mma(ctx, w.q, kl, vl, w.pos, w.kv_base, kv.tile_row0, kv.tile_n, kv.n_tiles, w.attn, nh, nkv, st));
+    else
+      CZ_TRY(launch_attn_rows(ctx, w.q, kl, vl, w.pos, w.kv_base, w.attn, n_rows, nh, nkv, st));
     g.a = w.attn; g.lda = D; g.b = m->w_o + (size_t)l * D * D; g.ldb = D; g.c = w.x; g.ldc = D;
     g.M = n_rows; g.N = D; g.K = D; g.epi = EPI_ADD_F32; g.bn = 192;
     CZ_TRY(gemm(ctx, c.engine, g, st));
@@ -257,13 +270,19 @@ int final_norm_gather(cz_model *m, int n_logit, cudaStream_t st) {
                         n_logit, c.d_model, c.norm_eps, st);
 }
 
-int lm_head(cz_model *m, int col0, int n_cols, float *logits, size_t ld, cudaStream_t st) {
+int launch_fill_i32(cz_ctx *ctx, int *p, int v, size_t n, cudaStream_t stream);
+
+int lm_head(cz_model *m, int col0, int n_cols, float *logits, size_t ld, cudaStream_t st, int *colmax, bool *colmax_valid) {
   const cz_model_config &c = m->cfg;
+  const bool fuse_max = colmax && c.engine == CZ_ENGINE_TCGEN05;
+  if (colmax_valid) *colmax_valid = fuse_max;
+  if (fuse_max) CZ_TRY(launch_fill_i32(m->ctx, colmax, INT_MIN, (size_t)n_cols, st));
   GemmArgs g{};
   g.a = m->embed; g.lda = c.d_model;                       // A = tied embedding [V][D]: vocab is the M dimension
   g.b = m->ws.xn_logit + (size_t)col0 * c.d_model; g.ldb = c.d_model;  // B = hidden states: tokens are the N dimension
   g.c = logits; g.ldc = (int)ld;                           // -> vocab-major logits [V][ld]
-  g.M = c.vocab; g.N = n_cols; g.K = c.d_model; g.epi = EPI_STORE_F32; g.bn = 256;
+  g.M = c.vocab; g.N = n_cols; g.K = c.d_model; g.epi = fuse_max ? EPI_STORE_F32_COLMAX : EPI_STORE_F32; g.bn = 256;
+  g.aux = colmax;
   return gemm(m->ctx, c.engine, g, st);
 }
 
@@ -382,7 +401,7 @@ void cz_model_free(cz_model *m) {
       if (s.dev) cudaFree(s.dev);
     void *ptrs[] = {m->w_qkv, m->w_o, m->w_gu, m->w_d, m->norms, m->cos_tab, m->sin_tab, m->ws.x, m->ws.xn, m->ws.qkv, m->ws.q,
                     m->ws.attn, m->ws.act, m->ws.kpack, m->ws.vpack, m->ws.tok, m->ws.pos, m->ws.kv_base, m->ws.logit_rows,
-                    m->ws.syms, m->ws.out_index, m->ws.xn_logit, m->ws.lo_tmp, m->ws.hi_tmp, m->ws.xe_tmp, m->ws.logits[0],
+                    m->ws.syms, m->ws.out_index, m->ws.tile_row0, m->ws.tile_n, m->ws.xn_logit, m->ws.lo_tmp, m->ws.hi_tmp, m->ws.xe_tmp, m->ws.colmax, m->ws.logits[0],
                     m->ws.logits[1]};
     for (void *p : ptrs)
       if (p) cudaFree(p);
