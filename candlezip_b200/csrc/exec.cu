@@ -592,17 +592,7 @@ int cz_decode(cz_model *m, const uint8_t *payload, const uint64_t *seg_off, size
       }
       CZ_TRY(ensure_workspace(m, std::max<size_t>(R, S), std::max<size_t>(NL, S), std::max<size_t>(w.n_tiles(), S)));
       Workspace &ws = m->ws;
-      const size_t b_src = R * 8, b_i = R * 4, b_l = NL * 4;
-      CZ_TRY(ensure_stage(m, b_src + 2 * b_i + b_l + 64));
-      char *h = (char *)ws.h_stage;
-      memcpy(h, w.src.data(), b_src);
-      memcpy(h + b_src, w.pos.data(), b_i);
-      memcpy(h + b_src + b_i, w.kv_base.data(), b_i);
-      memcpy(h + b_src + 2 * b_i, w.logit_rows.data(), b_l);
-      CZ_CUDA_TRY(cudaMemcpyAsync(d_src.p, h, b_src, cudaMemcpyHostToDevice, st));
-      CZ_CUDA_TRY(cudaMemcpyAsync(ws.pos, h + b_src, b_i, cudaMemcpyHostToDevice, st));
-      CZ_CUDA_TRY(cudaMemcpyAsync(ws.kv_base, h + b_src + b_i, b_i, cudaMemcpyHostToDevice, st));
-      CZ_CUDA_TRY(cudaMemcpyAsync(ws.logit_rows, h + b_src + 2 * b_i, b_l, cudaMemcpyHostToDevice, st));
+      CZ_TRY(stage_and_upload(m, w, d_src.as<long long>(), st));
       CZ_LAUNCH(ctx, CZ_K_OTHER,
                 (czk::gather_tokens_kernel<<<(unsigned)ceil_div(R, 256), 256, 0, st>>>(d_src.as<long long>(), d_ids.as<uint32_t>(), nullptr,
                                                                                       sched->bos, ws.tok, (int)R)));

@@ -3,6 +3,7 @@
 // step_logits_tensor / reprime_with_history_and_get_last_logits_tensor (src/models.rs:92-119).
 #include <limits.h>
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "gemm.h"
@@ -246,7 +247,8 @@ int forward_trunk(cz_model *m, int n_rows, const KvView &kv, cudaStream_t st) {
     g.M = n_rows; g.N = QKV; g.K = D; g.epi = EPI_STORE_F32; g.bn = 192;
     CZ_TRY(gemm(ctx, c.engine, g, st));
     CZ_TRY(launch_rope_split(ctx, w.qkv, w.pos, w.kv_base, m->cos_tab, m->sin_tab, w.q, kl, vl, n_rows, nh, nkv, st));
-    if (c.engine == CZ_ENGINE_TCGEN05)
+    static const bool force_rows = getenv("CZ_DEBUG_ATTN_ROWS") != nullptr;  // bisecting aid
+    if (c.engine == CZ_ENGINE_TCGEN05 && !force_rows)
       CZ_TRY(launch_attn_mma(ctx, w.q, kl, vl, w.pos, w.kv_base, kv.tile_row0, kv.tile_n, kv.n_tiles, w.attn, nh, nkv, st));
     else
       CZ_TRY(launch_attn_rows(ctx, w.q, kl, vl, w.pos, w.kv_base, w.attn, n_rows, nh, nkv, st));
@@ -274,7 +276,8 @@ int launch_fill_i32(cz_ctx *ctx, int *p, int v, size_t n, cudaStream_t stream);
 
 int lm_head(cz_model *m, int col0, int n_cols, float *logits, size_t ld, cudaStream_t st, int *colmax, bool *colmax_valid) {
   const cz_model_config &c = m->cfg;
-  const bool fuse_max = colmax && c.engine == CZ_ENGINE_TCGEN05;
+  static const bool no_colmax = getenv("CZ_DEBUG_NO_COLMAX") != nullptr;  // bisecting aid
+  const bool fuse_max = colmax && c.engine == CZ_ENGINE_TCGEN05 && !no_colmax;
   if (colmax_valid) *colmax_valid = fuse_max;
   if (fuse_max) CZ_TRY(launch_fill_i32(m->ctx, colmax, INT_MIN, (size_t)n_cols, st));
   GemmArgs g{};
