@@ -5,7 +5,7 @@
     python bench.py --impl reference --gpus N --steps K --warmup W   # the reference's CPU path (oracle port) on host cores
 
 A "step" is one pass of the hot path over one batch of synthetic input per GPU: 262,144 byte-level tokens
-(id = byte, 1 B/token -- no tokenizer.json exists offline) coded as 8 independent segments = 512 reprime-chunks
+(id = byte, 1 B/token -- no tokenizer.json exists offline) coded as 32 independent segments = 512 reprime-chunks
 (BASELINE.json configs[1]: "SmolLM-135M batched 512 chunks ... on 1xB200"), seeded random-init weights of the
 SmolLM2-135M architecture.  `value` is timed with CUDA events on the library's stream with the token ids already
 in HBM (cz_encode_dev); `e2e` goes through the public host-buffer call (cz_encode: pinned host ids in, payload out).
@@ -304,7 +304,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--tokens", type=int, default=262144)
-    ap.add_argument("--segments", type=int, default=8)
+    ap.add_argument("--segments", type=int, default=32)
     ap.add_argument("--decode-tokens", type=int, default=131072)
     ap.add_argument("--decode-segments", type=int, default=256)
     ap.add_argument("--ref-chunk", type=int, default=256, help="coded tokens per CPU-reference sample chunk (512 = the full reprime chunk)")

@@ -24,7 +24,7 @@ CZ_ARCH_SMOLLM, CZ_ARCH_RWKV7 = 0, 1
 CZ_DTYPE_F32, CZ_DTYPE_BF16, CZ_DTYPE_F16 = 0, 1, 2
 CZ_ENGINE_TCGEN05, CZ_ENGINE_SIMT = 0, 1
 CZ_FLAG_SEGMENTS = 1 << 8
-K_FAMILIES = ("gemm", "attn", "elemwise", "cdf", "coder", "other")
+K_FAMILIES = ("gemm_qkv", "attn", "elemwise", "cdf", "coder", "other", "gemm_o", "gemm_gu", "gemm_down", "gemm_head")
 
 
 class CzError(RuntimeError):

@@ -68,10 +68,14 @@ class Context:
         return int(lib.cz_ctx_stream(self._h) or 0)
 
     def profile_read(self, reset=True):
-        ms = (C.c_double * 6)()
-        n = (C.c_uint64 * 6)()
+        nf = len(_lib.K_FAMILIES)
+        ms = (C.c_double * nf)()
+        n = (C.c_uint64 * nf)()
         check(lib.cz_profile_read(self._h, ms, n, 1 if reset else 0))
-        return {k: (ms[i], int(n[i])) for i, k in enumerate(_lib.K_FAMILIES)}
+        out = {k: (ms[i], int(n[i])) for i, k in enumerate(_lib.K_FAMILIES)}
+        g = [v for k, v in out.items() if k.startswith("gemm_")]
+        out["gemm"] = (sum(x[0] for x in g), sum(x[1] for x in g))
+        return out
 
     # ---- K1 ----
     def cdf_bounds(self, logits_vm, syms, mode=_lib.CZ_CDF_SMOLLM):

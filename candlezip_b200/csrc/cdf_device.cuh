@@ -84,7 +84,39 @@ __device__ __forceinline__ float colmax_decode(int v) {
   return __int_as_float(v);
 }
 
+// Ascending walk over elements [0, n) of one column with the loads software-pipelined: the next group of CDF_GRP
+// values is already in flight (registers) while the current group is consumed, and an L2 prefetch runs CDF_PF rows
+// ahead.  Consecutive rows of a column are ld*4 bytes apart (a new DRAM page every row), so without this the kernel is
+// bound by memory latency x the few loads a warp has in flight, not by bandwidth.  f(v, x) returns false to stop the
+// lane; the walk ends when every lane of the warp has stopped (keeps the warp converged for the callers' shuffles).
+constexpr int CDF_GRP = 8;
+constexpr int CDF_PF = 48;
+template <class F>
+__device__ __forceinline__ void cdf_walk(const float *__restrict__ p, size_t ld, int n, F f) {
+  float cur[CDF_GRP], nxt[CDF_GRP];
+#pragma unroll
+  for (int k = 0; k < CDF_GRP; k++) cur[k] = k < n ? __ldg(p + (size_t)k * ld) : 0.f;
+  bool go = true;
+  for (int v0 = 0; v0 < n; v0 += CDF_GRP) {
+#pragma unroll
+    for (int k = 0; k < CDF_GRP; k++) {
+      const int v = v0 + CDF_GRP + k;
+      nxt[k] = v < n ? __ldg(p + (size_t)v * ld) : 0.f;
+      const int vp = v0 + CDF_PF + k;
+      if (vp < n) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + (size_t)vp * ld));
+    }
+#pragma unroll
+    for (int k = 0; k < CDF_GRP; k++) {
+      if (go && v0 + k < n) go = f(v0 + k, cur[k]);
+      cur[k] = nxt[k];
+    }
+    if (!__any_sync(0xffffffffu, go)) break;
+  }
+}
+
 // have_max: the column max was already computed (exactly) by the producer; otherwise pass A below finds it.
+// MUST be called by all 32 lanes of a warp (inactive lanes pass a clamped, valid column and active=false).
+// p points at logits[0][col]; element v of the column is p[v * ld].
 template <int MODE, int OP>
 __device__ __forceinline__ void cdf_col(const float *__restrict__ p, size_t ld, int V, uint32_t arg, bool active,
                                         const ExpTab &tab, uint32_t &sym_out, uint32_t &lo_out, uint32_t &hi_out,
@@ -99,22 +131,19 @@ __device__ __forceinline__ void cdf_col(const float *__restrict__ p, size_t ld, 
   if (have_max) {
     mx = known_max;
   } else {
-#pragma unroll 8
-    for (int v = 0; v < V; v++) {
-      float x = __ldg(p + (size_t)v * ld);
+    cdf_walk(p, ld, V, [&](int, float x) {
       if (x > mx) mx = x;
-    }
+      return true;
+    });
   }
   // pass B: S = sum_i (f64)expf(l_i - max), sequential
   double S = 0.0;
-#pragma unroll 4
-  for (int v = 0; v < V; v++) {
-    float x = __ldg(p + (size_t)v * ld);
+  cdf_walk(p, ld, V, [&](int, float x) {
     S = __dadd_rn(S, (double)cz_expf(__fsub_rn(x, mx), tab));
-  }
+    return true;
+  });
   if (!(S == S) && active) errbits |= CZ_DEVERR_NAN;
 
-  // element pdf before the final CDF accumulation
   double norm = 1.0, sum2 = 1.0;
   const double scale = 1.0 - 256.0 * CZ_P_FLOOR;
   const bool uniform = (MODE == CZ_CDF_SMOLLM && OP != OP_XE) && (S <= 0.0);  // src/main.rs:794-798
@@ -123,52 +152,46 @@ __device__ __forceinline__ void cdf_col(const float *__restrict__ p, size_t ld, 
   if (MODE == CZ_CDF_RWKV_LITERALS || OP == OP_XE) {
     // softmax_pdf_floor: norm = sum_i max(e_i / S, floor)   (src/main.rs:763-764)
     double acc = 0.0;
-#pragma unroll 4
-    for (int v = 0; v < V; v++) {
-      float x = __ldg(p + (size_t)v * ld);
-      double q = __ddiv_rn((double)cz_expf(__fsub_rn(x, mx), tab), S);
+    cdf_walk(p, ld, V, [&](int, float x) {
+      const double q = __ddiv_rn((double)cz_expf(__fsub_rn(x, mx), tab), S);
       acc = __dadd_rn(acc, fmax(q, CZ_P_FLOOR));
-    }
+      return true;
+    });
     norm = acc;
   }
   if (MODE == CZ_CDF_RWKV_LITERALS) {
     // combined_pdf_with_literals: sum2 over V scaled entries + 256 literal entries (src/main.rs:773-779)
     double acc = 0.0;
-#pragma unroll 4
-    for (int v = 0; v < V; v++) {
-      float x = __ldg(p + (size_t)v * ld);
+    cdf_walk(p, ld, V, [&](int, float x) {
       double q = __ddiv_rn((double)cz_expf(__fsub_rn(x, mx), tab), S);
       q = __ddiv_rn(fmax(q, CZ_P_FLOOR), norm);
       acc = __dadd_rn(acc, __dmul_rn(q, scale));
-    }
+      return true;
+    });
     for (int j = 0; j < 256; j++) acc = __dadd_rn(acc, CZ_P_FLOOR);
     sum2 = acc;
   }
 
-  auto pdf_at = [&](int v) -> double {  // final pdf entry v (v < n_sym)
+  // final pdf entry for vocab element v (< V) with logit x
+  auto pdf_vocab = [&](float x) -> double {
     if (MODE == CZ_CDF_RWKV_LITERALS) {
-      double q;
-      if (v < V) {
-        float x = __ldg(p + (size_t)v * ld);
-        q = __ddiv_rn((double)cz_expf(__fsub_rn(x, mx), tab), S);
-        q = __dmul_rn(__ddiv_rn(fmax(q, CZ_P_FLOOR), norm), scale);
-      } else {
-        q = CZ_P_FLOOR;
-      }
+      double q = __ddiv_rn((double)cz_expf(__fsub_rn(x, mx), tab), S);
+      q = __dmul_rn(__ddiv_rn(fmax(q, CZ_P_FLOOR), norm), scale);
       return sum2 > 0.0 ? __ddiv_rn(q, sum2) : q;
     } else if (OP == OP_XE) {
-      float x = __ldg(p + (size_t)v * ld);
-      double q = __ddiv_rn((double)cz_expf(__fsub_rn(x, mx), tab), S);
+      const double q = __ddiv_rn((double)cz_expf(__fsub_rn(x, mx), tab), S);
       return __ddiv_rn(fmax(q, CZ_P_FLOOR), norm);
     } else {
       if (uniform) return uni;
-      float x = __ldg(p + (size_t)v * ld);
       return __ddiv_rn((double)cz_expf(__fsub_rn(x, mx), tab), S);
     }
   };
+  const double pdf_literal = sum2 > 0.0 ? __ddiv_rn(CZ_P_FLOOR, sum2) : CZ_P_FLOOR;  // RWKV literal symbols v >= V
 
   if (OP == OP_XE) {
-    double pr = (int)arg < n_sym ? pdf_at((int)arg) : CZ_P_FLOOR;  // pdf.get(sym).unwrap_or(ac_p_min())
+    double pr = CZ_P_FLOOR;  // pdf.get(sym).unwrap_or(ac_p_min())
+    if ((int)arg < V) pr = pdf_vocab(__ldg(p + (size_t)arg * ld));
+    else if ((int)arg < n_sym) pr = pdf_literal;
     pr = fmax(pr, 1e-300);
     xe_out = -log2(pr);
     return;
@@ -179,23 +202,26 @@ __device__ __forceinline__ void cdf_col(const float *__restrict__ p, size_t ld, 
     bool sym_bad = false;
     if ((int)sym >= n_sym) {
       if (active) errbits |= CZ_DEVERR_SYM;
-      sym = 0;  // keep walking with the warp (shuffles below need every lane), result is discarded
+      sym = 0;  // keep walking with the warp, result is discarded
       sym_bad = true;
     }
     double acc = 0.0;
     uint32_t lo = 0, hi = 0;
-    // the warp walks to the largest symbol among its lanes; each lane snapshots at its own sym-1 / sym
-    uint32_t wmax = sym;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) wmax = max(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
-    for (uint32_t v = 0; v <= wmax; v++) {
-      if (v <= sym) {
-        acc = __dadd_rn(acc, pdf_at((int)v));
+    const int n_walk = (int)sym < V ? (int)sym + 1 : V;  // vocab part of the prefix
+    cdf_walk(p, ld, n_walk, [&](int v, float x) {
+      acc = __dadd_rn(acc, pdf_vocab(x));
+      if ((uint32_t)v + 1 == sym) lo = quant(acc);
+      if ((uint32_t)v == sym) hi = quant(acc);
+      return (uint32_t)v < sym;
+    });
+    if (MODE == CZ_CDF_RWKV_LITERALS && (int)sym >= V) {  // literal symbols follow the vocab
+      for (uint32_t v = (uint32_t)V; v <= sym; v++) {
+        acc = __dadd_rn(acc, pdf_literal);
         if (v + 1 == sym) lo = quant(acc);
         if (v == sym) hi = quant(acc);
       }
     }
-    if (hi < lo) hi = lo;                          // non-decreasing clamp (src/main.rs:818)
+    if (hi < lo) hi = lo;                             // non-decreasing clamp (src/main.rs:818)
     if ((int)sym == n_sym - 1) hi = CZ_AC_CDF_TOTAL;  // cdf[n] = total (src/main.rs:822)
     lo_out = sym_bad ? 0u : lo;
     hi_out = sym_bad ? 0u : hi;
@@ -207,22 +233,25 @@ __device__ __forceinline__ void cdf_col(const float *__restrict__ p, size_t ld, 
     double acc = 0.0;
     uint32_t prev = 0, found_sym = (uint32_t)(n_sym - 1), lo = 0, hi = CZ_AC_CDF_TOTAL;
     bool done = false;
-    for (int v = 0; v < n_sym; v++) {
-      if (!done) {
-        acc = __dadd_rn(acc, pdf_at(v));
-        uint32_t cur = quant(acc);
-        if (cur < prev) cur = prev;
-        if (v == n_sym - 1) cur = CZ_AC_CDF_TOTAL;
-        if (value < cur) {
-          found_sym = (uint32_t)v;
-          lo = prev;
-          hi = cur;
-          done = true;
-        }
-        prev = cur;
+    auto visit = [&](int v, double pr) {
+      acc = __dadd_rn(acc, pr);
+      uint32_t cur = quant(acc);
+      if (cur < prev) cur = prev;
+      if (v == n_sym - 1) cur = CZ_AC_CDF_TOTAL;
+      if (value < cur) {
+        found_sym = (uint32_t)v;
+        lo = prev;
+        hi = cur;
+        done = true;
       }
-      if (__all_sync(0xffffffffu, done)) break;
-    }
+      prev = cur;
+    };
+    cdf_walk(p, ld, V, [&](int v, float x) {
+      visit(v, pdf_vocab(x));
+      return !done;
+    });
+    if (MODE == CZ_CDF_RWKV_LITERALS)
+      for (int v = V; v < n_sym && !done; v++) visit(v, pdf_literal);
     sym_out = found_sym;
     lo_out = lo;
     hi_out = hi;

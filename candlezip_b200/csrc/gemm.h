@@ -23,6 +23,7 @@ struct GemmArgs {
   int lda, ldb, ldc;
   int epi;  // GemmEpilogue
   int bn;   // tile width: 192 or 256 (also the gate/up packing granularity for EPI_SWIGLU_BF16)
+  int fam = 0;         // profiling family (CZ_K_GEMM, CZ_K_GEMM_O, ...)
   int *aux = nullptr;  // EPI_STORE_F32_COLMAX: per-column running max, must be pre-filled with INT_MIN
 };
 

@@ -79,13 +79,14 @@ int gemm_simt(cz_ctx *ctx, const GemmArgs &g, cudaStream_t stream) {
     return CZ_ERR_INVALID;
   }
   dim3 grid((unsigned)ceil_div(g.N, czk::ST), (unsigned)ceil_div(g.M, czk::ST));
+  const int g_fam = g.fam;
   const __nv_bfloat16 *A = (const __nv_bfloat16 *)g.a, *B = (const __nv_bfloat16 *)g.b;
   if (g.epi == EPI_SWIGLU_BF16) {
     // two-step: f32 temp then the packed swiglu (temp lives in the ctx scratch)
     size_t bytes = (size_t)g.M * g.N * sizeof(float);
     CZ_TRY(ensure_scratch(ctx, bytes));
     float *T = (float *)ctx->scratch;
-    CZ_LAUNCH(ctx, CZ_K_GEMM,
+    CZ_LAUNCH(ctx, g_fam,
               (czk::gemm_simt_kernel<EPI_STORE_F32><<<grid, 256, 0, stream>>>(A, B, T, g.M, g.N, g.K, g.lda, g.ldb, g.N, g.bn)));
     CZ_CHECK_LAUNCH();
     size_t total = (size_t)g.M * (g.N / 2);
@@ -95,14 +96,14 @@ int gemm_simt(cz_ctx *ctx, const GemmArgs &g, cudaStream_t stream) {
     CZ_CHECK_LAUNCH();
     return CZ_OK;
   }
-  if (g.epi == EPI_STORE_F32)
-    CZ_LAUNCH(ctx, CZ_K_GEMM,
+  if (g.epi == EPI_STORE_F32 || g.epi == EPI_STORE_F32_COLMAX)
+    CZ_LAUNCH(ctx, g_fam,
               (czk::gemm_simt_kernel<EPI_STORE_F32><<<grid, 256, 0, stream>>>(A, B, g.c, g.M, g.N, g.K, g.lda, g.ldb, g.ldc, g.bn)));
   else if (g.epi == EPI_ADD_F32)
-    CZ_LAUNCH(ctx, CZ_K_GEMM,
+    CZ_LAUNCH(ctx, g_fam,
               (czk::gemm_simt_kernel<EPI_ADD_F32><<<grid, 256, 0, stream>>>(A, B, g.c, g.M, g.N, g.K, g.lda, g.ldb, g.ldc, g.bn)));
   else if (g.epi == EPI_STORE_BF16)
-    CZ_LAUNCH(ctx, CZ_K_GEMM,
+    CZ_LAUNCH(ctx, g_fam,
               (czk::gemm_simt_kernel<EPI_STORE_BF16><<<grid, 256, 0, stream>>>(A, B, g.c, g.M, g.N, g.K, g.lda, g.ldb, g.ldc, g.bn)));
   else {
     set_error("gemm_simt: unknown epilogue");

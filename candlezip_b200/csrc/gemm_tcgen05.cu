@@ -383,7 +383,7 @@ static int make_map(CUtensorMap *map, const void *ptr, int rows, int K, int ld_e
 
 template <int BN, int EPI>
 static int launch_tc(cz_ctx *ctx, const CUtensorMap &ta, const CUtensorMap &tb, void *c, int M, int N, int K, int ldc, int *aux,
-                     cudaStream_t stream) {
+                     int g_fam, cudaStream_t stream) {
   using Cfg = czk::GemmCfg<BN>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -392,7 +392,7 @@ static int launch_tc(cz_ctx *ctx, const CUtensorMap &ta, const CUtensorMap &tb, 
   }
   const int tiles = (int)(ceil_div(M, czk::BM) * ceil_div(N, BN));
   const int grid = tiles < ctx->sm_count ? tiles : ctx->sm_count;
-  CZ_LAUNCH(ctx, CZ_K_GEMM,
+  CZ_LAUNCH(ctx, g_fam,
             (czk::gemm_tc_kernel<BN, EPI><<<grid, czk::GEMM_THREADS, Cfg::kSmemBytes, stream>>>(ta, tb, c, M, N, K, ldc, aux)));
   CZ_CHECK_LAUNCH();
   return CZ_OK;
@@ -421,7 +421,7 @@ int gemm_tcgen05(cz_ctx *ctx, const GemmArgs &g, cudaStream_t stream) {
   CZ_TRY(make_map(&ta, g.a, g.M, g.K, g.lda, czk::BM));
   CZ_TRY(make_map(&tb, g.b, g.N, g.K, g.ldb, g.bn));
 #define CZ_TC_CASE(BN_, EPI_) \
-  if (g.bn == BN_ && g.epi == EPI_) return launch_tc<BN_, EPI_>(ctx, ta, tb, g.c, g.M, g.N, g.K, g.ldc, g.aux, stream)
+  if (g.bn == BN_ && g.epi == EPI_) return launch_tc<BN_, EPI_>(ctx, ta, tb, g.c, g.M, g.N, g.K, g.ldc, g.aux, g.fam, stream)
   CZ_TC_CASE(192, EPI_STORE_F32);
   CZ_TC_CASE(192, EPI_ADD_F32);
   CZ_TC_CASE(192, EPI_SWIGLU_BF16);

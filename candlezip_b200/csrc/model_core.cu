@@ -244,7 +244,7 @@ int forward_trunk(cz_model *m, int n_rows, const KvView &kv, cudaStream_t st) {
     CZ_TRY(launch_rmsnorm(ctx, w.x, n1, nullptr, w.xn, n_rows, D, c.norm_eps, st));
     GemmArgs g{};
     g.a = w.xn; g.lda = D; g.b = m->w_qkv + (size_t)l * QKV * D; g.ldb = D; g.c = w.qkv; g.ldc = QKV;
-    g.M = n_rows; g.N = QKV; g.K = D; g.epi = EPI_STORE_F32; g.bn = 192;
+    g.M = n_rows; g.N = QKV; g.K = D; g.epi = EPI_STORE_F32; g.bn = 192; g.fam = CZ_K_GEMM;
     CZ_TRY(gemm(ctx, c.engine, g, st));
     CZ_TRY(launch_rope_split(ctx, w.qkv, w.pos, w.kv_base, m->cos_tab, m->sin_tab, w.q, kl, vl, n_rows, nh, nkv, st));
     static const bool force_rows = getenv("CZ_DEBUG_ATTN_ROWS") != nullptr;  // bisecting aid
@@ -253,14 +253,14 @@ int forward_trunk(cz_model *m, int n_rows, const KvView &kv, cudaStream_t st) {
     else
       CZ_TRY(launch_attn_rows(ctx, w.q, kl, vl, w.pos, w.kv_base, w.attn, n_rows, nh, nkv, st));
     g.a = w.attn; g.lda = D; g.b = m->w_o + (size_t)l * D * D; g.ldb = D; g.c = w.x; g.ldc = D;
-    g.M = n_rows; g.N = D; g.K = D; g.epi = EPI_ADD_F32; g.bn = 192;
+    g.M = n_rows; g.N = D; g.K = D; g.epi = EPI_ADD_F32; g.bn = 192; g.fam = CZ_K_GEMM_O;
     CZ_TRY(gemm(ctx, c.engine, g, st));
     CZ_TRY(launch_rmsnorm(ctx, w.x, n2, nullptr, w.xn, n_rows, D, c.norm_eps, st));
     g.a = w.xn; g.lda = D; g.b = m->w_gu + (size_t)l * 2 * F * D; g.ldb = D; g.c = w.act; g.ldc = F;
-    g.M = n_rows; g.N = 2 * F; g.K = D; g.epi = EPI_SWIGLU_BF16; g.bn = m->gu_bn;
+    g.M = n_rows; g.N = 2 * F; g.K = D; g.epi = EPI_SWIGLU_BF16; g.bn = m->gu_bn; g.fam = CZ_K_GEMM_GU;
     CZ_TRY(gemm(ctx, c.engine, g, st));
     g.a = w.act; g.lda = F; g.b = m->w_d + (size_t)l * D * F; g.ldb = F; g.c = w.x; g.ldc = D;
-    g.M = n_rows; g.N = D; g.K = F; g.epi = EPI_ADD_F32; g.bn = 192;
+    g.M = n_rows; g.N = D; g.K = F; g.epi = EPI_ADD_F32; g.bn = 192; g.fam = CZ_K_GEMM_DOWN;
     CZ_TRY(gemm(ctx, c.engine, g, st));
   }
   return CZ_OK;
@@ -286,6 +286,7 @@ int lm_head(cz_model *m, int col0, int n_cols, float *logits, size_t ld, cudaStr
   g.c = logits; g.ldc = (int)ld;                           // -> vocab-major logits [V][ld]
   g.M = c.vocab; g.N = n_cols; g.K = c.d_model; g.epi = fuse_max ? EPI_STORE_F32_COLMAX : EPI_STORE_F32; g.bn = 256;
   g.aux = colmax;
+  g.fam = CZ_K_GEMM_HEAD;
   return gemm(m->ctx, c.engine, g, st);
 }
 
