@@ -258,4 +258,110 @@ __device__ __forceinline__ void cdf_col(const float *__restrict__ p, size_t ld, 
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Warp-per-column search for the stepwise decoder.  With only B (hundreds) columns per step the thread-per-column
+// walk above is a ~10^5-deep dependent chain per thread with nothing to overlap.  Here the 32 lanes evaluate expf /
+// the pdf for 32 consecutive vocab entries in parallel and only the order-dependent f64 accumulation is serial
+// (every lane performs it redundantly on shuffled values, so all lanes hold the same S / acc and branches stay
+// warp-uniform).  Same operations in the same order as cdf_col => bit-identical results.
+// p: column base (vocab-major, element v at p[v*ld]).  Must be called by a full warp.
+template <int MODE>
+__device__ __forceinline__ void cdf_search_warp(const float *__restrict__ p, size_t ld, int V, uint32_t value, float mx,
+                                                const ExpTab &tab, uint32_t &sym_out, uint32_t &lo_out, uint32_t &hi_out,
+                                                int &errbits) {
+  const int lane = threadIdx.x & 31;
+  const int n_sym = MODE == CZ_CDF_RWKV_LITERALS ? V + 256 : V;
+  const int n_grp = (V + 31) / 32;
+  auto ld_x = [&](int g) -> float {
+    const int v = g * 32 + lane;
+    return v < V ? p[(size_t)v * ld] : __int_as_float(0xff800000);
+  };
+  // generic sequential accumulation of f(x) over the vocab: acc = ((0 + f0) + f1) + ...
+  auto seq_sum = [&](auto f) -> double {
+    double acc = 0.0;
+    float x = ld_x(0);
+    for (int g = 0; g < n_grp; g++) {
+      const float xn = g + 1 < n_grp ? ld_x(g + 1) : 0.f;
+      const double t = f(x);
+      const int cnt = V - g * 32 < 32 ? V - g * 32 : 32;
+      if (cnt == 32) {
+#pragma unroll
+        for (int k = 0; k < 32; k++) acc = __dadd_rn(acc, __shfl_sync(0xffffffffu, t, k));
+      } else {
+        for (int k = 0; k < cnt; k++) acc = __dadd_rn(acc, __shfl_sync(0xffffffffu, t, k));
+      }
+      x = xn;
+    }
+    return acc;
+  };
+  const double S = seq_sum([&](float x) { return (double)cz_expf(__fsub_rn(x, mx), tab); });
+  if (!(S == S)) errbits |= CZ_DEVERR_NAN;
+  double norm = 1.0, sum2 = 1.0;
+  const double scale = 1.0 - 256.0 * CZ_P_FLOOR;
+  if (MODE == CZ_CDF_RWKV_LITERALS) {
+    norm = seq_sum([&](float x) { return fmax(__ddiv_rn((double)cz_expf(__fsub_rn(x, mx), tab), S), CZ_P_FLOOR); });
+    double acc = seq_sum([&](float x) {
+      const double q = fmax(__ddiv_rn((double)cz_expf(__fsub_rn(x, mx), tab), S), CZ_P_FLOOR);
+      return __dmul_rn(__ddiv_rn(q, norm), scale);
+    });
+    for (int j = 0; j < 256; j++) acc = __dadd_rn(acc, CZ_P_FLOOR);
+    sum2 = acc;
+  }
+  const bool uniform = MODE == CZ_CDF_SMOLLM && S <= 0.0;
+  const double uni = 1.0 / (double)V;
+  auto pdf_vocab = [&](float x) -> double {
+    if (MODE == CZ_CDF_RWKV_LITERALS) {
+      double q = fmax(__ddiv_rn((double)cz_expf(__fsub_rn(x, mx), tab), S), CZ_P_FLOOR);
+      q = __dmul_rn(__ddiv_rn(q, norm), scale);
+      return sum2 > 0.0 ? __ddiv_rn(q, sum2) : q;
+    }
+    if (uniform) return uni;
+    return __ddiv_rn((double)cz_expf(__fsub_rn(x, mx), tab), S);
+  };
+  double acc = 0.0;
+  uint32_t prev = 0, found = (uint32_t)(n_sym - 1), lo = 0, hi = CZ_AC_CDF_TOTAL;
+  bool done = false;
+  float x = ld_x(0);
+  for (int g = 0; g < n_grp && !done; g++) {
+    const float xn = g + 1 < n_grp ? ld_x(g + 1) : 0.f;
+    const double t = pdf_vocab(x);
+    const int cnt = V - g * 32 < 32 ? V - g * 32 : 32;
+    for (int k = 0; k < cnt; k++) {
+      acc = __dadd_rn(acc, __shfl_sync(0xffffffffu, t, k));
+      const int v = g * 32 + k;
+      uint32_t cur = quant(acc);
+      if (cur < prev) cur = prev;
+      if (v == n_sym - 1) cur = CZ_AC_CDF_TOTAL;
+      if (value < cur) {
+        found = (uint32_t)v;
+        lo = prev;
+        hi = cur;
+        done = true;
+        break;
+      }
+      prev = cur;
+    }
+    x = xn;
+  }
+  if (MODE == CZ_CDF_RWKV_LITERALS && !done) {
+    const double pl = sum2 > 0.0 ? __ddiv_rn(CZ_P_FLOOR, sum2) : CZ_P_FLOOR;
+    for (int v = V; v < n_sym; v++) {
+      acc = __dadd_rn(acc, pl);
+      uint32_t cur = quant(acc);
+      if (cur < prev) cur = prev;
+      if (v == n_sym - 1) cur = CZ_AC_CDF_TOTAL;
+      if (value < cur) {
+        found = (uint32_t)v;
+        lo = prev;
+        hi = cur;
+        break;
+      }
+      prev = cur;
+    }
+  }
+  sym_out = found;
+  lo_out = lo;
+  hi_out = hi;
+}
+
 }  // namespace czk

@@ -45,6 +45,40 @@ __global__ void __launch_bounds__(128) cdf_cols_kernel(const float *__restrict__
   }
 }
 
+// OP_SEARCH for a small number of columns (stepwise decode): one warp per column, see cdf_search_warp
+template <int MODE>
+__global__ void __launch_bounds__(256) cdf_search_warp_kernel(const float *__restrict__ logits, int V, size_t M, size_t ld,
+                                                              const uint32_t *__restrict__ values, uint32_t *__restrict__ sym_out,
+                                                              uint32_t *__restrict__ c_lo_out, uint32_t *__restrict__ c_hi_out,
+                                                              int *__restrict__ err, const int *__restrict__ colmax) {
+  __shared__ uint32_t s_lo[32 * 32], s_hi[32 * 32];
+  exp_tab_init(s_lo, s_hi);
+  ExpTab tab{s_lo, s_hi, (int)(threadIdx.x & 31)};
+  const size_t col = (size_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (col >= M) return;
+  float mx;
+  if (colmax) {
+    mx = colmax_decode(colmax[col]);
+  } else {
+    mx = __int_as_float(0xff800000);
+    for (int v = threadIdx.x & 31; v < V; v += 32) {
+      const float x = logits[(size_t)v * ld + col];
+      if (x > mx) mx = x;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  }
+  uint32_t sym, lo, hi;
+  int errbits = 0;
+  cdf_search_warp<MODE>(logits + col, ld, V, values[col], mx, tab, sym, lo, hi, errbits);
+  if ((threadIdx.x & 31) == 0) {
+    if (errbits) atomicOr(err, errbits);
+    sym_out[col] = sym;
+    c_lo_out[col] = lo;
+    c_hi_out[col] = hi;
+  }
+}
+
 // full CDF of one column (debug / watchdog parity): single thread, sequential
 template <int MODE>
 __global__ void cdf_full_kernel(const float *__restrict__ logits, int V, uint32_t *__restrict__ cdf) {
@@ -123,6 +157,23 @@ int launch_cdf_cols(cz_ctx *ctx, int op, int mode, const float *logits_dev, size
   if (V == 0 || V > (1u << 24) || ld < M) {
     set_error("cdf: bad shape");
     return CZ_ERR_INVALID;
+  }
+  if (op == czk::OP_SEARCH && M <= 8192) {  // decode-sized: warp per column
+    const unsigned g = (unsigned)ceil_div(M, 8);
+    if (mode == CZ_CDF_SMOLLM)
+      CZ_LAUNCH(ctx, CZ_K_CDF,
+                (czk::cdf_search_warp_kernel<CZ_CDF_SMOLLM><<<g, 256, 0, stream>>>(logits_dev, (int)V, M, ld, arg_dev, sym_out_dev, c_lo_dev,
+                                                                                   c_hi_dev, ctx->err_flag_dev, colmax_dev)));
+    else if (mode == CZ_CDF_RWKV_LITERALS)
+      CZ_LAUNCH(ctx, CZ_K_CDF,
+                (czk::cdf_search_warp_kernel<CZ_CDF_RWKV_LITERALS><<<g, 256, 0, stream>>>(logits_dev, (int)V, M, ld, arg_dev, sym_out_dev,
+                                                                                          c_lo_dev, c_hi_dev, ctx->err_flag_dev, colmax_dev)));
+    else {
+      set_error("cdf: unknown mode");
+      return CZ_ERR_INVALID;
+    }
+    CZ_CHECK_LAUNCH();
+    return CZ_OK;
   }
   const int threads = 128;
   dim3 grid((unsigned)ceil_div(M, threads));

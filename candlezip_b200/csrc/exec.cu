@@ -2,7 +2,9 @@
 // batch-of-1 LanguageModelSession shim.  Replaces the per-token loops of src/main.rs:1979-2355 (encode),
 // 2528-2653 (decode) and 1725-1751 (gate cross-entropy): logits never leave the GPU, the quantised CDF bounds
 // feed the on-device arithmetic-coder lanes directly, and the host only builds row metadata and launches kernels.
+#include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 #include <algorithm>
 #include <vector>
@@ -50,10 +52,11 @@ __global__ void ac_decoder_init_kernel(const uint8_t *__restrict__ payload, cons
   st[lane] = d.s;
 }
 
-// One thread per stream: AC target value -> CDF search over its logits column -> symbol -> AC state update.
+// One WARP per stream: AC target value -> CDF search over its logits column -> symbol -> AC state update.
 // (src/main.rs:2622-2626: to_vec1 + softmax_pdf + quantize_pdf_to_cdf + decode_symbol_counts, fused, on device.)
+// 8 warps per CTA take 8 adjacent columns so that the 32-byte sectors of the vocab-major logits are shared through L1.
 template <int MODE>
-__global__ void __launch_bounds__(128) decode_step_kernel(const float *__restrict__ logits, int V, size_t ld, int n_lanes,
+__global__ void __launch_bounds__(256) decode_step_kernel(const float *__restrict__ logits, int V, size_t ld, int n_lanes,
                                                           const uint8_t *__restrict__ payload, const uint64_t *__restrict__ seg_off,
                                                           const uint64_t *__restrict__ seg_start, uint64_t coded_index,
                                                           AcDecoderState *__restrict__ st, uint32_t *__restrict__ ids_out,
@@ -62,25 +65,35 @@ __global__ void __launch_bounds__(128) decode_step_kernel(const float *__restric
   __shared__ uint32_t s_lo[32 * 32], s_hi[32 * 32];
   exp_tab_init(s_lo, s_hi);
   ExpTab tab{s_lo, s_hi, (int)(threadIdx.x & 31)};
-  int lane = blockIdx.x * blockDim.x + threadIdx.x;
-  bool active = lane < n_lanes;
-  if (!active) lane = n_lanes - 1;
+  const int lane = blockIdx.x * 8 + (threadIdx.x >> 5);  // stream index (warp-uniform)
+  if (lane >= n_lanes) return;
   const uint64_t seg_len = seg_start[lane + 1] - seg_start[lane];
-  const bool live = active && coded_index < seg_len;  // streams past their end idle (ragged last segment)
+  if (coded_index >= seg_len) return;  // streams past their end idle (ragged last segments)
   AcDecoder d;
   d.resume(st[lane], payload + seg_off[lane], seg_off[lane + 1] - seg_off[lane]);
   const uint32_t value = d.peek_value();
+  float mx;
+  if (colmax) {
+    mx = colmax_decode(colmax[lane]);
+  } else {  // engines without the fused column max: parallel max (exact, order-independent)
+    mx = __int_as_float(0xff800000);
+    for (int v = threadIdx.x & 31; v < V; v += 32) {
+      const float x = logits[(size_t)v * ld + lane];
+      if (x > mx) mx = x;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  }
   uint32_t sym, lo, hi;
-  double xe;
   int errbits = 0;
-  cdf_col<MODE, OP_SEARCH>(logits + lane, ld, V, value, live, tab, sym, lo, hi, xe, errbits, colmax != nullptr,
-                           colmax ? colmax_decode(colmax[lane]) : 0.f);
-  if (!live) return;
-  if (errbits) atomicOr(err, errbits);
-  d.consume(lo, hi);
-  st[lane] = d.s;
-  ids_out[seg_start[lane] + coded_index] = sym;
-  next_tok[lane] = sym;
+  cdf_search_warp<MODE>(logits + lane, ld, V, value, mx, tab, sym, lo, hi, errbits);
+  if ((threadIdx.x & 31) == 0) {
+    if (errbits) atomicOr(err, errbits);
+    d.consume(lo, hi);
+    st[lane] = d.s;
+    ids_out[seg_start[lane] + coded_index] = sym;
+    next_tok[lane] = sym;
+  }
 }
 
 __global__ void fill_int_kernel(int *__restrict__ p, int v, int n) {
@@ -248,15 +261,25 @@ static int coded_mode(const cz_model *m) { return m->cfg.arch == CZ_ARCH_RWKV7 ?
 
 // Core of cz_encode / cz_encode_dev: ids already on the device.  Leaves the compacted payload in out_dev
 // (device) and the per-segment offsets in seg_off_host.
+static double host_ms() {
+  timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+}
+
 static int encode_core(cz_model *m, const uint32_t *ids_dev, size_t n_tokens, const cz_schedule *sched, uint8_t *out_dev,
                        size_t out_cap, uint64_t *seg_off_host) {
   cz_ctx *ctx = m->ctx;
   cudaStream_t st = ctx->stream;
+  static const bool dbg = getenv("CZ_DEBUG_TIMING") != nullptr;
+  const double t_begin = host_ms();
+  double t_build = 0, t_flush = 0;
   const uint32_t S = sched->n_segments;
   const size_t max_rows = sched->max_batch_tokens ? sched->max_batch_tokens : (size_t)262144;
-  DevBuf d_lo, d_hi, d_src, d_extra, d_lane, d_raw, d_misc;
-  CZ_TRY(d_lo.alloc(n_tokens * 4));
-  CZ_TRY(d_hi.alloc(n_tokens * 4));
+  GrowBuf &d_lo = m->sb[SB_LO], &d_hi = m->sb[SB_HI], &d_src = m->sb[SB_SRC], &d_extra = m->sb[SB_EXTRA], &d_lane = m->sb[SB_LANE],
+          &d_raw = m->sb[SB_RAW];
+  CZ_TRY(d_lo.reserve(n_tokens * 4, st));
+  CZ_TRY(d_hi.reserve(n_tokens * 4, st));
   // explicit prime token lists of the hint events
   std::vector<uint32_t> extra;
   std::vector<size_t> ev_off(sched->n_events + 1, 0);
@@ -264,25 +287,25 @@ static int encode_core(cz_model *m, const uint32_t *ids_dev, size_t n_tokens, co
     ev_off[e] = extra.size();
     extra.insert(extra.end(), sched->events[e].prime, sched->events[e].prime + sched->events[e].prime_len);
   }
-  CZ_TRY(d_extra.alloc(extra.size() * 4));
+  CZ_TRY(d_extra.reserve(extra.size() * 4 + 16, st));
   if (!extra.empty()) CZ_CUDA_TRY(cudaMemcpyAsync(d_extra.p, extra.data(), extra.size() * 4, cudaMemcpyHostToDevice, st));
 
-  size_t src_cap = 0;
   Wave w;
   size_t wave_first = 0;  // global coded index of the wave's first logit column
   size_t coded_done = 0;
+  double t_wave0 = host_ms();
   auto flush = [&]() -> int {
     if (w.n_rows() == 0) return CZ_OK;
-    if (w.n_rows() > src_cap) {
-      src_cap = w.n_rows() + w.n_rows() / 8 + 1024;
-      CZ_CUDA_TRY(cudaStreamSynchronize(st));
-      CZ_TRY(d_src.alloc(src_cap * 8));
-    }
+    const double t0 = host_ms();
+    t_build += t0 - t_wave0;
+    CZ_TRY(d_src.reserve(w.n_rows() * 8, st));
     CZ_TRY(run_wave_trunk(m, w, ids_dev, d_extra.as<uint32_t>(), sched->bos, d_src.as<long long>(), st));
     CZ_TRY(run_wave_head(m, w.n_logit(), czk::OP_BOUNDS, coded_mode(m), ids_dev + wave_first, d_lo.as<uint32_t>() + wave_first,
                          d_hi.as<uint32_t>() + wave_first, nullptr, st));
     wave_first += w.n_logit();
     w.clear();
+    t_wave0 = host_ms();
+    t_flush += t_wave0 - t0;
     return CZ_OK;
   };
   std::vector<Chunk> chunks;
@@ -317,7 +340,7 @@ static int encode_core(cz_model *m, const uint32_t *ids_dev, size_t n_tokens, co
   // ---- arithmetic-coder lanes: one per segment ----
   std::vector<uint64_t> lane_off(sched->seg_start, sched->seg_start + S + 1), raw_off(S + 1);
   for (uint32_t g = 0; g <= S; g++) raw_off[g] = 4 * lane_off[g] + 8 * (uint64_t)g;
-  CZ_TRY(d_lane.alloc((S + 1) * 8 * 4 + 64));
+  CZ_TRY(d_lane.reserve((S + 1) * 8 * 4 + 64, st));
   uint64_t *d_lane_off = d_lane.as<uint64_t>(), *d_raw_off = d_lane_off + (S + 1), *d_len = d_raw_off + (S + 1),
            *d_dst_off = d_len + (S + 1);
   unsigned long long *d_eidx = (unsigned long long *)(d_dst_off + (S + 1));
@@ -325,7 +348,7 @@ static int encode_core(cz_model *m, const uint32_t *ids_dev, size_t n_tokens, co
   CZ_CUDA_TRY(cudaMemcpyAsync(d_lane_off, lane_off.data(), (S + 1) * 8, cudaMemcpyHostToDevice, st));
   CZ_CUDA_TRY(cudaMemcpyAsync(d_raw_off, raw_off.data(), (S + 1) * 8, cudaMemcpyHostToDevice, st));
   CZ_CUDA_TRY(cudaMemcpyAsync(d_eidx, &none, 8, cudaMemcpyHostToDevice, st));
-  CZ_TRY(d_raw.alloc(raw_off[S] + 16));
+  CZ_TRY(d_raw.reserve(raw_off[S] + 16, st));
   CZ_TRY(launch_ac_encode_lanes(ctx, d_lo.as<uint32_t>(), d_hi.as<uint32_t>(), d_lane_off, S, d_raw.as<uint8_t>(), d_raw_off, d_len,
                                 d_eidx, st));
   std::vector<uint64_t> len(S);
@@ -340,7 +363,11 @@ static int encode_core(cz_model *m, const uint32_t *ids_dev, size_t n_tokens, co
   CZ_CUDA_TRY(cudaMemcpyAsync(d_dst_off, seg_off_host, (S + 1) * 8, cudaMemcpyHostToDevice, st));
   CZ_LAUNCH(ctx, CZ_K_CODER, (czk::compact_payload_kernel<<<S, 128, 0, st>>>(d_raw.as<uint8_t>(), d_raw_off, d_dst_off, out_dev)));
   CZ_CHECK_LAUNCH();
+  const double t_pre_sync = host_ms();
   CZ_CUDA_TRY(cudaStreamSynchronize(st));
+  if (dbg)
+    fprintf(stderr, "[cz timing] encode_core: total %.1f ms | host wave build %.1f | host launch (trunk+head) %.1f | final sync wait %.1f\n",
+            host_ms() - t_begin, t_build, t_flush, host_ms() - t_pre_sync);
   return CZ_OK;
 }
 
@@ -472,11 +499,11 @@ int cz_encode(cz_model *m, const uint32_t *ids, size_t n_tokens, const cz_schedu
   CZ_TRY(model_finalize(m));
   cz_ctx *ctx = m->ctx;
   CZ_CUDA_TRY(cudaSetDevice(ctx->device));
-  DevBuf d_ids, d_out;
-  CZ_TRY(d_ids.alloc(n_tokens * 4));
+  GrowBuf &d_ids = m->sb[SB_IDS], &d_out = m->sb[SB_OUT];
+  CZ_TRY(d_ids.reserve(n_tokens * 4 + 16, ctx->stream));
   if (n_tokens) CZ_CUDA_TRY(cudaMemcpyAsync(d_ids.p, ids, n_tokens * 4, cudaMemcpyHostToDevice, ctx->stream));
   const size_t cap = 4 * n_tokens + 8 * (size_t)sched->n_segments + 16;
-  CZ_TRY(d_out.alloc(cap));
+  CZ_TRY(d_out.reserve(cap, ctx->stream));
   CZ_TRY(encode_core(m, d_ids.as<uint32_t>(), n_tokens, sched, d_out.as<uint8_t>(), cap, out->seg_off));
   const uint64_t total = out->seg_off[sched->n_segments];
   if (total > out->cap) {
@@ -518,16 +545,17 @@ int cz_decode(cz_model *m, const uint8_t *payload, const uint64_t *seg_off, size
     return CZ_ERR_UNSUPPORTED;
   }
   const size_t S_pad = (S + 3) & ~(size_t)3;
-  DevBuf d_pay, d_off, d_start, d_state, d_ids, d_k, d_v, d_logits, d_src, d_kvb;
+  GrowBuf &d_pay = m->sb[SB_PAY], &d_off = m->sb[SB_OFF], &d_start = m->sb[SB_START], &d_state = m->sb[SB_STATE], &d_ids = m->sb[SB_DIDS],
+          &d_k = m->sb[SB_K], &d_v = m->sb[SB_V], &d_logits = m->sb[SB_LOGITS], &d_src = m->sb[SB_SRC], &d_kvb = m->sb[SB_KVB];
   const uint64_t pay_total = seg_off[S];
-  CZ_TRY(d_pay.alloc(pay_total + 16));
-  CZ_TRY(d_off.alloc((S + 1) * 8));
-  CZ_TRY(d_start.alloc((S + 1) * 8));
-  CZ_TRY(d_state.alloc(S * sizeof(czk::AcDecoderState)));
-  CZ_TRY(d_ids.alloc(n_tokens * 4));
-  CZ_TRY(d_k.alloc(L * S * max_pos * kvd * 2));
-  CZ_TRY(d_v.alloc(L * S * max_pos * kvd * 2));
-  CZ_TRY(d_logits.alloc((size_t)c.vocab * S_pad * 4));
+  CZ_TRY(d_pay.reserve(pay_total + 16, st));
+  CZ_TRY(d_off.reserve((S + 1) * 8, st));
+  CZ_TRY(d_start.reserve((S + 1) * 8, st));
+  CZ_TRY(d_state.reserve(S * sizeof(czk::AcDecoderState), st));
+  CZ_TRY(d_ids.reserve(n_tokens * 4, st));
+  CZ_TRY(d_k.reserve(L * S * max_pos * kvd * 2, st));
+  CZ_TRY(d_v.reserve(L * S * max_pos * kvd * 2, st));
+  CZ_TRY(d_logits.reserve((size_t)c.vocab * S_pad * 4, st));
   CZ_CUDA_TRY(cudaMemcpyAsync(d_pay.p, payload, pay_total, cudaMemcpyHostToDevice, st));
   CZ_CUDA_TRY(cudaMemcpyAsync(d_off.p, seg_off, (S + 1) * 8, cudaMemcpyHostToDevice, st));
   CZ_CUDA_TRY(cudaMemcpyAsync(d_start.p, sched->seg_start, (S + 1) * 8, cudaMemcpyHostToDevice, st));
@@ -539,7 +567,6 @@ int cz_decode(cz_model *m, const uint8_t *payload, const uint64_t *seg_off, size
   kv.k = d_k.as<__nv_bfloat16>();
   kv.v = d_v.as<__nv_bfloat16>();
   kv.layer_stride = (size_t)S * max_pos * kvd;
-  size_t src_cap = 0;
   Wave w;
   // per-stream constant metadata for the single-token steps
   std::vector<int> kvb(S), lrows(S);
@@ -547,7 +574,7 @@ int cz_decode(cz_model *m, const uint8_t *payload, const uint64_t *seg_off, size
     kvb[g] = (int)(g * max_pos);
     lrows[g] = (int)g;
   }
-  CZ_TRY(d_kvb.alloc(S * 12));
+  CZ_TRY(d_kvb.reserve(S * 12, st));
   int *d_kvb_i = d_kvb.as<int>(), *d_lrows_i = d_kvb_i + S, *d_ones_i = d_lrows_i + S;  // step tiles: row0 = g, n = 1
   std::vector<int> ones(S, 1);
   CZ_CUDA_TRY(cudaMemcpyAsync(d_kvb_i, kvb.data(), S * 4, cudaMemcpyHostToDevice, st));
@@ -585,11 +612,7 @@ int cz_decode(cz_model *m, const uint8_t *payload, const uint64_t *seg_off, size
     }
     {
       const size_t R = w.n_rows(), NL = w.n_logit();
-      if (R > src_cap) {
-        src_cap = R + R / 8 + 1024;
-        CZ_CUDA_TRY(cudaStreamSynchronize(st));
-        CZ_TRY(d_src.alloc(src_cap * 8));
-      }
+      CZ_TRY(d_src.reserve(R * 8, st));
       CZ_TRY(ensure_workspace(m, std::max<size_t>(R, S), std::max<size_t>(NL, S), std::max<size_t>(w.n_tiles(), S)));
       Workspace &ws = m->ws;
       CZ_TRY(stage_and_upload(m, w, d_src.as<long long>(), st));
@@ -610,12 +633,12 @@ int cz_decode(cz_model *m, const uint8_t *payload, const uint64_t *seg_off, size
       const uint64_t i = ch.first + j;
       if (coded_mode(m) == CZ_CDF_SMOLLM)
         CZ_LAUNCH(ctx, CZ_K_CDF,
-                  (czk::decode_step_kernel<CZ_CDF_SMOLLM><<<(unsigned)ceil_div(n_live, 128), 128, 0, st>>>(
+                  (czk::decode_step_kernel<CZ_CDF_SMOLLM><<<(unsigned)ceil_div(n_live, 8), 256, 0, st>>>(
                       d_logits.as<float>(), c.vocab, S_pad, n_live, d_pay.as<uint8_t>(), d_off.as<uint64_t>(), d_start.as<uint64_t>(), i,
                       d_state.as<czk::AcDecoderState>(), d_ids.as<uint32_t>(), ws.tok, ctx->err_flag_dev, have_max ? ws.colmax : nullptr)));
       else
         CZ_LAUNCH(ctx, CZ_K_CDF,
-                  (czk::decode_step_kernel<CZ_CDF_RWKV_LITERALS><<<(unsigned)ceil_div(n_live, 128), 128, 0, st>>>(
+                  (czk::decode_step_kernel<CZ_CDF_RWKV_LITERALS><<<(unsigned)ceil_div(n_live, 8), 256, 0, st>>>(
                       d_logits.as<float>(), c.vocab, S_pad, n_live, d_pay.as<uint8_t>(), d_off.as<uint64_t>(), d_start.as<uint64_t>(), i,
                       d_state.as<czk::AcDecoderState>(), d_ids.as<uint32_t>(), ws.tok, ctx->err_flag_dev, have_max ? ws.colmax : nullptr)));
       CZ_CHECK_LAUNCH();
@@ -667,25 +690,22 @@ int cz_xe_bits(cz_model *m, const cz_xe_job *jobs, size_t n_jobs, double *bits_o
     job_off[j + 1] = job_off[j] + jobs[j].n_targets;
   }
   const size_t n_cols = tgt.size();
-  DevBuf d_extra, d_tgt, d_bits, d_src, d_joff, d_out;
-  CZ_TRY(d_extra.alloc(extra.size() * 4));
-  CZ_TRY(d_tgt.alloc(n_cols * 4));
-  CZ_TRY(d_bits.alloc(n_cols * 8));
-  CZ_TRY(d_joff.alloc((n_jobs + 1) * 8));
-  CZ_TRY(d_out.alloc(n_jobs * 8));
+  GrowBuf &d_extra = m->sb[SB_EXTRA], &d_tgt = m->sb[SB_TGT], &d_bits = m->sb[SB_BITS], &d_src = m->sb[SB_SRC], &d_joff = m->sb[SB_JOFF],
+          &d_out = m->sb[SB_XOUT];
+  CZ_TRY(d_extra.reserve(extra.size() * 4 + 16, st));
+  CZ_TRY(d_tgt.reserve(n_cols * 4 + 16, st));
+  CZ_TRY(d_bits.reserve(n_cols * 8 + 16, st));
+  CZ_TRY(d_joff.reserve((n_jobs + 1) * 8, st));
+  CZ_TRY(d_out.reserve(n_jobs * 8, st));
   CZ_CUDA_TRY(cudaMemcpyAsync(d_extra.p, extra.data(), extra.size() * 4, cudaMemcpyHostToDevice, st));
   if (n_cols) CZ_CUDA_TRY(cudaMemcpyAsync(d_tgt.p, tgt.data(), n_cols * 4, cudaMemcpyHostToDevice, st));
   CZ_CUDA_TRY(cudaMemcpyAsync(d_joff.p, job_off.data(), (n_jobs + 1) * 8, cudaMemcpyHostToDevice, st));
   const size_t max_rows = 262144;
-  size_t src_cap = 0, col_first = 0;
+  size_t col_first = 0;
   Wave w;
   auto flush = [&]() -> int {
     if (w.n_rows() == 0) return CZ_OK;
-    if (w.n_rows() > src_cap) {
-      src_cap = w.n_rows() + w.n_rows() / 8 + 1024;
-      CZ_CUDA_TRY(cudaStreamSynchronize(st));
-      CZ_TRY(d_src.alloc(src_cap * 8));
-    }
+    CZ_TRY(d_src.reserve(w.n_rows() * 8, st));
     CZ_TRY(run_wave_trunk(m, w, nullptr, d_extra.as<uint32_t>(), 0, d_src.as<long long>(), st));
     CZ_TRY(run_wave_head(m, w.n_logit(), czk::OP_XE, coded_mode(m), d_tgt.as<uint32_t>() + col_first, nullptr, nullptr,
                          d_bits.as<double>() + col_first, st));
@@ -723,13 +743,13 @@ int cz_chunk_logits(cz_model *m, const uint32_t *prime, size_t prime_len, const 
   CZ_CUDA_TRY(cudaSetDevice(ctx->device));
   std::vector<uint32_t> extra(prime, prime + prime_len);
   if (n_targets > 1) extra.insert(extra.end(), targets, targets + n_targets - 1);
-  DevBuf d_extra, d_src;
-  CZ_TRY(d_extra.alloc(extra.size() * 4));
+  GrowBuf &d_extra = m->sb[SB_EXTRA], &d_src = m->sb[SB_SRC];
+  CZ_TRY(d_extra.reserve(extra.size() * 4 + 16, st));
   CZ_CUDA_TRY(cudaMemcpyAsync(d_extra.p, extra.data(), extra.size() * 4, cudaMemcpyHostToDevice, st));
   Wave w;
   w.add_chunk((uint32_t)prime_len, (uint32_t)n_targets, [&](uint32_t k) { return -2 - (long long)k; },
               [&](uint32_t q) { return -2 - (long long)(prime_len + q); });
-  CZ_TRY(d_src.alloc(w.n_rows() * 8));
+  CZ_TRY(d_src.reserve(w.n_rows() * 8, st));
   CZ_TRY(run_wave_trunk(m, w, nullptr, d_extra.as<uint32_t>(), 0, d_src.as<long long>(), st));
   Workspace &ws = m->ws;
   const size_t V = m->cfg.vocab;

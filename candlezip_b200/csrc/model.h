@@ -45,7 +45,20 @@ struct Workspace {
   cudaEvent_t stage_ev = nullptr;
 };
 
+// grow-only device buffer owned by the model: API calls are synchronous, so scratch is reused call to call instead of
+// paying cudaMalloc/cudaFree (tens of ms, far worse while anything polls the driver) on every encode/decode
+struct GrowBuf {
+  void *p = nullptr;
+  size_t cap = 0;
+  int reserve(size_t bytes, cudaStream_t st);
+  template <class T>
+  T *as() { return (T *)p; }
+};
+enum { SB_LO = 0, SB_HI, SB_SRC, SB_EXTRA, SB_LANE, SB_RAW, SB_IDS, SB_OUT, SB_PAY, SB_OFF, SB_START, SB_STATE, SB_DIDS, SB_K, SB_V,
+       SB_LOGITS, SB_KVB, SB_TGT, SB_BITS, SB_JOFF, SB_XOUT, SB_COUNT };
+
 struct cz_model {
+  GrowBuf sb[SB_COUNT];
   cz_ctx *ctx = nullptr;
   cz_model_config cfg;
   std::vector<TensorSlot> tensors;

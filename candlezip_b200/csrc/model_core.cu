@@ -10,6 +10,20 @@
 #include "llama_kernels.h"
 #include "model.h"
 
+int GrowBuf::reserve(size_t bytes, cudaStream_t st) {
+  if (bytes <= cap && p) return CZ_OK;
+  if (p) {
+    CZ_CUDA_TRY(cudaStreamSynchronize(st));
+    cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  const size_t want = bytes + (bytes >> 3) + 256;
+  CZ_CUDA_TRY(cudaMalloc(&p, want));
+  cap = want;
+  return CZ_OK;
+}
+
 namespace cz {
 
 static uint64_t splitmix64(uint64_t x) {
@@ -403,6 +417,8 @@ void cz_model_free(cz_model *m) {
     cudaDeviceSynchronize();
     for (auto &s : m->tensors)
       if (s.dev) cudaFree(s.dev);
+    for (auto &b : m->sb)
+      if (b.p) cudaFree(b.p);
     void *ptrs[] = {m->w_qkv, m->w_o, m->w_gu, m->w_d, m->norms, m->cos_tab, m->sin_tab, m->ws.x, m->ws.xn, m->ws.qkv, m->ws.q,
                     m->ws.attn, m->ws.act, m->ws.kpack, m->ws.vpack, m->ws.tok, m->ws.pos, m->ws.kv_base, m->ws.logit_rows,
                     m->ws.syms, m->ws.out_index, m->ws.tile_row0, m->ws.tile_n, m->ws.xn_logit, m->ws.lo_tmp, m->ws.hi_tmp, m->ws.xe_tmp, m->ws.colmax, m->ws.logits[0],
