@@ -223,9 +223,10 @@ static int run_wave_trunk(cz_model *m, const Wave &w, const uint32_t *ids_dev, c
 // syms_dev[j] is the symbol of column j; results go to lo_out/hi_out (OP_BOUNDS) or xe_out (OP_XE), indexed by column.
 static int run_wave_head(cz_model *m, size_t n_logit, int op, int mode, const uint32_t *syms_dev, uint32_t *lo_out, uint32_t *hi_out,
                          double *xe_out, cudaStream_t st) {
+  CZ_TRY(ensure_logits(m, n_logit));
   Workspace &ws = m->ws;
-  int buf = 0;
-  for (size_t c0 = 0; c0 < n_logit; c0 += ws.ld_sub, buf ^= 1) {
+  const int buf = 0;
+  for (size_t c0 = 0; c0 < n_logit; c0 += ws.ld_sub) {
     const size_t nc = std::min(ws.ld_sub, n_logit - c0);
     bool have_max = false;
     CZ_TRY(lm_head(m, (int)c0, (int)nc, ws.logits[buf], ws.ld_sub, st, ws.colmax, &have_max));
@@ -545,6 +546,7 @@ int cz_decode(cz_model *m, const uint8_t *payload, const uint64_t *seg_off, size
     return CZ_ERR_UNSUPPORTED;
   }
   const size_t S_pad = (S + 3) & ~(size_t)3;
+  CZ_TRY(ensure_logits(m, S));  // also provides ws.colmax for the fused LM-head column max
   GrowBuf &d_pay = m->sb[SB_PAY], &d_off = m->sb[SB_OFF], &d_start = m->sb[SB_START], &d_state = m->sb[SB_STATE], &d_ids = m->sb[SB_DIDS],
           &d_k = m->sb[SB_K], &d_v = m->sb[SB_V], &d_logits = m->sb[SB_LOGITS], &d_src = m->sb[SB_SRC], &d_kvb = m->sb[SB_KVB];
   const uint64_t pay_total = seg_off[S];
@@ -751,16 +753,18 @@ int cz_chunk_logits(cz_model *m, const uint32_t *prime, size_t prime_len, const 
               [&](uint32_t q) { return -2 - (long long)(prime_len + q); });
   CZ_TRY(d_src.reserve(w.n_rows() * 8, st));
   CZ_TRY(run_wave_trunk(m, w, nullptr, d_extra.as<uint32_t>(), 0, d_src.as<long long>(), st));
+  CZ_TRY(ensure_logits(m, 256));
   Workspace &ws = m->ws;
   const size_t V = m->cfg.vocab;
-  std::vector<float> tmp(V * ws.ld_sub);
-  for (size_t c0 = 0; c0 < n_targets; c0 += ws.ld_sub) {
-    const size_t nc = std::min(ws.ld_sub, n_targets - c0);
-    CZ_TRY(lm_head(m, (int)c0, (int)nc, ws.logits[0], ws.ld_sub, st));
-    CZ_CUDA_TRY(cudaMemcpyAsync(tmp.data(), ws.logits[0], V * ws.ld_sub * 4, cudaMemcpyDeviceToHost, st));
+  const size_t ld_c = std::min<size_t>(ws.ld_sub, 256);  // small sub-batches: this is a test / debugging entry point
+  std::vector<float> tmp(V * ld_c);
+  for (size_t c0 = 0; c0 < n_targets; c0 += ld_c) {
+    const size_t nc = std::min(ld_c, n_targets - c0);
+    CZ_TRY(lm_head(m, (int)c0, (int)nc, ws.logits[0], ld_c, st));
+    CZ_CUDA_TRY(cudaMemcpyAsync(tmp.data(), ws.logits[0], V * ld_c * 4, cudaMemcpyDeviceToHost, st));
     CZ_CUDA_TRY(cudaStreamSynchronize(st));
     for (size_t j = 0; j < nc; j++)
-      for (size_t v = 0; v < V; v++) logits_out[(c0 + j) * V + v] = tmp[v * ws.ld_sub + j];
+      for (size_t v = 0; v < V; v++) logits_out[(c0 + j) * V + v] = tmp[v * ld_c + j];
   }
   return CZ_OK;
 }

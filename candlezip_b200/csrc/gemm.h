@@ -13,6 +13,9 @@ enum GemmEpilogue {
   EPI_STORE_BF16 = 3,   // C[M][ldc] bf16 = A*B^T
   EPI_STORE_F32_COLMAX = 4,  // EPI_STORE_F32 + aux[n] = max over rows m of C[m][n], as an order-preserving int (atomicMax);
                              // used by the vocab-major LM head so the CDF kernel does not need its own max pass
+  EPI_TANH_BF16 = 5,     // C bf16 = tanh(A*B^T)       (RWKV-7 decay LoRA, rwkv7.rs:212)
+  EPI_SIGMOID_BF16 = 6,  // C bf16 = sigmoid(A*B^T)    (RWKV-7 gate LoRA, rwkv7.rs:234)
+  EPI_RELUSQ_BF16 = 7,   // C bf16 = relu(A*B^T)^2     (RWKV-7 FFN, rwkv7.rs:426)
 };
 
 struct GemmArgs {

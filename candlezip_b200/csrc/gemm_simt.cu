@@ -10,7 +10,7 @@ namespace czk {
 constexpr int ST = 64;   // tile
 constexpr int SK = 16;
 
-__device__ __forceinline__ float silu_mul_s(float g, float u) { return g / (1.0f + __expf(-g)) * u; }
+__device__ __forceinline__ float silu_mul_s(float g, float u) { return __fdividef(g, 1.0f + __expf(-g)) * u; }
 
 template <int EPI>
 __global__ void __launch_bounds__(256) gemm_simt_kernel(const __nv_bfloat16 *__restrict__ A, const __nv_bfloat16 *__restrict__ B,
@@ -52,6 +52,13 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const __nv_bfloat16 *__r
       if (EPI == cz::EPI_STORE_F32) ((float *)C)[(size_t)m * ldc + n] = acc[i][j];
       else if (EPI == cz::EPI_ADD_F32) ((float *)C)[(size_t)m * ldc + n] += acc[i][j];
       else if (EPI == cz::EPI_STORE_BF16) ((__nv_bfloat16 *)C)[(size_t)m * ldc + n] = __float2bfloat16_rn(acc[i][j]);
+      else if (EPI == cz::EPI_TANH_BF16) ((__nv_bfloat16 *)C)[(size_t)m * ldc + n] = __float2bfloat16_rn(tanhf(acc[i][j]));
+      else if (EPI == cz::EPI_SIGMOID_BF16)
+        ((__nv_bfloat16 *)C)[(size_t)m * ldc + n] = __float2bfloat16_rn(1.0f / (1.0f + expf(-acc[i][j])));
+      else if (EPI == cz::EPI_RELUSQ_BF16) {
+        const float q = fmaxf(acc[i][j], 0.f);
+        ((__nv_bfloat16 *)C)[(size_t)m * ldc + n] = __float2bfloat16_rn(q * q);
+      }
     }
   }
 }
@@ -105,6 +112,13 @@ int gemm_simt(cz_ctx *ctx, const GemmArgs &g, cudaStream_t stream) {
   else if (g.epi == EPI_STORE_BF16)
     CZ_LAUNCH(ctx, g_fam,
               (czk::gemm_simt_kernel<EPI_STORE_BF16><<<grid, 256, 0, stream>>>(A, B, g.c, g.M, g.N, g.K, g.lda, g.ldb, g.ldc, g.bn)));
+#define CZ_SIMT_CASE(E_)                                                                                                          \
+  else if (g.epi == E_) CZ_LAUNCH(ctx, g_fam,                                                                                     \
+                                  (czk::gemm_simt_kernel<E_><<<grid, 256, 0, stream>>>(A, B, g.c, g.M, g.N, g.K, g.lda, g.ldb, g.ldc, g.bn)))
+  CZ_SIMT_CASE(EPI_TANH_BF16);
+  CZ_SIMT_CASE(EPI_SIGMOID_BF16);
+  CZ_SIMT_CASE(EPI_RELUSQ_BF16);
+#undef CZ_SIMT_CASE
   else {
     set_error("gemm_simt: unknown epilogue");
     return CZ_ERR_INVALID;

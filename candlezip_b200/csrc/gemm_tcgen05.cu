@@ -28,6 +28,9 @@ using cz::EPI_STORE_BF16;
 using cz::EPI_STORE_F32;
 using cz::EPI_STORE_F32_COLMAX;
 using cz::EPI_SWIGLU_BF16;
+using cz::EPI_TANH_BF16;
+using cz::EPI_SIGMOID_BF16;
+using cz::EPI_RELUSQ_BF16;
 
 constexpr int BM = 128;
 constexpr int BK = 64;  // bf16 elements: 128 bytes = one swizzle row
@@ -41,7 +44,10 @@ struct GemmCfg {
   static constexpr int kBBytes = BN * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kTmemCols = 512;  // 2 accumulator stages of BN columns, power of two >= 2*BN
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kPatchBytes = 5120;  // per epilogue warp: a padded 32x33 f32 transpose patch (4224 B) or a dense 4 KB
+                                            // SWIZZLE_128B TMA box (reduce-add epilogue); 1024-aligned for the swizzle
+  static constexpr int kStagingOff = kStages * kStageBytes + 1024;  // the barriers live in the 1 KB before it
+  static constexpr int kSmemBytes = kStagingOff + 4 * kPatchBytes + 1024 /*align slack*/;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -122,11 +128,12 @@ __device__ __forceinline__ constexpr uint32_t make_idesc() {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 }
 
-__device__ __forceinline__ float silu_mul(float g, float u) { return g / (1.0f + __expf(-g)) * u; }
+__device__ __forceinline__ float silu_mul(float g, float u) { return __fdividef(g, 1.0f + __expf(-g)) * u; }
 
 template <int BN, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-    gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, void *__restrict__ c_ptr,
+    gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
+                   const __grid_constant__ CUtensorMap tm_c, void *__restrict__ c_ptr,
                    int M, int N, int K, int ldc, int *__restrict__ aux) {
   using Cfg = GemmCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
@@ -224,113 +231,160 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       }
     }
   } else {
-    // ===================== epilogue warps (TMEM -> registers -> global) =====================
+    // ===================== epilogue warps (TMEM -> registers -> smem transpose -> coalesced global) =====================
+    // tcgen05.ld 32x32b hands every lane one ROW of the accumulator; a direct store would touch 32 different rows per
+    // instruction (32 LSU wavefronts for 512 bytes).  Each warp therefore transposes its 32x32 sub-tile through a private
+    // padded shared-memory patch so that a store instruction covers 4 rows x 128 contiguous bytes.
     const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    uint8_t *patch = smem + Cfg::kStagingOff + (warp - 2) * Cfg::kPatchBytes;
+    float *stg = reinterpret_cast<float *>(patch);
+    const int rr0 = lane >> 3, cc = (lane & 7) * 4;
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, it++) {
       const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
       const int as = it & 1;
       mbar_wait(smem_u32(&tfull_bar[as]), (it >> 1) & 1);
       tc_fence_after();
-      const int row = m_blk * BM + quad * 32 + lane;
-      const bool row_ok = row < M;
+      const int row_base = m_blk * BM + quad * 32;
+      const bool row_ok = row_base + lane < M;
       const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BN);
-      if (EPI == EPI_SWIGLU_BF16) {
-        // tile columns [0, BN/2) are gate rows, [BN/2, BN) the matching up rows (weights are packed that way)
-        __nv_bfloat16 *out = (__nv_bfloat16 *)c_ptr;
-#pragma unroll 1
-        for (int c = 0; c < BN / 64; c++) {
-          uint32_t g[32], u[32];
-          tc_ld_32x32(t_row + (uint32_t)(c * 32), g);
-          tc_ld_32x32(t_row + (uint32_t)(BN / 2 + c * 32), u);
-          tc_ld_wait();
-          const int col0 = n_blk * (BN / 2) + c * 32;
-          if (row_ok && col0 < N / 2) {
-            uint32_t packed[16];
-#pragma unroll
-            for (int j = 0; j < 16; j++) {
-              float v0 = silu_mul(__uint_as_float(g[2 * j]), __uint_as_float(u[2 * j]));
-              float v1 = silu_mul(__uint_as_float(g[2 * j + 1]), __uint_as_float(u[2 * j + 1]));
-              __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
-              packed[j] = *reinterpret_cast<uint32_t *>(&h);
-            }
-            uint4 *dst = reinterpret_cast<uint4 *>(out + (size_t)row * ldc + col0);
-#pragma unroll
-            for (int j = 0; j < 4; j++) dst[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
-          }
-        }
-      } else {
+      constexpr bool kSwiglu = EPI == EPI_SWIGLU_BF16;
+      constexpr bool kOutBf16 = kSwiglu || EPI == EPI_STORE_BF16 || EPI == EPI_TANH_BF16 || EPI == EPI_SIGMOID_BF16 || EPI == EPI_RELUSQ_BF16;
+      constexpr int kChunks = kSwiglu ? BN / 64 : BN / 32;
+      const int n_out = kSwiglu ? N / 2 : N;  // output columns
+      if constexpr (EPI == EPI_ADD_F32) {
+        // Residual add without reading the residual: the 32x32 f32 patch goes to shared memory in the TMA box layout
+        // (dense 128-byte rows, SWIZZLE_128B) and one lane issues cp.reduce.async.bulk.tensor ... .add: the add is done
+        // at L2, rows >= M / columns >= N are clipped by the tensor map.  Every output element receives exactly one
+        // f32 add, so the result is deterministic.
+        const uint32_t patch_u32 = smem_u32(patch);
 #pragma unroll 1
         for (int c = 0; c < BN / 32; c++) {
+          const int col0 = n_blk * BN + c * 32;
+          if (col0 >= N) break;
           uint32_t r[32];
           tc_ld_32x32(t_row + (uint32_t)(c * 32), r);
+          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // previous patch has been read
+          __syncwarp();
           tc_ld_wait();
-          const int col0 = n_blk * BN + c * 32;
-          if (EPI == EPI_STORE_F32_COLMAX) {
-            // per-column max over this warp's 32 rows: floats mapped to order-preserving ints, one REDUX per column,
-            // lane j keeps column j, then one coalesced atomicMax per warp.  max is exact and order-independent.
-            int mine = INT_MIN;
 #pragma unroll
-            for (int j = 0; j < 32; j++) {
-              int v = (int)r[j];
-              v ^= (v >> 31) & 0x7fffffff;
-              if (!row_ok) v = INT_MIN;
-              const int mx = __reduce_max_sync(0xffffffffu, v);
-              if (lane == j) mine = mx;
-            }
-            if (col0 + lane < N) atomicMax(aux + col0 + lane, mine);
+          for (int q = 0; q < 8; q++) {
+            const uint32_t dst = patch_u32 + (uint32_t)(lane * 128 + ((q ^ (lane & 7)) << 4));
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(r[4 * q]), "r"(r[4 * q + 1]), "r"(r[4 * q + 2]),
+                         "r"(r[4 * q + 3])
+                         : "memory");
           }
-          if (!row_ok || col0 >= N) continue;
-          if (EPI == EPI_STORE_BF16) {
-            __nv_bfloat16 *out = (__nv_bfloat16 *)c_ptr + (size_t)row * ldc + col0;
-            if (col0 + 32 <= N) {
-              uint4 *dst = reinterpret_cast<uint4 *>(out);
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) {
+            asm volatile(
+                "cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(&tm_c),
+                "r"(patch_u32), "r"(col0), "r"(row_base)
+                : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[as]));
+        continue;
+      } else {
+#pragma unroll 1
+      for (int c = 0; c < kChunks; c++) {
+        uint32_t r[32];
+        int col0;
+        if (kSwiglu) {
+          // tile columns [0, BN/2) are gate rows, [BN/2, BN) the matching up rows (weights are packed that way)
+          uint32_t u[32];
+          tc_ld_32x32(t_row + (uint32_t)(c * 32), r);
+          tc_ld_32x32(t_row + (uint32_t)(BN / 2 + c * 32), u);
+          tc_ld_wait();
+          col0 = n_blk * (BN / 2) + c * 32;
 #pragma unroll
-              for (int j = 0; j < 4; j++) {
-                uint32_t pk[4];
+          for (int j = 0; j < 32; j++) r[j] = __float_as_uint(silu_mul(__uint_as_float(r[j]), __uint_as_float(u[j])));
+        } else {
+          tc_ld_32x32(t_row + (uint32_t)(c * 32), r);
+          tc_ld_wait();
+          col0 = n_blk * BN + c * 32;
+        }
+        if (col0 >= n_out) continue;  // warp-uniform
+        if (EPI == EPI_STORE_F32_COLMAX) {
+          // per-column max over this warp's 32 rows: floats mapped to order-preserving ints, one REDUX per column,
+          // lane j keeps column j, then one coalesced atomicMax per warp.  max is exact and order-independent.
+          int mine = INT_MIN;
 #pragma unroll
-                for (int q = 0; q < 4; q++) {
-                  __nv_bfloat162 h = __floats2bfloat162_rn(__uint_as_float(r[8 * j + 2 * q]), __uint_as_float(r[8 * j + 2 * q + 1]));
-                  pk[q] = *reinterpret_cast<uint32_t *>(&h);
-                }
-                dst[j] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          for (int j = 0; j < 32; j++) {
+            int v = (int)r[j];
+            v ^= (v >> 31) & 0x7fffffff;
+            if (!row_ok) v = INT_MIN;
+            const int mx = __reduce_max_sync(0xffffffffu, v);
+            if (lane == j) mine = mx;
+          }
+          if (col0 + lane < N) atomicMax(aux + col0 + lane, mine);
+        }
+        if (EPI == EPI_TANH_BF16) {
+#pragma unroll
+          for (int j = 0; j < 32; j++) r[j] = __float_as_uint(tanhf(__uint_as_float(r[j])));
+        } else if (EPI == EPI_SIGMOID_BF16) {
+#pragma unroll
+          for (int j = 0; j < 32; j++) r[j] = __float_as_uint(1.0f / (1.0f + expf(-__uint_as_float(r[j]))));
+        } else if (EPI == EPI_RELUSQ_BF16) {
+#pragma unroll
+          for (int j = 0; j < 32; j++) {
+            const float q = fmaxf(__uint_as_float(r[j]), 0.f);
+            r[j] = __float_as_uint(q * q);
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 32; j++) stg[lane * 33 + j] = __uint_as_float(r[j]);
+        __syncwarp();
+        const int gcol = col0 + cc;
+        if (gcol < n_out) {
+          const bool full = gcol + 3 < n_out;
+#pragma unroll
+          for (int i = 0; i < 8; i++) {
+            const int rr = i * 4 + rr0;
+            const int grow = row_base + rr;
+            if (grow >= M) continue;
+            const float *sp = stg + rr * 33 + cc;
+            float4 v = make_float4(sp[0], sp[1], sp[2], sp[3]);
+            if (kOutBf16) {
+              __nv_bfloat16 *out = (__nv_bfloat16 *)c_ptr + (size_t)grow * ldc + gcol;
+              if (full) {
+                __nv_bfloat162 h0 = __floats2bfloat162_rn(v.x, v.y), h1 = __floats2bfloat162_rn(v.z, v.w);
+                *reinterpret_cast<uint2 *>(out) = make_uint2(*reinterpret_cast<uint32_t *>(&h0), *reinterpret_cast<uint32_t *>(&h1));
+              } else {
+                const float e[4] = {v.x, v.y, v.z, v.w};
+                for (int q = 0; q < 4 && gcol + q < n_out; q++) out[q] = __float2bfloat16_rn(e[q]);
               }
             } else {
-              for (int j = 0; j < 32 && col0 + j < N; j++) out[j] = __float2bfloat16_rn(__uint_as_float(r[j]));
-            }
-          } else {
-            float *out = (float *)c_ptr + (size_t)row * ldc + col0;
-            if (col0 + 32 <= N) {
-              float4 *dst = reinterpret_cast<float4 *>(out);
-#pragma unroll
-              for (int j = 0; j < 8; j++) {
-                float4 v = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
-                                       __uint_as_float(r[4 * j + 3]));
+              float *out = (float *)c_ptr + (size_t)grow * ldc + gcol;
+              if (full) {
                 if (EPI == EPI_ADD_F32) {
-                  float4 o = dst[j];
+                  const float4 o = *reinterpret_cast<const float4 *>(out);
                   v.x += o.x;
                   v.y += o.y;
                   v.z += o.z;
                   v.w += o.w;
                 }
-                dst[j] = v;
-              }
-            } else {
-              for (int j = 0; j < 32 && col0 + j < N; j++) {
-                float v = __uint_as_float(r[j]);
-                if (EPI == EPI_ADD_F32) v += out[j];
-                out[j] = v;
+                *reinterpret_cast<float4 *>(out) = v;
+              } else {
+                const float e[4] = {v.x, v.y, v.z, v.w};
+                for (int q = 0; q < 4 && gcol + q < n_out; q++) out[q] = (EPI == EPI_ADD_F32) ? out[q] + e[q] : e[q];
               }
             }
           }
         }
+        __syncwarp();
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[as]));
+      }
     }
   }
 
+  if (EPI == EPI_ADD_F32 && warp >= 2 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
@@ -381,8 +435,28 @@ static int make_map(CUtensorMap *map, const void *ptr, int rows, int K, int ld_e
   return CZ_OK;
 }
 
+// f32 [rows][cols] row-major output, box = 32 x 32, 128-byte swizzle (the reduce-add epilogue's store target)
+static int make_map_c(CUtensorMap *map, void *ptr, int rows, int cols, int ld_elems) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled entry point not available");
+    return CZ_ERR_CUDA;
+  }
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)ld_elems * 4};
+  cuuint32_t box[2] = {32, 32};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, ptr, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (C) failed with CUresult " + std::to_string((int)r));
+    return CZ_ERR_CUDA;
+  }
+  return CZ_OK;
+}
+
 template <int BN, int EPI>
-static int launch_tc(cz_ctx *ctx, const CUtensorMap &ta, const CUtensorMap &tb, void *c, int M, int N, int K, int ldc, int *aux,
+static int launch_tc(cz_ctx *ctx, const CUtensorMap &ta, const CUtensorMap &tb, const CUtensorMap &tc, void *c, int M, int N, int K, int ldc, int *aux,
                      int g_fam, cudaStream_t stream) {
   using Cfg = czk::GemmCfg<BN>;
   static bool attr_set = false;
@@ -393,7 +467,7 @@ static int launch_tc(cz_ctx *ctx, const CUtensorMap &ta, const CUtensorMap &tb, 
   const int tiles = (int)(ceil_div(M, czk::BM) * ceil_div(N, BN));
   const int grid = tiles < ctx->sm_count ? tiles : ctx->sm_count;
   CZ_LAUNCH(ctx, g_fam,
-            (czk::gemm_tc_kernel<BN, EPI><<<grid, czk::GEMM_THREADS, Cfg::kSmemBytes, stream>>>(ta, tb, c, M, N, K, ldc, aux)));
+            (czk::gemm_tc_kernel<BN, EPI><<<grid, czk::GEMM_THREADS, Cfg::kSmemBytes, stream>>>(ta, tb, tc, c, M, N, K, ldc, aux)));
   CZ_CHECK_LAUNCH();
   return CZ_OK;
 }
@@ -413,15 +487,18 @@ int gemm_tcgen05(cz_ctx *ctx, const GemmArgs &g, cudaStream_t stream) {
     set_error("gemm_tcgen05: f32 output needs ldc % 4 == 0");
     return CZ_ERR_INVALID;
   }
-  if ((g.epi == EPI_STORE_BF16 || g.epi == EPI_SWIGLU_BF16) && (g.ldc % 8)) {
+  if ((g.epi == EPI_STORE_BF16 || g.epi == EPI_SWIGLU_BF16 || g.epi == EPI_TANH_BF16 || g.epi == EPI_SIGMOID_BF16 ||
+       g.epi == EPI_RELUSQ_BF16) && (g.ldc % 8)) {
     set_error("gemm_tcgen05: bf16 output needs ldc % 8 == 0");
     return CZ_ERR_INVALID;
   }
-  CUtensorMap ta, tb;
+  CUtensorMap ta, tb, tc;
   CZ_TRY(make_map(&ta, g.a, g.M, g.K, g.lda, czk::BM));
   CZ_TRY(make_map(&tb, g.b, g.N, g.K, g.ldb, g.bn));
+  if (g.epi == EPI_ADD_F32) CZ_TRY(make_map_c(&tc, g.c, g.M, g.N, g.ldc));
+  else tc = ta;  // unused by the other epilogues
 #define CZ_TC_CASE(BN_, EPI_) \
-  if (g.bn == BN_ && g.epi == EPI_) return launch_tc<BN_, EPI_>(ctx, ta, tb, g.c, g.M, g.N, g.K, g.ldc, g.aux, g.fam, stream)
+  if (g.bn == BN_ && g.epi == EPI_) return launch_tc<BN_, EPI_>(ctx, ta, tb, tc, g.c, g.M, g.N, g.K, g.ldc, g.aux, g.fam, stream)
   CZ_TC_CASE(192, EPI_STORE_F32);
   CZ_TC_CASE(192, EPI_ADD_F32);
   CZ_TC_CASE(192, EPI_SWIGLU_BF16);
@@ -429,6 +506,10 @@ int gemm_tcgen05(cz_ctx *ctx, const GemmArgs &g, cudaStream_t stream) {
   CZ_TC_CASE(256, EPI_STORE_F32);
   CZ_TC_CASE(256, EPI_STORE_BF16);
   CZ_TC_CASE(256, EPI_STORE_F32_COLMAX);
+  CZ_TC_CASE(192, EPI_TANH_BF16);
+  CZ_TC_CASE(192, EPI_SIGMOID_BF16);
+  CZ_TC_CASE(256, EPI_RELUSQ_BF16);
+  CZ_TC_CASE(256, EPI_ADD_F32);
 #undef CZ_TC_CASE
   set_error("gemm_tcgen05: unsupported (BN, epilogue) combination");
   return CZ_ERR_UNSUPPORTED;

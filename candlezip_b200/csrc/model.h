@@ -82,6 +82,7 @@ namespace cz {
 int model_finalize(cz_model *m);
 int ensure_workspace(cz_model *m, size_t rows, size_t n_logit, size_t n_tiles = 0);
 int ensure_stage(cz_model *m, size_t bytes);
+int ensure_logits(cz_model *m, size_t n_cols);
 
 // KV arena view: element (layer l, slot s) lives at base + l*layer_stride + s*kvd
 struct KvView {

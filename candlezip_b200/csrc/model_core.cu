@@ -6,6 +6,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
+
 #include "gemm.h"
 #include "llama_kernels.h"
 #include "model.h"
@@ -146,19 +148,32 @@ int ensure_workspace(cz_model *m, size_t rows, size_t n_logit, size_t n_tiles) {
     CZ_TRY(realloc_dev(w.xn_logit, r * D));
     w.cap_logit = r;
   }
-  if (!w.logits[0]) {
-    // sub-batch of LM-head columns: 32768 columns x V x 4 B (6.4 GB for V = 49152), two buffers. The thread-per-column
-    // CDF kernel gets its parallelism from the column count, so the sub-batch must be tens of thousands of columns.
-    size_t ld = 32768;
-    while (ld > 256 && ld * (size_t)c.vocab * 4 > ((size_t)7 << 30)) ld >>= 1;
-    w.ld_sub = ld;
-    CZ_TRY(realloc_dev(w.logits[0], ld * (size_t)c.vocab));
-    CZ_TRY(realloc_dev(w.logits[1], ld * (size_t)c.vocab));
-    CZ_TRY(realloc_dev(w.lo_tmp, ld));
-    CZ_TRY(realloc_dev(w.hi_tmp, ld));
-    CZ_TRY(realloc_dev(w.xe_tmp, ld));
-    CZ_TRY(realloc_dev(w.colmax, ld));
-  }
+  return CZ_OK;
+}
+
+// Logits sub-batch buffer [V][ld_sub] (vocab-major), grow-only, sized for the widest wave seen so far: up to 262,144
+// columns (51.5 GB for V = 49152).  The thread-per-column CDF kernel gets its parallelism -- and its ability to hide DRAM
+// latency -- from the column count: 32,768 columns are only 7 warps per SM (measured 10% of HBM peak,
+// profiles/ncu_summary_r01.md); a whole wave at once fills the SMs.
+int ensure_logits(cz_model *m, size_t n_cols) {
+  Workspace &w = m->ws;
+  const cz_model_config &c = m->cfg;
+  size_t want = (std::max<size_t>(n_cols, 256) + 1023) & ~(size_t)1023;
+  size_t max_ld = 262144;
+  if (const char *e = getenv("CZ_LOGITS_COLS")) max_ld = std::max<size_t>(256, (size_t)atoll(e));
+  want = std::min(want, max_ld);
+  if (want <= w.ld_sub) return CZ_OK;
+  CZ_CUDA_TRY(cudaSetDevice(m->ctx->device));
+  CZ_CUDA_TRY(cudaStreamSynchronize(m->ctx->stream));
+  CZ_TRY(realloc_dev(w.logits[0], 0));
+  CZ_TRY(realloc_dev(w.colmax, 0));
+  w.ld_sub = 0;
+  size_t free_b = 0, total_b = 0;
+  CZ_CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+  while (want > 256 && want * (size_t)c.vocab * 4 > free_b * 60 / 100) want >>= 1;
+  CZ_TRY(realloc_dev(w.logits[0], want * (size_t)c.vocab));
+  CZ_TRY(realloc_dev(w.colmax, want));
+  w.ld_sub = want;
   return CZ_OK;
 }
 

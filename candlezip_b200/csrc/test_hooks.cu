@@ -14,7 +14,7 @@ extern "C" int cz_test_gemm(cz_ctx *ctx, int engine, int M, int N, int K, const 
                             int bn, void *c_inout, int ldc) {
   CZ_TRY(require_device(ctx));
   CZ_CUDA_TRY(cudaSetDevice(ctx->device));
-  const bool out_bf16 = epi == EPI_STORE_BF16 || epi == EPI_SWIGLU_BF16;
+  const bool out_bf16 = epi == EPI_STORE_BF16 || epi == EPI_SWIGLU_BF16 || epi >= EPI_TANH_BF16;
   const size_t c_bytes = (size_t)M * ldc * (out_bf16 ? 2 : 4);
   void *da = nullptr, *db = nullptr, *dc = nullptr;
   CZ_CUDA_TRY(cudaMalloc(&da, (size_t)M * K * 2));

@@ -99,6 +99,7 @@ typedef struct {
   int vocab, d_model, n_layers, head_dim, d_ffn;
   int lora_w, lora_a, lora_v, lora_g;
   float norm_eps;
+  int round_bf16;     /* as in czo_llama_config */
 } czo_rwkv7_config;
 czo_session *czo_rwkv7_new(const czo_rwkv7_config *cfg);
 

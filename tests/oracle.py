@@ -106,6 +106,13 @@ class LlamaConfig(C.Structure):
     ]
 
 
+class Rwkv7Config(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("vocab", "d_model", "n_layers", "head_dim", "d_ffn", "lora_w", "lora_a", "lora_v", "lora_g")] + [
+        ("norm_eps", C.c_float),
+        ("round_bf16", C.c_int),
+    ]
+
+
 class PrimeEvent(C.Structure):
     _fields_ = [("i", C.c_size_t), ("prime", u32p), ("prime_len", C.c_size_t), ("hold_until", C.c_size_t)]
 
@@ -202,6 +209,17 @@ class Session:
         c = LlamaConfig(cfg["vocab"], cfg["d_model"], cfg["n_layers"], cfg["n_heads"], cfg["n_kv_heads"], cfg["head_dim"],
                         cfg["d_ffn"], cfg.get("rms_eps", 1e-5), cfg.get("rope_theta", 1e5), max_pos, round_bf16)
         s = cls(lib.czo_llama_new(C.byref(c)))
+        for name, arr in tensors.items():
+            a, p = _f32(arr)
+            if lib.czo_session_set_tensor(s._h, name.encode(), p, a.size) != 0:
+                raise KeyError(f"oracle rejected tensor {name} with {a.size} elements")
+        return s
+
+    @classmethod
+    def rwkv7(cls, cfg: dict, tensors: dict, round_bf16=0):
+        c = Rwkv7Config(cfg["vocab"], cfg["d_model"], cfg["n_layers"], cfg["head_dim"], cfg["d_ffn"], cfg["lora_w"], cfg["lora_a"],
+                        cfg["lora_v"], cfg["lora_g"], cfg.get("norm_eps", 1e-5), round_bf16)
+        s = cls(lib.czo_rwkv7_new(C.byref(c)))
         for name, arr in tensors.items():
             a, p = _f32(arr)
             if lib.czo_session_set_tensor(s._h, name.encode(), p, a.size) != 0:

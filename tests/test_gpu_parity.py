@@ -207,6 +207,22 @@ def test_gemm_epilogues(gpu_ctx, engine):
     assert np.abs(_bf16_to_f32(o16) - want).max() < 0.02 * max(1.0, np.abs(want).max())
 
 
+@pytest.mark.parametrize("engine", [_lib.CZ_ENGINE_SIMT, _lib.CZ_ENGINE_TCGEN05], ids=["simt", "tc"])
+@pytest.mark.parametrize("epi,bn,fn", [(5, 192, np.tanh), (6, 192, lambda x: 1 / (1 + np.exp(-x))), (7, 256, lambda x: np.maximum(x, 0) ** 2)],
+                         ids=["tanh", "sigmoid", "relusq"])
+def test_gemm_activation_epilogues(gpu_ctx, engine, epi, bn, fn):
+    """RWKV-7 LoRA / FFN epilogues (rwkv7.rs:212, 234, 426), incl. a ragged N (tail columns stay untouched)."""
+    rng = np.random.default_rng(epi)
+    M, K, N = 333, 128, 200
+    a16 = _bf16(rng.normal(0, 1, (M, K)))
+    b16 = _bf16(rng.normal(0, 0.15, (N, K)))
+    ldc = 208
+    out = _run_gemm(gpu_ctx, engine, a16, b16, epi, bn, np.full((M, ldc), 0x7FC0, np.uint16), ldc)
+    want = fn(_bf16_to_f32(a16).astype(np.float64) @ _bf16_to_f32(b16).astype(np.float64).T)
+    assert np.abs(_bf16_to_f32(out[:, :N]) - want).max() < 0.01 * max(1.0, np.abs(want).max())
+    assert np.all(out[:, N:] == 0x7FC0)
+
+
 def test_gemm_tcgen05_row_invariance(gpu_ctx):
     """decode safety: a row's result must not depend on batch size or on its position in the tile grid."""
     rng = np.random.default_rng(12)
