@@ -149,6 +149,11 @@ SMOLLM_TINY = dict(arch=0, vocab=1024, d_model=192, n_layers=2, n_heads=3, n_kv_
                    norm_eps=1e-5, rope_theta=1e5)
 
 
+# rwkv7-g1-0.1b (candle_rwkv7/convert_pth_direct.py:177-188)
+RWKV7_0P1B = dict(arch=1, vocab=65536, d_model=768, n_layers=12, n_heads=12, n_kv_heads=0, head_dim=64, d_ffn=3072, norm_eps=1e-5,
+                  rope_theta=0.0, lora_w=64, lora_a=64, lora_v=32, lora_g=128)
+
+
 def split_segments(n_tokens, n_segments):
     """Contiguous, non-increasing segment lengths (longest first), as the lock-step decoder needs."""
     n_segments = max(1, min(n_segments, max(1, n_tokens)))

@@ -23,6 +23,13 @@ int launch_ac_encode_lanes(cz_ctx *ctx, const uint32_t *c_lo_dev, const uint32_t
                            unsigned long long *err_index_dev, cudaStream_t stream);
 int require_device(cz_ctx *ctx);
 int fetch_device_status(cz_ctx *ctx, unsigned long long *err_index_dev, unsigned long long *err_index_out);
+// exec_rwkv.cu
+int rwkv_encode_bounds(cz_model *m, const uint32_t *ids_dev, const uint32_t *ids_host, size_t n_tokens, const cz_schedule *sched,
+                       const uint32_t *extra_dev, const std::vector<size_t> &ev_off, uint32_t *lo_dev, uint32_t *hi_dev, cudaStream_t st);
+int rwkv_xe_bits(cz_model *m, const cz_xe_job *jobs, size_t n_jobs, double *bits_out);
+int rwkv_chunk_logits(cz_model *m, const uint32_t *prime, size_t prime_len, const uint32_t *targets, size_t n_targets, float *logits_out);
+int rwkv_decode(cz_model *m, const uint8_t *payload, const uint64_t *seg_off, size_t n_tokens, const cz_schedule *sched, uint32_t *ids_out);
+int rwkv_session_forward(cz_model *m, RwkvState &stt, const uint32_t *tok, size_t n, bool reset, float *logits_dev4, float *logits_out);
 }  // namespace cz
 
 namespace czk {
@@ -111,6 +118,31 @@ __global__ void sum_bits_kernel(const double *__restrict__ bits, const uint64_t 
 }  // namespace czk
 
 namespace cz {
+
+size_t decoder_state_bytes() { return sizeof(czk::AcDecoderState); }
+int launch_decoder_init(cz_ctx *ctx, const uint8_t *payload, const uint64_t *seg_off, int n_lanes, void *decoder_state, cudaStream_t st) {
+  CZ_LAUNCH(ctx, CZ_K_CODER,
+            (czk::ac_decoder_init_kernel<<<(unsigned)ceil_div(n_lanes, 128), 128, 0, st>>>(payload, seg_off, n_lanes,
+                                                                                          (czk::AcDecoderState *)decoder_state)));
+  CZ_CHECK_LAUNCH();
+  return CZ_OK;
+}
+int launch_decode_step(cz_ctx *ctx, int mode, const float *logits, int V, size_t ld, int n_lanes, const uint8_t *payload,
+                       const uint64_t *seg_off, const uint64_t *seg_start, uint64_t coded_index, void *decoder_state, uint32_t *ids_out,
+                       uint32_t *next_tok, const int *colmax, cudaStream_t st) {
+  const unsigned grid = (unsigned)ceil_div(n_lanes, 8);
+  czk::AcDecoderState *ds = (czk::AcDecoderState *)decoder_state;
+  if (mode == CZ_CDF_SMOLLM)
+    CZ_LAUNCH(ctx, CZ_K_CDF,
+              (czk::decode_step_kernel<CZ_CDF_SMOLLM><<<grid, 256, 0, st>>>(logits, V, ld, n_lanes, payload, seg_off, seg_start, coded_index, ds,
+                                                                            ids_out, next_tok, ctx->err_flag_dev, colmax)));
+  else
+    CZ_LAUNCH(ctx, CZ_K_CDF,
+              (czk::decode_step_kernel<CZ_CDF_RWKV_LITERALS><<<grid, 256, 0, st>>>(logits, V, ld, n_lanes, payload, seg_off, seg_start, coded_index,
+                                                                                   ds, ids_out, next_tok, ctx->err_flag_dev, colmax)));
+  CZ_CHECK_LAUNCH();
+  return CZ_OK;
+}
 
 // -------------------------------------------------------------------------------------------------------------
 // Wave builder: rows of several chunks packed back to back (teacher-forced), each chunk its own sequence.
@@ -268,8 +300,8 @@ static double host_ms() {
   return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
 }
 
-static int encode_core(cz_model *m, const uint32_t *ids_dev, size_t n_tokens, const cz_schedule *sched, uint8_t *out_dev,
-                       size_t out_cap, uint64_t *seg_off_host) {
+static int encode_core(cz_model *m, const uint32_t *ids_dev, const uint32_t *ids_host, size_t n_tokens, const cz_schedule *sched,
+                       uint8_t *out_dev, size_t out_cap, uint64_t *seg_off_host) {
   cz_ctx *ctx = m->ctx;
   cudaStream_t st = ctx->stream;
   static const bool dbg = getenv("CZ_DEBUG_TIMING") != nullptr;
@@ -310,7 +342,11 @@ static int encode_core(cz_model *m, const uint32_t *ids_dev, size_t n_tokens, co
     return CZ_OK;
   };
   std::vector<Chunk> chunks;
-  for (uint32_t g = 0; g < S; g++) {
+  if (m->cfg.arch == CZ_ARCH_RWKV7) {
+    CZ_TRY(rwkv_encode_bounds(m, ids_dev, ids_host, n_tokens, sched, d_extra.as<uint32_t>(), ev_off, d_lo.as<uint32_t>(), d_hi.as<uint32_t>(), st));
+    coded_done = wave_first = n_tokens;
+  }
+  for (uint32_t g = 0; g < S && m->cfg.arch != CZ_ARCH_RWKV7; g++) {
     const uint64_t t0 = sched->seg_start[g], n = sched->seg_start[g + 1] - t0;
     build_chunks(n, sched->context, sched->reprime_interval, sched->events, sched->n_events, chunks);
     for (const Chunk &c : chunks) {
@@ -385,13 +421,24 @@ struct cz_session {
   float *logits_dev = nullptr;               // [V][4]
   long long *src_dev = nullptr;
   uint32_t *hist_dev = nullptr;
+  RwkvState rstate;  // RWKV-7: this session's recurrent state (one slot)
 };
 
-static int session_forward(cz_session *s, const uint32_t *tok, size_t n, float *logits_out) {
+static int session_forward(cz_session *s, const uint32_t *tok, size_t n, float *logits_out, bool reset = false) {
   cz_model *m = s->m;
   cz_ctx *ctx = m->ctx;
   cudaStream_t st = ctx->stream;
   CZ_CUDA_TRY(cudaSetDevice(ctx->device));
+  if (m->cfg.arch == CZ_ARCH_RWKV7) {
+    for (size_t i = 0; i < n; i++)
+      if (tok[i] >= (uint32_t)m->cfg.vocab) {
+        set_error("session: token id out of range");
+        return CZ_ERR_SYMBOL_RANGE;
+      }
+    CZ_TRY(rwkv_session_forward(m, s->rstate, tok, n, reset, s->logits_dev, logits_out));
+    s->index_pos = reset ? n : s->index_pos + n;
+    return CZ_OK;
+  }
   if (s->index_pos + n > (size_t)s->max_pos) {
     set_error("session: KV capacity exceeded");
     return CZ_ERR_INVALID;
@@ -445,8 +492,10 @@ int cz_session_new(cz_model *m, cz_session **out) {
   s->m = m;
   const size_t kvd = (size_t)m->cfg.n_kv_heads * 64, L = m->cfg.n_layers;
   CZ_CUDA_TRY(cudaSetDevice(m->ctx->device));
-  CZ_CUDA_TRY(cudaMalloc((void **)&s->k, L * s->max_pos * kvd * 2));
-  CZ_CUDA_TRY(cudaMalloc((void **)&s->v, L * s->max_pos * kvd * 2));
+  if (m->cfg.arch == CZ_ARCH_SMOLLM) {
+    CZ_CUDA_TRY(cudaMalloc((void **)&s->k, L * s->max_pos * kvd * 2));
+    CZ_CUDA_TRY(cudaMalloc((void **)&s->v, L * s->max_pos * kvd * 2));
+  }
   CZ_CUDA_TRY(cudaMalloc((void **)&s->logits_dev, (size_t)m->cfg.vocab * 16));
   *out = s;
   return CZ_OK;
@@ -458,6 +507,7 @@ void cz_session_free(cz_session *s) {
   if (s->k) cudaFree(s->k);
   if (s->v) cudaFree(s->v);
   if (s->logits_dev) cudaFree(s->logits_dev);
+  rwkv_state_free(s->rstate);
   delete s;
 }
 size_t cz_session_vocab_size(const cz_session *s) { return s ? (size_t)s->m->cfg.vocab : 0; }
@@ -475,8 +525,8 @@ int cz_session_reprime(cz_session *s, const uint32_t *history, size_t n, float *
     set_error("reprime called with empty history");
     return CZ_ERR_INVALID;
   }
-  s->index_pos = 0;  // fresh KV cache
-  return session_forward(s, history, n, logits_out);
+  s->index_pos = 0;  // fresh KV cache / fresh recurrent state
+  return session_forward(s, history, n, logits_out, /*reset=*/true);
 }
 
 // -------------------------------------------------------------------------------------------------------------
@@ -490,7 +540,7 @@ int cz_encode_dev(cz_model *m, const uint32_t *ids_dev, size_t n_tokens, const c
   if (n_tokens == 0) {
     // every segment is an empty stream: finish() alone emits 0x40 (1 byte)
   }
-  return encode_core(m, ids_dev, n_tokens, sched, out_dev, out_cap, seg_off_host);
+  return encode_core(m, ids_dev, nullptr, n_tokens, sched, out_dev, out_cap, seg_off_host);
 }
 
 int cz_encode(cz_model *m, const uint32_t *ids, size_t n_tokens, const cz_schedule *sched, cz_bitstreams *out) {
@@ -505,7 +555,7 @@ int cz_encode(cz_model *m, const uint32_t *ids, size_t n_tokens, const cz_schedu
   if (n_tokens) CZ_CUDA_TRY(cudaMemcpyAsync(d_ids.p, ids, n_tokens * 4, cudaMemcpyHostToDevice, ctx->stream));
   const size_t cap = 4 * n_tokens + 8 * (size_t)sched->n_segments + 16;
   CZ_TRY(d_out.reserve(cap, ctx->stream));
-  CZ_TRY(encode_core(m, d_ids.as<uint32_t>(), n_tokens, sched, d_out.as<uint8_t>(), cap, out->seg_off));
+  CZ_TRY(encode_core(m, d_ids.as<uint32_t>(), ids, n_tokens, sched, d_out.as<uint8_t>(), cap, out->seg_off));
   const uint64_t total = out->seg_off[sched->n_segments];
   if (total > out->cap) {
     set_error("cz_encode: output capacity " + std::to_string(out->cap) + " < payload " + std::to_string(total));
@@ -531,6 +581,7 @@ int cz_decode(cz_model *m, const uint8_t *payload, const uint64_t *seg_off, size
   cz_ctx *ctx = m->ctx;
   cudaStream_t st = ctx->stream;
   CZ_CUDA_TRY(cudaSetDevice(ctx->device));
+  if (m->cfg.arch == CZ_ARCH_RWKV7) return rwkv_decode(m, payload, seg_off, n_tokens, sched, ids_out);
   const cz_model_config &c = m->cfg;
   const uint32_t S = sched->n_segments;
   const size_t kvd = (size_t)c.n_kv_heads * 64, L = c.n_layers;
@@ -674,6 +725,7 @@ int cz_xe_bits(cz_model *m, const cz_xe_job *jobs, size_t n_jobs, double *bits_o
   cz_ctx *ctx = m->ctx;
   cudaStream_t st = ctx->stream;
   CZ_CUDA_TRY(cudaSetDevice(ctx->device));
+  if (m->cfg.arch == CZ_ARCH_RWKV7) return rwkv_xe_bits(m, jobs, n_jobs, bits_out);
   // all tokens go to the `extra` buffer: [prime_0 | targets_0 | prime_1 | targets_1 | ...]; a parallel buffer holds
   // the targets contiguously in job order so that column j's symbol is tgt[j]
   std::vector<uint32_t> extra, tgt;
@@ -743,6 +795,7 @@ int cz_chunk_logits(cz_model *m, const uint32_t *prime, size_t prime_len, const 
   cz_ctx *ctx = m->ctx;
   cudaStream_t st = ctx->stream;
   CZ_CUDA_TRY(cudaSetDevice(ctx->device));
+  if (m->cfg.arch == CZ_ARCH_RWKV7) return rwkv_chunk_logits(m, prime, prime_len, targets, n_targets, logits_out);
   std::vector<uint32_t> extra(prime, prime + prime_len);
   if (n_targets > 1) extra.insert(extra.end(), targets, targets + n_targets - 1);
   GrowBuf &d_extra = m->sb[SB_EXTRA], &d_src = m->sb[SB_SRC];

@@ -252,8 +252,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       constexpr bool kOutBf16 = kSwiglu || EPI == EPI_STORE_BF16 || EPI == EPI_TANH_BF16 || EPI == EPI_SIGMOID_BF16 || EPI == EPI_RELUSQ_BF16;
       constexpr int kChunks = kSwiglu ? BN / 64 : BN / 32;
       const int n_out = kSwiglu ? N / 2 : N;  // output columns
-      if constexpr (EPI == EPI_ADD_F32) {
-        // Residual add without reading the residual: the 32x32 f32 patch goes to shared memory in the TMA box layout
+      constexpr bool kTmaF32 = EPI == EPI_ADD_F32 || EPI == EPI_STORE_F32 || EPI == EPI_STORE_F32_COLMAX;
+      if constexpr (kTmaF32) {
+        // f32 outputs leave through TMA.  Residual add without reading the residual: the 32x32 f32 patch goes to shared memory in the TMA box layout
         // (dense 128-byte rows, SWIZZLE_128B) and one lane issues cp.reduce.async.bulk.tensor ... .add: the add is done
         // at L2, rows >= M / columns >= N are clipped by the tensor map.  Every output element receives exactly one
         // f32 add, so the result is deterministic.
@@ -267,6 +268,20 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
           if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // previous patch has been read
           __syncwarp();
           tc_ld_wait();
+          if (EPI == EPI_STORE_F32_COLMAX) {
+            // per-column max over this warp's 32 rows: floats mapped to order-preserving ints, one REDUX per column,
+            // lane j keeps column j, then one coalesced atomicMax per warp.  max is exact and order-independent.
+            int mine = INT_MIN;
+#pragma unroll
+            for (int j = 0; j < 32; j++) {
+              int v = (int)r[j];
+              v ^= (v >> 31) & 0x7fffffff;
+              if (!row_ok) v = INT_MIN;
+              const int mx = __reduce_max_sync(0xffffffffu, v);
+              if (lane == j) mine = mx;
+            }
+            if (col0 + lane < N) atomicMax(aux + col0 + lane, mine);
+          }
 #pragma unroll
           for (int q = 0; q < 8; q++) {
             const uint32_t dst = patch_u32 + (uint32_t)(lane * 128 + ((q ^ (lane & 7)) << 4));
@@ -277,10 +292,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           __syncwarp();
           if (lane == 0) {
-            asm volatile(
-                "cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(&tm_c),
-                "r"(patch_u32), "r"(col0), "r"(row_base)
-                : "memory");
+            if (EPI == EPI_ADD_F32)
+              asm volatile(
+                  "cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(&tm_c),
+                  "r"(patch_u32), "r"(col0), "r"(row_base)
+                  : "memory");
+            else
+              asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(&tm_c),
+                           "r"(patch_u32), "r"(col0), "r"(row_base)
+                           : "memory");
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
         }
@@ -384,7 +404,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     }
   }
 
-  if (EPI == EPI_ADD_F32 && warp >= 2 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  if (warp >= 2 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
@@ -495,7 +515,7 @@ int gemm_tcgen05(cz_ctx *ctx, const GemmArgs &g, cudaStream_t stream) {
   CUtensorMap ta, tb, tc;
   CZ_TRY(make_map(&ta, g.a, g.M, g.K, g.lda, czk::BM));
   CZ_TRY(make_map(&tb, g.b, g.N, g.K, g.ldb, g.bn));
-  if (g.epi == EPI_ADD_F32) CZ_TRY(make_map_c(&tc, g.c, g.M, g.N, g.ldc));
+  if (g.epi == EPI_ADD_F32 || g.epi == EPI_STORE_F32 || g.epi == EPI_STORE_F32_COLMAX) CZ_TRY(make_map_c(&tc, g.c, g.M, g.N, g.ldc));
   else tc = ta;  // unused by the other epilogues
 #define CZ_TC_CASE(BN_, EPI_) \
   if (g.bn == BN_ && g.epi == EPI_) return launch_tc<BN_, EPI_>(ctx, ta, tb, tc, g.c, g.M, g.N, g.K, g.ldc, g.aux, g.fam, stream)

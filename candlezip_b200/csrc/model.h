@@ -55,10 +55,46 @@ struct GrowBuf {
   T *as() { return (T *)p; }
 };
 enum { SB_LO = 0, SB_HI, SB_SRC, SB_EXTRA, SB_LANE, SB_RAW, SB_IDS, SB_OUT, SB_PAY, SB_OFF, SB_START, SB_STATE, SB_DIDS, SB_K, SB_V,
-       SB_LOGITS, SB_KVB, SB_TGT, SB_BITS, SB_JOFF, SB_XOUT, SB_COUNT };
+       SB_LOGITS, SB_KVB, SB_TGT, SB_BITS, SB_JOFF, SB_XOUT, SB_RW_OIDX, SB_RW_SYMS, SB_RW_LO, SB_RW_HI, SB_RW_XE, SB_RW_FRESH,
+       SB_COUNT };
+
+// ---- RWKV-7 (rwkv7.cu) ----
+enum { RV_PRE_W = 0, RV_PRE_B, RV_LN1_W, RV_LN1_B, RV_LN2_W, RV_LN2_B, RV_XR, RV_XW, RV_XK, RV_XV, RV_XA, RV_XG, RV_KK, RV_KA, RV_RK,
+       RV_W0, RV_A0, RV_V0, RV_GNW, RV_GNB, RV_FXK, RV_COUNT };
+struct RwkvLayerW {
+  __nv_bfloat16 *wr, *wk, *wv, *wo, *w1, *w2, *a1, *a2, *v1, *v2, *g1, *g2, *fk, *fv;
+};
+struct RwkvWeights {
+  std::vector<RwkvLayerW> layers;
+  float *vecs = nullptr;            // [L][RV_COUNT][C] + ln_out weight, bias
+  __nv_bfloat16 *v_pad = nullptr;   // v-LoRA matrices zero-padded to rank 64
+};
+struct RwkvWs {
+  size_t cap_rows = 0, cap_streams = 0;
+  __nv_bfloat16 *mix[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // xr xw xk xv xa xg  [rows][C]
+  float *f[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // r k v w-lora a-lora v-lora g  [rows][C]
+  float *v_first = nullptr;        // [rows][C]
+  __nv_bfloat16 *lo = nullptr;     // [rows][128] LoRA bottleneck activations
+  __nv_bfloat16 *att = nullptr;    // [rows][C]
+  __nv_bfloat16 *act = nullptr;    // [rows][F]
+  int *prev_row = nullptr, *slot = nullptr, *flags = nullptr;         // per row
+  int *row_begin = nullptr, *row_end = nullptr, *stream_slot = nullptr;  // per stream of the slab
+};
+// recurrent state of `cap` stream slots: WKV state + the two token-shift rows per layer (rwkv7.rs:35-61)
+struct RwkvState {
+  size_t cap = 0, n = 0;
+  float *S = nullptr;                       // [L][cap][H][4096], (j/4, i, j%4) order inside a head
+  float *xa[2] = {nullptr, nullptr};        // [L][cap][C] attention token shift, ping-pong across slabs
+  float *xf[2] = {nullptr, nullptr};        // [L][cap][C] feed-forward token shift
+  int cur = 0;
+};
 
 struct cz_model {
   GrowBuf sb[SB_COUNT];
+  RwkvWeights rw;
+  RwkvWs rws;
+  RwkvState rstate;
+  __nv_bfloat16 *head_w = nullptr;  // LM head [V][D] (SmolLM: tied to the embedding)
   cz_ctx *ctx = nullptr;
   cz_model_config cfg;
   std::vector<TensorSlot> tensors;
@@ -103,5 +139,15 @@ int final_norm_gather(cz_model *m, int n_logit, cudaStream_t st);
 // says whether this engine produced it
 int lm_head(cz_model *m, int col0, int n_cols, float *logits, size_t ld, cudaStream_t st, int *colmax = nullptr,
             bool *colmax_valid = nullptr);
+
+
+// ---- RWKV-7 ----
+int rwkv_finalize(cz_model *m);
+void rwkv_free(cz_model *m);
+int rwkv_ensure_ws(cz_model *m, size_t rows, size_t n_streams);
+int rwkv_state_reset(cz_model *m, RwkvState &s, size_t n, cudaStream_t st);
+void rwkv_state_free(RwkvState &s);
+int rwkv_forward(cz_model *m, int n_rows, int n_streams, RwkvState &stt, bool in_place, const int *stream_active, cudaStream_t st);
+int rwkv_final_norm_gather(cz_model *m, int n_logit, cudaStream_t st);
 
 }  // namespace cz

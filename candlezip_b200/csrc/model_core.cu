@@ -120,6 +120,11 @@ int ensure_workspace(cz_model *m, size_t rows, size_t n_logit, size_t n_tiles) {
     CZ_CUDA_TRY(cudaStreamSynchronize(m->ctx->stream));
     size_t r = rows + rows / 8 + 128;
     CZ_TRY(realloc_dev(w.x, r * D));
+    CZ_TRY(realloc_dev(w.tok, r));
+    if (c.arch == CZ_ARCH_RWKV7) {  // the RWKV-7 activations live in RwkvWs (rwkv7.cu)
+      w.cap_rows = r;
+      return ensure_workspace(m, rows, n_logit, n_tiles);
+    }
     CZ_TRY(realloc_dev(w.xn, r * D));
     CZ_TRY(realloc_dev(w.qkv, r * QKV));
     CZ_TRY(realloc_dev(w.q, r * D));
@@ -127,7 +132,6 @@ int ensure_workspace(cz_model *m, size_t rows, size_t n_logit, size_t n_tiles) {
     CZ_TRY(realloc_dev(w.act, r * F));
     CZ_TRY(realloc_dev(w.kpack, r * kvd));
     CZ_TRY(realloc_dev(w.vpack, r * kvd));
-    CZ_TRY(realloc_dev(w.tok, r));
     CZ_TRY(realloc_dev(w.pos, r));
     CZ_TRY(realloc_dev(w.kv_base, r));
     w.cap_rows = r;
@@ -183,15 +187,16 @@ int model_finalize(cz_model *m) {
     set_error("model needs a GPU ctx for compute");
     return CZ_ERR_NO_DEVICE;
   }
-  if (m->cfg.arch != CZ_ARCH_SMOLLM) {
-    set_error("RWKV-7 forward is not built yet in this round");
-    return CZ_ERR_UNSUPPORTED;
-  }
   for (auto &s : m->tensors)
     if (!s.set) {
       set_error("tensor not set: " + s.name);
       return CZ_ERR_INVALID;
     }
+  if (m->cfg.arch == CZ_ARCH_RWKV7) {
+    CZ_TRY(rwkv_finalize(m));
+    m->finalized = true;
+    return CZ_OK;
+  }
   const cz_model_config &c = m->cfg;
   const size_t D = c.d_model, F = c.d_ffn, kvd = (size_t)c.n_kv_heads * 64, QKV = D + 2 * kvd, L = c.n_layers;
   if (D % 64 || F % 64 || c.head_dim != 64 || c.n_heads * 64 != (int)D || c.n_heads % c.n_kv_heads || c.n_heads / c.n_kv_heads > 4) {
@@ -243,6 +248,7 @@ int model_finalize(cz_model *m) {
   CZ_TRY(fetch_norm("model.norm.weight", &norms[L * 2 * D]));
   CZ_CUDA_TRY(cudaMemcpy(m->norms, norms.data(), norms.size() * 4, cudaMemcpyHostToDevice));
   m->embed = dev("model.embed_tokens.weight");
+  m->head_w = m->embed;  // tied
   // RoPE tables, same formulas as the oracle (f32 inv_freq, f32 angle, libm cosf/sinf)
   std::vector<float> ct((size_t)m->rope_max_pos * 32), stab((size_t)m->rope_max_pos * 32);
   for (int j = 0; j < 32; j++) {
@@ -310,7 +316,7 @@ int lm_head(cz_model *m, int col0, int n_cols, float *logits, size_t ld, cudaStr
   if (colmax_valid) *colmax_valid = fuse_max;
   if (fuse_max) CZ_TRY(launch_fill_i32(m->ctx, colmax, INT_MIN, (size_t)n_cols, st));
   GemmArgs g{};
-  g.a = m->embed; g.lda = c.d_model;                       // A = tied embedding [V][D]: vocab is the M dimension
+  g.a = m->head_w; g.lda = c.d_model;                      // A = LM head [V][D] (SmolLM: the tied embedding): vocab is the M dimension
   g.b = m->ws.xn_logit + (size_t)col0 * c.d_model; g.ldb = c.d_model;  // B = hidden states: tokens are the N dimension
   g.c = logits; g.ldc = (int)ld;                           // -> vocab-major logits [V][ld]
   g.M = c.vocab; g.N = n_cols; g.K = c.d_model; g.epi = fuse_max ? EPI_STORE_F32_COLMAX : EPI_STORE_F32; g.bn = 256;
@@ -441,6 +447,7 @@ void cz_model_free(cz_model *m) {
     for (void *p : ptrs)
       if (p) cudaFree(p);
     if (m->ws.h_stage) cudaFreeHost(m->ws.h_stage);
+    rwkv_free(m);
   }
   delete m;
 }
