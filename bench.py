@@ -261,6 +261,36 @@ def run_ours(args):
         decode = {"value": world * nd / float(t.item()) / 1e6, "unit": "MB/s", "tokens": nd, "segments": sd,
                   "roundtrip_ok": bool(np.array_equal(out, ids_d)), "timing": "wall clock around cz_decode (host payload in, ids out)"}
 
+    # ---- RWKV-7 0.1B (BASELINE config 3), extra figures: slab-fused encode + lock-step decode, random-init weights ----
+    rwkv = None
+    if args.rwkv_tokens > 0:
+        model.close()
+        rmodel = cz.Model(ctx, cz.RWKV7_0P1B).random_init(0, 0.02, 0.02)
+        nr = args.rwkv_tokens
+        ids_r = synth_tokens(nr, 7 + rank)
+        rmodel.encode(ids_r, n_segments=args.rwkv_segments)  # warm-up at full size (grow-only buffers, function attributes)
+        barrier()
+        t0 = time.perf_counter()
+        pays_r, seg_r = rmodel.encode(ids_r, n_segments=args.rwkv_segments)
+        barrier()
+        enc_s = time.perf_counter() - t0
+        nd = min(nr, args.rwkv_decode_tokens)
+        pays_d, seg_d = rmodel.encode(ids_r[:nd], n_segments=args.rwkv_decode_segments)
+        barrier()
+        t0 = time.perf_counter()
+        out_r = rmodel.decode(pays_d, seg_d)
+        barrier()
+        dec_s = time.perf_counter() - t0
+        tt = torch.tensor([enc_s, dec_s], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        rwkv = {"model": "rwkv7-g1-0.1b shape (random-init)", "encode_MB_per_s": world * nr / float(tt[0].item()) / 1e6,
+                "encode_tokens": nr, "encode_segments": args.rwkv_segments,
+                "decode_MB_per_s": world * nd / float(tt[1].item()) / 1e6, "decode_tokens": nd, "decode_segments": args.rwkv_decode_segments,
+                "roundtrip_ok": bool(np.array_equal(out_r, ids_r[:nd])), "compressed_bytes": int(sum(len(p) for p in pays_r)),
+                "timing": "wall clock around cz_encode / cz_decode (host buffers in and out)"}
+        rmodel.close()
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -285,7 +315,7 @@ def run_ours(args):
                      "flops_per_step": gemm_flops, "kernel_ms_per_step": gemm_ms, "peak_source": peak_src},
         "kernel_ms_per_step": {k: v[0] / args.steps for k, v in fam.items()},
         "kernel_launches_per_step": {k: v[1] // max(1, args.steps) for k, v in fam.items()},
-        "compressed_bytes_per_step": payload_bytes, "decode": decode,
+        "compressed_bytes_per_step": payload_bytes, "decode": decode, "rwkv7": rwkv,
     }
     if world == 1 and not args.no_cpu_baseline:
         one_chunk, n_tok, cores = oracle_chunk_sample(args.ref_chunk)
@@ -305,12 +335,19 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--tokens", type=int, default=262144)
     ap.add_argument("--segments", type=int, default=32)
-    ap.add_argument("--decode-tokens", type=int, default=131072)
-    ap.add_argument("--decode-segments", type=int, default=256)
+    ap.add_argument("--decode-tokens", type=int, default=262144)
+    ap.add_argument("--decode-segments", type=int, default=2048,
+                    help="lock-step streams of the stepwise decoder (its throughput scales with the stream count)")
     ap.add_argument("--ref-chunk", type=int, default=256, help="coded tokens per CPU-reference sample chunk (512 = the full reprime chunk)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--rwkv-tokens", type=int, default=131072, help="RWKV-7 extra figures (0 = skip)")
+    ap.add_argument("--rwkv-segments", type=int, default=64)
+    ap.add_argument("--rwkv-decode-tokens", type=int, default=65536)
+    ap.add_argument("--rwkv-decode-segments", type=int, default=1024)
     args = ap.parse_args()
     if args.impl == "reference":
+        # torchrun exports OMP_NUM_THREADS=1; the reference arm is meant to use every host core it can
+        os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
         run_reference(args)
     else:
         run_ours(args)

@@ -199,6 +199,13 @@ __global__ void __launch_bounds__(128 * G) attn_mma_kernel(const __nv_bfloat16 *
 
 namespace cz {
 
+void attn_set_carveout() {
+  cudaFuncSetAttribute(czk::attn_mma_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  cudaFuncSetAttribute(czk::attn_mma_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  cudaFuncSetAttribute(czk::attn_mma_kernel<3>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  cudaFuncSetAttribute(czk::attn_mma_kernel<4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+}
+
 int launch_attn_mma(cz_ctx *ctx, const __nv_bfloat16 *q, const __nv_bfloat16 *k_arena, const __nv_bfloat16 *v_arena, const int *pos,
                     const int *kv_base, const int *tile_row0, const int *tile_n, int n_tiles, __nv_bfloat16 *out, int nh, int nkv,
                     cudaStream_t st) {

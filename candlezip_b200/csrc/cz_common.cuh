@@ -45,6 +45,7 @@ struct cz_ctx {
   // per-family profiling: mode 1 = synchronous (event pair + sync per launch), mode 2 = deferred (event pairs are
   // pooled and only read in cz_profile_read, so the timed region is not perturbed by host syncs)
   int prof_mode = 0;
+  bool capturing = false;  // a CUDA graph capture is in progress on `stream`: no profiling events, no host syncs
   std::vector<cudaEvent_t> ev_pool;       // [2*i], [2*i+1] = start/stop of pooled launch i
   std::vector<int> ev_fam;
   size_t ev_used = 0;
@@ -68,6 +69,7 @@ struct LaunchScope {
   int fam;
   size_t slot = 0;
   LaunchScope(cz_ctx *c, int f) : ctx(c), fam(f) {
+    if (ctx->capturing) return;
     if (ctx->prof_mode == 2) {
       slot = ctx->ev_used++;
       if (ctx->ev_pool.size() < 2 * ctx->ev_used) {
@@ -87,6 +89,7 @@ struct LaunchScope {
   ~LaunchScope() {
     ctx->launches++;
     ctx->prof_launches[fam]++;
+    if (ctx->capturing) return;
     if (ctx->prof_mode == 2) {
       cudaEventRecord(ctx->ev_pool[2 * slot + 1], ctx->stream);
     } else if (ctx->prof_on) {

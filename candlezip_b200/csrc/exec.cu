@@ -68,7 +68,8 @@ __global__ void __launch_bounds__(256) decode_step_kernel(const float *__restric
                                                           const uint64_t *__restrict__ seg_start, uint64_t coded_index,
                                                           AcDecoderState *__restrict__ st, uint32_t *__restrict__ ids_out,
                                                           uint32_t *__restrict__ next_tok, int *__restrict__ err,
-                                                          const int *__restrict__ colmax) {
+                                                          const int *__restrict__ colmax, const unsigned long long *__restrict__ ctr) {
+  if (ctr) coded_index = ctr[0];  // device-resident step counter: lets one captured CUDA graph serve every step
   __shared__ uint32_t s_lo[32 * 32], s_hi[32 * 32];
   exp_tab_init(s_lo, s_hi);
   ExpTab tab{s_lo, s_hi, (int)(threadIdx.x & 31)};
@@ -107,6 +108,19 @@ __global__ void fill_int_kernel(int *__restrict__ p, int v, int n) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = v;
 }
+// step counters of the lock-step decoder: ctr[0] = coded index, ctr[1] = KV position of the token being fed
+__global__ void set_ctr_kernel(unsigned long long *ctr, unsigned long long a, unsigned long long b) {
+  ctr[0] = a;
+  ctr[1] = b;
+}
+__global__ void advance_ctr_kernel(unsigned long long *ctr) {
+  ctr[0] += 1;
+  ctr[1] += 1;
+}
+__global__ void fill_pos_from_ctr_kernel(int *__restrict__ p, const unsigned long long *__restrict__ ctr, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = (int)ctr[1];
+}
 __global__ void sum_bits_kernel(const double *__restrict__ bits, const uint64_t *__restrict__ job_off, double *__restrict__ out, int n_jobs) {
   int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n_jobs) return;
@@ -119,7 +133,31 @@ __global__ void sum_bits_kernel(const double *__restrict__ bits, const uint64_t 
 
 namespace cz {
 
+void llama_kernels_set_carveout();
+void attn_set_carveout();
+static void decode_set_carveout() {
+  static bool done = false;
+  if (done || !getenv("CZ_CARVEOUT_HINT")) return;  // opt-in experiment: measured no gain on B200 (profiles/decode_r01.md)
+  done = true;
+  llama_kernels_set_carveout();
+  attn_set_carveout();
+  const auto mx = cudaSharedmemCarveoutMaxShared;
+  cudaFuncSetAttribute(czk::decode_step_kernel<CZ_CDF_SMOLLM>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
+  cudaFuncSetAttribute(czk::decode_step_kernel<CZ_CDF_RWKV_LITERALS>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
+  cudaFuncSetAttribute(czk::fill_pos_from_ctr_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
+  cudaFuncSetAttribute(czk::advance_ctr_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
+}
 size_t decoder_state_bytes() { return sizeof(czk::AcDecoderState); }
+int launch_set_ctr(cz_ctx *ctx, unsigned long long *ctr, unsigned long long a, unsigned long long b, cudaStream_t st) {
+  CZ_LAUNCH(ctx, CZ_K_OTHER, (czk::set_ctr_kernel<<<1, 1, 0, st>>>(ctr, a, b)));
+  CZ_CHECK_LAUNCH();
+  return CZ_OK;
+}
+int launch_advance_ctr(cz_ctx *ctx, unsigned long long *ctr, cudaStream_t st) {
+  CZ_LAUNCH(ctx, CZ_K_OTHER, (czk::advance_ctr_kernel<<<1, 1, 0, st>>>(ctr)));
+  CZ_CHECK_LAUNCH();
+  return CZ_OK;
+}
 int launch_decoder_init(cz_ctx *ctx, const uint8_t *payload, const uint64_t *seg_off, int n_lanes, void *decoder_state, cudaStream_t st) {
   CZ_LAUNCH(ctx, CZ_K_CODER,
             (czk::ac_decoder_init_kernel<<<(unsigned)ceil_div(n_lanes, 128), 128, 0, st>>>(payload, seg_off, n_lanes,
@@ -129,17 +167,17 @@ int launch_decoder_init(cz_ctx *ctx, const uint8_t *payload, const uint64_t *seg
 }
 int launch_decode_step(cz_ctx *ctx, int mode, const float *logits, int V, size_t ld, int n_lanes, const uint8_t *payload,
                        const uint64_t *seg_off, const uint64_t *seg_start, uint64_t coded_index, void *decoder_state, uint32_t *ids_out,
-                       uint32_t *next_tok, const int *colmax, cudaStream_t st) {
+                       uint32_t *next_tok, const int *colmax, cudaStream_t st, const unsigned long long *ctr) {
   const unsigned grid = (unsigned)ceil_div(n_lanes, 8);
   czk::AcDecoderState *ds = (czk::AcDecoderState *)decoder_state;
   if (mode == CZ_CDF_SMOLLM)
     CZ_LAUNCH(ctx, CZ_K_CDF,
               (czk::decode_step_kernel<CZ_CDF_SMOLLM><<<grid, 256, 0, st>>>(logits, V, ld, n_lanes, payload, seg_off, seg_start, coded_index, ds,
-                                                                            ids_out, next_tok, ctx->err_flag_dev, colmax)));
+                                                                            ids_out, next_tok, ctx->err_flag_dev, colmax, ctr)));
   else
     CZ_LAUNCH(ctx, CZ_K_CDF,
               (czk::decode_step_kernel<CZ_CDF_RWKV_LITERALS><<<grid, 256, 0, st>>>(logits, V, ld, n_lanes, payload, seg_off, seg_start, coded_index,
-                                                                                   ds, ids_out, next_tok, ctx->err_flag_dev, colmax)));
+                                                                                   ds, ids_out, next_tok, ctx->err_flag_dev, colmax, ctr)));
   CZ_CHECK_LAUNCH();
   return CZ_OK;
 }
@@ -581,6 +619,7 @@ int cz_decode(cz_model *m, const uint8_t *payload, const uint64_t *seg_off, size
   cz_ctx *ctx = m->ctx;
   cudaStream_t st = ctx->stream;
   CZ_CUDA_TRY(cudaSetDevice(ctx->device));
+  decode_set_carveout();
   if (m->cfg.arch == CZ_ARCH_RWKV7) return rwkv_decode(m, payload, seg_off, n_tokens, sched, ids_out);
   const cz_model_config &c = m->cfg;
   const uint32_t S = sched->n_segments;
@@ -627,8 +666,10 @@ int cz_decode(cz_model *m, const uint8_t *payload, const uint64_t *seg_off, size
     kvb[g] = (int)(g * max_pos);
     lrows[g] = (int)g;
   }
-  CZ_TRY(d_kvb.reserve(S * 12, st));
+  CZ_TRY(d_kvb.reserve(S * 12 + 64, st));
   int *d_kvb_i = d_kvb.as<int>(), *d_lrows_i = d_kvb_i + S, *d_ones_i = d_lrows_i + S;  // step tiles: row0 = g, n = 1
+  unsigned long long *d_ctr = (unsigned long long *)(d_kvb.as<char>() + (((size_t)S * 12 + 15) & ~(size_t)15));
+  const bool use_graph = getenv("CZ_DECODE_NO_GRAPH") == nullptr;
   std::vector<int> ones(S, 1);
   CZ_CUDA_TRY(cudaMemcpyAsync(d_kvb_i, kvb.data(), S * 4, cudaMemcpyHostToDevice, st));
   CZ_CUDA_TRY(cudaMemcpyAsync(d_lrows_i, lrows.data(), S * 4, cudaMemcpyHostToDevice, st));
@@ -682,33 +723,69 @@ int cz_decode(cz_model *m, const uint8_t *payload, const uint64_t *seg_off, size
     }
     const int n_live = (int)live.size();
     Workspace &ws = m->ws;
-    for (uint32_t j = 0; j < ch.n_coded; j++) {
-      const uint64_t i = ch.first + j;
-      if (coded_mode(m) == CZ_CDF_SMOLLM)
-        CZ_LAUNCH(ctx, CZ_K_CDF,
-                  (czk::decode_step_kernel<CZ_CDF_SMOLLM><<<(unsigned)ceil_div(n_live, 8), 256, 0, st>>>(
-                      d_logits.as<float>(), c.vocab, S_pad, n_live, d_pay.as<uint8_t>(), d_off.as<uint64_t>(), d_start.as<uint64_t>(), i,
-                      d_state.as<czk::AcDecoderState>(), d_ids.as<uint32_t>(), ws.tok, ctx->err_flag_dev, have_max ? ws.colmax : nullptr)));
-      else
-        CZ_LAUNCH(ctx, CZ_K_CDF,
-                  (czk::decode_step_kernel<CZ_CDF_RWKV_LITERALS><<<(unsigned)ceil_div(n_live, 8), 256, 0, st>>>(
-                      d_logits.as<float>(), c.vocab, S_pad, n_live, d_pay.as<uint8_t>(), d_off.as<uint64_t>(), d_start.as<uint64_t>(), i,
-                      d_state.as<czk::AcDecoderState>(), d_ids.as<uint32_t>(), ws.tok, ctx->err_flag_dev, have_max ? ws.colmax : nullptr)));
+    // per-chunk constants of the single-token steps: row g = stream g, one attention tile per row
+    CZ_CUDA_TRY(cudaMemcpyAsync(ws.kv_base, d_kvb_i, (size_t)n_live * 4, cudaMemcpyDeviceToDevice, st));
+    CZ_CUDA_TRY(cudaMemcpyAsync(ws.logit_rows, d_lrows_i, (size_t)n_live * 4, cudaMemcpyDeviceToDevice, st));
+    kv.tile_row0 = d_lrows_i;
+    kv.tile_n = d_ones_i;
+    kv.n_tiles = n_live;
+    CZ_LAUNCH(ctx, CZ_K_OTHER, (czk::set_ctr_kernel<<<1, 1, 0, st>>>(d_ctr, ch.first, ch.prime_len)));
+    CZ_CHECK_LAUNCH();
+    // one step: decode the symbol of every live stream from its logits column, then feed it back (a single-token
+    // forward at position ctr[1]) to get the next logits.  All step-varying scalars live in d_ctr, so the same
+    // sequence of ~250 launches is captured ONCE per chunk into a CUDA graph and replayed (the eager loop is
+    // launch-bound: ~15 us of host work per launch against ~2 us of device work).
+    auto decode_syms = [&]() -> int {
+      return launch_decode_step(ctx, coded_mode(m), d_logits.as<float>(), c.vocab, S_pad, n_live, d_pay.as<uint8_t>(), d_off.as<uint64_t>(),
+                                d_start.as<uint64_t>(), 0, d_state.p, d_ids.as<uint32_t>(), ws.tok, have_max ? ws.colmax : nullptr, st, d_ctr);
+    };
+    auto step = [&]() -> int {
+      CZ_TRY(decode_syms());
+      CZ_LAUNCH(ctx, CZ_K_OTHER, (czk::fill_pos_from_ctr_kernel<<<(unsigned)ceil_div(n_live, 256), 256, 0, st>>>(ws.pos, d_ctr, n_live)));
       CZ_CHECK_LAUNCH();
-      if (j + 1 == ch.n_coded) break;  // the step after the chunk's last symbol is never used (next chunk re-primes)
-      // single-token step for every live stream: tok = symbol just decoded, position = prime_len + j
-      CZ_LAUNCH(ctx, CZ_K_OTHER,
-                (czk::fill_int_kernel<<<(unsigned)ceil_div(n_live, 256), 256, 0, st>>>(ws.pos, (int)(ch.prime_len + j), n_live)));
-      CZ_CHECK_LAUNCH();
-      CZ_CUDA_TRY(cudaMemcpyAsync(ws.kv_base, d_kvb_i, (size_t)n_live * 4, cudaMemcpyDeviceToDevice, st));
-      CZ_CUDA_TRY(cudaMemcpyAsync(ws.logit_rows, d_lrows_i, (size_t)n_live * 4, cudaMemcpyDeviceToDevice, st));
-      kv.tile_row0 = d_lrows_i;
-      kv.tile_n = d_ones_i;
-      kv.n_tiles = n_live;
       CZ_TRY(forward_trunk(m, n_live, kv, st));
       CZ_TRY(final_norm_gather(m, n_live, st));
       CZ_TRY(lm_head(m, 0, n_live, d_logits.as<float>(), S_pad, st, ws.colmax, &have_max));
+      CZ_LAUNCH(ctx, CZ_K_OTHER, (czk::advance_ctr_kernel<<<1, 1, 0, st>>>(d_ctr)));
+      CZ_CHECK_LAUNCH();
+      return CZ_OK;
+    };
+    const uint32_t n_steps = ch.n_coded - 1;  // the step after the chunk's last symbol is never used (next chunk re-primes)
+    cudaGraphExec_t gexec = nullptr;
+    uint64_t nodes = 0;
+    int rc = CZ_OK;
+    for (uint32_t j = 0; j < n_steps && rc == CZ_OK; j++) {
+      if (j == 0 || !use_graph || n_steps < 4) {
+        rc = step();  // first step eager: warms function attributes / lazy allocations outside any capture
+      } else if (!gexec) {
+        cudaGraph_t graph = nullptr;
+        const uint64_t l0 = ctx->launches;
+        ctx->capturing = true;
+        cudaError_t e = cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed);
+        if (e == cudaSuccess) {
+          rc = step();
+          e = cudaStreamEndCapture(st, &graph);
+        }
+        ctx->capturing = false;
+        nodes = ctx->launches - l0;
+        if (rc == CZ_OK && e == cudaSuccess) e = cudaGraphInstantiate(&gexec, graph, 0);
+        if (graph) cudaGraphDestroy(graph);
+        if (rc == CZ_OK && e != cudaSuccess) {
+          set_error(std::string("decode step graph capture failed: ") + cudaGetErrorString(e));
+          rc = CZ_ERR_CUDA;
+        }
+        if (rc == CZ_OK && cudaGraphLaunch(gexec, st) != cudaSuccess) rc = CZ_ERR_CUDA;
+      } else {
+        if (cudaGraphLaunch(gexec, st) != cudaSuccess) {
+          set_error("cudaGraphLaunch failed");
+          rc = CZ_ERR_CUDA;
+        }
+        ctx->launches += nodes;
+      }
     }
+    if (gexec) cudaGraphExecDestroy(gexec);
+    CZ_TRY(rc);
+    CZ_TRY(decode_syms());  // the chunk's last symbol
     CZ_TRY(fetch_device_status(ctx, nullptr, nullptr));
   }
   CZ_CUDA_TRY(cudaMemcpyAsync(ids_out, d_ids.p, n_tokens * 4, cudaMemcpyDeviceToHost, st));

@@ -25,9 +25,11 @@ int launch_cdf_cols(cz_ctx *ctx, int op, int mode, const float *logits_dev, size
 int fetch_device_status(cz_ctx *ctx, unsigned long long *err_index_dev, unsigned long long *err_index_out);
 int launch_decode_step(cz_ctx *ctx, int mode, const float *logits, int V, size_t ld, int n_lanes, const uint8_t *payload,
                        const uint64_t *seg_off, const uint64_t *seg_start, uint64_t coded_index, void *decoder_state, uint32_t *ids_out,
-                       uint32_t *next_tok, const int *colmax, cudaStream_t st);
+                       uint32_t *next_tok, const int *colmax, cudaStream_t st, const unsigned long long *ctr = nullptr);
 int launch_decoder_init(cz_ctx *ctx, const uint8_t *payload, const uint64_t *seg_off, int n_lanes, void *decoder_state, cudaStream_t st);
 size_t decoder_state_bytes();
+int launch_set_ctr(cz_ctx *ctx, unsigned long long *ctr, unsigned long long a, unsigned long long b, cudaStream_t st);
+int launch_advance_ctr(cz_ctx *ctx, unsigned long long *ctr, cudaStream_t st);
 }  // namespace cz
 
 namespace czk {
@@ -66,10 +68,11 @@ __global__ void rw_sum_bits_kernel(const double *__restrict__ bits, const uint64
 }
 // stepwise decode: which streams step the model after this symbol (main.rs:2832-2834), and with which token
 __global__ void rw_decode_flags_kernel(const uint32_t *__restrict__ sym, uint32_t V, const uint64_t *__restrict__ seg_start,
-                                       uint64_t coded_index, int n_lanes, int *__restrict__ flags, int *__restrict__ active,
-                                       uint32_t *__restrict__ tok) {
+                                       const unsigned long long *__restrict__ ctr, int n_lanes, int *__restrict__ flags,
+                                       int *__restrict__ active, uint32_t *__restrict__ tok) {
   int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= n_lanes) return;
+  const uint64_t coded_index = ctr[0];
   const uint64_t len = seg_start[s + 1] - seg_start[s];
   const bool act = coded_index + 1 < len && sym[s] < V;  // the step after a stream's last symbol is never needed
   active[s] = act ? 1 : 0;
@@ -425,18 +428,65 @@ int rwkv_decode(cz_model *m, const uint8_t *payload, const uint64_t *seg_off, si
     return CZ_OK;
   };
   CZ_TRY(step_model());  // logits after BOS (main.rs:2709)
-  bool use_cm = c.engine == CZ_ENGINE_TCGEN05 && getenv("CZ_DEBUG_NO_COLMAX") == nullptr;
-  for (uint64_t i = 0; i < max_len; i++) {
-    CZ_TRY(launch_decode_step(ctx, CZ_CDF_RWKV_LITERALS, d_keep.as<float>(), (int)V, S_pad, (int)S, d_pay.as<uint8_t>(), d_off.as<uint64_t>(),
-                              d_start.as<uint64_t>(), i, d_state.p, d_ids.as<uint32_t>(), (uint32_t *)d_sym, use_cm ? d_cm_keep : nullptr, st));
-    if (i + 1 == max_len) break;
+  const bool use_cm = c.engine == CZ_ENGINE_TCGEN05 && getenv("CZ_DEBUG_NO_COLMAX") == nullptr;
+  const bool use_graph = getenv("CZ_DECODE_NO_GRAPH") == nullptr;
+  unsigned long long *d_ctr = (unsigned long long *)(((uintptr_t)(d_sym + S) + 15) & ~(uintptr_t)15);  // aligned tail of d_meta
+  CZ_TRY(launch_set_ctr(ctx, d_ctr, 0, 0, st));
+  auto decode_syms = [&]() -> int {
+    return launch_decode_step(ctx, CZ_CDF_RWKV_LITERALS, d_keep.as<float>(), (int)V, S_pad, (int)S, d_pay.as<uint8_t>(), d_off.as<uint64_t>(),
+                              d_start.as<uint64_t>(), 0, d_state.p, d_ids.as<uint32_t>(), (uint32_t *)d_sym, use_cm ? d_cm_keep : nullptr, st,
+                              d_ctr);
+  };
+  // one step = decode a symbol per stream, decide which streams step (literals do not), single-token forward, commit the new
+  // logits columns.  The step-varying scalar (coded index) lives in d_ctr, so the launch sequence is captured once into a CUDA
+  // graph and replayed for the remaining steps.
+  auto step = [&]() -> int {
+    CZ_TRY(decode_syms());
     CZ_LAUNCH(ctx, CZ_K_OTHER,
-              (czk::rw_decode_flags_kernel<<<(unsigned)ceil_div(S, 128), 128, 0, st>>>((const uint32_t *)d_sym, (uint32_t)V, d_start.as<uint64_t>(), i,
+              (czk::rw_decode_flags_kernel<<<(unsigned)ceil_div(S, 128), 128, 0, st>>>((const uint32_t *)d_sym, (uint32_t)V, d_start.as<uint64_t>(), d_ctr,
                                                                                       (int)S, rw.flags, d_active, ws.tok)));
     CZ_CHECK_LAUNCH();
     CZ_TRY(step_model());
-    if ((i & 255) == 255) CZ_TRY(fetch_device_status(ctx, nullptr, nullptr));
+    CZ_TRY(launch_advance_ctr(ctx, d_ctr, st));
+    return CZ_OK;
+  };
+  cudaGraphExec_t gexec = nullptr;
+  uint64_t nodes = 0;
+  int rc = CZ_OK;
+  const uint64_t n_steps = max_len - 1;
+  for (uint64_t i = 0; i < n_steps && rc == CZ_OK; i++) {
+    if (i == 0 || !use_graph || n_steps < 4) {
+      rc = step();
+    } else if (!gexec) {
+      cudaGraph_t graph = nullptr;
+      const uint64_t l0 = ctx->launches;
+      ctx->capturing = true;
+      cudaError_t e = cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed);
+      if (e == cudaSuccess) {
+        rc = step();
+        e = cudaStreamEndCapture(st, &graph);
+      }
+      ctx->capturing = false;
+      nodes = ctx->launches - l0;
+      if (rc == CZ_OK && e == cudaSuccess) e = cudaGraphInstantiate(&gexec, graph, 0);
+      if (graph) cudaGraphDestroy(graph);
+      if (rc == CZ_OK && e != cudaSuccess) {
+        set_error(std::string("rwkv decode step graph capture failed: ") + cudaGetErrorString(e));
+        rc = CZ_ERR_CUDA;
+      }
+      if (rc == CZ_OK && cudaGraphLaunch(gexec, st) != cudaSuccess) rc = CZ_ERR_CUDA;
+    } else {
+      if (cudaGraphLaunch(gexec, st) != cudaSuccess) {
+        set_error("cudaGraphLaunch failed");
+        rc = CZ_ERR_CUDA;
+      }
+      ctx->launches += nodes;
+    }
+    if (rc == CZ_OK && (i & 1023) == 1023) rc = fetch_device_status(ctx, nullptr, nullptr);
   }
+  if (gexec) cudaGraphExecDestroy(gexec);
+  CZ_TRY(rc);
+  CZ_TRY(decode_syms());  // every stream's last symbol
   CZ_TRY(fetch_device_status(ctx, nullptr, nullptr));
   CZ_CUDA_TRY(cudaMemcpyAsync(ids_out, d_ids.p, n_tokens * 4, cudaMemcpyDeviceToHost, st));
   CZ_CUDA_TRY(cudaStreamSynchronize(st));

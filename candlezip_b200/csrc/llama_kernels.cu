@@ -172,6 +172,19 @@ __global__ void __launch_bounds__(128) attn_rows_kernel(const __nv_bfloat16 *__r
 
 namespace cz {
 
+// Every kernel of the step prefers the maximum shared-memory carve-out, like the 227 KB tcgen05 GEMM it alternates with:
+// a carve-out change between two kernels makes the SM drain and reconfigure, several microseconds per launch in the
+// launch-bound stepwise decoder.
+template <class K>
+static void prefer_max_smem(K kernel) {
+  cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+}
+void llama_kernels_set_carveout() {
+  prefer_max_smem(czk::embed_kernel);
+  prefer_max_smem(czk::rmsnorm_kernel);
+  prefer_max_smem(czk::rope_split_kernel);
+}
+
 int launch_embed(cz_ctx *ctx, const __nv_bfloat16 *table, const uint32_t *tok, float *x, int n_rows, int d, cudaStream_t st) {
   if (n_rows == 0) return CZ_OK;
   CZ_LAUNCH(ctx, CZ_K_ELEMWISE, (czk::embed_kernel<<<n_rows, 128, 0, st>>>(table, tok, x, n_rows, d)));

@@ -3,7 +3,7 @@
 # Every ncu run is preceded by the identical plain command (B200_PROFILING.md).  Usage: scripts/gpu_profile.sh [tag]
 TAG=${1:-r01}
 mkdir -p gpurun_out
-CMD="python bench.py --steps 1 --warmup 1 --decode-tokens 0 --no-cpu-baseline"
+CMD="python bench.py --steps 1 --warmup 1 --decode-tokens 0 --no-cpu-baseline --rwkv-tokens 0"
 $CMD > gpurun_out/prof_plain_$TAG.json 2> gpurun_out/prof_plain_$TAG.err || { echo "plain run failed"; tail -5 gpurun_out/prof_plain_$TAG.err; exit 1; }
 # launch list of the SECOND (timed) step: skip the warm-up step's launches
 N=$(python -c "import json;print(json.load(open('gpurun_out/prof_plain_$TAG.json'))['gpu_launches'])")
