@@ -16,6 +16,16 @@ enum GemmEpilogue {
   EPI_TANH_BF16 = 5,     // C bf16 = tanh(A*B^T)       (RWKV-7 decay LoRA, rwkv7.rs:212)
   EPI_SIGMOID_BF16 = 6,  // C bf16 = sigmoid(A*B^T)    (RWKV-7 gate LoRA, rwkv7.rs:234)
   EPI_RELUSQ_BF16 = 7,   // C bf16 = relu(A*B^T)^2     (RWKV-7 FFN, rwkv7.rs:426)
+  EPI_QKV_ROPE = 8,      // SmolLM q/k/v projection: rotate-half RoPE on the q and k heads, bf16 q rows + K/V arena scatter
+                         // (N = (nh + 2 nkv) * 64, BN = 192 = three whole heads per tile); needs GemmArgs::rope
+};
+
+// extra operands of EPI_QKV_ROPE (all device pointers)
+struct RopeExt {
+  const int *pos = nullptr, *kv_base = nullptr;        // per row: position, first KV slot of its sequence
+  const float *cos_tab = nullptr, *sin_tab = nullptr;  // [max_pos][32]
+  void *q = nullptr, *k_arena = nullptr, *v_arena = nullptr;  // bf16: q [M][nh*64]; arenas [slot][nkv*64]
+  int nh = 0, nkv = 0;
 };
 
 struct GemmArgs {
@@ -28,6 +38,7 @@ struct GemmArgs {
   int bn;   // tile width: 192 or 256 (also the gate/up packing granularity for EPI_SWIGLU_BF16)
   int fam = 0;         // profiling family (CZ_K_GEMM, CZ_K_GEMM_O, ...)
   int *aux = nullptr;  // EPI_STORE_F32_COLMAX: per-column running max, must be pre-filled with INT_MIN
+  RopeExt rope;        // EPI_QKV_ROPE
 };
 
 int gemm_tcgen05(cz_ctx *ctx, const GemmArgs &g, cudaStream_t stream);

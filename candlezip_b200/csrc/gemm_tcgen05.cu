@@ -31,20 +31,22 @@ using cz::EPI_SWIGLU_BF16;
 using cz::EPI_TANH_BF16;
 using cz::EPI_SIGMOID_BF16;
 using cz::EPI_RELUSQ_BF16;
+using cz::EPI_QKV_ROPE;
+using cz::RopeExt;
 
 constexpr int BM = 128;
 constexpr int BK = 64;  // bf16 elements: 128 bytes = one swizzle row
 constexpr int UMMA_K = 16;
 constexpr int GEMM_THREADS = 192;
 
-template <int BN>
+template <int BN, int EPI = 0>
 struct GemmCfg {
-  static constexpr int kStages = BN <= 192 ? 5 : 4;
+  static constexpr int kStages = (BN <= 192 && EPI != cz::EPI_QKV_ROPE) ? 5 : 4;  // the RoPE epilogue stages two patches per warp
   static constexpr int kABytes = BM * BK * 2;
   static constexpr int kBBytes = BN * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kTmemCols = 512;  // 2 accumulator stages of BN columns, power of two >= 2*BN
-  static constexpr int kPatchBytes = 5120;  // per epilogue warp: a padded 32x33 f32 transpose patch (4224 B) or a dense 4 KB
+  static constexpr int kPatchBytes = EPI == cz::EPI_QKV_ROPE ? 9216 : 5120;  // per epilogue warp: a padded 32x33 f32 transpose patch (4224 B) or a dense 4 KB
                                             // SWIZZLE_128B TMA box (reduce-add epilogue); 1024-aligned for the swizzle
   static constexpr int kStagingOff = kStages * kStageBytes + 1024;  // the barriers live in the 1 KB before it
   static constexpr int kSmemBytes = kStagingOff + 4 * kPatchBytes + 1024 /*align slack*/;
@@ -134,8 +136,8 @@ template <int BN, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
     gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                    const __grid_constant__ CUtensorMap tm_c, void *__restrict__ c_ptr,
-                   int M, int N, int K, int ldc, int *__restrict__ aux) {
-  using Cfg = GemmCfg<BN>;
+                   int M, int N, int K, int ldc, int *__restrict__ aux, const __grid_constant__ RopeExt rx) {
+  using Cfg = GemmCfg<BN, EPI>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t *smem_a = smem;
@@ -253,7 +255,64 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       constexpr int kChunks = kSwiglu ? BN / 64 : BN / 32;
       const int n_out = kSwiglu ? N / 2 : N;  // output columns
       constexpr bool kTmaF32 = EPI == EPI_ADD_F32 || EPI == EPI_STORE_F32 || EPI == EPI_STORE_F32_COLMAX;
-      if constexpr (kTmaF32) {
+      if constexpr (EPI == EPI_QKV_ROPE) {
+        // The tile is three whole heads (BN = 192).  Per head: both 32-column halves go to two padded patches, then every
+        // lane rotates 4 (j, j+32) pairs of 8 rows (rotate-half RoPE in fp32 on the accumulators, like the reference's
+        // f32 path) and stores bf16: q rows, or the K / V arena rows at slot kv_base[row] + pos[row].
+        float *pa = stg, *pb = stg + 32 * 33;
+        const int my_row = row_base + lane;
+        const int my_pos = my_row < M ? rx.pos[my_row] : 0;
+        const int my_slot = my_row < M ? rx.kv_base[my_row] + my_pos : 0;
+        const int dq = rx.nh * 64, dkv = rx.nkv * 64;
+#pragma unroll 1
+        for (int hh = 0; hh < BN / 64; hh++) {
+          const int head = n_blk * (BN / 64) + hh;  // 0..nh-1 q heads, then nkv k heads, then nkv v heads
+          if (head >= rx.nh + 2 * rx.nkv) break;
+          uint32_t ra[32], rb[32];
+          tc_ld_32x32(t_row + (uint32_t)(hh * 64), ra);
+          tc_ld_32x32(t_row + (uint32_t)(hh * 64 + 32), rb);
+          tc_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; j++) {
+            pa[lane * 33 + j] = __uint_as_float(ra[j]);
+            pb[lane * 33 + j] = __uint_as_float(rb[j]);
+          }
+          __syncwarp();
+          const bool is_q = head < rx.nh, is_v = head >= rx.nh + rx.nkv;
+#pragma unroll
+          for (int i = 0; i < 8; i++) {
+            const int rr = i * 4 + rr0;
+            const int grow = row_base + rr;
+            const int p = __shfl_sync(0xffffffffu, my_pos, rr), slot = __shfl_sync(0xffffffffu, my_slot, rr);
+            if (grow >= M) continue;
+            const float *sa = pa + rr * 33 + cc, *sb = pb + rr * 33 + cc;
+            float a[4] = {sa[0], sa[1], sa[2], sa[3]}, b[4] = {sb[0], sb[1], sb[2], sb[3]};
+            if (!is_v) {
+              const float4 c4 = *reinterpret_cast<const float4 *>(rx.cos_tab + (size_t)p * 32 + cc);
+              const float4 s4 = *reinterpret_cast<const float4 *>(rx.sin_tab + (size_t)p * 32 + cc);
+              const float cs[4] = {c4.x, c4.y, c4.z, c4.w}, sn[4] = {s4.x, s4.y, s4.z, s4.w};
+#pragma unroll
+              for (int e = 0; e < 4; e++) {
+                const float x = a[e], y = b[e];
+                a[e] = x * cs[e] - y * sn[e];
+                b[e] = y * cs[e] + x * sn[e];
+              }
+            }
+            __nv_bfloat16 *dst = is_q ? (__nv_bfloat16 *)rx.q + (size_t)grow * dq + head * 64
+                                      : (is_v ? (__nv_bfloat16 *)rx.v_arena + (size_t)slot * dkv + (head - rx.nh - rx.nkv) * 64
+                                              : (__nv_bfloat16 *)rx.k_arena + (size_t)slot * dkv + (head - rx.nh) * 64);
+            __nv_bfloat162 h0 = __floats2bfloat162_rn(a[0], a[1]), h1 = __floats2bfloat162_rn(a[2], a[3]);
+            __nv_bfloat162 h2 = __floats2bfloat162_rn(b[0], b[1]), h3 = __floats2bfloat162_rn(b[2], b[3]);
+            *reinterpret_cast<uint2 *>(dst + cc) = make_uint2(*reinterpret_cast<uint32_t *>(&h0), *reinterpret_cast<uint32_t *>(&h1));
+            *reinterpret_cast<uint2 *>(dst + 32 + cc) = make_uint2(*reinterpret_cast<uint32_t *>(&h2), *reinterpret_cast<uint32_t *>(&h3));
+          }
+          __syncwarp();
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[as]));
+        continue;
+      } else if constexpr (kTmaF32) {
         // f32 outputs leave through TMA.  Residual add without reading the residual: the 32x32 f32 patch goes to shared memory in the TMA box layout
         // (dense 128-byte rows, SWIZZLE_128B) and one lane issues cp.reduce.async.bulk.tensor ... .add: the add is done
         // at L2, rows >= M / columns >= N are clipped by the tensor map.  Every output element receives exactly one
@@ -477,8 +536,8 @@ static int make_map_c(CUtensorMap *map, void *ptr, int rows, int cols, int ld_el
 
 template <int BN, int EPI>
 static int launch_tc(cz_ctx *ctx, const CUtensorMap &ta, const CUtensorMap &tb, const CUtensorMap &tc, void *c, int M, int N, int K, int ldc, int *aux,
-                     int g_fam, cudaStream_t stream) {
-  using Cfg = czk::GemmCfg<BN>;
+                     int g_fam, cudaStream_t stream, const RopeExt &rx) {
+  using Cfg = czk::GemmCfg<BN, EPI>;
   static bool attr_set = false;
   if (!attr_set) {
     CZ_CUDA_TRY(cudaFuncSetAttribute(czk::gemm_tc_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
@@ -487,7 +546,7 @@ static int launch_tc(cz_ctx *ctx, const CUtensorMap &ta, const CUtensorMap &tb, 
   const int tiles = (int)(ceil_div(M, czk::BM) * ceil_div(N, BN));
   const int grid = tiles < ctx->sm_count ? tiles : ctx->sm_count;
   CZ_LAUNCH(ctx, g_fam,
-            (czk::gemm_tc_kernel<BN, EPI><<<grid, czk::GEMM_THREADS, Cfg::kSmemBytes, stream>>>(ta, tb, tc, c, M, N, K, ldc, aux)));
+            (czk::gemm_tc_kernel<BN, EPI><<<grid, czk::GEMM_THREADS, Cfg::kSmemBytes, stream>>>(ta, tb, tc, c, M, N, K, ldc, aux, rx)));
   CZ_CHECK_LAUNCH();
   return CZ_OK;
 }
@@ -512,13 +571,18 @@ int gemm_tcgen05(cz_ctx *ctx, const GemmArgs &g, cudaStream_t stream) {
     set_error("gemm_tcgen05: bf16 output needs ldc % 8 == 0");
     return CZ_ERR_INVALID;
   }
+  if (g.epi == EPI_QKV_ROPE && (g.bn != 192 || g.N != (g.rope.nh + 2 * g.rope.nkv) * 64 || !g.rope.pos || !g.rope.kv_base || !g.rope.cos_tab ||
+                                !g.rope.sin_tab || !g.rope.q || !g.rope.k_arena || !g.rope.v_arena)) {
+    set_error("gemm_tcgen05: EPI_QKV_ROPE needs BN = 192, N = (nh + 2 nkv) * 64 and all RopeExt operands");
+    return CZ_ERR_INVALID;
+  }
   CUtensorMap ta, tb, tc;
   CZ_TRY(make_map(&ta, g.a, g.M, g.K, g.lda, czk::BM));
   CZ_TRY(make_map(&tb, g.b, g.N, g.K, g.ldb, g.bn));
   if (g.epi == EPI_ADD_F32 || g.epi == EPI_STORE_F32 || g.epi == EPI_STORE_F32_COLMAX) CZ_TRY(make_map_c(&tc, g.c, g.M, g.N, g.ldc));
   else tc = ta;  // unused by the other epilogues
 #define CZ_TC_CASE(BN_, EPI_) \
-  if (g.bn == BN_ && g.epi == EPI_) return launch_tc<BN_, EPI_>(ctx, ta, tb, tc, g.c, g.M, g.N, g.K, g.ldc, g.aux, g.fam, stream)
+  if (g.bn == BN_ && g.epi == EPI_) return launch_tc<BN_, EPI_>(ctx, ta, tb, tc, g.c, g.M, g.N, g.K, g.ldc, g.aux, g.fam, stream, g.rope)
   CZ_TC_CASE(192, EPI_STORE_F32);
   CZ_TC_CASE(192, EPI_ADD_F32);
   CZ_TC_CASE(192, EPI_SWIGLU_BF16);
@@ -530,6 +594,7 @@ int gemm_tcgen05(cz_ctx *ctx, const GemmArgs &g, cudaStream_t stream) {
   CZ_TC_CASE(192, EPI_SIGMOID_BF16);
   CZ_TC_CASE(256, EPI_RELUSQ_BF16);
   CZ_TC_CASE(256, EPI_ADD_F32);
+  CZ_TC_CASE(192, EPI_QKV_ROPE);
 #undef CZ_TC_CASE
   set_error("gemm_tcgen05: unsupported (BN, epilogue) combination");
   return CZ_ERR_UNSUPPORTED;

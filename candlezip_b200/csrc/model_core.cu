@@ -280,8 +280,19 @@ int forward_trunk(cz_model *m, int n_rows, const KvView &kv, cudaStream_t st) {
     GemmArgs g{};
     g.a = w.xn; g.lda = D; g.b = m->w_qkv + (size_t)l * QKV * D; g.ldb = D; g.c = w.qkv; g.ldc = QKV;
     g.M = n_rows; g.N = QKV; g.K = D; g.epi = EPI_STORE_F32; g.bn = 192; g.fam = CZ_K_GEMM;
-    CZ_TRY(gemm(ctx, c.engine, g, st));
-    CZ_TRY(launch_rope_split(ctx, w.qkv, w.pos, w.kv_base, m->cos_tab, m->sin_tab, w.q, kl, vl, n_rows, nh, nkv, st));
+    static const bool no_fused_rope = getenv("CZ_DEBUG_NO_FUSED_ROPE") != nullptr;  // bisecting aid
+    if (c.engine == CZ_ENGINE_TCGEN05 && !no_fused_rope) {
+      // RoPE + bf16 conversion + K/V arena scatter fused into the projection's epilogue: the fp32 qkv rows never reach HBM
+      g.epi = EPI_QKV_ROPE;
+      g.c = nullptr;
+      g.rope.pos = w.pos; g.rope.kv_base = w.kv_base; g.rope.cos_tab = m->cos_tab; g.rope.sin_tab = m->sin_tab;
+      g.rope.q = w.q; g.rope.k_arena = kl; g.rope.v_arena = vl; g.rope.nh = nh; g.rope.nkv = nkv;
+      CZ_TRY(gemm(ctx, c.engine, g, st));
+      g.rope = RopeExt();
+    } else {
+      CZ_TRY(gemm(ctx, c.engine, g, st));
+      CZ_TRY(launch_rope_split(ctx, w.qkv, w.pos, w.kv_base, m->cos_tab, m->sin_tab, w.q, kl, vl, n_rows, nh, nkv, st));
+    }
     static const bool force_rows = getenv("CZ_DEBUG_ATTN_ROWS") != nullptr;  // bisecting aid
     if (c.engine == CZ_ENGINE_TCGEN05 && !force_rows)
       CZ_TRY(launch_attn_mma(ctx, w.q, kl, vl, w.pos, w.kv_base, kv.tile_row0, kv.tile_n, kv.n_tiles, w.attn, nh, nkv, st));
