@@ -254,10 +254,11 @@ class Model:
         pay = [data[int(seg_off[g]) : int(seg_off[g + 1])].tobytes() for g in range(int(s.n_segments))]
         return pay, seg_start
 
-    def decode(self, payloads, seg_start, bos=0, context=512, reprime_interval=512, max_batch_tokens=0):
+    def decode(self, payloads, seg_start, bos=0, context=512, reprime_interval=512, max_batch_tokens=0, events=None):
+        """events: the same gated hint primes the encoder was given (src/main.rs:2586-2614), single segment only"""
         seg_start = np.asarray(seg_start, np.uint64)
         n = int(seg_start[-1])
-        s, keep = self._schedule(n, seg_start, bos, context, reprime_interval, None, max_batch_tokens)
+        s, keep = self._schedule(n, seg_start, bos, context, reprime_interval, events, max_batch_tokens)
         lens = np.array([len(p) for p in payloads], dtype=np.uint64)
         seg_off = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
         blob, blobp = _u8(np.frombuffer(b"".join(payloads) + b"\0", dtype=np.uint8))

@@ -611,10 +611,6 @@ int cz_decode(cz_model *m, const uint8_t *payload, const uint64_t *seg_off, size
   CZ_TRY(require_device(m->ctx));
   CZ_TRY(check_schedule(sched, n_tokens));
   CZ_TRY(model_finalize(m));
-  if (sched->n_events) {
-    set_error("cz_decode: hint prime events are not wired into the batched decoder yet (use the session shim)");
-    return CZ_ERR_UNSUPPORTED;
-  }
   if (n_tokens == 0) return CZ_OK;
   cz_ctx *ctx = m->ctx;
   cudaStream_t st = ctx->stream;
@@ -627,7 +623,7 @@ int cz_decode(cz_model *m, const uint8_t *payload, const uint64_t *seg_off, size
   uint64_t max_len = 0;
   for (uint32_t g = 0; g < S; g++) max_len = std::max<uint64_t>(max_len, sched->seg_start[g + 1] - sched->seg_start[g]);
   std::vector<Chunk> chunks;  // master timeline = chunk structure of the longest segment
-  build_chunks(max_len, sched->context, sched->reprime_interval, nullptr, 0, chunks);
+  build_chunks(max_len, sched->context, sched->reprime_interval, sched->events, sched->n_events, chunks);  // events: S == 1
   size_t max_pos = 0;
   for (const Chunk &ch : chunks) max_pos = std::max<size_t>(max_pos, (size_t)ch.prime_len + ch.n_coded);
   max_pos = (max_pos + 63) & ~(size_t)63;
@@ -651,6 +647,16 @@ int cz_decode(cz_model *m, const uint8_t *payload, const uint64_t *seg_off, size
   CZ_CUDA_TRY(cudaMemcpyAsync(d_pay.p, payload, pay_total, cudaMemcpyHostToDevice, st));
   CZ_CUDA_TRY(cudaMemcpyAsync(d_off.p, seg_off, (S + 1) * 8, cudaMemcpyHostToDevice, st));
   CZ_CUDA_TRY(cudaMemcpyAsync(d_start.p, sched->seg_start, (S + 1) * 8, cudaMemcpyHostToDevice, st));
+  // explicit prime token lists of the gated hint events (src/main.rs:2586-2614)
+  std::vector<uint32_t> extra;
+  std::vector<size_t> ev_off(sched->n_events + 1, 0);
+  for (uint32_t e = 0; e < sched->n_events; e++) {
+    ev_off[e] = extra.size();
+    extra.insert(extra.end(), sched->events[e].prime, sched->events[e].prime + sched->events[e].prime_len);
+  }
+  GrowBuf &d_extra = m->sb[SB_EXTRA];
+  CZ_TRY(d_extra.reserve(extra.size() * 4 + 16, st));
+  if (!extra.empty()) CZ_CUDA_TRY(cudaMemcpyAsync(d_extra.p, extra.data(), extra.size() * 4, cudaMemcpyHostToDevice, st));
   CZ_LAUNCH(ctx, CZ_K_CODER,
             (czk::ac_decoder_init_kernel<<<(unsigned)ceil_div(S, 128), 128, 0, st>>>(d_pay.as<uint8_t>(), d_off.as<uint64_t>(), (int)S,
                                                                                     d_state.as<czk::AcDecoderState>())));
@@ -697,7 +703,8 @@ int cz_decode(cz_model *m, const uint8_t *payload, const uint64_t *seg_off, size
       const int r0 = (int)w.src.size();
       for (uint32_t k = 0; k < ch.prime_len; k++) {
         const uint64_t si = ch.prime_start + k;
-        w.src.push_back(si == 0 ? -1ll : (long long)(t0 + si - 1));
+        if (ch.event >= 0) w.src.push_back(-2 - (long long)(ev_off[ch.event] + k));
+        else w.src.push_back(si == 0 ? -1ll : (long long)(t0 + si - 1));
         w.pos.push_back((int)k);
         w.kv_base.push_back(base);
       }
@@ -711,8 +718,8 @@ int cz_decode(cz_model *m, const uint8_t *payload, const uint64_t *seg_off, size
       Workspace &ws = m->ws;
       CZ_TRY(stage_and_upload(m, w, d_src.as<long long>(), st));
       CZ_LAUNCH(ctx, CZ_K_OTHER,
-                (czk::gather_tokens_kernel<<<(unsigned)ceil_div(R, 256), 256, 0, st>>>(d_src.as<long long>(), d_ids.as<uint32_t>(), nullptr,
-                                                                                      sched->bos, ws.tok, (int)R)));
+                (czk::gather_tokens_kernel<<<(unsigned)ceil_div(R, 256), 256, 0, st>>>(d_src.as<long long>(), d_ids.as<uint32_t>(),
+                                                                                      d_extra.as<uint32_t>(), sched->bos, ws.tok, (int)R)));
       CZ_CHECK_LAUNCH();
       kv.tile_row0 = ws.tile_row0;
       kv.tile_n = ws.tile_n;

@@ -397,28 +397,18 @@ int rwkv_decode(cz_model *m, const uint8_t *payload, const uint64_t *seg_off, si
   CZ_CUDA_TRY(cudaMemcpyAsync(d_off.p, seg_off, (S + 1) * 8, cudaMemcpyHostToDevice, st));
   CZ_CUDA_TRY(cudaMemcpyAsync(d_start.p, sched->seg_start, (S + 1) * 8, cudaMemcpyHostToDevice, st));
   CZ_TRY(launch_decoder_init(ctx, d_pay.as<uint8_t>(), d_off.as<uint64_t>(), (int)S, d_state.p, st));
-  // constant per-stream metadata: row s = stream s, one row per stream, state slot s
+  const bool use_cm = c.engine == CZ_ENGINE_TCGEN05 && getenv("CZ_DEBUG_NO_COLMAX") == nullptr;
+  const bool use_graph = getenv("CZ_DECODE_NO_GRAPH") == nullptr;
+  unsigned long long *d_ctr = (unsigned long long *)(((uintptr_t)(d_sym + S) + 15) & ~(uintptr_t)15);  // aligned tail of d_meta
+  const size_t total = V * S_pad;
   std::vector<int> iota(S), minus1(S, -1), ones(S, 1), next(S);
-  std::vector<uint32_t> bos(S, sched->bos);
   for (uint32_t g = 0; g < S; g++) {
     iota[g] = (int)g;
     next[g] = (int)g + 1;
   }
-  CZ_CUDA_TRY(cudaMemcpyAsync(rw.prev_row, minus1.data(), S * 4, cudaMemcpyHostToDevice, st));
-  CZ_CUDA_TRY(cudaMemcpyAsync(rw.slot, iota.data(), S * 4, cudaMemcpyHostToDevice, st));
-  CZ_CUDA_TRY(cudaMemcpyAsync(rw.flags, ones.data(), S * 4, cudaMemcpyHostToDevice, st));
-  CZ_CUDA_TRY(cudaMemcpyAsync(rw.row_begin, iota.data(), S * 4, cudaMemcpyHostToDevice, st));
-  CZ_CUDA_TRY(cudaMemcpyAsync(rw.row_end, next.data(), S * 4, cudaMemcpyHostToDevice, st));
-  CZ_CUDA_TRY(cudaMemcpyAsync(rw.stream_slot, iota.data(), S * 4, cudaMemcpyHostToDevice, st));
-  CZ_CUDA_TRY(cudaMemcpyAsync(ws.logit_rows, iota.data(), S * 4, cudaMemcpyHostToDevice, st));
-  CZ_CUDA_TRY(cudaMemcpyAsync(ws.tok, bos.data(), S * 4, cudaMemcpyHostToDevice, st));
-  CZ_CUDA_TRY(cudaMemcpyAsync(d_active, ones.data(), S * 4, cudaMemcpyHostToDevice, st));
-  CZ_CUDA_TRY(cudaStreamSynchronize(st));
-  CZ_TRY(rwkv_state_reset(m, m->rstate, S, st));
-  const size_t total = V * S_pad;
-  auto step_model = [&]() -> int {
+  // head + commit of the freshly computed logits columns of the streams flagged in d_active
+  auto head_commit = [&]() -> int {
     bool have_max = false;
-    CZ_TRY(rwkv_forward(m, (int)S, (int)S, m->rstate, /*in_place=*/true, d_active, st));
     CZ_TRY(rwkv_final_norm_gather(m, (int)S, st));
     CZ_TRY(lm_head(m, 0, (int)S, d_fresh.as<float>(), S_pad, st, ws.colmax, &have_max));
     CZ_LAUNCH(ctx, CZ_K_OTHER,
@@ -427,11 +417,48 @@ int rwkv_decode(cz_model *m, const uint8_t *payload, const uint64_t *seg_off, si
     CZ_CHECK_LAUNCH();
     return CZ_OK;
   };
-  CZ_TRY(step_model());  // logits after BOS (main.rs:2709)
-  const bool use_cm = c.engine == CZ_ENGINE_TCGEN05 && getenv("CZ_DEBUG_NO_COLMAX") == nullptr;
-  const bool use_graph = getenv("CZ_DECODE_NO_GRAPH") == nullptr;
-  unsigned long long *d_ctr = (unsigned long long *)(((uintptr_t)(d_sym + S) + 15) & ~(uintptr_t)15);  // aligned tail of d_meta
-  CZ_TRY(launch_set_ctr(ctx, d_ctr, 0, 0, st));
+  // (re)start every stream from a zero state and feed `first` (BOS, or a gated hint prime: main.rs:2803-2812 ->
+  // models.rs:162-170), leaving the logits of its last token in d_keep; then restore the single-row step metadata
+  auto prime_all = [&](const std::vector<uint32_t> &first) -> int {
+    const size_t n = first.size(), R = (size_t)S * n;
+    CZ_TRY(ensure_workspace(m, R, S, 0));
+    CZ_TRY(rwkv_ensure_ws(m, R, S));
+    std::vector<uint32_t> tok(R);
+    std::vector<int> prev(R), slot(R), flags(R, 0), rb(S), re(S), lrows(S);
+    for (uint32_t g = 0; g < S; g++) {
+      for (size_t k = 0; k < n; k++) {
+        const size_t r = (size_t)g * n + k;
+        tok[r] = first[k];
+        prev[r] = k == 0 ? -1 : (int)r - 1;
+        slot[r] = (int)g;
+      }
+      flags[(size_t)g * n + n - 1] = 1;
+      rb[g] = (int)(g * n);
+      re[g] = (int)(g * n + n);
+      lrows[g] = (int)(g * n + n - 1);
+    }
+    CZ_CUDA_TRY(cudaMemcpyAsync(ws.tok, tok.data(), R * 4, cudaMemcpyHostToDevice, st));
+    CZ_CUDA_TRY(cudaMemcpyAsync(rw.prev_row, prev.data(), R * 4, cudaMemcpyHostToDevice, st));
+    CZ_CUDA_TRY(cudaMemcpyAsync(rw.slot, slot.data(), R * 4, cudaMemcpyHostToDevice, st));
+    CZ_CUDA_TRY(cudaMemcpyAsync(rw.flags, flags.data(), R * 4, cudaMemcpyHostToDevice, st));
+    CZ_CUDA_TRY(cudaMemcpyAsync(rw.row_begin, rb.data(), S * 4, cudaMemcpyHostToDevice, st));
+    CZ_CUDA_TRY(cudaMemcpyAsync(rw.row_end, re.data(), S * 4, cudaMemcpyHostToDevice, st));
+    CZ_CUDA_TRY(cudaMemcpyAsync(rw.stream_slot, iota.data(), S * 4, cudaMemcpyHostToDevice, st));
+    CZ_CUDA_TRY(cudaMemcpyAsync(ws.logit_rows, lrows.data(), S * 4, cudaMemcpyHostToDevice, st));
+    CZ_CUDA_TRY(cudaMemcpyAsync(d_active, ones.data(), S * 4, cudaMemcpyHostToDevice, st));
+    CZ_TRY(rwkv_state_reset(m, m->rstate, S, st));
+    CZ_TRY(rwkv_forward(m, (int)R, (int)S, m->rstate, /*in_place=*/n == 1, nullptr, st));
+    CZ_TRY(head_commit());
+    // single-row step metadata: row s = stream s, state slot s
+    CZ_CUDA_TRY(cudaMemcpyAsync(rw.prev_row, minus1.data(), S * 4, cudaMemcpyHostToDevice, st));
+    CZ_CUDA_TRY(cudaMemcpyAsync(rw.slot, iota.data(), S * 4, cudaMemcpyHostToDevice, st));
+    CZ_CUDA_TRY(cudaMemcpyAsync(rw.flags, ones.data(), S * 4, cudaMemcpyHostToDevice, st));
+    CZ_CUDA_TRY(cudaMemcpyAsync(rw.row_begin, iota.data(), S * 4, cudaMemcpyHostToDevice, st));
+    CZ_CUDA_TRY(cudaMemcpyAsync(rw.row_end, next.data(), S * 4, cudaMemcpyHostToDevice, st));
+    CZ_CUDA_TRY(cudaMemcpyAsync(ws.logit_rows, iota.data(), S * 4, cudaMemcpyHostToDevice, st));
+    CZ_CUDA_TRY(cudaStreamSynchronize(st));  // the staging vectors are stack-owned
+    return CZ_OK;
+  };
   auto decode_syms = [&]() -> int {
     return launch_decode_step(ctx, CZ_CDF_RWKV_LITERALS, d_keep.as<float>(), (int)V, S_pad, (int)S, d_pay.as<uint8_t>(), d_off.as<uint64_t>(),
                               d_start.as<uint64_t>(), 0, d_state.p, d_ids.as<uint32_t>(), (uint32_t *)d_sym, use_cm ? d_cm_keep : nullptr, st,
@@ -446,46 +473,64 @@ int rwkv_decode(cz_model *m, const uint8_t *payload, const uint64_t *seg_off, si
               (czk::rw_decode_flags_kernel<<<(unsigned)ceil_div(S, 128), 128, 0, st>>>((const uint32_t *)d_sym, (uint32_t)V, d_start.as<uint64_t>(), d_ctr,
                                                                                       (int)S, rw.flags, d_active, ws.tok)));
     CZ_CHECK_LAUNCH();
-    CZ_TRY(step_model());
+    CZ_TRY(rwkv_forward(m, (int)S, (int)S, m->rstate, /*in_place=*/true, d_active, st));
+    CZ_TRY(head_commit());
     CZ_TRY(launch_advance_ctr(ctx, d_ctr, st));
     return CZ_OK;
   };
-  cudaGraphExec_t gexec = nullptr;
-  uint64_t nodes = 0;
-  int rc = CZ_OK;
-  const uint64_t n_steps = max_len - 1;
-  for (uint64_t i = 0; i < n_steps && rc == CZ_OK; i++) {
-    if (i == 0 || !use_graph || n_steps < 4) {
-      rc = step();
-    } else if (!gexec) {
-      cudaGraph_t graph = nullptr;
-      const uint64_t l0 = ctx->launches;
-      ctx->capturing = true;
-      cudaError_t e = cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed);
-      if (e == cudaSuccess) {
+  // units: [0, e_0), [e_0, e_1), ... ; each starts from a fresh state primed with BOS / the event's prime (events: S == 1)
+  std::vector<uint64_t> cut{0};
+  for (uint32_t e = 0; e < sched->n_events; e++)
+    if (sched->events[e].i > cut.back() && sched->events[e].i < max_len) cut.push_back(sched->events[e].i);
+  cut.push_back(max_len);
+  for (size_t u = 0; u + 1 < cut.size(); u++) {
+    std::vector<uint32_t> first{sched->bos};
+    for (uint32_t e = 0; e < sched->n_events; e++)
+      if (sched->events[e].i == cut[u] && (u > 0 || cut[u] == 0) && sched->events[e].i == cut[u]) {
+        std::vector<uint32_t> pr;
+        for (uint32_t k = 0; k < sched->events[e].prime_len; k++)
+          if (sched->events[e].prime[k] < V) pr.push_back(sched->events[e].prime[k]);
+        if (!pr.empty()) first = pr;
+      }
+    CZ_TRY(prime_all(first));
+    CZ_TRY(launch_set_ctr(ctx, d_ctr, cut[u], 0, st));
+    cudaGraphExec_t gexec = nullptr;
+    uint64_t nodes = 0;
+    int rc = CZ_OK;
+    const uint64_t n_steps = cut[u + 1] - cut[u] - (u + 2 == cut.size() ? 1 : 0);  // the very last symbol needs no step after it
+    for (uint64_t i = 0; i < n_steps && rc == CZ_OK; i++) {
+      if (i == 0 || !use_graph || n_steps < 4) {
         rc = step();
-        e = cudaStreamEndCapture(st, &graph);
+      } else if (!gexec) {
+        cudaGraph_t graph = nullptr;
+        const uint64_t l0 = ctx->launches;
+        ctx->capturing = true;
+        cudaError_t e = cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed);
+        if (e == cudaSuccess) {
+          rc = step();
+          e = cudaStreamEndCapture(st, &graph);
+        }
+        ctx->capturing = false;
+        nodes = ctx->launches - l0;
+        if (rc == CZ_OK && e == cudaSuccess) e = cudaGraphInstantiate(&gexec, graph, 0);
+        if (graph) cudaGraphDestroy(graph);
+        if (rc == CZ_OK && e != cudaSuccess) {
+          set_error(std::string("rwkv decode step graph capture failed: ") + cudaGetErrorString(e));
+          rc = CZ_ERR_CUDA;
+        }
+        if (rc == CZ_OK && cudaGraphLaunch(gexec, st) != cudaSuccess) rc = CZ_ERR_CUDA;
+      } else {
+        if (cudaGraphLaunch(gexec, st) != cudaSuccess) {
+          set_error("cudaGraphLaunch failed");
+          rc = CZ_ERR_CUDA;
+        }
+        ctx->launches += nodes;
       }
-      ctx->capturing = false;
-      nodes = ctx->launches - l0;
-      if (rc == CZ_OK && e == cudaSuccess) e = cudaGraphInstantiate(&gexec, graph, 0);
-      if (graph) cudaGraphDestroy(graph);
-      if (rc == CZ_OK && e != cudaSuccess) {
-        set_error(std::string("rwkv decode step graph capture failed: ") + cudaGetErrorString(e));
-        rc = CZ_ERR_CUDA;
-      }
-      if (rc == CZ_OK && cudaGraphLaunch(gexec, st) != cudaSuccess) rc = CZ_ERR_CUDA;
-    } else {
-      if (cudaGraphLaunch(gexec, st) != cudaSuccess) {
-        set_error("cudaGraphLaunch failed");
-        rc = CZ_ERR_CUDA;
-      }
-      ctx->launches += nodes;
+      if (rc == CZ_OK && (i & 1023) == 1023) rc = fetch_device_status(ctx, nullptr, nullptr);
     }
-    if (rc == CZ_OK && (i & 1023) == 1023) rc = fetch_device_status(ctx, nullptr, nullptr);
+    if (gexec) cudaGraphExecDestroy(gexec);
+    CZ_TRY(rc);
   }
-  if (gexec) cudaGraphExecDestroy(gexec);
-  CZ_TRY(rc);
   CZ_TRY(decode_syms());  // every stream's last symbol
   CZ_TRY(fetch_device_status(ctx, nullptr, nullptr));
   CZ_CUDA_TRY(cudaMemcpyAsync(ids_out, d_ids.p, n_tokens * 4, cudaMemcpyDeviceToHost, st));

@@ -469,6 +469,29 @@ def test_rwkv7_hint_prime_event_matches_oracle_loop(gpu_ctx):
     assert oracle.ac_encode(bounds) == pays[0]
 
 
+def test_hint_prime_events_roundtrip_both_backends(gpu_ctx):
+    """gated hint primes in the main stream (src/main.rs:2123-2149 encode, 2586-2614 decode): the prime replaces
+    the context, `hold_until` suppresses the next context re-prime; the batched decoder must follow the same schedule."""
+    rng = np.random.default_rng(41)
+    # SmolLM: events at a chunk-interior index and right before a re-prime boundary that the hold-off then suppresses
+    model = _tiny(gpu_ctx, _lib.CZ_ENGINE_TCGEN05)
+    ids = rng.integers(0, 1024, 1500).astype(np.uint32)
+    ev = [(200, rng.integers(0, 1024, 300).astype(np.uint32), 200 + 512), (900, rng.integers(0, 1024, 63).astype(np.uint32), 900 + 512)]
+    pays, seg = model.encode(ids, n_segments=1, events=ev)
+    plain, _ = model.encode(ids, n_segments=1)
+    assert pays != plain
+    orc = _oracle_for(model, round_bf16=0)
+    ref, rep = orc.encode_tokens(np.concatenate([[0], ids]).astype(np.uint32), events=ev)
+    assert abs(len(pays[0]) - len(ref)) <= 0.005 * len(ref) + 2
+    assert np.array_equal(model.decode(pays, seg, events=ev), ids)
+    # RWKV-7: a prime resets the recurrent state (src/models.rs:162-170)
+    rmodel, cfg, _ = _rwkv_tiny(gpu_ctx)
+    rid = rng.integers(0, cfg["vocab"], 400).astype(np.uint32)
+    rev = [(0, rng.integers(0, cfg["vocab"], 9).astype(np.uint32), 64), (150, rng.integers(0, cfg["vocab"], 40).astype(np.uint32), 214)]
+    rp, rs = rmodel.encode(rid, n_segments=1, events=rev)
+    assert np.array_equal(rmodel.decode(rp, rs, events=rev), rid)
+
+
 def test_rwkv7_full_size_roundtrip(gpu_ctx):
     """rwkv7-g1-0.1b shape (random-init): logits vs the oracle on a few positions, then a multi-segment round trip."""
     model = cz.Model(gpu_ctx, cz.RWKV7_0P1B).random_init(3, 0.02, 0.05)
