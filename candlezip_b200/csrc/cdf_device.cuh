@@ -32,14 +32,14 @@ __device__ __forceinline__ void exp_tab_init(uint32_t *s_lo, uint32_t *s_hi) {
   __syncthreads();
 }
 
+// Branch-free: every lane always evaluates the polynomial and the two range cases are selects at the end (a divergent
+// early-out costs a BSSY/BSYNC pair per element in the unrolled column walk, profiles/ncu_summary_r01.md).
 __device__ __forceinline__ float cz_expf(float x, const ExpTab &tab) {
   const double inv_ln2_n = 0x1.71547652b82fep+0 * 32;
   const double shift = 0x1.8p+52;
   const double c0 = 0x1.c6af84b912394p-5 / 32 / 32 / 32;
   const double c1 = 0x1.ebfce50fac4f3p-3 / 32 / 32;
   const double c2 = 0x1.62e42ff0c52d6p-1 / 32;
-  if (x < -0x1.9fe368p6f) return 0.0f;
-  if (x > 0x1.62e42ep6f) return __int_as_float(0x7f800000);
   double xd = (double)x;
   double z = __dmul_rn(inv_ln2_n, xd);
   double kd = __dadd_rn(z, shift);
@@ -55,7 +55,10 @@ __device__ __forceinline__ float cz_expf(float x, const ExpTab &tab) {
   double y = __fma_rn(c2, r, 1.0);
   y = __fma_rn(p, r2, y);
   y = __dmul_rn(y, s);
-  return __double2float_rn(y);
+  float out = __double2float_rn(y);
+  out = (x < -0x1.9fe368p6f) ? 0.0f : out;                       // underflow to zero
+  out = (x > 0x1.62e42ep6f) ? __int_as_float(0x7f800000) : out;  // overflow
+  return out;
 }
 
 // floor(acc * 2^30) clamped to [0, 2^30]  (src/main.rs:813-815; NaN -> 0 like Rust's `as i64`)
@@ -97,13 +100,28 @@ __device__ __forceinline__ void cdf_walk(const float *__restrict__ p, size_t ld,
 #pragma unroll
   for (int k = 0; k < CDF_GRP; k++) cur[k] = k < n ? __ldg(p + (size_t)k * ld) : 0.f;
   bool go = true;
-  for (int v0 = 0; v0 < n; v0 += CDF_GRP) {
+  int v0 = 0;
+  // main loop: the current AND the next group are entirely in range -> no per-element bounds checks
+  for (; v0 + 2 * CDF_GRP <= n; v0 += CDF_GRP) {
+#pragma unroll
+    for (int k = 0; k < CDF_GRP; k++) {
+      nxt[k] = __ldg(p + (size_t)(v0 + CDF_GRP + k) * ld);
+      const int vp = min(v0 + CDF_PF + k, n - 1);
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(p + (size_t)vp * ld));
+    }
+#pragma unroll
+    for (int k = 0; k < CDF_GRP; k++) {
+      if (go) go = f(v0 + k, cur[k]);
+      cur[k] = nxt[k];
+    }
+    if (!__any_sync(0xffffffffu, go)) return;
+  }
+  // tail: at most two groups, checked
+  for (; v0 < n; v0 += CDF_GRP) {
 #pragma unroll
     for (int k = 0; k < CDF_GRP; k++) {
       const int v = v0 + CDF_GRP + k;
       nxt[k] = v < n ? __ldg(p + (size_t)v * ld) : 0.f;
-      const int vp = v0 + CDF_PF + k;
-      if (vp < n) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + (size_t)vp * ld));
     }
 #pragma unroll
     for (int k = 0; k < CDF_GRP; k++) {

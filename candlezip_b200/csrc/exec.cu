@@ -186,6 +186,7 @@ int launch_decode_step(cz_ctx *ctx, int mode, const float *logits, int V, size_t
 // Wave builder: rows of several chunks packed back to back (teacher-forced), each chunk its own sequence.
 // -------------------------------------------------------------------------------------------------------------
 struct Wave {
+  int tile = 64;  // query positions per attention tile (cz_model::attn_tile)
   std::vector<long long> src;
   std::vector<int> pos, kv_base, logit_rows, tile_row0, tile_n;
   size_t n_rows() const { return src.size(); }
@@ -201,9 +202,9 @@ struct Wave {
   }
   // attention tiles of one sequence occupying rows [base, base + rows): 64 positions each, anchored at position 0
   void add_tiles(int base, int rows) {
-    for (int p = 0; p < rows; p += 64) {
+    for (int p = 0; p < rows; p += tile) {
       tile_row0.push_back(base + p);
-      tile_n.push_back(rows - p < 64 ? rows - p : 64);
+      tile_n.push_back(rows - p < tile ? rows - p : tile);
     }
   }
   // prime_src(k), coded_src(j): token source of prime position k / coded token j
@@ -222,6 +223,16 @@ struct Wave {
       kv_base.push_back(base);
     }
     for (uint32_t j = 0; j < n_coded; j++) logit_rows.push_back(base + (int)prime_len - 1 + (int)j);
+    // Every sequence must start at a row (= KV slot) that is a multiple of 8: the tcgen05 attention kernel TMA-loads the
+    // transposed V with the slot as the INNER coordinate, which has to be 16-byte aligned.  The sequence is therefore
+    // extended to a multiple of 8 rows with dummy BOS tokens at the following positions: causally invisible to the real
+    // rows, attended like any other row (so their K/V stay finite: masked slots are multiplied by P = 0, and 0 * NaN = NaN),
+    // and without a logits row.
+    while (src.size() % 8) {
+      src.push_back(-1);
+      pos.push_back(p++);
+      kv_base.push_back(base);
+    }
     add_tiles(base, p);
   }
 };
@@ -281,6 +292,10 @@ static int run_wave_trunk(cz_model *m, const Wave &w, const uint32_t *ids_dev, c
   kv.k = ws.kpack;
   kv.v = ws.vpack;
   kv.layer_stride = 0;
+  kv.vt = ws.vtpack;
+  kv.vt_layer_stride = 0;
+  kv.ldv = (int)ws.ldv_pack;
+  kv.n_slots = (int)R;
   kv.tile_row0 = ws.tile_row0;
   kv.tile_n = ws.tile_n;
   kv.n_tiles = (int)w.n_tiles();
@@ -362,6 +377,7 @@ static int encode_core(cz_model *m, const uint32_t *ids_dev, const uint32_t *ids
   if (!extra.empty()) CZ_CUDA_TRY(cudaMemcpyAsync(d_extra.p, extra.data(), extra.size() * 4, cudaMemcpyHostToDevice, st));
 
   Wave w;
+  w.tile = m->attn_tile;
   size_t wave_first = 0;  // global coded index of the wave's first logit column
   size_t coded_done = 0;
   double t_wave0 = host_ms();
@@ -484,9 +500,9 @@ static int session_forward(cz_session *s, const uint32_t *tok, size_t n, float *
   std::vector<int> pos(n), base(n, 0), trow, tn;
   for (size_t i = 0; i < n; i++) pos[i] = (int)(s->index_pos + i);
   if (s->index_pos == 0) {
-    for (size_t p = 0; p < n; p += 64) {
+    for (size_t p = 0; p < n; p += (size_t)m->attn_tile) {
       trow.push_back((int)p);
-      tn.push_back((int)std::min<size_t>(64, n - p));
+      tn.push_back((int)std::min<size_t>((size_t)m->attn_tile, n - p));
     }
   } else {  // continuing an existing sequence: one tile per new row (tiles must start at a multiple of 64 or be single rows)
     for (size_t i = 0; i < n; i++) {
@@ -508,9 +524,14 @@ static int session_forward(cz_session *s, const uint32_t *tok, size_t n, float *
   kv.k = s->k;
   kv.v = s->v;
   kv.layer_stride = (size_t)s->max_pos * m->cfg.n_kv_heads * 64;
+  kv.vt = s->v;  // attn_tc: the V arena is [L][kvd][max_pos]
+  kv.vt_layer_stride = kv.layer_stride;
+  kv.ldv = s->max_pos;
+  kv.n_slots = s->max_pos;
   kv.tile_row0 = ws.tile_row0;
   kv.tile_n = ws.tile_n;
   kv.n_tiles = (int)trow.size();
+  kv.single_rows = s->index_pos != 0;  // continuing a sequence: one tile per new row
   CZ_TRY(forward_trunk(m, (int)n, kv, st));
   CZ_TRY(final_norm_gather(m, 1, st));
   CZ_TRY(lm_head(m, 0, 1, s->logits_dev, 4, st));
@@ -533,6 +554,8 @@ int cz_session_new(cz_model *m, cz_session **out) {
   if (m->cfg.arch == CZ_ARCH_SMOLLM) {
     CZ_CUDA_TRY(cudaMalloc((void **)&s->k, L * s->max_pos * kvd * 2));
     CZ_CUDA_TRY(cudaMalloc((void **)&s->v, L * s->max_pos * kvd * 2));
+    CZ_CUDA_TRY(cudaMemset(s->k, 0, L * s->max_pos * kvd * 2));  // unwritten slots must be finite for the masked P V product
+    CZ_CUDA_TRY(cudaMemset(s->v, 0, L * s->max_pos * kvd * 2));
   }
   CZ_CUDA_TRY(cudaMalloc((void **)&s->logits_dev, (size_t)m->cfg.vocab * 16));
   *out = s;
@@ -665,7 +688,16 @@ int cz_decode(cz_model *m, const uint8_t *payload, const uint64_t *seg_off, size
   kv.k = d_k.as<__nv_bfloat16>();
   kv.v = d_v.as<__nv_bfloat16>();
   kv.layer_stride = (size_t)S * max_pos * kvd;
+  if (m->attn_tc) {  // transposed V arena [L][kvd][S*max_pos]; masked / unwritten slots must hold finite values (0 * NaN = NaN in P V)
+    kv.vt = d_v.as<__nv_bfloat16>();
+    kv.vt_layer_stride = (size_t)S * max_pos * kvd;
+    kv.ldv = (int)(S * max_pos);
+    CZ_CUDA_TRY(cudaMemsetAsync(d_v.p, 0, L * S * max_pos * kvd * 2, st));
+    CZ_CUDA_TRY(cudaMemsetAsync(d_k.p, 0, L * S * max_pos * kvd * 2, st));
+  }
+  kv.n_slots = (int)(S * max_pos);
   Wave w;
+  w.tile = m->attn_tile;
   // per-stream constant metadata for the single-token steps
   std::vector<int> kvb(S), lrows(S);
   for (uint32_t g = 0; g < S; g++) {
@@ -724,6 +756,7 @@ int cz_decode(cz_model *m, const uint8_t *payload, const uint64_t *seg_off, size
       kv.tile_row0 = ws.tile_row0;
       kv.tile_n = ws.tile_n;
       kv.n_tiles = (int)w.n_tiles();
+      kv.single_rows = false;
       CZ_TRY(forward_trunk(m, (int)R, kv, st));
       CZ_TRY(final_norm_gather(m, (int)NL, st));
       CZ_TRY(lm_head(m, 0, (int)NL, d_logits.as<float>(), S_pad, st, ws.colmax, &have_max));
@@ -736,6 +769,7 @@ int cz_decode(cz_model *m, const uint8_t *payload, const uint64_t *seg_off, size
     kv.tile_row0 = d_lrows_i;
     kv.tile_n = d_ones_i;
     kv.n_tiles = n_live;
+    kv.single_rows = true;
     CZ_LAUNCH(ctx, CZ_K_OTHER, (czk::set_ctr_kernel<<<1, 1, 0, st>>>(d_ctr, ch.first, ch.prime_len)));
     CZ_CHECK_LAUNCH();
     // one step: decode the symbol of every live stream from its logits column, then feed it back (a single-token
@@ -841,6 +875,7 @@ int cz_xe_bits(cz_model *m, const cz_xe_job *jobs, size_t n_jobs, double *bits_o
   const size_t max_rows = 262144;
   size_t col_first = 0;
   Wave w;
+  w.tile = m->attn_tile;
   auto flush = [&]() -> int {
     if (w.n_rows() == 0) return CZ_OK;
     CZ_TRY(d_src.reserve(w.n_rows() * 8, st));
@@ -886,6 +921,7 @@ int cz_chunk_logits(cz_model *m, const uint32_t *prime, size_t prime_len, const 
   CZ_TRY(d_extra.reserve(extra.size() * 4 + 16, st));
   CZ_CUDA_TRY(cudaMemcpyAsync(d_extra.p, extra.data(), extra.size() * 4, cudaMemcpyHostToDevice, st));
   Wave w;
+  w.tile = m->attn_tile;
   w.add_chunk((uint32_t)prime_len, (uint32_t)n_targets, [&](uint32_t k) { return -2 - (long long)k; },
               [&](uint32_t q) { return -2 - (long long)(prime_len + q); });
   CZ_TRY(d_src.reserve(w.n_rows() * 8, st));

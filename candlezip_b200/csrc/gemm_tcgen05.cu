@@ -208,6 +208,20 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
           }
           __syncwarp();
           const bool is_q = head < rx.nh, is_v = head >= rx.nh + rx.nkv;
+          if (is_v && rx.ldv > 0) {
+            // transposed V for the tcgen05 attention kernel: vt[(kvh*64 + d) * ldv + slot]; this thread holds all 64 dims of
+            // its row, and the 32 rows of a warp are consecutive slots in a teacher-forced wave -> 64-byte coalesced stores
+            if (my_row < M) {
+              __nv_bfloat16 *vt = (__nv_bfloat16 *)rx.v_arena + (size_t)((head - rx.nh - rx.nkv) * 64) * rx.ldv + my_slot;
+#pragma unroll
+              for (int j = 0; j < 32; j++) {
+                vt[(size_t)j * rx.ldv] = __float2bfloat16_rn(pa[lane * 33 + j]);
+                vt[(size_t)(j + 32) * rx.ldv] = __float2bfloat16_rn(pb[lane * 33 + j]);
+              }
+            }
+            __syncwarp();
+            continue;
+          }
 #pragma unroll
           for (int i = 0; i < 8; i++) {
             const int rr = i * 4 + rr0;
@@ -423,7 +437,7 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 // 2D bf16 [rows][K] row-major, box = 64 x box_rows, 128-byte swizzle, OOB rows read as zero
-static int make_map(CUtensorMap *map, const void *ptr, int rows, int K, int ld_elems, int box_rows) {
+int make_map_bf16(CUtensorMap *map, const void *ptr, int rows, int K, int ld_elems, int box_rows) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) {
     set_error("cuTensorMapEncodeTiled entry point not available");
@@ -506,8 +520,8 @@ int gemm_tcgen05(cz_ctx *ctx, const GemmArgs &g, cudaStream_t stream) {
     return CZ_ERR_INVALID;
   }
   CUtensorMap ta, tb, tc;
-  CZ_TRY(make_map(&ta, g.a, g.M, g.K, g.lda, czk::BM));
-  CZ_TRY(make_map(&tb, g.b, g.N, g.K, g.ldb, g.bn));
+  CZ_TRY(make_map_bf16(&ta, g.a, g.M, g.K, g.lda, czk::BM));
+  CZ_TRY(make_map_bf16(&tb, g.b, g.N, g.K, g.ldb, g.bn));
   if (g.epi == EPI_ADD_F32 || g.epi == EPI_STORE_F32 || g.epi == EPI_STORE_F32_COLMAX) CZ_TRY(make_map_c(&tc, g.c, g.M, g.N, g.ldc));
   else tc = ta;  // unused by the other epilogues
 #define CZ_TC_CASE(BN_, EPI_) \

@@ -15,4 +15,7 @@ int launch_attn_rows(cz_ctx *ctx, const __nv_bfloat16 *q, const __nv_bfloat16 *k
 int launch_attn_mma(cz_ctx *ctx, const __nv_bfloat16 *q, const __nv_bfloat16 *k_arena, const __nv_bfloat16 *v_arena, const int *pos,
                     const int *kv_base, const int *tile_row0, const int *tile_n, int n_tiles, __nv_bfloat16 *out, int nh, int nkv,
                     cudaStream_t st);
+int launch_attn_tc(cz_ctx *ctx, const __nv_bfloat16 *q, int n_rows, const __nv_bfloat16 *k_arena, const __nv_bfloat16 *vt_arena, int n_slots,
+                   int ldv, const int *pos, const int *kv_base, const int *tile_row0, const int *tile_n, int n_tiles, __nv_bfloat16 *out,
+                   int nh, int nkv, bool single_rows, cudaStream_t st);
 }  // namespace cz

@@ -24,6 +24,8 @@ struct Workspace {
   __nv_bfloat16 *act = nullptr;       // [rows][F]
   __nv_bfloat16 *kpack = nullptr;     // packed-mode (teacher-forced) K rows of the current layer [rows][kvd]
   __nv_bfloat16 *vpack = nullptr;
+  __nv_bfloat16 *vtpack = nullptr;    // attn_tc: transposed packed V [kvd][ldv_pack]
+  size_t ldv_pack = 0;
   uint32_t *tok = nullptr;            // row metadata
   int *pos = nullptr;
   int *kv_base = nullptr;
@@ -110,6 +112,8 @@ struct cz_model {
   float *cos_tab = nullptr, *sin_tab = nullptr;  // [rope_max_pos][32]
   int rope_max_pos = 2048;
   int gu_bn = 192;
+  bool attn_tc = false;  // tcgen05 attention kernel (attn_tc.cu) with transposed V; else the mma.sync kernel (attn_mma.cu)
+  int attn_tile = 64;    // query positions per attention tile (128 with attn_tc)
   Workspace ws;
 };
 
@@ -128,6 +132,12 @@ struct KvView {
   // starting at a position that is a multiple of 64 (or a single decode row)
   const int *tile_row0 = nullptr, *tile_n = nullptr;
   int n_tiles = 0;
+  // tcgen05 attention (model->attn_tc): V is kept transposed, element (layer l, kv dim d, slot s) at vt + l*vt_layer_stride + d*ldv + s
+  __nv_bfloat16 *vt = nullptr;
+  size_t vt_layer_stride = 0;  // elements
+  int ldv = 0;                 // multiple of 8
+  int n_slots = 0;             // valid slots of the arena (rows of k / columns of vt)
+  bool single_rows = false;    // every tile is a single position (stepwise decode)
 };
 
 // embedding + all layers over n_rows rows whose metadata (tok/pos/kv_base) is already in m->ws; leaves the residual in ws.x

@@ -132,6 +132,8 @@ int ensure_workspace(cz_model *m, size_t rows, size_t n_logit, size_t n_tiles) {
     CZ_TRY(realloc_dev(w.act, r * F));
     CZ_TRY(realloc_dev(w.kpack, r * kvd));
     CZ_TRY(realloc_dev(w.vpack, r * kvd));
+    w.ldv_pack = (r + 7) & ~(size_t)7;
+    CZ_TRY(realloc_dev(w.vtpack, m->attn_tc ? kvd * w.ldv_pack : 0));
     CZ_TRY(realloc_dev(w.pos, r));
     CZ_TRY(realloc_dev(w.kv_base, r));
     w.cap_rows = r;
@@ -249,6 +251,8 @@ int model_finalize(cz_model *m) {
   CZ_CUDA_TRY(cudaMemcpy(m->norms, norms.data(), norms.size() * 4, cudaMemcpyHostToDevice));
   m->embed = dev("model.embed_tokens.weight");
   m->head_w = m->embed;  // tied
+  m->attn_tc = c.engine == CZ_ENGINE_TCGEN05 && getenv("CZ_ATTN_MMA") == nullptr && getenv("CZ_DEBUG_NO_FUSED_ROPE") == nullptr;
+  m->attn_tile = m->attn_tc ? 128 : 64;
   // RoPE tables, same formulas as the oracle (f32 inv_freq, f32 angle, libm cosf/sinf)
   std::vector<float> ct((size_t)m->rope_max_pos * 32), stab((size_t)m->rope_max_pos * 32);
   for (int j = 0; j < 32; j++) {
@@ -286,7 +290,13 @@ int forward_trunk(cz_model *m, int n_rows, const KvView &kv, cudaStream_t st) {
       g.epi = EPI_QKV_ROPE;
       g.c = nullptr;
       g.rope.pos = w.pos; g.rope.kv_base = w.kv_base; g.rope.cos_tab = m->cos_tab; g.rope.sin_tab = m->sin_tab;
-      g.rope.q = w.q; g.rope.k_arena = kl; g.rope.v_arena = vl; g.rope.nh = nh; g.rope.nkv = nkv;
+      g.rope.q = w.q; g.rope.k_arena = kl; g.rope.nh = nh; g.rope.nkv = nkv;
+      if (m->attn_tc) {
+        g.rope.v_arena = kv.vt + (size_t)l * kv.vt_layer_stride;
+        g.rope.ldv = kv.ldv;
+      } else {
+        g.rope.v_arena = vl;
+      }
       CZ_TRY(gemm(ctx, c.engine, g, st));
       g.rope = RopeExt();
     } else {
@@ -294,7 +304,10 @@ int forward_trunk(cz_model *m, int n_rows, const KvView &kv, cudaStream_t st) {
       CZ_TRY(launch_rope_split(ctx, w.qkv, w.pos, w.kv_base, m->cos_tab, m->sin_tab, w.q, kl, vl, n_rows, nh, nkv, st));
     }
     static const bool force_rows = getenv("CZ_DEBUG_ATTN_ROWS") != nullptr;  // bisecting aid
-    if (c.engine == CZ_ENGINE_TCGEN05 && !force_rows)
+    if (m->attn_tc)
+      CZ_TRY(launch_attn_tc(ctx, w.q, n_rows, kl, kv.vt + (size_t)l * kv.vt_layer_stride, kv.n_slots, kv.ldv, w.pos, w.kv_base, kv.tile_row0,
+                            kv.tile_n, kv.n_tiles, w.attn, nh, nkv, kv.single_rows, st));
+    else if (c.engine == CZ_ENGINE_TCGEN05 && !force_rows)
       CZ_TRY(launch_attn_mma(ctx, w.q, kl, vl, w.pos, w.kv_base, kv.tile_row0, kv.tile_n, kv.n_tiles, w.attn, nh, nkv, st));
     else
       CZ_TRY(launch_attn_rows(ctx, w.q, kl, vl, w.pos, w.kv_base, w.attn, n_rows, nh, nkv, st));
@@ -452,7 +465,7 @@ void cz_model_free(cz_model *m) {
     for (auto &b : m->sb)
       if (b.p) cudaFree(b.p);
     void *ptrs[] = {m->w_qkv, m->w_o, m->w_gu, m->w_d, m->norms, m->cos_tab, m->sin_tab, m->ws.x, m->ws.xn, m->ws.qkv, m->ws.q,
-                    m->ws.attn, m->ws.act, m->ws.kpack, m->ws.vpack, m->ws.tok, m->ws.pos, m->ws.kv_base, m->ws.logit_rows,
+                    m->ws.attn, m->ws.act, m->ws.kpack, m->ws.vpack, m->ws.vtpack, m->ws.tok, m->ws.pos, m->ws.kv_base, m->ws.logit_rows,
                     m->ws.syms, m->ws.out_index, m->ws.tile_row0, m->ws.tile_n, m->ws.xn_logit, m->ws.lo_tmp, m->ws.hi_tmp, m->ws.xe_tmp, m->ws.colmax, m->ws.logits[0],
                     m->ws.logits[1]};
     for (void *p : ptrs)
