@@ -38,19 +38,27 @@ using cz::RopeExt;
 constexpr int BM = 128;
 constexpr int BK = 64;  // bf16 elements: 128 bytes = one swizzle row
 constexpr int UMMA_K = 16;
-constexpr int GEMM_THREADS = 192;
 
 template <int BN, int EPI = 0>
 struct GemmCfg {
-  static constexpr int kStages = (BN <= 192 && EPI != cz::EPI_QKV_ROPE) ? 5 : 4;  // the RoPE epilogue stages two patches per warp
+  // Epilogues that do real math per element (SwiGLU, RoPE, tanh / sigmoid / relu^2) are latency-bound on four warps (gate-up ran the
+  // tensor pipe at 53%, profiles/ncu_summary_r01.md): they get EIGHT epilogue warps, two per TMEM lane quadrant, each taking every
+  // other 32-column chunk.  The store-only epilogues (TMA store / reduce-add) keep four warps and the deeper operand pipeline.
+  static constexpr bool kHeavy = EPI == cz::EPI_SWIGLU_BF16 || EPI == cz::EPI_QKV_ROPE || EPI == cz::EPI_STORE_BF16 ||
+                                 EPI == cz::EPI_TANH_BF16 || EPI == cz::EPI_SIGMOID_BF16 || EPI == cz::EPI_RELUSQ_BF16;
+  static constexpr int kEpiWarps = kHeavy ? 8 : 4;
+  static constexpr int kThreads = 64 + 32 * kEpiWarps;
+  static constexpr int kStages = (BN <= 192 && (!kHeavy || EPI == cz::EPI_QKV_ROPE)) ? 5 : 4;  // RoPE stages nothing in smem
   static constexpr int kABytes = BM * BK * 2;
   static constexpr int kBBytes = BN * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kTmemCols = 512;  // 2 accumulator stages of BN columns, power of two >= 2*BN
-  static constexpr int kPatchBytes = EPI == cz::EPI_QKV_ROPE ? 9216 : 5120;  // per epilogue warp: a padded 32x33 f32 transpose patch (4224 B) or a dense 4 KB
-                                            // SWIZZLE_128B TMA box (reduce-add epilogue); 1024-aligned for the swizzle
+  // per epilogue warp: a padded 32x33 f32 transpose patch (4224 B), two of them for the RoPE epilogue, or a dense 4 KB
+  // SWIZZLE_128B TMA box (1024-aligned) for the f32 store / reduce-add epilogues
+  static constexpr int kPatchBytes = EPI == cz::EPI_QKV_ROPE ? 0 : (kHeavy ? 4224 : 5120);
   static constexpr int kStagingOff = kStages * kStageBytes + 1024;  // the barriers live in the 1 KB before it
-  static constexpr int kSmemBytes = kStagingOff + 4 * kPatchBytes + 1024 /*align slack*/;
+  static constexpr int kSmemBytes = kStagingOff + kEpiWarps * kPatchBytes + 1024 /*align slack*/;
+  static_assert(kSmemBytes <= 232448, "shared memory budget");
 };
 
 // Instruction descriptor, kind::f16 (cute::UMMA::InstrDescriptor): D=F32, A=B=BF16, both K-major, M=128, N=BN.
@@ -62,7 +70,7 @@ __device__ __forceinline__ constexpr uint32_t make_idesc() {
 __device__ __forceinline__ float silu_mul(float g, float u) { return __fdividef(g, 1.0f + __expf(-g)) * u; }
 
 template <int BN, int EPI>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __launch_bounds__((GemmCfg<BN, EPI>::kThreads), 1)
     gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                    const __grid_constant__ CUtensorMap tm_c, void *__restrict__ c_ptr,
                    int M, int N, int K, int ldc, int *__restrict__ aux, const __grid_constant__ RopeExt rx) {
@@ -94,7 +102,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     }
     for (int s = 0; s < 2; s++) {
       mbar_init(smem_u32(&tfull_bar[s]), 1);
-      mbar_init(smem_u32(&tempty_bar[s]), 4);  // one arrival per epilogue warp
+      mbar_init(smem_u32(&tempty_bar[s]), Cfg::kEpiWarps);  // one arrival per epilogue warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -167,6 +175,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     // instruction (32 LSU wavefronts for 512 bytes).  Each warp therefore transposes its 32x32 sub-tile through a private
     // padded shared-memory patch so that a store instruction covers 4 rows x 128 contiguous bytes.
     const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    constexpr int kColSplit = Cfg::kEpiWarps / 4;  // warps sharing a quadrant take interleaved column chunks
+    const int half = (warp - 2) >> 2;
     uint8_t *patch = smem + Cfg::kStagingOff + (warp - 2) * Cfg::kPatchBytes;
     float *stg = reinterpret_cast<float *>(patch);
     const int rr0 = lane >> 3, cc = (lane & 7) * 4;
@@ -185,71 +195,71 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       const int n_out = kSwiglu ? N / 2 : N;  // output columns
       constexpr bool kTmaF32 = EPI == EPI_ADD_F32 || EPI == EPI_STORE_F32 || EPI == EPI_STORE_F32_COLMAX;
       if constexpr (EPI == EPI_QKV_ROPE) {
-        // The tile is three whole heads (BN = 192).  Per head: both 32-column halves go to two padded patches, then every
-        // lane rotates 4 (j, j+32) pairs of 8 rows (rotate-half RoPE in fp32 on the accumulators, like the reference's
-        // f32 path) and stores bf16: q rows, or the K / V arena rows at slot kv_base[row] + pos[row].
-        float *pa = stg, *pb = stg + 32 * 33;
+        // The tile is three whole heads (BN = 192).  tcgen05.ld hands every lane one ROW, i.e. one position: the thread loads
+        // that position's cos / sin once per tile and rotates in registers (rotate-half RoPE in fp32 on the accumulators,
+        // like the reference's f32 path).  The two warps of a TMEM lane quadrant split the 32 rotation pairs (j, j + 32) of a
+        // head in halves.  Stores go straight from registers: bf16 q rows, K arena rows at slot kv_base[row] + pos[row], and V
+        // either as arena rows or TRANSPOSED (vt[dim][slot], tcgen05 attention), where a warp's 32 rows are 32 consecutive
+        // slots of a teacher-forced wave = one 64-byte line per dim.
         const int my_row = row_base + lane;
-        const int my_pos = my_row < M ? rx.pos[my_row] : 0;
-        const int my_slot = my_row < M ? rx.kv_base[my_row] + my_pos : 0;
+        const bool ok = my_row < M;
+        const int my_pos = ok ? rx.pos[my_row] : 0;
+        const size_t my_slot = ok ? (size_t)rx.kv_base[my_row] + (size_t)my_pos : 0;
         const int dq = rx.nh * 64, dkv = rx.nkv * 64;
+        const int j0 = half * 16;
+        float cs[16], sn[16];
+        {
+          const float4 *c4 = reinterpret_cast<const float4 *>(rx.cos_tab + (size_t)my_pos * 32 + j0);
+          const float4 *s4 = reinterpret_cast<const float4 *>(rx.sin_tab + (size_t)my_pos * 32 + j0);
+#pragma unroll
+          for (int q = 0; q < 4; q++) {
+            const float4 c = c4[q], sv = s4[q];
+            cs[4 * q] = c.x; cs[4 * q + 1] = c.y; cs[4 * q + 2] = c.z; cs[4 * q + 3] = c.w;
+            sn[4 * q] = sv.x; sn[4 * q + 1] = sv.y; sn[4 * q + 2] = sv.z; sn[4 * q + 3] = sv.w;
+          }
+        }
 #pragma unroll 1
         for (int hh = 0; hh < BN / 64; hh++) {
           const int head = n_blk * (BN / 64) + hh;  // 0..nh-1 q heads, then nkv k heads, then nkv v heads
           if (head >= rx.nh + 2 * rx.nkv) break;
-          uint32_t ra[32], rb[32];
-          tc_ld_32x32(t_row + (uint32_t)(hh * 64), ra);
-          tc_ld_32x32(t_row + (uint32_t)(hh * 64 + 32), rb);
+          uint32_t ra[16], rb[16];
+          tc_ld_32x16(t_row + (uint32_t)(hh * 64 + j0), ra);
+          tc_ld_32x16(t_row + (uint32_t)(hh * 64 + 32 + j0), rb);
           tc_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 32; j++) {
-            pa[lane * 33 + j] = __uint_as_float(ra[j]);
-            pb[lane * 33 + j] = __uint_as_float(rb[j]);
-          }
-          __syncwarp();
+          if (!ok) continue;
           const bool is_q = head < rx.nh, is_v = head >= rx.nh + rx.nkv;
           if (is_v && rx.ldv > 0) {
-            // transposed V for the tcgen05 attention kernel: vt[(kvh*64 + d) * ldv + slot]; this thread holds all 64 dims of
-            // its row, and the 32 rows of a warp are consecutive slots in a teacher-forced wave -> 64-byte coalesced stores
-            if (my_row < M) {
-              __nv_bfloat16 *vt = (__nv_bfloat16 *)rx.v_arena + (size_t)((head - rx.nh - rx.nkv) * 64) * rx.ldv + my_slot;
+            __nv_bfloat16 *vt = (__nv_bfloat16 *)rx.v_arena + (size_t)((head - rx.nh - rx.nkv) * 64 + j0) * rx.ldv + my_slot;
 #pragma unroll
-              for (int j = 0; j < 32; j++) {
-                vt[(size_t)j * rx.ldv] = __float2bfloat16_rn(pa[lane * 33 + j]);
-                vt[(size_t)(j + 32) * rx.ldv] = __float2bfloat16_rn(pb[lane * 33 + j]);
-              }
+            for (int j = 0; j < 16; j++) {
+              vt[(size_t)j * rx.ldv] = __float2bfloat16_rn(__uint_as_float(ra[j]));
+              vt[(size_t)(j + 32) * rx.ldv] = __float2bfloat16_rn(__uint_as_float(rb[j]));
             }
-            __syncwarp();
             continue;
           }
+          uint32_t wa[8], wb[8];
 #pragma unroll
-          for (int i = 0; i < 8; i++) {
-            const int rr = i * 4 + rr0;
-            const int grow = row_base + rr;
-            const int p = __shfl_sync(0xffffffffu, my_pos, rr), slot = __shfl_sync(0xffffffffu, my_slot, rr);
-            if (grow >= M) continue;
-            const float *sa = pa + rr * 33 + cc, *sb = pb + rr * 33 + cc;
-            float a[4] = {sa[0], sa[1], sa[2], sa[3]}, b[4] = {sb[0], sb[1], sb[2], sb[3]};
+          for (int j = 0; j < 16; j += 2) {
+            float a0 = __uint_as_float(ra[j]), a1 = __uint_as_float(ra[j + 1]), b0 = __uint_as_float(rb[j]), b1 = __uint_as_float(rb[j + 1]);
             if (!is_v) {
-              const float4 c4 = *reinterpret_cast<const float4 *>(rx.cos_tab + (size_t)p * 32 + cc);
-              const float4 s4 = *reinterpret_cast<const float4 *>(rx.sin_tab + (size_t)p * 32 + cc);
-              const float cs[4] = {c4.x, c4.y, c4.z, c4.w}, sn[4] = {s4.x, s4.y, s4.z, s4.w};
-#pragma unroll
-              for (int e = 0; e < 4; e++) {
-                const float x = a[e], y = b[e];
-                a[e] = x * cs[e] - y * sn[e];
-                b[e] = y * cs[e] + x * sn[e];
-              }
+              const float x0 = a0, y0 = b0, x1 = a1, y1 = b1;
+              a0 = x0 * cs[j] - y0 * sn[j];
+              b0 = y0 * cs[j] + x0 * sn[j];
+              a1 = x1 * cs[j + 1] - y1 * sn[j + 1];
+              b1 = y1 * cs[j + 1] + x1 * sn[j + 1];
             }
-            __nv_bfloat16 *dst = is_q ? (__nv_bfloat16 *)rx.q + (size_t)grow * dq + head * 64
-                                      : (is_v ? (__nv_bfloat16 *)rx.v_arena + (size_t)slot * dkv + (head - rx.nh - rx.nkv) * 64
-                                              : (__nv_bfloat16 *)rx.k_arena + (size_t)slot * dkv + (head - rx.nh) * 64);
-            __nv_bfloat162 h0 = __floats2bfloat162_rn(a[0], a[1]), h1 = __floats2bfloat162_rn(a[2], a[3]);
-            __nv_bfloat162 h2 = __floats2bfloat162_rn(b[0], b[1]), h3 = __floats2bfloat162_rn(b[2], b[3]);
-            *reinterpret_cast<uint2 *>(dst + cc) = make_uint2(*reinterpret_cast<uint32_t *>(&h0), *reinterpret_cast<uint32_t *>(&h1));
-            *reinterpret_cast<uint2 *>(dst + 32 + cc) = make_uint2(*reinterpret_cast<uint32_t *>(&h2), *reinterpret_cast<uint32_t *>(&h3));
+            __nv_bfloat162 ha = __floats2bfloat162_rn(a0, a1), hb = __floats2bfloat162_rn(b0, b1);
+            wa[j >> 1] = *reinterpret_cast<uint32_t *>(&ha);
+            wb[j >> 1] = *reinterpret_cast<uint32_t *>(&hb);
           }
-          __syncwarp();
+          __nv_bfloat16 *dst = is_q ? (__nv_bfloat16 *)rx.q + (size_t)my_row * dq + head * 64
+                                    : (is_v ? (__nv_bfloat16 *)rx.v_arena + my_slot * dkv + (head - rx.nh - rx.nkv) * 64
+                                            : (__nv_bfloat16 *)rx.k_arena + my_slot * dkv + (head - rx.nh) * 64);
+          uint4 *da = reinterpret_cast<uint4 *>(dst + j0), *db = reinterpret_cast<uint4 *>(dst + 32 + j0);
+          da[0] = make_uint4(wa[0], wa[1], wa[2], wa[3]);
+          da[1] = make_uint4(wa[4], wa[5], wa[6], wa[7]);
+          db[0] = make_uint4(wb[0], wb[1], wb[2], wb[3]);
+          db[1] = make_uint4(wb[4], wb[5], wb[6], wb[7]);
         }
         tc_fence_before();
         __syncwarp();
@@ -262,7 +272,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         // f32 add, so the result is deterministic.
         const uint32_t patch_u32 = smem_u32(patch);
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; c++) {
+        for (int c = half; c < BN / 32; c += kColSplit) {
           const int col0 = n_blk * BN + c * 32;
           if (col0 >= N) break;
           uint32_t r[32];
@@ -312,7 +322,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         continue;
       } else {
 #pragma unroll 1
-      for (int c = 0; c < kChunks; c++) {
+      for (int c = half; c < kChunks; c += kColSplit) {
         uint32_t r[32];
         int col0;
         if (kSwiglu) {
@@ -489,7 +499,7 @@ static int launch_tc(cz_ctx *ctx, const CUtensorMap &ta, const CUtensorMap &tb, 
   const int tiles = (int)(ceil_div(M, czk::BM) * ceil_div(N, BN));
   const int grid = tiles < ctx->sm_count ? tiles : ctx->sm_count;
   CZ_LAUNCH(ctx, g_fam,
-            (czk::gemm_tc_kernel<BN, EPI><<<grid, czk::GEMM_THREADS, Cfg::kSmemBytes, stream>>>(ta, tb, tc, c, M, N, K, ldc, aux, rx)));
+            (czk::gemm_tc_kernel<BN, EPI><<<grid, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(ta, tb, tc, c, M, N, K, ldc, aux, rx)));
   CZ_CHECK_LAUNCH();
   return CZ_OK;
 }
@@ -538,6 +548,7 @@ int gemm_tcgen05(cz_ctx *ctx, const GemmArgs &g, cudaStream_t stream) {
   CZ_TC_CASE(256, EPI_RELUSQ_BF16);
   CZ_TC_CASE(256, EPI_ADD_F32);
   CZ_TC_CASE(192, EPI_QKV_ROPE);
+  CZ_TC_CASE(256, EPI_SWIGLU_BF16);
 #undef CZ_TC_CASE
   set_error("gemm_tcgen05: unsupported (BN, epilogue) combination");
   return CZ_ERR_UNSUPPORTED;

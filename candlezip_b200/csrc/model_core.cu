@@ -205,14 +205,11 @@ int model_finalize(cz_model *m) {
     set_error("unsupported SmolLM shape (need head_dim 64, d_model/d_ffn multiples of 64, GQA group <= 4)");
     return CZ_ERR_UNSUPPORTED;
   }
-  if (F % 96 == 0) m->gu_bn = 192;
-  else if (F % 128 == 0) m->gu_bn = 256;
+  // gate/up tile width: 256 (two 64-column chunk pairs per epilogue warp) when d_ffn allows it, else 192
+  if (F % 128 == 0) m->gu_bn = 256;
+  else if (F % 96 == 0) m->gu_bn = 192;
   else {
     set_error("d_ffn must be a multiple of 96 or 128");
-    return CZ_ERR_UNSUPPORTED;
-  }
-  if (m->gu_bn == 256 && c.engine == CZ_ENGINE_TCGEN05) {
-    set_error("tcgen05 swiglu epilogue is instantiated for d_ffn % 96 == 0 only");
     return CZ_ERR_UNSUPPORTED;
   }
   CZ_CUDA_TRY(cudaSetDevice(m->ctx->device));
