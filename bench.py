@@ -270,10 +270,14 @@ def run_ours(args):
         ids_r = synth_tokens(nr, 7 + rank)
         rmodel.encode(ids_r, n_segments=args.rwkv_segments)  # warm-up at full size (grow-only buffers, function attributes)
         barrier()
+        ctx.profile(2)
+        ctx.profile_read(reset=True)
         t0 = time.perf_counter()
         pays_r, seg_r = rmodel.encode(ids_r, n_segments=args.rwkv_segments)
         barrier()
         enc_s = time.perf_counter() - t0
+        rfam = ctx.profile_read(reset=True)
+        ctx.profile(0)
         nd = min(nr, args.rwkv_decode_tokens)
         pays_d, seg_d = rmodel.encode(ids_r[:nd], n_segments=args.rwkv_decode_segments)
         barrier()
@@ -288,6 +292,8 @@ def run_ours(args):
                 "encode_tokens": nr, "encode_segments": args.rwkv_segments,
                 "decode_MB_per_s": world * nd / float(tt[1].item()) / 1e6, "decode_tokens": nd, "decode_segments": args.rwkv_decode_segments,
                 "roundtrip_ok": bool(np.array_equal(out_r, ids_r[:nd])), "compressed_bytes": int(sum(len(p) for p in pays_r)),
+                "encode_kernel_ms": {k: round(v[0], 2) for k, v in rfam.items()},
+                "encode_kernel_launches": {k: v[1] for k, v in rfam.items()},
                 "timing": "wall clock around cz_encode / cz_decode (host buffers in and out)"}
         rmodel.close()
 
@@ -341,7 +347,7 @@ def main():
     ap.add_argument("--ref-chunk", type=int, default=256, help="coded tokens per CPU-reference sample chunk (512 = the full reprime chunk)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--rwkv-tokens", type=int, default=131072, help="RWKV-7 extra figures (0 = skip)")
-    ap.add_argument("--rwkv-segments", type=int, default=64)
+    ap.add_argument("--rwkv-segments", type=int, default=256)
     ap.add_argument("--rwkv-decode-tokens", type=int, default=65536)
     ap.add_argument("--rwkv-decode-segments", type=int, default=1024)
     args = ap.parse_args()
