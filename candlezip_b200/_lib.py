@@ -41,7 +41,7 @@ class ModelConfig(C.Structure):
 
 
 class PrimeEvent(C.Structure):
-    _fields_ = [("i", C.c_uint64), ("prime", u32p), ("prime_len", C.c_uint32), ("hold_until", C.c_uint64)]
+    _fields_ = [("i", C.c_uint64), ("prime", u32p), ("prime_len", C.c_uint32), ("hold_until", C.c_uint64), ("hist_take", C.c_uint32)]
 
 
 class Schedule(C.Structure):

@@ -231,10 +231,11 @@ class Model:
         keep = [seg]
         if events:
             arr = (_lib.PrimeEvent * len(events))()
-            for k, (i, prime, hold) in enumerate(events):
+            for k, ev in enumerate(events):  # (i, explicit prime tokens, hold_until[, hist_take])
+                i, prime, hold = ev[:3]
                 a, p = _u32(prime)
                 keep.append(a)
-                arr[k] = _lib.PrimeEvent(i, p, a.shape[0], hold)
+                arr[k] = _lib.PrimeEvent(i, p, a.shape[0], hold, ev[3] if len(ev) > 3 else 0)
             s.events = arr
             s.n_events = len(events)
             keep.append(arr)

@@ -412,8 +412,16 @@ static int encode_core(cz_model *m, const uint32_t *ids_dev, const uint32_t *ids
       if (w.n_rows() + rows > max_rows && w.n_rows() > 0) CZ_TRY(flush());
       // S[k] = k == 0 ? bos : ids[t0 + k - 1];  coded token j of the chunk = ids[t0 + first + j]
       if (c.event >= 0) {
+        // prime = tail(S[..=i], hist) ++ explicit tokens, S[0] = BOS, S[k] = ids[t0 + k - 1]
         const long long e0 = (long long)ev_off[c.event];
-        w.add_chunk(c.prime_len, c.n_coded, [&](uint32_t k) { return (long long)(-2 - (e0 + k)); },
+        const uint32_t hist = c.prime_len - sched->events[c.event].prime_len;
+        const uint64_t s0 = c.first + 1 - hist;
+        w.add_chunk(c.prime_len, c.n_coded,
+                    [&](uint32_t k) {
+                      if (k >= hist) return (long long)(-2 - (e0 + (k - hist)));
+                      const uint64_t si = s0 + k;
+                      return si == 0 ? -1ll : (long long)(t0 + si - 1);
+                    },
                     [&](uint32_t j) { return (long long)(t0 + c.first + j); });
       } else {
         w.add_chunk(c.prime_len, c.n_coded,
@@ -735,8 +743,14 @@ int cz_decode(cz_model *m, const uint8_t *payload, const uint64_t *seg_off, size
       const int r0 = (int)w.src.size();
       for (uint32_t k = 0; k < ch.prime_len; k++) {
         const uint64_t si = ch.prime_start + k;
-        if (ch.event >= 0) w.src.push_back(-2 - (long long)(ev_off[ch.event] + k));
-        else w.src.push_back(si == 0 ? -1ll : (long long)(t0 + si - 1));
+        if (ch.event >= 0) {  // tail of what this stream has decoded so far, then the explicit hint tokens
+          const uint32_t hist = ch.prime_len - sched->events[ch.event].prime_len;
+          const uint64_t sh = ch.first + 1 - hist + k;
+          if (k >= hist) w.src.push_back(-2 - (long long)(ev_off[ch.event] + (k - hist)));
+          else w.src.push_back(sh == 0 ? -1ll : (long long)(t0 + sh - 1));
+        } else {
+          w.src.push_back(si == 0 ? -1ll : (long long)(t0 + si - 1));
+        }
         w.pos.push_back((int)k);
         w.kv_base.push_back(base);
       }

@@ -269,6 +269,14 @@ int rwkv_encode_bounds(cz_model *m, const uint32_t *ids_dev, const uint32_t *ids
       while (ev < sched->n_events && a + sched->events[ev].i < cur) ev++;
       if (ev < sched->n_events && a + sched->events[ev].i == cur) {
         first.clear();
+        {  // tail of the in-vocabulary history (literals filtered out, main.rs:2139-2141), then the explicit hint tokens
+          std::vector<long long> hist;
+          const uint64_t want = sched->events[ev].hist_take;
+          for (uint64_t t = cur; t > a && hist.size() < want; t--)
+            if (ids_host[t - 1] < V) hist.push_back((long long)(t - 1));
+          if (hist.size() < want) hist.push_back(-1ll);  // BOS is S[0]
+          first.assign(hist.rbegin(), hist.rend());
+        }
         for (uint32_t k = 0; k < sched->events[ev].prime_len; k++)
           if (sched->events[ev].prime[k] < V) first.push_back(-2 - (long long)(ev_off[ev] + k));
         if (first.empty()) {
@@ -478,6 +486,11 @@ int rwkv_decode(cz_model *m, const uint8_t *payload, const uint64_t *seg_off, si
     CZ_TRY(launch_advance_ctr(ctx, d_ctr, st));
     return CZ_OK;
   };
+  for (uint32_t e = 0; e < sched->n_events; e++)
+    if (sched->events[e].hist_take) {
+      set_error("rwkv decode: hint primes with a history tail (hist_take > 0) need the decoded tokens on the host; pass explicit primes");
+      return CZ_ERR_UNSUPPORTED;
+    }
   // units: [0, e_0), [e_0, e_1), ... ; each starts from a fresh state primed with BOS / the event's prime (events: S == 1)
   std::vector<uint64_t> cut{0};
   for (uint32_t e = 0; e < sched->n_events; e++)

@@ -36,7 +36,7 @@ void build_chunks(uint64_t n_tokens, uint32_t context, uint32_t reprime_interval
     if (ev < n_events && events[ev].i == i) {  // src/main.rs:1981, 2137/2146
       nc.first = i;
       nc.prime_start = 0;
-      nc.prime_len = events[ev].prime_len;
+      nc.prime_len = events[ev].prime_len + (uint32_t)std::min<uint64_t>(events[ev].hist_take, i + 1);  // history tail ++ explicit tokens
       nc.event = (int)ev;
       hold_until = events[ev].hold_until;
       ev++;

@@ -161,9 +161,12 @@ int cz_session_reprime(cz_session *s, const uint32_t *history, size_t n, float *
 /* ---------------------------------------------------------------- batched hot path */
 typedef struct {
   uint64_t i;                /* loop index at which the prime is applied (i + 1 == agent boundary) */
-  const uint32_t *prime;     /* history tail ++ hint[..budget] (src/main.rs:2123-2146) */
+  const uint32_t *prime;     /* explicit tokens fed after the history tail: hint[..budget] (src/main.rs:2123-2146) */
   uint32_t prime_len;
   uint64_t hold_until;       /* src/main.rs:2149 */
+  uint32_t hist_take;        /* tokens taken from the stream itself before `prime`: tail(ids[..=i], hist_take) with ids[0] = BOS
+                                (src/main.rs:2132-2134, 2596-2600).  The decoder rebuilds this part from what it has decoded, so a
+                                gated stream decodes in one call.  0: `prime` is the whole prime (SmolLM only when > 0). */
 } cz_prime_event;
 
 typedef struct {

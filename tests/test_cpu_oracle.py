@@ -409,3 +409,41 @@ def test_oracle_rwkv7_roundtrip_with_literal_escapes():
     assert np.array_equal(out, ids)
     # a literal costs about -log2(2^-29) = 29 bits
     assert 8 * len(payload) > 29 * int(lit.sum())
+
+
+# ------------------------------------------------------------------ agentic gate host logic
+def test_gate_candidates_budgets_and_selection():
+    from candlezip_b200 import gate
+
+    c = gate.build_candidates("Alice met Bob\tin 1865.\nThe Rabbit ran")
+    assert c[0] == "Alice met Bob in 1865. The Rabbit ran"       # control characters -> spaces (main.rs:2019)
+    assert c[1] == c[0] and c[2] == c[0]                          # < 2000 bytes; the single line contains a digit
+    assert c[3] == "Alice Bob The Rabbit"                         # Capitalised words (main.rs:2026-2030)
+    assert gate.build_candidates("no digits here")[2] == ""
+    assert len(gate.build_candidates("x" * 3000)[1]) == 2000
+    assert gate.budgets(511) == [63, 127, 255, 383]               # main.rs:2034-2035
+
+    ids = np.arange(1, 1301, dtype=np.uint32) % 250
+    texts = {1: "Hint One 42", 2: ""}
+    tok = lambda s, m: [ord(ch) for ch in s][:m]
+    jobs, plan = gate.plan_scan(ids, texts, tok, agent_chunk=512, scan_lookahead=512)
+    assert [e["i"] for e in plan] == [511, 1023] and plan[0]["chunk_index"] == 1
+    # boundary 1: baseline + 16 conditioned; boundary 2: empty hint -> all conditioned slots reuse the baseline
+    assert plan[0]["job0"] == 0 and all(s is not None for s in plan[0]["slots"]) and plan[1]["slots"] == [None] * 16
+    prime, targets = jobs[0]
+    assert len(prime) == 511 and prime[0] == 0 and len(targets) == 512 and targets[0] == ids[510]   # seq[0] = BOS
+    assert list(jobs[1][0][-11:]) == [ord(ch) for ch in "Hint One 42"] and len(jobs[1][0]) == 511
+    bits = np.full(len(jobs), 1000.0)
+    bits[plan[0]["slots"][2 * 4 + 1]] = 900.0   # cand 2 / budget 1 saves the most
+    bits[plan[0]["slots"][3 * 4 + 3]] = 950.0
+    rec, ev, rows = gate.decide(plan, bits)
+    assert rec == [1 | (2 << 1) | (1 << 3), 0 | (0 << 1) | (0 << 3)]  # no improvement -> first (cand 0, budget 0) wins with saved == 0, gate 0
+    assert len(ev) == 1 and ev[0][0] == 511 and ev[0][2] == 511 + 512 and ev[0][3] == 511 - 127
+    assert rows[0]["bits_saved"] == 100.0 and rows[1]["gate"] == 0
+    # thresholds (main.rs:2069-2071)
+    rec2, ev2, _ = gate.decide(plan, bits, thr_pct=20.0)
+    assert rec2[0] & 1 == 0 and not ev2
+    # decode side rebuilds the same events from the records
+    hints = [e["hints"] for e in plan]
+    ev3 = gate.events_from_records(rec, hints, 512, len(ids))
+    assert len(ev3) == 1 and ev3[0][0] == 511 and np.array_equal(ev3[0][1], ev[0][1]) and ev3[0][3] == ev[0][3]

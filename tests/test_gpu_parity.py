@@ -492,6 +492,52 @@ def test_hint_prime_events_roundtrip_both_backends(gpu_ctx):
     assert np.array_equal(rmodel.decode(rp, rs, events=rev), rid)
 
 
+def test_gate_scan_paired_streams_vs_oracle_and_roundtrip(gpu_ctx):
+    """BASELINE config 4 in miniature: the agentic gate replayed from cached agent texts.  All baseline / hint-conditioned
+    cross-entropy evaluations of all boundaries run as ONE batch of paired streams (src/main.rs:2043-2054), the gated
+    boundaries become hint primes of the main stream (2123-2149), the container carries AGT2 records, and the decoder
+    rebuilds the same primes from the records + what it has decoded (2586-2614)."""
+    from candlezip_b200 import container, gate
+
+    model = _tiny(gpu_ctx, _lib.CZ_ENGINE_TCGEN05)  # flat-ish logits: random tokens must not hit zero-width intervals
+    rng = np.random.default_rng(77)
+    ids = rng.integers(0, 1024, 1400).astype(np.uint32)
+    # "agent texts": strings whose characters map to token ids (a stand-in for tokenizer + agent, both absent offline)
+    tok = lambda s, m: [(ord(ch) * 7) % 1024 for ch in s][:m]
+    texts = {1: "Alpha Beta 12 gamma " * 9, 2: "", 3: "Delta 7 Epsilon " * 30, 5: "Zeta"}
+    pays, seg, records, rows, events = gate.scan_encode(model, ids, texts, tok, agent_chunk=256, scan_lookahead=200)
+    assert len(records) == 5 and [r["chunk_index"] for r in rows] == [1, 2, 3, 4, 5]
+    # (1) XE parity of the paired streams against the oracle running cross_entropy_bits_over_span
+    orc = _oracle_for(model, round_bf16=1)
+    seq = np.concatenate([[0], ids]).astype(np.uint32)
+    jobs, plan = gate.plan_scan(ids, texts, tok, 256, 200)
+    bits = model.xe_bits(jobs)
+    for e in plan[:3]:
+        i = e["i"]
+        hist, targets = seq[max(0, i - 511):i], seq[i:min(i + 200, len(seq))]
+        want = orc.xe_bits(hist, targets)
+        assert abs(bits[e["job0"]] - want) <= 0.01 * want
+        slot = e["slots"][0 * 4 + 1]
+        if slot is not None:
+            want_c = orc.xe_bits(hist, targets, e["hints"][0][:127])
+            assert abs(bits[slot] - want_c) <= 0.01 * want_c
+    assert rows[1]["gate"] == 0 and rows[1]["bits_saved"] == 0.0 and rows[3]["gate"] == 0   # empty hints never gate
+    # (2) the gated stream decodes in one call from (records, agent texts) alone
+    hints = [e["hints"] for e in plan]
+    dec_events = gate.events_from_records(records, hints, 256, len(ids), scan_lookahead=200)
+    assert len(dec_events) == len(events) == sum(r & 1 for r in records)
+    assert np.array_equal(model.decode(pays, seg, events=dec_events or None), ids)
+    # (3) the same schedule on the oracle (explicit primes) gives the same compressed size within 0.5 %
+    ev_explicit = [(i, np.concatenate([seq[i + 1 - ht:i + 1], h]).astype(np.uint32), hold) for (i, h, hold, ht) in events]
+    ref, _ = _oracle_for(model, round_bf16=0).encode_tokens(seq, events=ev_explicit)
+    assert abs(len(pays[0]) - len(ref)) <= 0.005 * len(ref) + 2
+    # (4) container with the AGT2 section (flag bit 2), byte layout of src/main.rs:658-670
+    blob = container.write_container(dict(token_count=len(ids), orig_len_bytes=len(ids), vocab_size=1024, reserved_flags=1), b"m", pays,
+                                     gates=records)
+    f, _, g, _, _, p2 = container.read_container(blob)
+    assert g == records and p2 == pays and f["reserved_flags"] & 4
+
+
 def test_rwkv7_full_size_roundtrip(gpu_ctx):
     """rwkv7-g1-0.1b shape (random-init): logits vs the oracle on a few positions, then a multi-segment round trip."""
     model = cz.Model(gpu_ctx, cz.RWKV7_0P1B).random_init(3, 0.02, 0.05)
