@@ -171,7 +171,9 @@ __global__ void __launch_bounds__(AT_THREADS) attn_tc_kernel(const __grid_consta
         // tile's first position take the mask-free path (warp-uniform); both paths compute identical values for unmasked keys.
         const int lim = pos_r - kb * 128;
         const bool need_mask = kb * 128 + 127 > p0;
-        float raw = -INFINITY;
+        // four independent running maxima / sums (combined in a fixed order): a single 128-long dependent chain of
+        // FMNMX / FADD would cost more cycles than the exp2 work itself
+        float r4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll 1
         for (int c = 0; c < 2; c++) {
           uint32_t v[64];
@@ -180,16 +182,17 @@ __global__ void __launch_bounds__(AT_THREADS) attn_tc_kernel(const __grid_consta
           tc_ld_wait();
           if (need_mask) {
 #pragma unroll
-            for (int j = 0; j < 64; j++) raw = fmaxf(raw, (c * 64 + j <= lim) ? __uint_as_float(v[j]) : -INFINITY);
+            for (int j = 0; j < 64; j++) r4[j & 3] = fmaxf(r4[j & 3], (c * 64 + j <= lim) ? __uint_as_float(v[j]) : -INFINITY);
           } else {
 #pragma unroll
-            for (int j = 0; j < 64; j++) raw = fmaxf(raw, __uint_as_float(v[j]));
+            for (int j = 0; j < 64; j++) r4[j & 3] = fmaxf(r4[j & 3], __uint_as_float(v[j]));
           }
         }
+        const float raw = fmaxf(fmaxf(r4[0], r4[1]), fmaxf(r4[2], r4[3]));
         const float mx = fmaxf(m, raw * c_log2);
         alpha = at_ex2(m - mx);  // first block: ex2(-inf) = 0
         m = mx;
-        float sum = 0.f;
+        float s4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
         for (int c = 0; c < 4; c++) {
           uint32_t v[32];
@@ -203,8 +206,8 @@ __global__ void __launch_bounds__(AT_THREADS) attn_tc_kernel(const __grid_consta
               pa = (c * 32 + j <= lim) ? pa : 0.f;
               pb = (c * 32 + j + 1 <= lim) ? pb : 0.f;
             }
-            sum += pa;
-            sum += pb;
+            s4[j & 2] += pa;
+            s4[(j & 2) + 1] += pb;
             __nv_bfloat162 h = __floats2bfloat162_rn(pa, pb);
             pk[j >> 1] = *reinterpret_cast<uint32_t *>(&h);
           }
@@ -218,7 +221,7 @@ __global__ void __launch_bounds__(AT_THREADS) attn_tc_kernel(const __grid_consta
                          : "memory");
           }
         }
-        l = fmaf(l, alpha, sum);
+        l = fmaf(l, alpha, (s4[0] + s4[1]) + (s4[2] + s4[3]));
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       tc_fence_before();

@@ -46,7 +46,9 @@ struct GemmCfg {
   // other 32-column chunk.  The store-only epilogues (TMA store / reduce-add) keep four warps and the deeper operand pipeline.
   static constexpr bool kHeavy = EPI == cz::EPI_SWIGLU_BF16 || EPI == cz::EPI_QKV_ROPE || EPI == cz::EPI_STORE_BF16 ||
                                  EPI == cz::EPI_TANH_BF16 || EPI == cz::EPI_SIGMOID_BF16 || EPI == cz::EPI_RELUSQ_BF16;
-  static constexpr int kEpiWarps = kHeavy ? 8 : 4;
+  // the LM-head epilogue (store + 32 warp-wide max reductions per chunk) also takes eight warps, but stays on the TMA store path
+  static constexpr bool kColmax = EPI == cz::EPI_STORE_F32_COLMAX;
+  static constexpr int kEpiWarps = (kHeavy || kColmax) ? 8 : 4;
   static constexpr int kThreads = 64 + 32 * kEpiWarps;
   static constexpr int kStages = (BN <= 192 && (!kHeavy || EPI == cz::EPI_QKV_ROPE)) ? 5 : 4;  // RoPE stages nothing in smem
   static constexpr int kABytes = BM * BK * 2;
@@ -55,7 +57,7 @@ struct GemmCfg {
   static constexpr int kTmemCols = 512;  // 2 accumulator stages of BN columns, power of two >= 2*BN
   // per epilogue warp: a padded 32x33 f32 transpose patch (4224 B), two of them for the RoPE epilogue, or a dense 4 KB
   // SWIZZLE_128B TMA box (1024-aligned) for the f32 store / reduce-add epilogues
-  static constexpr int kPatchBytes = EPI == cz::EPI_QKV_ROPE ? 0 : (kHeavy ? 4224 : 5120);
+  static constexpr int kPatchBytes = EPI == cz::EPI_QKV_ROPE ? 0 : (kHeavy ? 4224 : (kColmax ? 4096 : 5120));
   static constexpr int kStagingOff = kStages * kStageBytes + 1024;  // the barriers live in the 1 KB before it
   static constexpr int kSmemBytes = kStagingOff + kEpiWarps * kPatchBytes + 1024 /*align slack*/;
   static_assert(kSmemBytes <= 232448, "shared memory budget");

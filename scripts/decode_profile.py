@@ -18,8 +18,8 @@ model = cz.Model(ctx, cfg).random_init(0, 0.02, 0.02)
 rng = np.random.default_rng(0)
 ids = rng.integers(97, 123, n).astype(np.uint32)
 pays, seg = model.encode(ids, n_segments=segs)
-model.decode(pays[:8], seg[:9])  # warm
-res = {}
+model.decode(pays, seg)  # warm (allocations)
+res = {"arch": arch, "tokens": n, "segments": segs}
 for graph in (1, 0):
     os.environ.pop("CZ_DECODE_NO_GRAPH", None)
     if not graph:
@@ -30,10 +30,10 @@ for graph in (1, 0):
     out = model.decode(pays, seg)
     dt = time.perf_counter() - t0
     assert np.array_equal(out, ids)
-    res["graph" if graph else "eager"] = {"s": dt, "tok_per_s": n / dt, "ms_per_step": 1e3 * dt / (n / segs)}
+    res["graph" if graph else "eager"] = {"s": round(dt, 4), "tok_per_s": round(n / dt), "ms_per_step": round(1e3 * dt / (n / segs), 3)}
     if not graph:
         fam = ctx.profile_read(reset=True)
         steps = n / segs
-        res["family_ms_per_step"] = {k: v[0] / steps for k, v in fam.items()}
-        res["family_launches_per_step"] = {k: v[1] / steps for k, v in fam.items()}
-print(json.dumps(res, indent=1))
+        res["family_ms_per_step"] = {k: round(v[0] / steps, 4) for k, v in fam.items()}
+        res["family_launches_per_step"] = {k: round(v[1] / steps, 1) for k, v in fam.items()}
+print(json.dumps(res))
