@@ -311,7 +311,7 @@ def run_ours(args):
         "config": {"workload": "SmolLM-135M (seeded random-init, bf16 weights, fp32 accumulate), ctx 512 / reprime 512: "
                                f"{n} byte-level tokens per GPU per step as {S} segments = {n_chunks} reprime-chunks ({rows} teacher-forced rows)",
                    "tokens_per_step_per_gpu": n, "segments": S, "chunks": n_chunks, "bytes_per_token": 1,
-                   "l2": "per-step working set (>= 3 GB activations + 1.6 GB logits sub-batches) exceeds the 126 MB L2; no explicit flush",
+                   "l2": "per-step working set (about 3 GB of activations per wave + a 51.5 GB logits batch) exceeds the 126 MB L2 by orders of magnitude; no explicit flush",
                    "engine": "tcgen05"},
         "tokens_per_s": value * 1e6, "clocks": clocks, "gpu_launches": int(launches),
         "e2e": {"value": e2e_value, "unit": "MB/s", "h2d_bytes_per_step": int(4 * n + 16 * rows + 4 * n),

@@ -3,4 +3,4 @@ behind the reference's LanguageModelSession boundary.  See DESIGN.md and include
 from ._lib import (CZ_ARCH_RWKV7, CZ_ARCH_SMOLLM, CZ_CDF_RWKV_LITERALS, CZ_CDF_SMOLLM, CZ_ENGINE_SIMT,  # noqa: F401
                    CZ_ENGINE_TCGEN05, CzError)
 from .api import RWKV7_0P1B, SMOLLM_135M, SMOLLM_TINY, Context, Model, Session, split_segments, xe_make_prime  # noqa: F401
-from . import container  # noqa: F401
+from . import codec, container, gate, sharding  # noqa: F401

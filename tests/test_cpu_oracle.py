@@ -447,3 +447,77 @@ def test_gate_candidates_budgets_and_selection():
     hints = [e["hints"] for e in plan]
     ev3 = gate.events_from_records(rec, hints, 512, len(ids))
     assert len(ev3) == 1 and ev3[0][0] == 511 and np.array_equal(ev3[0][1], ev[0][1]) and ev3[0][3] == ev[0][3]
+
+
+# ------------------------------------------------------------------ safetensors loader (SmolLmSession::load, src/models.rs:48-61)
+def test_safetensors_loader_roundtrip(tmp_path):
+    """write HF-named tensors with the `safetensors` package (F32, BF16 and F16 files, a tied lm_head and an unknown tensor),
+    load them through cz_model_load_safetensors on a host-only ctx and read them back"""
+    import candlezip_b200 as cz
+    import torch
+    from safetensors.torch import save_file
+
+    host = cz.Context(-1)
+    ref = cz.Model(host, cz.SMOLLM_TINY).random_init(3, 0.05, 0.1)
+    want = ref.tensors()
+    shapes = {}
+    for name, n in ref.tensor_names():
+        if name.endswith("norm.weight"):
+            shapes[name] = (n,)
+        elif "embed_tokens" in name:
+            shapes[name] = (cz.SMOLLM_TINY["vocab"], cz.SMOLLM_TINY["d_model"])
+        else:
+            shapes[name] = (n // cz.SMOLLM_TINY["d_model"], cz.SMOLLM_TINY["d_model"]) if "down_proj" not in name else (cz.SMOLLM_TINY["d_model"], n // cz.SMOLLM_TINY["d_model"])
+    names = list(want)
+    parts = [names[0::3], names[1::3], names[2::3]]
+    dtypes = [torch.float32, torch.bfloat16, torch.float16]
+    paths = []
+    for k, (part, dt) in enumerate(zip(parts, dtypes)):
+        tensors = {nm: torch.from_numpy(want[nm].reshape(shapes[nm]).copy()).to(dt) for nm in part}
+        if k == 0:
+            tensors["some.unknown.tensor"] = torch.zeros(3)
+        p = str(tmp_path / f"model-{k}.safetensors")
+        save_file(tensors, p)
+        paths.append(p)
+    m = cz.Model(host, cz.SMOLLM_TINY).load_safetensors(paths)
+    got = m.tensors()
+    for nm in names:
+        if nm in parts[2]:  # went through f16: bf16-exact values are not all f16-exact
+            assert np.allclose(got[nm], want[nm], rtol=2e-3, atol=1e-4), nm
+        else:
+            assert np.array_equal(got[nm], want[nm]), nm
+    with pytest.raises(cz.CzError):
+        cz.Model(host, cz.SMOLLM_TINY).load_safetensors([str(tmp_path / "missing.safetensors")])
+
+
+# ------------------------------------------------------------------ tokenisation glue (SURVEY 8 f-2)
+def _toy_rwkv_vocab():
+    toks = {bytes([b]): b + 1 for b in range(256) if b not in (0xFF,)}  # 0xFF has no token: forces the literal path
+    extra = [b"th", b"the", b"the ", b"he", b"in", b"ing", b"\xe2\x82\xac", b"ab", b"abc", b"abcd"]
+    for k, t in enumerate(extra):
+        toks[t] = 300 + k
+    return toks
+
+
+def test_rwkv_trie_tokenizer_semantics():
+    from candlezip_b200 import codec
+
+    tok = codec.RwkvTokenizer(_toy_rwkv_vocab())
+    # first match in DESCENDING id order among tokens sharing the first two bytes (rwkv7.rs:566-573, 584-589):
+    # "the " (302) beats "the" (301) beats "th" (300); "abcd" (309) beats "abc" / "ab"
+    assert list(tok.encode_bytes(b"the cat")) == [302, ord("c") + 1, ord("a") + 1, ord("t") + 1]
+    assert list(tok.encode_bytes(b"then")) == [301, ord("n") + 1]
+    assert list(tok.encode_bytes(b"abcab")) == [308, 307]
+    data = "the thing in the € abcd ab".encode()
+    ids = tok.encode_bytes(data)
+    assert tok.decode_bytes(ids) == data
+    with pytest.raises(KeyError):
+        tok.encode_bytes(b"x\xffy")
+    # plan_rwkv_symbols: a vocabulary gap makes EVERY byte a literal escape (main.rs:857-862)
+    V = 320
+    sym = codec.plan_rwkv_symbols(b"x\xffy", tok, V)
+    assert list(sym) == [V + ord("x"), V + 0xFF, V + ord("y")]
+    assert codec.rwkv_detok_with_literals(tok, sym, V) == b"x\xffy"
+    mixed = np.array([302, V + 0xFF, 308, V + 0], np.uint32)
+    assert codec.rwkv_detok_with_literals(tok, mixed, V) == b"the \xffabc\x00"
+    assert codec.ByteTokenizer().decode_bytes(codec.ByteTokenizer().encode_bytes(bytes(range(256)))) == bytes(range(256))

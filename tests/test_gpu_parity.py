@@ -538,6 +538,42 @@ def test_gate_scan_paired_streams_vs_oracle_and_roundtrip(gpu_ctx):
     assert g == records and p2 == pays and f["reserved_flags"] & 4
 
 
+def test_file_level_compress_decompress_both_backends(gpu_ctx):
+    """bytes -> container -> bytes (the reference's compress / decompress / self-test, src/main.rs:156-221, minus the CLI):
+    byte-level SmolLM (every input round-trips, incl. non-UTF-8), RWKV-7 with a trie vocabulary + literal escapes, segmented
+    containers, header fields, and the BLAKE3 check of the decoded bytes that the reference never performs."""
+    from candlezip_b200 import codec, container
+
+    rng = np.random.default_rng(9)
+    text = (b"It was the best of times, it was the worst of times. " * 40) + bytes(rng.integers(0, 256, 300, dtype=np.uint8))
+    model = _tiny(gpu_ctx, _lib.CZ_ENGINE_TCGEN05)
+    for nseg in (1, 4):
+        blob = codec.compress(model, text, n_segments=nseg)
+        f, rep, gates, eng, st, pays = container.read_container(blob)
+        assert f["token_count"] == len(text) and f["orig_len_bytes"] == len(text) and f["vocab_size"] == 1024
+        assert f["context_window"] == 512 and f["reprime_interval"] == 512 and f["orig_hash16"] == container.blake3_16(text)
+        assert (st is None) == (nseg == 1) and len(pays) == nseg
+        assert codec.decompress(model, blob) == text
+    bad = bytearray(blob)
+    bad[-3] ^= 0x10  # corrupt the payload: decode yields other bytes, caught by the hash check
+    with pytest.raises((ValueError, cz.CzError)):
+        codec.decompress(model, bytes(bad))
+    assert codec.decompress(model, codec.compress(model, b"")) == b""
+    # RWKV-7 with a toy trie vocabulary (ids < 320) and bytes the vocabulary cannot express
+    import test_cpu_oracle as tco
+
+    rmodel, cfg, _ = _rwkv_tiny(gpu_ctx)
+    tok = codec.RwkvTokenizer(tco._toy_rwkv_vocab())
+    rtext = b"the thing in the abcd " * 30
+    rblob = codec.compress(rmodel, rtext, tokenizer=tok, n_segments=2)
+    assert codec.decompress(rmodel, rblob, tokenizer=tok) == rtext
+    assert container.read_container(rblob)[0]["token_count"] < len(rtext)  # multi-byte tokens
+    gap = b"abc\xffdef the end"
+    gblob = codec.compress(rmodel, gap, tokenizer=tok)
+    assert container.read_container(gblob)[0]["token_count"] == len(gap)  # every byte a literal escape
+    assert codec.decompress(rmodel, gblob, tokenizer=tok) == gap
+
+
 def test_rwkv7_full_size_roundtrip(gpu_ctx):
     """rwkv7-g1-0.1b shape (random-init): logits vs the oracle on a few positions, then a multi-segment round trip."""
     model = cz.Model(gpu_ctx, cz.RWKV7_0P1B).random_init(3, 0.02, 0.05)
