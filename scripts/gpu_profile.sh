@@ -23,7 +23,7 @@ C=$(python -c "import json;d=json.load(open('gpurun_out/prof_plain_$TAG.json'))[
 # the bench runs: warm-up step, timed step, then two e2e steps -> skip one whole step (G gemm launches) before capturing
 full gemm_trunk "gemm_tc_kernel" $((G + 8)) 4          # layer 2 of the first wave: qkv(+rope), o, gate-up, down
 full gemm_head "gemm_tc_kernel" $((2 * G - H)) 1       # the first LM-head launch of the timed step
-full attn "attn_mma_kernel" $((A + 2)) 1
+full attn "attn_tc_kernel|attn_mma_kernel" $((A + 2)) 1
 full cdf "cdf_cols_kernel" $C 1
 full elem "rmsnorm_kernel|ac_encode_lanes_kernel" 200 2
 for r in gemm_trunk gemm_head attn cdf elem; do
