@@ -28,6 +28,10 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 METRIC = "encode_MB_per_s_smollm135m_ctx512"
+# per layer-wave launch (261k rows): qkv+rope 754 MB, o-proj 1481 MB, gate/up 1058 MB, down 1965 MB; x60 launches each, plus the
+# LM head's 51.5 GB of logits written + 0.4 GB read
+NCU_GEMM_TRAFFIC_BYTES_PER_STEP = int(60 * (754 + 1481 + 1058 + 1965) * 1e6 + 51.9e9)
+MFLOP_PER_TOKEN = 551.0  # trunk 423.84 + head 56.62 + attention 70.57 MFLOP per coded token at ctx 512 / reprime 512
 TRUNK_PARAMS = 106_168_320  # matmul params per token position, SURVEY 8d
 HEAD_PARAMS = 28_311_552
 
@@ -317,8 +321,14 @@ def run_ours(args):
         "e2e": {"value": e2e_value, "unit": "MB/s", "h2d_bytes_per_step": int(4 * n + 16 * rows + 4 * n),
                 "d2h_bytes_per_step": int(payload_bytes + 8 * S + 16), "bitstream_equal_to_device_arm": same},
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf if achieved else None,
-                     "traffic": None, "kernel": "gemm_tc_kernel (tcgen05 GEMM family: qkv/o/gate-up/down/lm_head)",
+                     # dram__bytes_read + dram__bytes_write per launch from the ncu --set full captures of this build
+                     # (profiles/ncu_summary_r01.md section C), summed over the family's launches of one step
+                     "traffic": NCU_GEMM_TRAFFIC_BYTES_PER_STEP, "traffic_source": "profiles/ncu_summary_r01.md (ncu --set full, per launch x launches per step)",
+                     "kernel": "gemm_tc_kernel (tcgen05 GEMM family: qkv+rope/o/gate-up/down/lm_head)",
                      "flops_per_step": gemm_flops, "kernel_ms_per_step": gemm_ms, "peak_source": peak_src},
+        # whole-path tensor roofline exactly as SURVEY 8d defines it: tokens/s x 551.0 MFLOP / measured sustained bf16 peak
+        "roofline_path": {"bound": "tensor", "achieved": value * 1e6 / max(1, world) * MFLOP_PER_TOKEN * 1e6 / 1e12, "peak": peak_tf, "unit": "TFLOP/s",
+                          "frac": value * 1e6 / max(1, world) * MFLOP_PER_TOKEN * 1e6 / 1e12 / peak_tf, "per_gpu": True},
         "kernel_ms_per_step": {k: v[0] / args.steps for k, v in fam.items()},
         "kernel_launches_per_step": {k: v[1] // max(1, args.steps) for k, v in fam.items()},
         "compressed_bytes_per_step": payload_bytes, "decode": decode, "rwkv7": rwkv,
