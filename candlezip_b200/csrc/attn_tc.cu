@@ -4,13 +4,12 @@
 //
 // Replaces candle-transformers llama attention (repeat_kv + QK^T/sqrt(d) + f32 softmax + PV) reached from src/models.rs:94,110.
 //
-//   warp 4 (one elected thread): TMA loads (Q once; K block [128 keys x 64] and V^T block [64 dims x 128 keys], double
-//           buffered) and the MMAs:  S = Q K^T  (128 x 128 x 64: 4 UMMA k-steps)  and  O_blk = P V  (128 x 64 x 128: 8 k-steps)
+//   warp 4 (one elected thread): TMA loads (Q once; K block and V block [128 keys x 64 dims]; K single-, V double-buffered) and the MMAs:  S = Q K^T  (128 x 128 x 64: 4 UMMA k-steps)  and  O_blk = P V  (128 x 64 x 128: 8 k-steps)
 //   warps 0-3: thread r owns query row r of the tile (tcgen05.ld 32x32b hands a TMEM lane to a thread): row max, exp2, row sum
 //           need no shuffles; P goes back as bf16 through shared memory (K-major SWIZZLE_128B, the A operand of P V);
 //           the running output row lives in 64 registers: O = O * alpha + O_blk.
-// V is kept TRANSPOSED in HBM ([kv dim][slot]) so that the P V product reads it K-major like every other operand; the QKV
-// projection's epilogue writes it that way (gemm_tcgen05.cu, EPI_QKV_ROPE).
+// V stays in its natural row layout ([slot][kv dim]): the P V product takes it as an MN-major B operand (instruction
+// descriptor bit 16), whose canonical SWIZZLE_128B shared-memory layout is exactly what TMA writes for a [128 keys][64 dims] box.
 //
 // ROW INVARIANCE (decode safety).  For a given (sequence, position, head) the arithmetic is a fixed sequence: keys in blocks of
 // 128 anchored at key 0; per block one UMMA chain over the 64 dims, mask (exact -inf -> exp2 = 0), m' = max(m, rowmax),
@@ -49,7 +48,7 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map
 // A (position, head) row goes through exactly the same arithmetic in both modes.
 template <bool STACKED>
 __global__ void __launch_bounds__(AT_THREADS) attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
-                                                             const __grid_constant__ CUtensorMap tm_vt, const int *__restrict__ pos,
+                                                             const __grid_constant__ CUtensorMap tm_v, const int *__restrict__ pos,
                                                              const int *__restrict__ kv_base, const int *__restrict__ tile_row0,
                                                              const int *__restrict__ tile_n, __nv_bfloat16 *__restrict__ out, int nh, int nkv) {
   extern __shared__ uint8_t smem_raw[];
@@ -70,7 +69,7 @@ __global__ void __launch_bounds__(AT_THREADS) attn_tc_kernel(const __grid_consta
   if (warp == 4 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_q) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_k) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_vt) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_v) : "memory");
     mbar_init(q_full, 1);
     mbar_init(k_full, 1);
     mbar_init(k_empty, 1);
@@ -102,8 +101,7 @@ __global__ void __launch_bounds__(AT_THREADS) attn_tc_kernel(const __grid_consta
       auto load_v = [&](int kb, int st) {
         const uint32_t fb = v_full + 8 * st;
         mbar_expect_tx(fb, 16384);
-        tma_load_2d(sV + st * 16384, &tm_vt, fb, base + kb * 128, kvh * 64);
-        tma_load_2d(sV + st * 16384 + 8192, &tm_vt, fb, base + kb * 128 + 64, kvh * 64);
+        tma_load_2d(sV + st * 16384, &tm_v, fb, kvh * 64, base + kb * 128);  // [128 keys][64 dims], like the K block
       };
       // q viewed as [row][head][64]: a box of 128 rows x 1 head, or 1 row x G heads
       mbar_expect_tx(q_full, STACKED ? G * 128 : 16384);
@@ -111,7 +109,8 @@ __global__ void __launch_bounds__(AT_THREADS) attn_tc_kernel(const __grid_consta
       load_k(0);
       load_v(0, 0);
       if (nb > 1) load_v(1, 1);
-      constexpr uint32_t idesc_qk = make_idesc_mn(128, 128), idesc_pv = make_idesc_mn(128, 64);
+      // P V: the B operand V [128 keys][64 dims] has the dims (N) contiguous -> MN-major B (instruction descriptor bit 16)
+      constexpr uint32_t idesc_qk = make_idesc_mn(128, 128), idesc_pv = make_idesc_mn(128, 64) | (1u << 16);
       const uint64_t q_desc = make_kmajor_sw128_desc(sQ), k_desc = make_kmajor_sw128_desc(sK);
       auto issue_qk = [&]() {
 #pragma unroll
@@ -141,7 +140,9 @@ __global__ void __launch_bounds__(AT_THREADS) attn_tc_kernel(const __grid_consta
 #pragma unroll
         for (int ks = 0; ks < 8; ks++) {
           const uint64_t p_desc = make_kmajor_sw128_desc(sP + (ks >> 2) * 16384) + (uint64_t)((ks & 3) * 2);
-          const uint64_t v_desc = make_kmajor_sw128_desc(sV + st * 16384 + (ks >> 2) * 8192) + (uint64_t)((ks & 3) * 2);
+          // canonical MN-major SWIZZLE_128B layout ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units: one 128-byte row per key,
+          // 8-key groups 1024 B apart (SBO), n = 1; a K-step of 16 keys advances the start address by 16 rows = 2048 B
+          const uint64_t v_desc = make_kmajor_sw128_desc(sV + st * 16384) + (uint64_t)(ks * 128);
           tc_mma_bf16(tmem_base + 128, p_desc, v_desc, idesc_pv, ks ? 1u : 0u);
         }
         tc_commit(o_full);
@@ -297,16 +298,12 @@ static int make_q_map(CUtensorMap *map, const void *q, int n_rows, int nh, int b
   return CZ_OK;
 }
 
-// q [n_rows][nh*64] bf16; k_arena [n_slots][nkv*64] bf16; vt_arena [nkv*64][ldv] bf16 (transposed V, n_slots valid columns).
+// q [n_rows][nh*64] bf16; k_arena, v_arena [n_slots][nkv*64] bf16.
 // single_rows: every tile is one position (stepwise decode) -> the GQA group is stacked into one CTA.
-int launch_attn_tc(cz_ctx *ctx, const __nv_bfloat16 *q, int n_rows, const __nv_bfloat16 *k_arena, const __nv_bfloat16 *vt_arena, int n_slots,
-                   int ldv, const int *pos, const int *kv_base, const int *tile_row0, const int *tile_n, int n_tiles, __nv_bfloat16 *out,
+int launch_attn_tc(cz_ctx *ctx, const __nv_bfloat16 *q, int n_rows, const __nv_bfloat16 *k_arena, const __nv_bfloat16 *v_arena, int n_slots,
+                   int /*unused*/, const int *pos, const int *kv_base, const int *tile_row0, const int *tile_n, int n_tiles, __nv_bfloat16 *out,
                    int nh, int nkv, bool single_rows, cudaStream_t st) {
   if (n_tiles == 0) return CZ_OK;
-  if (ldv % 8) {
-    set_error("attention: transposed-V leading dimension must be a multiple of 8");
-    return CZ_ERR_INVALID;
-  }
   static bool attr = false;
   if (!attr) {
     CZ_CUDA_TRY(cudaFuncSetAttribute(czk::attn_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, czk::AT_SMEM));
@@ -316,7 +313,7 @@ int launch_attn_tc(cz_ctx *ctx, const __nv_bfloat16 *q, int n_rows, const __nv_b
   CUtensorMap tq, tk, tv;
   CZ_TRY(make_q_map(&tq, q, n_rows, nh, single_rows ? nh / nkv : 1, single_rows ? 1 : 128));
   CZ_TRY(make_map_bf16(&tk, k_arena, n_slots, nkv * 64, nkv * 64, 128));
-  CZ_TRY(make_map_bf16(&tv, vt_arena, nkv * 64, n_slots, ldv, 64));
+  CZ_TRY(make_map_bf16(&tv, v_arena, n_slots, nkv * 64, nkv * 64, 128));  // V rows [slot][nkv*64], same box as K
   if (single_rows) {
     dim3 grid((unsigned)n_tiles, (unsigned)nkv);
     CZ_LAUNCH(ctx, CZ_K_ATTN,

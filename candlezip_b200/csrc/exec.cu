@@ -223,16 +223,6 @@ struct Wave {
       kv_base.push_back(base);
     }
     for (uint32_t j = 0; j < n_coded; j++) logit_rows.push_back(base + (int)prime_len - 1 + (int)j);
-    // Every sequence must start at a row (= KV slot) that is a multiple of 8: the tcgen05 attention kernel TMA-loads the
-    // transposed V with the slot as the INNER coordinate, which has to be 16-byte aligned.  The sequence is therefore
-    // extended to a multiple of 8 rows with dummy BOS tokens at the following positions: causally invisible to the real
-    // rows, attended like any other row (so their K/V stay finite: masked slots are multiplied by P = 0, and 0 * NaN = NaN),
-    // and without a logits row.
-    while (src.size() % 8) {
-      src.push_back(-1);
-      pos.push_back(p++);
-      kv_base.push_back(base);
-    }
     add_tiles(base, p);
   }
 };
@@ -292,9 +282,6 @@ static int run_wave_trunk(cz_model *m, const Wave &w, const uint32_t *ids_dev, c
   kv.k = ws.kpack;
   kv.v = ws.vpack;
   kv.layer_stride = 0;
-  kv.vt = ws.vtpack;
-  kv.vt_layer_stride = 0;
-  kv.ldv = (int)ws.ldv_pack;
   kv.n_slots = (int)R;
   kv.tile_row0 = ws.tile_row0;
   kv.tile_n = ws.tile_n;
@@ -532,9 +519,6 @@ static int session_forward(cz_session *s, const uint32_t *tok, size_t n, float *
   kv.k = s->k;
   kv.v = s->v;
   kv.layer_stride = (size_t)s->max_pos * m->cfg.n_kv_heads * 64;
-  kv.vt = s->v;  // attn_tc: the V arena is [L][kvd][max_pos]
-  kv.vt_layer_stride = kv.layer_stride;
-  kv.ldv = s->max_pos;
   kv.n_slots = s->max_pos;
   kv.tile_row0 = ws.tile_row0;
   kv.tile_n = ws.tile_n;
@@ -696,10 +680,7 @@ int cz_decode(cz_model *m, const uint8_t *payload, const uint64_t *seg_off, size
   kv.k = d_k.as<__nv_bfloat16>();
   kv.v = d_v.as<__nv_bfloat16>();
   kv.layer_stride = (size_t)S * max_pos * kvd;
-  if (m->attn_tc) {  // transposed V arena [L][kvd][S*max_pos]; masked / unwritten slots must hold finite values (0 * NaN = NaN in P V)
-    kv.vt = d_v.as<__nv_bfloat16>();
-    kv.vt_layer_stride = (size_t)S * max_pos * kvd;
-    kv.ldv = (int)(S * max_pos);
+  if (m->attn_tc) {  // unwritten slots inside a 128-key block are masked (P = 0), but 0 * NaN = NaN: they must hold finite values
     CZ_CUDA_TRY(cudaMemsetAsync(d_v.p, 0, L * S * max_pos * kvd * 2, st));
     CZ_CUDA_TRY(cudaMemsetAsync(d_k.p, 0, L * S * max_pos * kvd * 2, st));
   }

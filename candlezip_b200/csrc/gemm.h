@@ -26,7 +26,6 @@ struct RopeExt {
   const float *cos_tab = nullptr, *sin_tab = nullptr;  // [max_pos][32]
   void *q = nullptr, *k_arena = nullptr, *v_arena = nullptr;  // bf16: q [M][nh*64]; arenas [slot][nkv*64]
   int nh = 0, nkv = 0;
-  long long ldv = 0;  // > 0: V is stored transposed, v_arena = vt [nkv*64][ldv] (tcgen05 attention); 0: rows [slot][nkv*64]
 };
 
 struct GemmArgs {

@@ -184,6 +184,7 @@ __global__ void __launch_bounds__((GemmCfg<BN, EPI>::kThreads), 1)
     uint8_t *patch = smem + Cfg::kStagingOff + (warp - 2) * Cfg::kPatchBytes;
     float *stg = reinterpret_cast<float *>(patch);
     const int rr0 = lane >> 3, cc = (lane & 7) * 4;
+    uint32_t n_store = 0;  // bulk stores issued by this warp so far (selects the TMA patch)
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, it++) {
       const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
@@ -202,9 +203,7 @@ __global__ void __launch_bounds__((GemmCfg<BN, EPI>::kThreads), 1)
         // The tile is three whole heads (BN = 192).  tcgen05.ld hands every lane one ROW, i.e. one position: the thread loads
         // that position's cos / sin once per tile and rotates in registers (rotate-half RoPE in fp32 on the accumulators,
         // like the reference's f32 path).  The two warps of a TMEM lane quadrant split the 32 rotation pairs (j, j + 32) of a
-        // head in halves.  Stores go straight from registers: bf16 q rows, K arena rows at slot kv_base[row] + pos[row], and V
-        // either as arena rows or TRANSPOSED (vt[dim][slot], tcgen05 attention), where a warp's 32 rows are 32 consecutive
-        // slots of a teacher-forced wave = one 64-byte line per dim.
+        // head in halves.  Stores go straight from registers: bf16 q rows, K and V arena rows at slot kv_base[row] + pos[row].
         const int my_row = row_base + lane;
         const bool ok = my_row < M;
         const int my_pos = ok ? rx.pos[my_row] : 0;
@@ -232,15 +231,6 @@ __global__ void __launch_bounds__((GemmCfg<BN, EPI>::kThreads), 1)
           tc_ld_wait();
           if (!ok) continue;
           const bool is_q = head < rx.nh, is_v = head >= rx.nh + rx.nkv;
-          if (is_v && rx.ldv > 0) {
-            __nv_bfloat16 *vt = (__nv_bfloat16 *)rx.v_arena + (size_t)((head - rx.nh - rx.nkv) * 64 + j0) * rx.ldv + my_slot;
-#pragma unroll
-            for (int j = 0; j < 16; j++) {
-              vt[(size_t)j * rx.ldv] = __float2bfloat16_rn(__uint_as_float(ra[j]));
-              vt[(size_t)(j + 32) * rx.ldv] = __float2bfloat16_rn(__uint_as_float(rb[j]));
-            }
-            continue;
-          }
           uint32_t wa[8], wb[8];
 #pragma unroll
           for (int j = 0; j < 16; j += 2) {
@@ -282,7 +272,7 @@ __global__ void __launch_bounds__((GemmCfg<BN, EPI>::kThreads), 1)
           uint32_t r[32];
           tc_ld_32x32(t_row + (uint32_t)(c * 32), r);
           // the patch about to be overwritten was handed to TMA kTmaPatches chunks ago: wait until that store has read it
-          const uint32_t patch_u32 = patch_base + (uint32_t)((c & (Cfg::kTmaPatches - 1)) * 4096);
+          const uint32_t patch_u32 = patch_base + (uint32_t)(((n_store++) & (Cfg::kTmaPatches - 1)) * 4096);  // alternate per STORE, not per chunk
           if (lane == 0) {
             if (Cfg::kTmaPatches == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
             else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");

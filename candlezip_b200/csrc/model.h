@@ -24,8 +24,6 @@ struct Workspace {
   __nv_bfloat16 *act = nullptr;       // [rows][F]
   __nv_bfloat16 *kpack = nullptr;     // packed-mode (teacher-forced) K rows of the current layer [rows][kvd]
   __nv_bfloat16 *vpack = nullptr;
-  __nv_bfloat16 *vtpack = nullptr;    // attn_tc: transposed packed V [kvd][ldv_pack]
-  size_t ldv_pack = 0;
   uint32_t *tok = nullptr;            // row metadata
   int *pos = nullptr;
   int *kv_base = nullptr;
@@ -112,7 +110,7 @@ struct cz_model {
   float *cos_tab = nullptr, *sin_tab = nullptr;  // [rope_max_pos][32]
   int rope_max_pos = 2048;
   int gu_bn = 192;
-  bool attn_tc = false;  // tcgen05 attention kernel (attn_tc.cu) with transposed V; else the mma.sync kernel (attn_mma.cu)
+  bool attn_tc = false;  // tcgen05 attention kernel (attn_tc.cu); else the mma.sync kernel (attn_mma.cu)
   int attn_tile = 64;    // query positions per attention tile (128 with attn_tc)
   Workspace ws;
 };
@@ -132,11 +130,7 @@ struct KvView {
   // starting at a position that is a multiple of 64 (or a single decode row)
   const int *tile_row0 = nullptr, *tile_n = nullptr;
   int n_tiles = 0;
-  // tcgen05 attention (model->attn_tc): V is kept transposed, element (layer l, kv dim d, slot s) at vt + l*vt_layer_stride + d*ldv + s
-  __nv_bfloat16 *vt = nullptr;
-  size_t vt_layer_stride = 0;  // elements
-  int ldv = 0;                 // multiple of 8
-  int n_slots = 0;             // valid slots of the arena (rows of k / columns of vt)
+  int n_slots = 0;             // valid slots of the arena (rows of k / v): TMA zero-fills beyond them
   bool single_rows = false;    // every tile is a single position (stepwise decode)
 };
 

@@ -132,8 +132,6 @@ int ensure_workspace(cz_model *m, size_t rows, size_t n_logit, size_t n_tiles) {
     CZ_TRY(realloc_dev(w.act, r * F));
     CZ_TRY(realloc_dev(w.kpack, r * kvd));
     CZ_TRY(realloc_dev(w.vpack, r * kvd));
-    w.ldv_pack = (r + 7) & ~(size_t)7;
-    CZ_TRY(realloc_dev(w.vtpack, m->attn_tc ? kvd * w.ldv_pack : 0));
     CZ_TRY(realloc_dev(w.pos, r));
     CZ_TRY(realloc_dev(w.kv_base, r));
     w.cap_rows = r;
@@ -288,12 +286,7 @@ int forward_trunk(cz_model *m, int n_rows, const KvView &kv, cudaStream_t st) {
       g.c = nullptr;
       g.rope.pos = w.pos; g.rope.kv_base = w.kv_base; g.rope.cos_tab = m->cos_tab; g.rope.sin_tab = m->sin_tab;
       g.rope.q = w.q; g.rope.k_arena = kl; g.rope.nh = nh; g.rope.nkv = nkv;
-      if (m->attn_tc) {
-        g.rope.v_arena = kv.vt + (size_t)l * kv.vt_layer_stride;
-        g.rope.ldv = kv.ldv;
-      } else {
-        g.rope.v_arena = vl;
-      }
+      g.rope.v_arena = vl;  // V rows [slot][nkv*64] for both attention kernels (the tcgen05 one reads them as an MN-major operand)
       CZ_TRY(gemm(ctx, c.engine, g, st));
       g.rope = RopeExt();
     } else {
@@ -302,7 +295,7 @@ int forward_trunk(cz_model *m, int n_rows, const KvView &kv, cudaStream_t st) {
     }
     static const bool force_rows = getenv("CZ_DEBUG_ATTN_ROWS") != nullptr;  // bisecting aid
     if (m->attn_tc)
-      CZ_TRY(launch_attn_tc(ctx, w.q, n_rows, kl, kv.vt + (size_t)l * kv.vt_layer_stride, kv.n_slots, kv.ldv, w.pos, w.kv_base, kv.tile_row0,
+      CZ_TRY(launch_attn_tc(ctx, w.q, n_rows, kl, vl, kv.n_slots, 0, w.pos, w.kv_base, kv.tile_row0,
                             kv.tile_n, kv.n_tiles, w.attn, nh, nkv, kv.single_rows, st));
     else if (c.engine == CZ_ENGINE_TCGEN05 && !force_rows)
       CZ_TRY(launch_attn_mma(ctx, w.q, kl, vl, w.pos, w.kv_base, kv.tile_row0, kv.tile_n, kv.n_tiles, w.attn, nh, nkv, st));
@@ -462,7 +455,7 @@ void cz_model_free(cz_model *m) {
     for (auto &b : m->sb)
       if (b.p) cudaFree(b.p);
     void *ptrs[] = {m->w_qkv, m->w_o, m->w_gu, m->w_d, m->norms, m->cos_tab, m->sin_tab, m->ws.x, m->ws.xn, m->ws.qkv, m->ws.q,
-                    m->ws.attn, m->ws.act, m->ws.kpack, m->ws.vpack, m->ws.vtpack, m->ws.tok, m->ws.pos, m->ws.kv_base, m->ws.logit_rows,
+                    m->ws.attn, m->ws.act, m->ws.kpack, m->ws.vpack, m->ws.tok, m->ws.pos, m->ws.kv_base, m->ws.logit_rows,
                     m->ws.syms, m->ws.out_index, m->ws.tile_row0, m->ws.tile_n, m->ws.xn_logit, m->ws.lo_tmp, m->ws.hi_tmp, m->ws.xe_tmp, m->ws.colmax, m->ws.logits[0],
                     m->ws.logits[1]};
     for (void *p : ptrs)

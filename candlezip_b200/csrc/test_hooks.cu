@@ -23,7 +23,13 @@ extern "C" int cz_test_gemm(cz_ctx *ctx, int engine, int M, int N, int K, const 
   CZ_CUDA_TRY(cudaMemcpy(da, a_bf16, (size_t)M * K * 2, cudaMemcpyHostToDevice));
   CZ_CUDA_TRY(cudaMemcpy(db, b_bf16, (size_t)N * K * 2, cudaMemcpyHostToDevice));
   CZ_CUDA_TRY(cudaMemcpy(dc, c_inout, c_bytes, cudaMemcpyHostToDevice));
+  int *daux = nullptr;
+  if (epi == EPI_STORE_F32_COLMAX) {  // the column max itself is checked through the CDF parity tests; here it only must not corrupt C
+    CZ_CUDA_TRY(cudaMalloc((void **)&daux, (size_t)N * 4 + 16));
+    CZ_CUDA_TRY(cudaMemset(daux, 0x80, (size_t)N * 4 + 16));
+  }
   GemmArgs g{};
+  g.aux = daux;
   g.a = da; g.b = db; g.c = dc; g.M = M; g.N = N; g.K = K; g.lda = K; g.ldb = K; g.ldc = ldc; g.epi = epi; g.bn = bn;
   int rc = gemm(ctx, engine, g, ctx->stream);
   if (rc == CZ_OK) {
@@ -35,6 +41,7 @@ extern "C" int cz_test_gemm(cz_ctx *ctx, int engine, int M, int N, int K, const 
       cudaMemcpy(c_inout, dc, c_bytes, cudaMemcpyDeviceToHost);
     }
   }
+  if (daux) cudaFree(daux);
   cudaFree(da);
   cudaFree(db);
   cudaFree(dc);

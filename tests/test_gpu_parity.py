@@ -223,6 +223,21 @@ def test_gemm_activation_epilogues(gpu_ctx, engine, epi, bn, fn):
     assert np.all(out[:, N:] == 0x7FC0)
 
 
+@pytest.mark.parametrize("epi", [0, 4], ids=["store", "colmax"])
+def test_gemm_tma_store_many_tiles_few_columns(gpu_ctx, epi):
+    """decode-shaped LM head: thousands of vocab rows (many M tiles per CTA), a handful of columns.  Every tile then stores
+    through the same 32-column chunk: regression test for the double-buffered TMA patch being alternated per chunk index
+    instead of per store (consecutive tiles overwrote a patch that a bulk store was still reading)."""
+    rng = np.random.default_rng(40 + epi)
+    M, N, K = 128 * 148 * 3 + 77, 3, 128
+    a16 = _bf16(rng.normal(0, 1, (M, K)))
+    b16 = _bf16(rng.normal(0, 1, (N, K)))
+    c = _run_gemm(gpu_ctx, _lib.CZ_ENGINE_TCGEN05, a16, b16, epi, 256, np.zeros((M, 4), np.float32), 4)
+    want = _bf16_to_f32(a16).astype(np.float64) @ _bf16_to_f32(b16).astype(np.float64).T
+    assert np.abs(c[:, :N] - want).max() < 5e-3
+    assert np.all(c[:, N:] == 0)
+
+
 def test_gemm_tcgen05_row_invariance(gpu_ctx):
     """decode safety: a row's result must not depend on batch size or on its position in the tile grid."""
     rng = np.random.default_rng(12)
