@@ -392,8 +392,8 @@ static int encode_core(cz_model *m, const uint32_t *ids_dev, const uint32_t *ids
     build_chunks(n, sched->context, sched->reprime_interval, sched->events, sched->n_events, chunks);
     for (const Chunk &c : chunks) {
       const size_t rows = (size_t)c.prime_len + c.n_coded - 1;
-      if (rows > 2000) {
-        set_error("schedule produces a sequence longer than the attention kernel supports (2000 positions)");
+      if (rows > (size_t)m->max_seq()) {
+        set_error("schedule produces a sequence longer than the attention kernel supports (" + std::to_string(m->max_seq()) + " positions)");
         return CZ_ERR_UNSUPPORTED;
       }
       if (w.n_rows() + rows > max_rows && w.n_rows() > 0) CZ_TRY(flush());
@@ -642,7 +642,7 @@ int cz_decode(cz_model *m, const uint8_t *payload, const uint64_t *seg_off, size
   size_t max_pos = 0;
   for (const Chunk &ch : chunks) max_pos = std::max<size_t>(max_pos, (size_t)ch.prime_len + ch.n_coded);
   max_pos = (max_pos + 63) & ~(size_t)63;
-  if (max_pos > 2000) {
+  if (max_pos > (size_t)m->max_seq() + 64) {
     set_error("schedule produces a sequence longer than the attention kernel supports");
     return CZ_ERR_UNSUPPORTED;
   }
@@ -884,7 +884,7 @@ int cz_xe_bits(cz_model *m, const cz_xe_job *jobs, size_t n_jobs, double *bits_o
   for (size_t j = 0; j < n_jobs; j++) {
     if (jobs[j].n_targets == 0) continue;
     const size_t rows = (size_t)jobs[j].prime_len + jobs[j].n_targets - 1;
-    if (rows > 2000) {
+    if (rows > (size_t)m->max_seq()) {
       set_error("xe job longer than the attention kernel supports");
       return CZ_ERR_UNSUPPORTED;
     }

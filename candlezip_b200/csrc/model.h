@@ -108,7 +108,9 @@ struct cz_model {
   __nv_bfloat16 *embed = nullptr;  // alias of the embed_tokens slot
   float *norms = nullptr;          // [L][2][D] + [D]
   float *cos_tab = nullptr, *sin_tab = nullptr;  // [rope_max_pos][32]
-  int rope_max_pos = 2048;
+  int rope_max_pos = 8192;  // SmolLM2 max_position_embeddings
+  // longest sequence (prime + coded tokens of one chunk) the attention kernel in use can take
+  int max_seq() const { return attn_tc ? rope_max_pos - 1 : 2000; }
   int gu_bn = 192;
   bool attn_tc = false;  // tcgen05 attention kernel (attn_tc.cu); else the mma.sync kernel (attn_mma.cu)
   int attn_tile = 64;    // query positions per attention tile (128 with attn_tc)

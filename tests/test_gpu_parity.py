@@ -589,6 +589,40 @@ def test_file_level_compress_decompress_both_backends(gpu_ctx):
     assert codec.decompress(rmodel, gblob, tokenizer=tok) == gap
 
 
+def test_full_size_smollm_multi_chunk_invariance_and_roundtrip(gpu_ctx):
+    """BASELINE config 2 shape in miniature at FULL model size: many segments, several reprime chunks each.  Size-independent
+    properties: identical bytes whatever the wave size; a segment's stream equals the single-stream encode of its tokens
+    (batch-size invariance); decode(encode(x)) == x through the lock-step decoder (graph-replayed steps, chunk re-primes)."""
+    model = cz.Model(gpu_ctx, cz.SMOLLM_135M).random_init(0, 0.02, 0.02)
+    rng = np.random.default_rng(5)
+    n, nseg = 24 * 1100, 24
+    ids = rng.integers(0, 256, n).astype(np.uint32)  # byte-level ids, like the bench
+    p1, s1 = model.encode(ids, n_segments=nseg)
+    p2, s2 = model.encode(ids, n_segments=nseg, max_batch_tokens=9000)
+    assert p1 == p2 and np.array_equal(s1, s2)
+    solo, _ = model.encode(ids[int(s1[3]) : int(s1[4])], n_segments=1)
+    assert solo[0] == p1[3]
+    assert np.array_equal(model.decode(p1, s1), ids)
+    # long reprime interval: one chunk of 511 + 3000 positions (beyond the old 2000-position limit of the mma.sync kernel)
+    long_ids = rng.integers(0, 256, 3600).astype(np.uint32)
+    pl, sl = model.encode(long_ids, n_segments=1, reprime_interval=3000)
+    assert np.array_equal(model.decode(pl, sl, reprime_interval=3000), long_ids)
+
+
+def test_cli_twin_self_test(gpu_ctx, tmp_path):
+    """`python -m candlezip_b200 self-test` (src/main.rs:156-221) on a small file, both backends, segmented"""
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    p = tmp_path / "sample.txt"
+    p.write_bytes((b"the quick brown fox jumps over the lazy dog. " * 30) + bytes(range(256)))
+    for backend in ("smollm", "rwkv7"):
+        r = subprocess.run([sys.executable, "-m", "candlezip_b200", "self-test", str(p), "--backend", backend, "--segments", "4"], cwd=root,
+                           capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0 and "roundtrip OK" in r.stdout, (r.stdout, r.stderr[-500:])
+
+
 def test_rwkv7_full_size_roundtrip(gpu_ctx):
     """rwkv7-g1-0.1b shape (random-init): logits vs the oracle on a few positions, then a multi-segment round trip."""
     model = cz.Model(gpu_ctx, cz.RWKV7_0P1B).random_init(3, 0.02, 0.05)
