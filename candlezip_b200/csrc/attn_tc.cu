@@ -44,7 +44,9 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map
 
 // STACKED = false: tile rows are up to 128 consecutive positions of one query head (grid.y = query heads).
 // STACKED = true (stepwise decode, one position per sequence): tile rows are the G query heads that share one KV head, all at
-//   the same position (grid.y = KV heads), so a sequence's K/V block is loaded once for the whole GQA group.
+//   the same position, and ONE CTA walks all KV heads of the sequence back to back (grid.y = 1): the per-CTA set-up (TMEM
+//   allocation, barriers, descriptor prefetch) is paid once per sequence and the next head's Q / K / V loads are already in
+//   flight while the current head is processed.
 // A (position, head) row goes through exactly the same arithmetic in both modes.
 template <bool STACKED>
 __global__ void __launch_bounds__(AT_THREADS) attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
@@ -54,7 +56,8 @@ __global__ void __launch_bounds__(AT_THREADS) attn_tc_kernel(const __grid_consta
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const int G = nh / nkv;
-  const int tile = blockIdx.x, kvh = STACKED ? (int)blockIdx.y : (int)blockIdx.y / G, head0 = STACKED ? kvh * G : (int)blockIdx.y;
+  const int tile = blockIdx.x, kvh0 = STACKED ? 0 : (int)blockIdx.y / G, head0 = STACKED ? 0 : (int)blockIdx.y;
+  const int n_loop = STACKED ? nkv : 1;  // KV heads handled by this CTA
   const int row0 = tile_row0[tile], n_pos = STACKED ? 1 : tile_n[tile];
   const int nq = STACKED ? G : n_pos;  // valid tile rows
   const int p0 = pos[row0], base = kv_base[row0];
@@ -94,21 +97,25 @@ __global__ void __launch_bounds__(AT_THREADS) attn_tc_kernel(const __grid_consta
 
   if (warp == 4) {
     if (lane == 0) {
-      auto load_k = [&](int kb) {
+      const int total = n_loop * nb;  // flattened (head, key block) iterations; every barrier's phase follows this counter
+      auto load_k = [&](int g) {
         mbar_expect_tx(k_full, 16384);
-        tma_load_2d(sK, &tm_k, k_full, kvh * 64, base + kb * 128);
+        tma_load_2d(sK, &tm_k, k_full, (kvh0 + g / nb) * 64, base + (g % nb) * 128);
       };
-      auto load_v = [&](int kb, int st) {
+      auto load_v = [&](int g, int st) {
         const uint32_t fb = v_full + 8 * st;
         mbar_expect_tx(fb, 16384);
-        tma_load_2d(sV + st * 16384, &tm_v, fb, kvh * 64, base + kb * 128);  // [128 keys][64 dims], like the K block
+        tma_load_2d(sV + st * 16384, &tm_v, fb, (kvh0 + g / nb) * 64, base + (g % nb) * 128);  // [128 keys][64 dims], like the K block
       };
       // q viewed as [row][head][64]: a box of 128 rows x 1 head, or 1 row x G heads
-      mbar_expect_tx(q_full, STACKED ? G * 128 : 16384);
-      tma_load_3d(sQ, &tm_q, q_full, 0, head0, row0);
+      auto load_q = [&](int hh) {
+        mbar_expect_tx(q_full, STACKED ? G * 128 : 16384);
+        tma_load_3d(sQ, &tm_q, q_full, 0, STACKED ? hh * G : head0, row0);
+      };
+      load_q(0);
       load_k(0);
       load_v(0, 0);
-      if (nb > 1) load_v(1, 1);
+      if (total > 1) load_v(1, 1);
       // P V: the B operand V [128 keys][64 dims] has the dims (N) contiguous -> MN-major B (instruction descriptor bit 16)
       constexpr uint32_t idesc_qk = make_idesc_mn(128, 128), idesc_pv = make_idesc_mn(128, 64) | (1u << 16);
       const uint64_t q_desc = make_kmajor_sw128_desc(sQ), k_desc = make_kmajor_sw128_desc(sK);
@@ -122,20 +129,23 @@ __global__ void __launch_bounds__(AT_THREADS) attn_tc_kernel(const __grid_consta
       mbar_wait(k_full, 0);
       tc_fence_after();
       issue_qk();
-      for (int kb = 0; kb < nb; kb++) {
-        const int st = kb & 1;
-        if (kb + 1 < nb) {
-          mbar_wait(k_empty, kb & 1);  // S(kb) = Q K(kb)^T is done: the K buffer can take the next block while the softmax runs
-          load_k(kb + 1);
+      for (int g = 0; g < total; g++) {
+        const int st = g & 1;
+        const bool next_head = (g + 1) % nb == 0;  // iteration g + 1 starts a new KV head
+        if (g + 1 < total) {
+          mbar_wait(k_empty, g & 1);  // S(g) = Q K^T is done: the K buffer (and, at a head boundary, Q) can be refilled while the softmax runs
+          if (next_head) load_q((g + 1) / nb);
+          load_k(g + 1);
         }
-        mbar_wait(p_ready, kb & 1);  // P(kb) is in shared memory and S has been consumed
+        mbar_wait(p_ready, g & 1);  // P(g) is in shared memory and S has been consumed
         tc_fence_after();
-        if (kb + 1 < nb) {
-          mbar_wait(k_full, (kb + 1) & 1);
+        if (g + 1 < total) {
+          if (next_head) mbar_wait(q_full, ((g + 1) / nb) & 1);
+          mbar_wait(k_full, (g + 1) & 1);
           tc_fence_after();
-          issue_qk();  // S(kb+1): overlaps P V (kb) and the softmax warps' output update
+          issue_qk();  // S(g+1): overlaps P V (g) and the softmax warps' output update
         }
-        mbar_wait(v_full + 8 * st, (kb >> 1) & 1);
+        mbar_wait(v_full + 8 * st, (g >> 1) & 1);
         tc_fence_after();
 #pragma unroll
         for (int ks = 0; ks < 8; ks++) {
@@ -147,9 +157,9 @@ __global__ void __launch_bounds__(AT_THREADS) attn_tc_kernel(const __grid_consta
         }
         tc_commit(o_full);
         tc_commit(v_empty + 8 * st);
-        if (kb + 2 < nb) {
-          mbar_wait(v_empty + 8 * st, (kb >> 1) & 1);
-          load_v(kb + 2, st);
+        if (g + 2 < total) {
+          mbar_wait(v_empty + 8 * st, (g >> 1) & 1);
+          load_v(g + 2, st);
         }
       }
     }
@@ -161,10 +171,16 @@ __global__ void __launch_bounds__(AT_THREADS) attn_tc_kernel(const __grid_consta
     const float c_log2 = 0.125f * 1.4426950408889634f;  // 1/sqrt(64) * log2(e)
     float m = -INFINITY, l = 0.f;
     float o[64];
+    const int total = n_loop * nb;
+    for (int g = 0; g < total; g++) {
+      const int kb = g % nb;
+      if (kb == 0) {  // new head: fresh online-softmax state
+        m = -INFINITY;
+        l = 0.f;
 #pragma unroll
-    for (int j = 0; j < 64; j++) o[j] = 0.f;
-    for (int kb = 0; kb < nb; kb++) {
-      mbar_wait(s_full, kb & 1);
+        for (int j = 0; j < 64; j++) o[j] = 0.f;
+      }
+      mbar_wait(s_full, g & 1);
       tc_fence_after();
       float alpha = 1.f;
       if (warp_valid) {
@@ -227,7 +243,7 @@ __global__ void __launch_bounds__(AT_THREADS) attn_tc_kernel(const __grid_consta
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       tc_fence_before();
       mbar_arrive(p_ready);
-      mbar_wait(o_full, kb & 1);
+      mbar_wait(o_full, g & 1);
       tc_fence_after();
       if (warp_valid) {
         uint32_t v[64];
@@ -238,19 +254,20 @@ __global__ void __launch_bounds__(AT_THREADS) attn_tc_kernel(const __grid_consta
         for (int j = 0; j < 64; j++) o[j] = fmaf(o[j], alpha, __uint_as_float(v[j]));
       }
       tc_fence_before();
-    }
-    if (r < nq) {
-      const float inv = 1.0f / l;
-      __nv_bfloat16 *dst = out + (size_t)(STACKED ? row0 : row0 + r) * (nh * 64) + (STACKED ? head0 + r : head0) * 64;
+      if (kb == nb - 1 && r < nq) {  // head finished: normalise and store its output row
+        const float inv = 1.0f / l;
+        const int head = STACKED ? (g / nb) * G + r : head0;
+        __nv_bfloat16 *dst = out + (size_t)(STACKED ? row0 : row0 + r) * (nh * 64) + head * 64;
 #pragma unroll
-      for (int j = 0; j < 64; j += 8) {
-        uint32_t w[4];
+        for (int j = 0; j < 64; j += 8) {
+          uint32_t w[4];
 #pragma unroll
-        for (int e = 0; e < 4; e++) {
-          __nv_bfloat162 h = __floats2bfloat162_rn(o[j + 2 * e] * inv, o[j + 2 * e + 1] * inv);
-          w[e] = *reinterpret_cast<uint32_t *>(&h);
+          for (int e = 0; e < 4; e++) {
+            __nv_bfloat162 h = __floats2bfloat162_rn(o[j + 2 * e] * inv, o[j + 2 * e + 1] * inv);
+            w[e] = *reinterpret_cast<uint32_t *>(&h);
+          }
+          *reinterpret_cast<uint4 *>(dst + j) = make_uint4(w[0], w[1], w[2], w[3]);
         }
-        *reinterpret_cast<uint4 *>(dst + j) = make_uint4(w[0], w[1], w[2], w[3]);
       }
     }
   }
@@ -315,7 +332,7 @@ int launch_attn_tc(cz_ctx *ctx, const __nv_bfloat16 *q, int n_rows, const __nv_b
   CZ_TRY(make_map_bf16(&tk, k_arena, n_slots, nkv * 64, nkv * 64, 128));
   CZ_TRY(make_map_bf16(&tv, v_arena, n_slots, nkv * 64, nkv * 64, 128));  // V rows [slot][nkv*64], same box as K
   if (single_rows) {
-    dim3 grid((unsigned)n_tiles, (unsigned)nkv);
+    dim3 grid((unsigned)n_tiles, 1);
     CZ_LAUNCH(ctx, CZ_K_ATTN,
               (czk::attn_tc_kernel<true><<<grid, czk::AT_THREADS, czk::AT_SMEM, st>>>(tq, tk, tv, pos, kv_base, tile_row0, tile_n, out, nh, nkv)));
   } else {
