@@ -56,8 +56,11 @@ __global__ void __launch_bounds__(AT_THREADS) attn_tc_kernel(const __grid_consta
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const int G = nh / nkv;
-  const int tile = blockIdx.x, kvh0 = STACKED ? 0 : (int)blockIdx.y / G, head0 = STACKED ? 0 : (int)blockIdx.y;
-  const int n_loop = STACKED ? nkv : 1;  // KV heads handled by this CTA
+  // One CTA walks n_loop (head, key block) sequences back to back with ONE flattened load / MMA pipeline, so the per-CTA set-up
+  // is amortised and the next head's loads are in flight while the current one is processed:
+  //   STACKED:  all nkv KV heads of the sequence (grid.y = 1);  else: the G query heads of KV head blockIdx.y (grid.y = nkv).
+  const int tile = blockIdx.x, kvh0 = STACKED ? 0 : (int)blockIdx.y, head0 = STACKED ? 0 : (int)blockIdx.y * G;
+  const int n_loop = STACKED ? nkv : G;
   const int row0 = tile_row0[tile], n_pos = STACKED ? 1 : tile_n[tile];
   const int nq = STACKED ? G : n_pos;  // valid tile rows
   const int p0 = pos[row0], base = kv_base[row0];
@@ -100,17 +103,17 @@ __global__ void __launch_bounds__(AT_THREADS) attn_tc_kernel(const __grid_consta
       const int total = n_loop * nb;  // flattened (head, key block) iterations; every barrier's phase follows this counter
       auto load_k = [&](int g) {
         mbar_expect_tx(k_full, 16384);
-        tma_load_2d(sK, &tm_k, k_full, (kvh0 + g / nb) * 64, base + (g % nb) * 128);
+        tma_load_2d(sK, &tm_k, k_full, (STACKED ? g / nb : kvh0) * 64, base + (g % nb) * 128);
       };
       auto load_v = [&](int g, int st) {
         const uint32_t fb = v_full + 8 * st;
         mbar_expect_tx(fb, 16384);
-        tma_load_2d(sV + st * 16384, &tm_v, fb, (kvh0 + g / nb) * 64, base + (g % nb) * 128);  // [128 keys][64 dims], like the K block
+        tma_load_2d(sV + st * 16384, &tm_v, fb, (STACKED ? g / nb : kvh0) * 64, base + (g % nb) * 128);  // [128 keys][64 dims], like the K block
       };
       // q viewed as [row][head][64]: a box of 128 rows x 1 head, or 1 row x G heads
       auto load_q = [&](int hh) {
         mbar_expect_tx(q_full, STACKED ? G * 128 : 16384);
-        tma_load_3d(sQ, &tm_q, q_full, 0, STACKED ? hh * G : head0, row0);
+        tma_load_3d(sQ, &tm_q, q_full, 0, STACKED ? hh * G : head0 + hh, row0);
       };
       load_q(0);
       load_k(0);
@@ -169,9 +172,24 @@ __global__ void __launch_bounds__(AT_THREADS) attn_tc_kernel(const __grid_consta
     const int pos_r = STACKED ? p0 : p0 + r;
     const uint32_t t_s = tmem_base + ((uint32_t)(warp * 32) << 16), t_o = t_s + 128;
     const float c_log2 = 0.125f * 1.4426950408889634f;  // 1/sqrt(64) * log2(e)
-    float m = -INFINITY, l = 0.f;
+    float m = -INFINITY, l = 0.f, alpha_prev = 1.f;
+    bool pending = false;  // the previous block's O update (O = O * alpha + P V) is still owed
     float o[64];
     const int total = n_loop * nb;
+    // O = O * a + (P V of iteration gi), read from TMEM once that product has completed
+    auto o_update = [&](int gi, float a) {
+      mbar_wait(o_full, gi & 1);
+      tc_fence_after();
+      if (warp_valid) {
+        uint32_t v[64];
+        tc_ld_32x32(t_o, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+        tc_ld_32x32(t_o + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
+        tc_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 64; j++) o[j] = fmaf(o[j], a, __uint_as_float(v[j]));
+      }
+      tc_fence_before();
+    };
     for (int g = 0; g < total; g++) {
       const int kb = g % nb;
       if (kb == 0) {  // new head: fresh online-softmax state
@@ -182,12 +200,12 @@ __global__ void __launch_bounds__(AT_THREADS) attn_tc_kernel(const __grid_consta
       }
       mbar_wait(s_full, g & 1);
       tc_fence_after();
-      float alpha = 1.f;
+      float alpha = 1.f, mx = 0.f;
+      const int lim = pos_r - kb * 128;
+      const bool need_mask = kb * 128 + 127 > p0;
       if (warp_valid) {
         // causal mask: columns > lim of this block are keys after the row's position.  Blocks entirely at or before the
         // tile's first position take the mask-free path (warp-uniform); both paths compute identical values for unmasked keys.
-        const int lim = pos_r - kb * 128;
-        const bool need_mask = kb * 128 + 127 > p0;
         // four independent running maxima / sums (combined in a fixed order): a single 128-long dependent chain of
         // FMNMX / FADD would cost more cycles than the exp2 work itself
         float r4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
@@ -206,9 +224,17 @@ __global__ void __launch_bounds__(AT_THREADS) attn_tc_kernel(const __grid_consta
           }
         }
         const float raw = fmaxf(fmaxf(r4[0], r4[1]), fmaxf(r4[2], r4[3]));
-        const float mx = fmaxf(m, raw * c_log2);
+        mx = fmaxf(m, raw * c_log2);
         alpha = at_ex2(m - mx);  // first block: ex2(-inf) = 0
         m = mx;
+      }
+      // The previous block's output update is applied HERE, after this block's max pass: its P V product ran while the max was
+      // being computed, so its latency is hidden.  It must precede pass 2, which overwrites the P buffer that product read.
+      if (pending) {
+        o_update(g - 1, alpha_prev);
+        pending = false;
+      }
+      if (warp_valid) {
         float s4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
         for (int c = 0; c < 4; c++) {
@@ -243,20 +269,15 @@ __global__ void __launch_bounds__(AT_THREADS) attn_tc_kernel(const __grid_consta
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       tc_fence_before();
       mbar_arrive(p_ready);
-      mbar_wait(o_full, g & 1);
-      tc_fence_after();
-      if (warp_valid) {
-        uint32_t v[64];
-        tc_ld_32x32(t_o, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
-        tc_ld_32x32(t_o + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
-        tc_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 64; j++) o[j] = fmaf(o[j], alpha, __uint_as_float(v[j]));
+      if (kb == nb - 1) {
+        o_update(g, alpha);  // last block of the head: nothing left to hide behind
+      } else {
+        pending = true;
+        alpha_prev = alpha;
       }
-      tc_fence_before();
       if (kb == nb - 1 && r < nq) {  // head finished: normalise and store its output row
         const float inv = 1.0f / l;
-        const int head = STACKED ? (g / nb) * G + r : head0;
+        const int head = STACKED ? (g / nb) * G + r : head0 + g / nb;
         __nv_bfloat16 *dst = out + (size_t)(STACKED ? row0 : row0 + r) * (nh * 64) + head * 64;
 #pragma unroll
         for (int j = 0; j < 64; j += 8) {
@@ -336,7 +357,7 @@ int launch_attn_tc(cz_ctx *ctx, const __nv_bfloat16 *q, int n_rows, const __nv_b
     CZ_LAUNCH(ctx, CZ_K_ATTN,
               (czk::attn_tc_kernel<true><<<grid, czk::AT_THREADS, czk::AT_SMEM, st>>>(tq, tk, tv, pos, kv_base, tile_row0, tile_n, out, nh, nkv)));
   } else {
-    dim3 grid((unsigned)n_tiles, (unsigned)nh);
+    dim3 grid((unsigned)n_tiles, (unsigned)nkv);
     CZ_LAUNCH(ctx, CZ_K_ATTN,
               (czk::attn_tc_kernel<false><<<grid, czk::AT_THREADS, czk::AT_SMEM, st>>>(tq, tk, tv, pos, kv_base, tile_row0, tile_n, out, nh, nkv)));
   }
