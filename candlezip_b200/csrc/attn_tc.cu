@@ -1,21 +1,34 @@
-// K5, engine v3: causal GQA attention on the 5th-generation tensor cores (tcgen05.mma, accumulators in TMEM, operands fed by
-// TMA), flash-style online softmax.  One CTA = one tile of up to 128 consecutive query positions of ONE sequence x one query
-// head; two CTAs are resident per SM (112 KB shared memory, 256 TMEM columns each) so one CTA's softmax overlaps the other's MMAs.
+// K5, engine v4: causal GQA attention on the 5th-generation tensor cores (tcgen05.mma, accumulators in TMEM, operands fed by
+// TMA), flash-style online softmax.  One CTA = one tile of up to 128 consecutive query positions of ONE sequence x one KV head
+// (it walks the G query heads of that group); two CTAs are resident per SM (64 KB shared memory, 256 TMEM columns each) so one
+// CTA's softmax overlaps the other's MMAs.
 //
 // Replaces candle-transformers llama attention (repeat_kv + QK^T/sqrt(d) + f32 softmax + PV) reached from src/models.rs:94,110.
 //
-//   warp 4 (one elected thread): TMA loads (Q once; K block and V block [128 keys x 64 dims]; K single-, V double-buffered) and the MMAs:  S = Q K^T  (128 x 128 x 64: 4 UMMA k-steps)  and  O_blk = P V  (128 x 64 x 128: 8 k-steps)
-//   warps 0-3: thread r owns query row r of the tile (tcgen05.ld 32x32b hands a TMEM lane to a thread): row max, exp2, row sum
-//           need no shuffles; P goes back as bf16 through shared memory (K-major SWIZZLE_128B, the A operand of P V);
-//           the running output row lives in 64 registers: O = O * alpha + O_blk.
+//   warp 4 (one elected thread): TMA loads (Q per head; K block and V block [128 keys x 64 dims]; K single-, V double-buffered)
+//           and the MMAs:  S = Q K^T  (128 x 128 x 64: 4 UMMA k-steps, both operands in shared memory)  and
+//           O += P V  (128 x 64 x 128: 8 k-steps, A = P read from TENSOR MEMORY, B = V in shared memory, accumulating in TMEM
+//           across the key blocks of a head).
+//   warps 0-3: thread r owns query row r of the tile (tcgen05.ld 32x32b hands a TMEM lane to a thread).  S is read from TMEM
+//           ONCE into 128 registers (the S columns are handed back to the MMA warp right away, so S(g+1) = Q K^T runs under
+//           the softmax of block g); row max (3-input FMNMX), p = exp2(s*c - m) (packed FFMA2), row sum (packed FADD2); P goes
+//           back as packed bf16 with tcgen05.st into 64 TMEM columns -- no shared-memory round trip, no proxy fence.
+//           The output row is NOT kept in registers: it stays in TMEM and is rescaled there only when a row's running max
+//           grows by more than 2^8 (lazy rescale, below); the only regular TMEM read per block is S itself
+//           (tcgen05.ld moves 64 B/clk: re-reading S for a second pass and reading O_blk every block was what bound v3).
 // V stays in its natural row layout ([slot][kv dim]): the P V product takes it as an MN-major B operand (instruction
 // descriptor bit 16), whose canonical SWIZZLE_128B shared-memory layout is exactly what TMA writes for a [128 keys][64 dims] box.
+// TMEM columns (per CTA, 256): S [0,128) fp32 | O [128,192) fp32 | P [192,256) bf16 pairs (A operand, K-major: lane = row,
+// one 32-bit column = two consecutive keys; a 16-key UMMA k-step is 8 columns).
 //
 // ROW INVARIANCE (decode safety).  For a given (sequence, position, head) the arithmetic is a fixed sequence: keys in blocks of
-// 128 anchored at key 0; per block one UMMA chain over the 64 dims, mask (exact -inf -> exp2 = 0), m' = max(m, rowmax),
-// p = exp2(s*c - m'), l = l*a + sum(p) in column order, O = O*a + (bf16(p) V by one UMMA chain over the block's 128 keys).
-// Nothing depends on which other rows share the tile or on the tile's size, so the same kernel serves 128-row teacher-forced
-// tiles and single-row decode tiles and gives bit-identical outputs (tests: stepwise == teacher-forced bitwise).
+// 128 anchored at key 0; per block one UMMA chain over the 64 dims, mask (exact -inf -> exp2 = 0), row max, then
+//   if (rowmax*c > m + 8) { a = exp2(m - rowmax*c); m = rowmax*c; l *= a; O *= a; }     (decision from the row's own data only)
+//   p = exp2(s*c - m);  l += sum(p) in a fixed order;  O += bf16(p) V  (one UMMA chain over the block's 128 keys, accumulated in TMEM).
+// The O rescale is a warp-collective TMEM read-modify-write performed when ANY row of the warp asks for it; rows that did not ask
+// are multiplied by exactly 1.0f, so what the other rows of a tile do never changes a row's bits.  Nothing depends on which other rows share the tile or
+// on the tile's size, so the same kernel serves 128-row teacher-forced tiles and single-row decode tiles and gives bit-identical
+// outputs (tests: stepwise == teacher-forced bitwise).
 #include <cuda.h>
 
 #include "cz_common.cuh"
@@ -26,13 +39,62 @@ namespace czk {
 
 constexpr int AT_THREADS = 160;
 // shared memory: Q 16 KB | K 16 KB (single buffer: it is free again as soon as S = Q K^T has been computed, long before the
-// next block needs it) | V^T 2 x 16 KB | P 32 KB | barriers; 1 KB of slack to align the SWIZZLE_128B tiles.  ~98 KB: two CTAs per SM.
-constexpr int AT_Q = 0, AT_K = 16384, AT_V = 32768, AT_P = 65536, AT_BAR = 98304, AT_SMEM = AT_BAR + 128 + 1024;
+// next block needs it) | V 2 x 16 KB | barriers; 1 KB of slack to align the SWIZZLE_128B tiles.  ~66 KB: two CTAs per SM
+// (the TMEM columns, 2 x 256, are what limits residency).
+constexpr int AT_Q = 0, AT_K = 16384, AT_V = 32768, AT_BAR = 65536, AT_SMEM = AT_BAR + 128 + 1024;
+constexpr int AT_TM_S = 0, AT_TM_O = 128, AT_TM_P = 192;
+constexpr float AT_RESCALE_LOG2 = 8.0f;  // lazy-rescale threshold on the log2-domain running max
 
 __device__ __forceinline__ float at_ex2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+}
+__device__ __forceinline__ float at_max3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+// (x0, x1) * c + nm on the packed-f32 FMA path (FFMA2): two IEEE fmas, bit-identical to two scalar fmaf
+__device__ __forceinline__ void at_fma2(float &x0, float &x1, uint64_t c2, uint64_t nm2) {
+  uint64_t x, y;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(x) : "f"(x0), "f"(x1));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(y) : "l"(x), "l"(c2), "l"(nm2));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(x0), "=f"(x1) : "l"(y));
+}
+__device__ __forceinline__ uint64_t at_pack2(float a, float b) {
+  uint64_t x;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(x) : "f"(a), "f"(b));
+  return x;
+}
+__device__ __forceinline__ uint64_t at_add2(uint64_t a, uint64_t b) {
+  uint64_t y;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(y) : "l"(a), "l"(b));
+  return y;
+}
+__device__ __forceinline__ void at_unpack2(uint64_t x, float &a, float &b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(x)); }
+
+__device__ __forceinline__ void tc_st_32x32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]),
+      "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]),
+      "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tc_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// D[tmem] (+)= A[tmem] * B[smem]: the A operand (P) is read from tensor memory
+__device__ __forceinline__ void tc_mma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc)
+      : "memory");
 }
 
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1, int c2) {
@@ -42,17 +104,17 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map
       : "memory");
 }
 
-// STACKED = false: tile rows are up to 128 consecutive positions of one query head (grid.y = query heads).
+// STACKED = false: tile rows are up to 128 consecutive positions of one query head (grid.y = KV heads).
 // STACKED = true (stepwise decode, one position per sequence): tile rows are the G query heads that share one KV head, all at
 //   the same position, and ONE CTA walks all KV heads of the sequence back to back (grid.y = 1): the per-CTA set-up (TMEM
 //   allocation, barriers, descriptor prefetch) is paid once per sequence and the next head's Q / K / V loads are already in
 //   flight while the current head is processed.
 // A (position, head) row goes through exactly the same arithmetic in both modes.
 template <bool STACKED>
-__global__ void __launch_bounds__(AT_THREADS) attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
-                                                             const __grid_constant__ CUtensorMap tm_v, const int *__restrict__ pos,
-                                                             const int *__restrict__ kv_base, const int *__restrict__ tile_row0,
-                                                             const int *__restrict__ tile_n, __nv_bfloat16 *__restrict__ out, int nh, int nkv) {
+__global__ void __launch_bounds__(AT_THREADS, 2) attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
+                                                                const __grid_constant__ CUtensorMap tm_v, const int *__restrict__ pos,
+                                                                const int *__restrict__ kv_base, const int *__restrict__ tile_row0,
+                                                                const int *__restrict__ tile_n, __nv_bfloat16 *__restrict__ out, int nh, int nkv) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const int G = nh / nkv;
@@ -65,12 +127,14 @@ __global__ void __launch_bounds__(AT_THREADS) attn_tc_kernel(const __grid_consta
   const int nq = STACKED ? G : n_pos;  // valid tile rows
   const int p0 = pos[row0], base = kv_base[row0];
   const int nb = (p0 + n_pos + 127) >> 7;
+  const int total = n_loop * nb;  // flattened (head, key block) iterations; every barrier's phase follows this counter
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem + AT_BAR);
   const uint32_t q_full = smem_u32(&bars[0]), k_full = smem_u32(&bars[1]), k_empty = smem_u32(&bars[2]), v_full = smem_u32(&bars[3]) /*[2]*/,
-                 v_empty = smem_u32(&bars[5]) /*[2]*/, s_full = smem_u32(&bars[7]), p_ready = smem_u32(&bars[8]), o_full = smem_u32(&bars[9]);
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(&bars[10]);
-  const uint32_t sQ = smem_u32(smem + AT_Q), sK = smem_u32(smem + AT_K), sV = smem_u32(smem + AT_V), sP = smem_u32(smem + AT_P);
+                 v_empty = smem_u32(&bars[5]) /*[2]*/, s_full = smem_u32(&bars[7]), p_ready = smem_u32(&bars[8]), o_full = smem_u32(&bars[9]),
+                 s_free = smem_u32(&bars[10]);
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(&bars[11]);
+  const uint32_t sQ = smem_u32(smem + AT_Q), sK = smem_u32(smem + AT_K), sV = smem_u32(smem + AT_V);
 
   if (warp == 4 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_q) : "memory");
@@ -86,6 +150,7 @@ __global__ void __launch_bounds__(AT_THREADS) attn_tc_kernel(const __grid_consta
     mbar_init(s_full, 1);
     mbar_init(p_ready, 128);
     mbar_init(o_full, 1);
+    mbar_init(s_free, 128);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -100,7 +165,6 @@ __global__ void __launch_bounds__(AT_THREADS) attn_tc_kernel(const __grid_consta
 
   if (warp == 4) {
     if (lane == 0) {
-      const int total = n_loop * nb;  // flattened (head, key block) iterations; every barrier's phase follows this counter
       auto load_k = [&](int g) {
         mbar_expect_tx(k_full, 16384);
         tma_load_2d(sK, &tm_k, k_full, (STACKED ? g / nb : kvh0) * 64, base + (g % nb) * 128);
@@ -124,7 +188,8 @@ __global__ void __launch_bounds__(AT_THREADS) attn_tc_kernel(const __grid_consta
       const uint64_t q_desc = make_kmajor_sw128_desc(sQ), k_desc = make_kmajor_sw128_desc(sK);
       auto issue_qk = [&]() {
 #pragma unroll
-        for (int ks = 0; ks < 4; ks++) tc_mma_bf16(tmem_base, q_desc + (uint64_t)(ks * 2), k_desc + (uint64_t)(ks * 2), idesc_qk, ks ? 1u : 0u);
+        for (int ks = 0; ks < 4; ks++)
+          tc_mma_bf16(tmem_base + AT_TM_S, q_desc + (uint64_t)(ks * 2), k_desc + (uint64_t)(ks * 2), idesc_qk, ks ? 1u : 0u);
         tc_commit(s_full);
         tc_commit(k_empty);
       };
@@ -134,161 +199,173 @@ __global__ void __launch_bounds__(AT_THREADS) attn_tc_kernel(const __grid_consta
       issue_qk();
       for (int g = 0; g < total; g++) {
         const int st = g & 1;
-        const bool next_head = (g + 1) % nb == 0;  // iteration g + 1 starts a new KV head
+        const bool next_head = (g + 1) % nb == 0;  // iteration g + 1 starts a new head
         if (g + 1 < total) {
-          mbar_wait(k_empty, g & 1);  // S(g) = Q K^T is done: the K buffer (and, at a head boundary, Q) can be refilled while the softmax runs
+          mbar_wait(k_empty, g & 1);  // S(g) = Q K^T is done: the K buffer (and, at a head boundary, Q) can be refilled
           if (next_head) load_q((g + 1) / nb);
           load_k(g + 1);
-        }
-        mbar_wait(p_ready, g & 1);  // P(g) is in shared memory and S has been consumed
-        tc_fence_after();
-        if (g + 1 < total) {
+          if (g >= 1) {  // P V (g-1) has finished long ago: its V stage takes block g + 1
+            mbar_wait(v_empty + 8 * (st ^ 1), ((g - 1) >> 1) & 1);
+            load_v(g + 1, st ^ 1);
+          }
+          mbar_wait(s_free, g & 1);  // the softmax warps hold S(g) in registers
           if (next_head) mbar_wait(q_full, ((g + 1) / nb) & 1);
           mbar_wait(k_full, (g + 1) & 1);
           tc_fence_after();
-          issue_qk();  // S(g+1): overlaps P V (g) and the softmax warps' output update
+          issue_qk();  // S(g+1): runs under the softmax of block g
         }
+        mbar_wait(p_ready, g & 1);  // P(g) is in tensor memory, O has been rescaled if a row asked for it
         mbar_wait(v_full + 8 * st, (g >> 1) & 1);
         tc_fence_after();
+        const uint32_t first = (g % nb == 0) ? 0u : 1u;  // a head's first block overwrites O
 #pragma unroll
         for (int ks = 0; ks < 8; ks++) {
-          const uint64_t p_desc = make_kmajor_sw128_desc(sP + (ks >> 2) * 16384) + (uint64_t)((ks & 3) * 2);
           // canonical MN-major SWIZZLE_128B layout ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units: one 128-byte row per key,
           // 8-key groups 1024 B apart (SBO), n = 1; a K-step of 16 keys advances the start address by 16 rows = 2048 B
           const uint64_t v_desc = make_kmajor_sw128_desc(sV + st * 16384) + (uint64_t)(ks * 128);
-          tc_mma_bf16(tmem_base + 128, p_desc, v_desc, idesc_pv, ks ? 1u : 0u);
+          tc_mma_bf16_ts(tmem_base + AT_TM_O, tmem_base + AT_TM_P + (uint32_t)(ks * 8), v_desc, idesc_pv, ks ? 1u : first);
         }
         tc_commit(o_full);
         tc_commit(v_empty + 8 * st);
-        if (g + 2 < total) {
-          mbar_wait(v_empty + 8 * st, (g >> 1) & 1);
-          load_v(g + 2, st);
-        }
       }
     }
   } else {
     const int r = warp * 32 + lane;
     const bool warp_valid = warp * 32 < nq;
     const int pos_r = STACKED ? p0 : p0 + r;
-    const uint32_t t_s = tmem_base + ((uint32_t)(warp * 32) << 16), t_o = t_s + 128;
+    const int pos_w_lo = STACKED ? p0 : p0 + warp * 32;  // the warp's first position
+    const uint32_t t_lane = tmem_base + ((uint32_t)(warp * 32) << 16);
+    const uint32_t t_s = t_lane + AT_TM_S, t_o = t_lane + AT_TM_O, t_p = t_lane + AT_TM_P;
     const float c_log2 = 0.125f * 1.4426950408889634f;  // 1/sqrt(64) * log2(e)
-    float m = -INFINITY, l = 0.f, alpha_prev = 1.f;
-    bool pending = false;  // the previous block's O update (O = O * alpha + P V) is still owed
-    float o[64];
-    const int total = n_loop * nb;
-    // O = O * a + (P V of iteration gi), read from TMEM once that product has completed
-    auto o_update = [&](int gi, float a) {
-      mbar_wait(o_full, gi & 1);
-      tc_fence_after();
-      if (warp_valid) {
-        uint32_t v[64];
-        tc_ld_32x32(t_o, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
-        tc_ld_32x32(t_o + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
-        tc_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 64; j++) o[j] = fmaf(o[j], a, __uint_as_float(v[j]));
+    const uint64_t c2 = at_pack2(c_log2, c_log2);
+    float m = -INFINITY, l = 0.f;
+    if (!warp_valid) {  // no valid row in this warp (short tile / stacked decode): keep the barrier protocol, touch nothing.
+      // The o_full waits keep these warps in lock step with the valid ones: without them they would run ahead and their
+      // arrivals for block g + 1 would complete p_ready's phase g before the valid warps have written P(g).
+      for (int g = 0; g < total; g++) {
+        const int kb = g % nb;
+        mbar_wait(s_full, g & 1);
+        mbar_arrive(s_free);
+        if (kb > 0) mbar_wait(o_full, (g - 1) & 1);
+        mbar_arrive(p_ready);
+        if (kb == nb - 1) mbar_wait(o_full, g & 1);
       }
-      tc_fence_before();
-    };
+    } else
     for (int g = 0; g < total; g++) {
       const int kb = g % nb;
       if (kb == 0) {  // new head: fresh online-softmax state
         m = -INFINITY;
         l = 0.f;
-#pragma unroll
-        for (int j = 0; j < 64; j++) o[j] = 0.f;
       }
+      const int lim = pos_r - kb * 128;
+      uint32_t w[128];  // S(g) as raw f32 bits; the packed bf16 P overwrites w[0, 64) in place (pair (j, j+1) -> w[j/2], j/2 <= j)
       mbar_wait(s_full, g & 1);
       tc_fence_after();
-      float alpha = 1.f, mx = 0.f;
-      const int lim = pos_r - kb * 128;
-      const bool need_mask = kb * 128 + 127 > p0;
-      if (warp_valid) {
-        // causal mask: columns > lim of this block are keys after the row's position.  Blocks entirely at or before the
-        // tile's first position take the mask-free path (warp-uniform); both paths compute identical values for unmasked keys.
-        // four independent running maxima / sums (combined in a fixed order): a single 128-long dependent chain of
-        // FMNMX / FADD would cost more cycles than the exp2 work itself
+#pragma unroll
+      for (int c = 0; c < 4; c++)
+        tc_ld_32x32(t_s + (uint32_t)(c * 32), *reinterpret_cast<uint32_t(*)[32]>(&w[c * 32]));
+      tc_ld_wait();
+      tc_fence_before();
+      mbar_arrive(s_free);  // S(g) is in registers: the MMA warp may overwrite the S columns with S(g+1)
+
+      float alpha = 1.f;
+      {
+        // causal mask: keys after the row's position become -inf (exp2 -> exact 0).  Chunks entirely at or before the warp's
+        // first position take the mask-free path (warp-uniform); both paths compute identical values for unmasked keys.
         float r4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-#pragma unroll 1
-        for (int c = 0; c < 2; c++) {
-          uint32_t v[64];
-          tc_ld_32x32(t_s + (uint32_t)(c * 64), *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
-          tc_ld_32x32(t_s + (uint32_t)(c * 64 + 32), *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
-          tc_ld_wait();
-          if (need_mask) {
+        if (kb * 128 + 127 > pos_w_lo) {
 #pragma unroll
-            for (int j = 0; j < 64; j++) r4[j & 3] = fmaxf(r4[j & 3], (c * 64 + j <= lim) ? __uint_as_float(v[j]) : -INFINITY);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 64; j++) r4[j & 3] = fmaxf(r4[j & 3], __uint_as_float(v[j]));
-          }
+          for (int j = 0; j < 128; j++) w[j] = (j <= lim) ? w[j] : 0xff800000u;
         }
-        const float raw = fmaxf(fmaxf(r4[0], r4[1]), fmaxf(r4[2], r4[3]));
-        mx = fmaxf(m, raw * c_log2);
-        alpha = at_ex2(m - mx);  // first block: ex2(-inf) = 0
-        m = mx;
-      }
-      // The previous block's output update is applied HERE, after this block's max pass: its P V product ran while the max was
-      // being computed, so its latency is hidden.  It must precede pass 2, which overwrites the P buffer that product read.
-      if (pending) {
-        o_update(g - 1, alpha_prev);
-        pending = false;
-      }
-      if (warp_valid) {
-        float s4[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 1
+#pragma unroll
         for (int c = 0; c < 4; c++) {
-          uint32_t v[32];
-          tc_ld_32x32(t_s + (uint32_t)(c * 32), v);
-          tc_ld_wait();
-          uint32_t pk[16];
 #pragma unroll
-          for (int j = 0; j < 32; j += 2) {
-            float pa = at_ex2(fmaf(__uint_as_float(v[j]), c_log2, -mx)), pb = at_ex2(fmaf(__uint_as_float(v[j + 1]), c_log2, -mx));
-            if (need_mask) {
-              pa = (c * 32 + j <= lim) ? pa : 0.f;
-              pb = (c * 32 + j + 1 <= lim) ? pb : 0.f;
-            }
-            s4[j & 2] += pa;
-            s4[(j & 2) + 1] += pb;
-            __nv_bfloat162 h = __floats2bfloat162_rn(pa, pb);
-            pk[j >> 1] = *reinterpret_cast<uint32_t *>(&h);
-          }
-          // row r, keys [c*32, c*32+32): 16-byte chunks (c&1)*4 .. +3 of the row's 128-byte line in K-atom (c>>1)
-          const uint32_t rowp = sP + (uint32_t)((c >> 1) * 16384 + r * 128);
-#pragma unroll
-          for (int q = 0; q < 4; q++) {
-            const uint32_t dst = rowp + (uint32_t)(((((c & 1) * 4 + q) ^ (r & 7))) << 4);
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(pk[4 * q]), "r"(pk[4 * q + 1]), "r"(pk[4 * q + 2]),
-                         "r"(pk[4 * q + 3])
-                         : "memory");
+          for (int j = 0; j < 32; j += 8) {
+            r4[0] = at_max3(r4[0], __uint_as_float(w[c * 32 + j]), __uint_as_float(w[c * 32 + j + 1]));
+            r4[1] = at_max3(r4[1], __uint_as_float(w[c * 32 + j + 2]), __uint_as_float(w[c * 32 + j + 3]));
+            r4[2] = at_max3(r4[2], __uint_as_float(w[c * 32 + j + 4]), __uint_as_float(w[c * 32 + j + 5]));
+            r4[3] = at_max3(r4[3], __uint_as_float(w[c * 32 + j + 6]), __uint_as_float(w[c * 32 + j + 7]));
           }
         }
-        l = fmaf(l, alpha, (s4[0] + s4[1]) + (s4[2] + s4[3]));
+        const float raw = fmaxf(fmaxf(r4[0], r4[1]), fmaxf(r4[2], r4[3])) * c_log2;
+        // lazy rescale: the running max only moves when the block's max exceeds it by more than 2^8 (p stays <= 256)
+        if (raw > m + AT_RESCALE_LOG2) {
+          alpha = at_ex2(m - raw);  // first block: ex2(-inf) = 0 (l = 0 and O is overwritten anyway)
+          m = raw;
+        }
+        const uint64_t nm2 = at_pack2(-m, -m);
+        uint64_t sa = at_pack2(0.f, 0.f), sb = sa;  // (sum of p[j], p[j+1]) over j = 0 mod 4 / j = 2 mod 4
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float a0 = __uint_as_float(w[c * 32 + j]), a1 = __uint_as_float(w[c * 32 + j + 1]), b0 = __uint_as_float(w[c * 32 + j + 2]),
+                  b1 = __uint_as_float(w[c * 32 + j + 3]);
+            at_fma2(a0, a1, c2, nm2);
+            at_fma2(b0, b1, c2, nm2);
+            a0 = at_ex2(a0);
+            a1 = at_ex2(a1);
+            b0 = at_ex2(b0);
+            b1 = at_ex2(b1);
+            sa = at_add2(sa, at_pack2(a0, a1));
+            sb = at_add2(sb, at_pack2(b0, b1));
+            __nv_bfloat162 ha = __floats2bfloat162_rn(a0, a1), hb = __floats2bfloat162_rn(b0, b1);
+            w[(c * 32 + j) >> 1] = *reinterpret_cast<uint32_t *>(&ha);
+            w[((c * 32 + j) >> 1) + 1] = *reinterpret_cast<uint32_t *>(&hb);
+          }
+        }
+        float s0, s1, s2, s3;
+        at_unpack2(sa, s0, s1);
+        at_unpack2(sb, s2, s3);
+        l = fmaf(l, alpha, (s0 + s1) + (s2 + s3));
       }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      // P V (g-1) must have completed before its A operand (the P columns) is overwritten and before O is rescaled
+      if (kb > 0) {
+        mbar_wait(o_full, (g - 1) & 1);
+        tc_fence_after();
+      }
+      {
+        if (kb > 0 && __any_sync(0xffffffffu, alpha != 1.f)) {  // O *= alpha in tensor memory (rows that did not ask: * 1.0f, exact)
+          uint32_t v[64];
+          tc_ld_32x32(t_o, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+          tc_ld_32x32(t_o + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
+          tc_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 64; j++) v[j] = __float_as_uint(__uint_as_float(v[j]) * alpha);
+          tc_st_32x32(t_o, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+          tc_st_32x32(t_o + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
+        }
+        tc_st_32x32(t_p, *reinterpret_cast<uint32_t(*)[32]>(&w[0]));
+        tc_st_32x32(t_p + 32, *reinterpret_cast<uint32_t(*)[32]>(&w[32]));
+        tc_st_wait();
+      }
       tc_fence_before();
       mbar_arrive(p_ready);
-      if (kb == nb - 1) {
-        o_update(g, alpha);  // last block of the head: nothing left to hide behind
-      } else {
-        pending = true;
-        alpha_prev = alpha;
-      }
-      if (kb == nb - 1 && r < nq) {  // head finished: normalise and store its output row
-        const float inv = 1.0f / l;
-        const int head = STACKED ? (g / nb) * G + r : head0 + g / nb;
-        __nv_bfloat16 *dst = out + (size_t)(STACKED ? row0 : row0 + r) * (nh * 64) + head * 64;
+      if (kb == nb - 1) {  // head finished: wait for its last P V, normalise and store the output rows
+        mbar_wait(o_full, g & 1);
+        tc_fence_after();
+        {
+          uint32_t v[64];
+          tc_ld_32x32(t_o, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+          tc_ld_32x32(t_o + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
+          tc_ld_wait();
+          if (r < nq) {
+            const float inv = 1.0f / l;
+            const int head = STACKED ? (g / nb) * G + r : head0 + g / nb;
+            __nv_bfloat16 *dst = out + (size_t)(STACKED ? row0 : row0 + r) * (nh * 64) + head * 64;
 #pragma unroll
-        for (int j = 0; j < 64; j += 8) {
-          uint32_t w[4];
+            for (int j = 0; j < 64; j += 8) {
+              uint32_t w[4];
 #pragma unroll
-          for (int e = 0; e < 4; e++) {
-            __nv_bfloat162 h = __floats2bfloat162_rn(o[j + 2 * e] * inv, o[j + 2 * e + 1] * inv);
-            w[e] = *reinterpret_cast<uint32_t *>(&h);
+              for (int e = 0; e < 4; e++) {
+                __nv_bfloat162 h = __floats2bfloat162_rn(__uint_as_float(v[j + 2 * e]) * inv, __uint_as_float(v[j + 2 * e + 1]) * inv);
+                w[e] = *reinterpret_cast<uint32_t *>(&h);
+              }
+              *reinterpret_cast<uint4 *>(dst + j) = make_uint4(w[0], w[1], w[2], w[3]);
+            }
           }
-          *reinterpret_cast<uint4 *>(dst + j) = make_uint4(w[0], w[1], w[2], w[3]);
         }
+        tc_fence_before();
       }
     }
   }
