@@ -37,11 +37,10 @@
 
 namespace czk {
 
-constexpr int AT_THREADS = 160;
-// shared memory: Q 16 KB | K 16 KB (single buffer: it is free again as soon as S = Q K^T has been computed, long before the
-// next block needs it) | V 2 x 16 KB | barriers; 1 KB of slack to align the SWIZZLE_128B tiles.  ~66 KB: two CTAs per SM
-// (the TMEM columns, 2 x 256, are what limits residency).
-constexpr int AT_Q = 0, AT_K = 16384, AT_V = 32768, AT_BAR = 65536, AT_SMEM = AT_BAR + 128 + 1024;
+constexpr int AT_THREADS = 256;  // warpgroup 0: four softmax warps; warpgroup 1: warp 4 = loader + MMA issuer, warps 5-7 only donate registers
+// shared memory: Q 2 x 16 KB | K 2 x 16 KB | V 2 x 16 KB | barriers | item ring; 1 KB of slack to align the SWIZZLE_128B tiles.
+// ~98 KB: two CTAs per SM (the TMEM columns, 2 x 256, are what limits residency).
+constexpr int AT_Q = 0, AT_K = 32768, AT_V = 65536, AT_BAR = 98304, AT_RING = AT_BAR + 256, AT_SMEM = AT_RING + 4 * 32 + 1024;
 constexpr int AT_TM_S = 0, AT_TM_O = 128, AT_TM_P = 192;
 constexpr float AT_RESCALE_LOG2 = 8.0f;  // lazy-rescale threshold on the log2-domain running max
 
@@ -104,36 +103,40 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map
       : "memory");
 }
 
-// STACKED = false: tile rows are up to 128 consecutive positions of one query head (grid.y = KV heads).
-// STACKED = true (stepwise decode, one position per sequence): tile rows are the G query heads that share one KV head, all at
-//   the same position, and ONE CTA walks all KV heads of the sequence back to back (grid.y = 1): the per-CTA set-up (TMEM
-//   allocation, barriers, descriptor prefetch) is paid once per sequence and the next head's Q / K / V loads are already in
-//   flight while the current head is processed.
+// Work items.  STACKED = false: item = (tile of up to 128 consecutive positions of one sequence, KV head); the CTA walks the G
+//   query heads of that KV head, so a K / V block is fetched once per group.
+// STACKED = true (stepwise decode, one position per sequence): item = one sequence; tile rows are the G query heads that share
+//   one KV head, all at the same position, and the CTA walks all nkv KV heads back to back.
 // A (position, head) row goes through exactly the same arithmetic in both modes.
+//
+// PERSISTENT: the grid is 2 CTAs per SM; each CTA pulls items from a global counter and runs them through ONE flattened
+// (item, head, key block) pipeline: TMEM allocation / barrier set-up is paid once per CTA, the next item's Q / K / V loads and its
+// first S = Q K^T are in flight while the softmax warps finish the current item, and a head's output rows are read out of TMEM
+// one iteration late (when the next iteration has to wait for that P V product anyway), so no warp ever idles on a P V.
+struct AtItem {  // published by the loader thread, one per item (ring of 4)
+  int row0, n_pos, p0, base, nb, head0, valid, pad;
+};
+
 template <bool STACKED>
 __global__ void __launch_bounds__(AT_THREADS, 2) attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                                                                 const __grid_constant__ CUtensorMap tm_v, const int *__restrict__ pos,
                                                                 const int *__restrict__ kv_base, const int *__restrict__ tile_row0,
-                                                                const int *__restrict__ tile_n, __nv_bfloat16 *__restrict__ out, int nh, int nkv) {
+                                                                const int *__restrict__ tile_n, __nv_bfloat16 *__restrict__ out, int nh, int nkv,
+                                                                int n_tiles, int *__restrict__ work_counter) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const int G = nh / nkv;
-  // One CTA walks n_loop (head, key block) sequences back to back with ONE flattened load / MMA pipeline, so the per-CTA set-up
-  // is amortised and the next head's loads are in flight while the current one is processed:
-  //   STACKED:  all nkv KV heads of the sequence (grid.y = 1);  else: the G query heads of KV head blockIdx.y (grid.y = nkv).
-  const int tile = blockIdx.x, kvh0 = STACKED ? 0 : (int)blockIdx.y, head0 = STACKED ? 0 : (int)blockIdx.y * G;
-  const int n_loop = STACKED ? nkv : G;
-  const int row0 = tile_row0[tile], n_pos = STACKED ? 1 : tile_n[tile];
-  const int nq = STACKED ? G : n_pos;  // valid tile rows
-  const int p0 = pos[row0], base = kv_base[row0];
-  const int nb = (p0 + n_pos + 127) >> 7;
-  const int total = n_loop * nb;  // flattened (head, key block) iterations; every barrier's phase follows this counter
+  const int n_loop = STACKED ? nkv : G;            // heads walked per item
+  const int n_items = STACKED ? n_tiles : n_tiles * nkv;
+  const int nq_stacked = G;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem + AT_BAR);
-  const uint32_t q_full = smem_u32(&bars[0]), k_full = smem_u32(&bars[1]), k_empty = smem_u32(&bars[2]), v_full = smem_u32(&bars[3]) /*[2]*/,
-                 v_empty = smem_u32(&bars[5]) /*[2]*/, s_full = smem_u32(&bars[7]), p_ready = smem_u32(&bars[8]), o_full = smem_u32(&bars[9]),
-                 s_free = smem_u32(&bars[10]);
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(&bars[11]);
+  const uint32_t q_full = smem_u32(&bars[0]) /*[2]*/, k_full = smem_u32(&bars[2]) /*[2]*/, k_empty = smem_u32(&bars[4]) /*[2]*/,
+                 v_full = smem_u32(&bars[6]) /*[2]*/, v_empty = smem_u32(&bars[8]) /*[2]*/, s_full = smem_u32(&bars[10]),
+                 p_ready = smem_u32(&bars[11]), o_full = smem_u32(&bars[12]), s_free = smem_u32(&bars[13]), item_ready = smem_u32(&bars[14]),
+                 item_taken = smem_u32(&bars[15]);
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(&bars[16]);
+  volatile AtItem *ring = reinterpret_cast<volatile AtItem *>(smem + AT_RING);
   const uint32_t sQ = smem_u32(smem + AT_Q), sK = smem_u32(smem + AT_K), sV = smem_u32(smem + AT_V);
 
   if (warp == 4 && lane == 0) {
@@ -141,8 +144,11 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_tc_kernel(const __grid_con
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_k) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_v) : "memory");
     mbar_init(q_full, 1);
+    mbar_init(q_full + 8, 1);
     mbar_init(k_full, 1);
+    mbar_init(k_full + 8, 1);
     mbar_init(k_empty, 1);
+    mbar_init(k_empty + 8, 1);
     mbar_init(v_full, 1);
     mbar_init(v_full + 8, 1);
     mbar_init(v_empty, 1);
@@ -151,6 +157,8 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_tc_kernel(const __grid_con
     mbar_init(p_ready, 128);
     mbar_init(o_full, 1);
     mbar_init(s_free, 128);
+    mbar_init(item_ready, 1);
+    mbar_init(item_taken, 128);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -163,210 +171,282 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_tc_kernel(const __grid_con
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 4) {
-    if (lane == 0) {
-      auto load_k = [&](int g) {
-        mbar_expect_tx(k_full, 16384);
-        tma_load_2d(sK, &tm_k, k_full, (STACKED ? g / nb : kvh0) * 64, base + (g % nb) * 128);
+  // Register split (setmaxnreg is a warpgroup-wide instruction, hence the padded second warpgroup): the launch gives every
+  // thread 128 registers (2 CTAs x 256 threads); warpgroup 1 keeps 40 and the softmax warps -- which hold a whole 128-column S
+  // row per thread -- grow to 216.
+  if (warp >= 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
+  }
+  if (warp >= 4) {
+    if (warp == 4 && lane == 0) {
+      // cursor over the flattened (item, head, key block) iteration space
+      struct Cur {
+        int row0, base, nb, head0, kvh, hh, kb;
+        bool valid;
       };
-      auto load_v = [&](int g, int st) {
+      int n_pub = 0;  // items published so far
+      auto fetch_item = [&](Cur &c) {
+        const int item = atomicAdd(work_counter, 1);
+        // never more than one unconsumed descriptor: item_ready's phase parity stays unambiguous for the waiting warps
+        if (n_pub >= 1) mbar_wait(item_taken, (n_pub - 1) & 1);
+        volatile AtItem *slot = &ring[n_pub & 3];
+        if (item >= n_items) {
+          c.valid = false;
+          slot->valid = 0;
+        } else {
+          const int tile = STACKED ? item : item / nkv;
+          c.kvh = STACKED ? 0 : item - tile * nkv;
+          c.row0 = tile_row0[tile];
+          const int n_pos = STACKED ? 1 : tile_n[tile];
+          const int p0 = pos[c.row0];
+          c.base = kv_base[c.row0];
+          c.nb = (p0 + n_pos + 127) >> 7;
+          c.head0 = STACKED ? 0 : c.kvh * G;
+          c.hh = 0;
+          c.kb = 0;
+          c.valid = true;
+          slot->row0 = c.row0;
+          slot->n_pos = n_pos;
+          slot->p0 = p0;
+          slot->base = c.base;
+          slot->nb = c.nb;
+          slot->head0 = c.head0;
+          slot->valid = 1;
+        }
+        n_pub++;
+        mbar_arrive(item_ready);  // release: the slot's contents are visible to whoever observes this phase
+      };
+      auto advance = [&](Cur &c) {
+        if (++c.kb == c.nb) {
+          c.kb = 0;
+          if (++c.hh == n_loop) fetch_item(c);
+        }
+      };
+      // Q and K are double-buffered (stage = head count & 1 / iteration & 1), V double-buffered: K(it+2) and, at a head
+      // boundary, Q are requested two iterations ahead so that S(it+1) = Q K^T never waits for a TMA round trip.
+      auto load_k = [&](const Cur &c, int st) {
+        const uint32_t fb = k_full + 8 * st;
+        mbar_expect_tx(fb, 16384);
+        tma_load_2d(sK + st * 16384, &tm_k, fb, (STACKED ? c.hh : c.kvh) * 64, c.base + c.kb * 128);
+      };
+      auto load_v = [&](const Cur &c, int st) {
         const uint32_t fb = v_full + 8 * st;
         mbar_expect_tx(fb, 16384);
-        tma_load_2d(sV + st * 16384, &tm_v, fb, (STACKED ? g / nb : kvh0) * 64, base + (g % nb) * 128);  // [128 keys][64 dims], like the K block
+        tma_load_2d(sV + st * 16384, &tm_v, fb, (STACKED ? c.hh : c.kvh) * 64, c.base + c.kb * 128);  // [128 keys][64 dims], like the K block
       };
       // q viewed as [row][head][64]: a box of 128 rows x 1 head, or 1 row x G heads
-      auto load_q = [&](int hh) {
-        mbar_expect_tx(q_full, STACKED ? G * 128 : 16384);
-        tma_load_3d(sQ, &tm_q, q_full, 0, STACKED ? hh * G : head0 + hh, row0);
+      int n_q_loaded = 0, n_q_used = 0;  // heads whose Q tile has been requested / consumed by a first Q K^T
+      auto load_q = [&](const Cur &c) {
+        const int st = n_q_loaded & 1;
+        const uint32_t fb = q_full + 8 * st;
+        mbar_expect_tx(fb, STACKED ? G * 128 : 16384);
+        tma_load_3d(sQ + st * 16384, &tm_q, fb, 0, STACKED ? c.hh * G : c.head0 + c.hh, c.row0);
+        n_q_loaded++;
       };
-      load_q(0);
-      load_k(0);
-      load_v(0, 0);
-      if (total > 1) load_v(1, 1);
       // P V: the B operand V [128 keys][64 dims] has the dims (N) contiguous -> MN-major B (instruction descriptor bit 16)
       constexpr uint32_t idesc_qk = make_idesc_mn(128, 128), idesc_pv = make_idesc_mn(128, 64) | (1u << 16);
-      const uint64_t q_desc = make_kmajor_sw128_desc(sQ), k_desc = make_kmajor_sw128_desc(sK);
-      auto issue_qk = [&]() {
+      // S(j) = Q K^T for iteration j (cursor c): waits for its operands, issues, and signals s_full / k_empty[j & 1]
+      auto issue_qk = [&](const Cur &c, int j) {
+        if (c.kb == 0) {  // first block of a head: its Q tile
+          mbar_wait(q_full + 8 * (n_q_used & 1), (n_q_used >> 1) & 1);
+          n_q_used++;
+        }
+        const int qs = (n_q_used - 1) & 1, ks_ = j & 1;
+        mbar_wait(k_full + 8 * ks_, (j >> 1) & 1);
+        tc_fence_after();
+        const uint64_t q_desc = make_kmajor_sw128_desc(sQ + qs * 16384), k_desc = make_kmajor_sw128_desc(sK + ks_ * 16384);
 #pragma unroll
         for (int ks = 0; ks < 4; ks++)
           tc_mma_bf16(tmem_base + AT_TM_S, q_desc + (uint64_t)(ks * 2), k_desc + (uint64_t)(ks * 2), idesc_qk, ks ? 1u : 0u);
         tc_commit(s_full);
-        tc_commit(k_empty);
+        tc_commit(k_empty + 8 * ks_);
       };
-      mbar_wait(q_full, 0);
-      mbar_wait(k_full, 0);
-      tc_fence_after();
-      issue_qk();
-      for (int g = 0; g < total; g++) {
-        const int st = g & 1;
-        const bool next_head = (g + 1) % nb == 0;  // iteration g + 1 starts a new head
-        if (g + 1 < total) {
-          mbar_wait(k_empty, g & 1);  // S(g) = Q K^T is done: the K buffer (and, at a head boundary, Q) can be refilled
-          if (next_head) load_q((g + 1) / nb);
-          load_k(g + 1);
-          if (g >= 1) {  // P V (g-1) has finished long ago: its V stage takes block g + 1
-            mbar_wait(v_empty + 8 * (st ^ 1), ((g - 1) >> 1) & 1);
-            load_v(g + 1, st ^ 1);
+      Cur n0;
+      fetch_item(n0);
+      if (n0.valid) {
+        Cur n1 = n0;
+        advance(n1);
+        load_q(n0);
+        load_k(n0, 0);
+        load_v(n0, 0);
+        if (n1.valid) {
+          if (n1.kb == 0) load_q(n1);
+          load_k(n1, 1);
+        }
+        issue_qk(n0, 0);
+        for (int it = 0;; it++) {  // `it` counts iterations across items: every barrier's phase follows it
+          const Cur cur = n0;
+          const int st = it & 1;
+          if (n1.valid) {
+            mbar_wait(s_free, it & 1);  // the softmax warps hold S(it) in registers
+            issue_qk(n1, it + 1);       // S(it+1): runs under the softmax of iteration it
           }
-          mbar_wait(s_free, g & 1);  // the softmax warps hold S(g) in registers
-          if (next_head) mbar_wait(q_full, ((g + 1) / nb) & 1);
-          mbar_wait(k_full, (g + 1) & 1);
+          Cur n2 = n1;
+          if (n1.valid) advance(n2);
+          if (n1.valid && n2.valid) {
+            // S(it) is done (and with it every earlier Q K^T): K stage it & 1 and the Q stage of the head before last are free
+            mbar_wait(k_empty + 8 * st, (it >> 1) & 1);
+            if (n2.kb == 0) load_q(n2);
+            load_k(n2, st);
+          }
+          if (n1.valid) {
+            if (it >= 1) mbar_wait(v_empty + 8 * (st ^ 1), ((it - 1) >> 1) & 1);  // P V (it-1) is done: its V stage takes block it + 1
+            load_v(n1, st ^ 1);
+          }
+          mbar_wait(p_ready, it & 1);  // P(it) is in tensor memory; O has been rescaled / the previous head's O has been read out
+          mbar_wait(v_full + 8 * st, (it >> 1) & 1);
           tc_fence_after();
-          issue_qk();  // S(g+1): runs under the softmax of block g
-        }
-        mbar_wait(p_ready, g & 1);  // P(g) is in tensor memory, O has been rescaled if a row asked for it
-        mbar_wait(v_full + 8 * st, (g >> 1) & 1);
-        tc_fence_after();
-        const uint32_t first = (g % nb == 0) ? 0u : 1u;  // a head's first block overwrites O
+          const uint32_t first = cur.kb == 0 ? 0u : 1u;  // a head's first block overwrites O
 #pragma unroll
-        for (int ks = 0; ks < 8; ks++) {
-          // canonical MN-major SWIZZLE_128B layout ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units: one 128-byte row per key,
-          // 8-key groups 1024 B apart (SBO), n = 1; a K-step of 16 keys advances the start address by 16 rows = 2048 B
-          const uint64_t v_desc = make_kmajor_sw128_desc(sV + st * 16384) + (uint64_t)(ks * 128);
-          tc_mma_bf16_ts(tmem_base + AT_TM_O, tmem_base + AT_TM_P + (uint32_t)(ks * 8), v_desc, idesc_pv, ks ? 1u : first);
+          for (int ks = 0; ks < 8; ks++) {
+            // canonical MN-major SWIZZLE_128B layout ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units: one 128-byte row per key,
+            // 8-key groups 1024 B apart (SBO), n = 1; a K-step of 16 keys advances the start address by 16 rows = 2048 B
+            const uint64_t v_desc = make_kmajor_sw128_desc(sV + st * 16384) + (uint64_t)(ks * 128);
+            tc_mma_bf16_ts(tmem_base + AT_TM_O, tmem_base + AT_TM_P + (uint32_t)(ks * 8), v_desc, idesc_pv, ks ? 1u : first);
+          }
+          tc_commit(o_full);
+          tc_commit(v_empty + 8 * st);
+          if (!n1.valid) break;
+          n0 = n1;
+          n1 = n2;
         }
-        tc_commit(o_full);
-        tc_commit(v_empty + 8 * st);
       }
     }
   } else {
     const int r = warp * 32 + lane;
-    const bool warp_valid = warp * 32 < nq;
-    const int pos_r = STACKED ? p0 : p0 + r;
-    const int pos_w_lo = STACKED ? p0 : p0 + warp * 32;  // the warp's first position
     const uint32_t t_lane = tmem_base + ((uint32_t)(warp * 32) << 16);
     const uint32_t t_s = t_lane + AT_TM_S, t_o = t_lane + AT_TM_O, t_p = t_lane + AT_TM_P;
     const float c_log2 = 0.125f * 1.4426950408889634f;  // 1/sqrt(64) * log2(e)
     const uint64_t c2 = at_pack2(c_log2, c_log2);
     float m = -INFINITY, l = 0.f;
-    if (!warp_valid) {  // no valid row in this warp (short tile / stacked decode): keep the barrier protocol, touch nothing.
-      // The o_full waits keep these warps in lock step with the valid ones: without them they would run ahead and their
-      // arrivals for block g + 1 would complete p_ready's phase g before the valid warps have written P(g).
-      for (int g = 0; g < total; g++) {
-        const int kb = g % nb;
-        mbar_wait(s_full, g & 1);
-        mbar_arrive(s_free);
-        if (kb > 0) mbar_wait(o_full, (g - 1) & 1);
-        mbar_arrive(p_ready);
-        if (kb == nb - 1) mbar_wait(o_full, g & 1);
-      }
-    } else
-    for (int g = 0; g < total; g++) {
-      const int kb = g % nb;
-      if (kb == 0) {  // new head: fresh online-softmax state
-        m = -INFINITY;
-        l = 0.f;
-      }
-      const int lim = pos_r - kb * 128;
-      uint32_t w[128];  // S(g) as raw f32 bits; the packed bf16 P overwrites w[0, 64) in place (pair (j, j+1) -> w[j/2], j/2 <= j)
-      mbar_wait(s_full, g & 1);
-      tc_fence_after();
-#pragma unroll
-      for (int c = 0; c < 4; c++)
-        tc_ld_32x32(t_s + (uint32_t)(c * 32), *reinterpret_cast<uint32_t(*)[32]>(&w[c * 32]));
+    // a finished head whose output rows are still in TMEM: read out one iteration late (or after the last item)
+    bool owed = false;
+    float owed_inv = 0.f;
+    __nv_bfloat16 *owed_dst = nullptr;
+    auto read_out = [&]() {
+      uint32_t v[64];
+      tc_ld_32x32(t_o, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+      tc_ld_32x32(t_o + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
       tc_ld_wait();
-      tc_fence_before();
-      mbar_arrive(s_free);  // S(g) is in registers: the MMA warp may overwrite the S columns with S(g+1)
+      if (owed_dst != nullptr) {
+#pragma unroll
+        for (int j = 0; j < 64; j += 8) {
+          uint32_t o4[4];
+#pragma unroll
+          for (int e = 0; e < 4; e++) {
+            __nv_bfloat162 h = __floats2bfloat162_rn(__uint_as_float(v[j + 2 * e]) * owed_inv, __uint_as_float(v[j + 2 * e + 1]) * owed_inv);
+            o4[e] = *reinterpret_cast<uint32_t *>(&h);
+          }
+          *reinterpret_cast<uint4 *>(owed_dst + j) = make_uint4(o4[0], o4[1], o4[2], o4[3]);
+        }
+      }
+    };
+    int it = 0;
+    for (int n_item = 0;; n_item++) {
+      mbar_wait(item_ready, n_item & 1);
+      volatile AtItem *slot = &ring[n_item & 3];
+      if (!slot->valid) break;  // (no arrival on item_taken: nothing is published after the end marker)
+      const int row0 = slot->row0, n_pos = slot->n_pos, p0 = slot->p0, nb = slot->nb, head0 = slot->head0;
+      mbar_arrive(item_taken);
+      const int nq = STACKED ? nq_stacked : n_pos;  // valid tile rows
+      const int pos_r = STACKED ? p0 : p0 + r;
+      const int pos_w_lo = STACKED ? p0 : p0 + warp * 32;  // the warp's first position
+      for (int hh = 0; hh < n_loop; hh++) {
+        m = -INFINITY;  // new head: fresh online-softmax state
+        l = 0.f;
+        for (int kb = 0; kb < nb; kb++, it++) {
+          const int lim = pos_r - kb * 128;
+          uint32_t w[128];  // S as raw f32 bits; the packed bf16 P overwrites w[0, 64) in place (pair (j, j+1) -> w[j/2], j/2 <= j)
+          mbar_wait(s_full, it & 1);
+          tc_fence_after();
+#pragma unroll
+          for (int c = 0; c < 4; c++) tc_ld_32x32(t_s + (uint32_t)(c * 32), *reinterpret_cast<uint32_t(*)[32]>(&w[c * 32]));
+          tc_ld_wait();
+          tc_fence_before();
+          mbar_arrive(s_free);  // S is in registers: the MMA warp may overwrite the S columns with the next S
 
-      float alpha = 1.f;
-      {
-        // causal mask: keys after the row's position become -inf (exp2 -> exact 0).  Chunks entirely at or before the warp's
-        // first position take the mask-free path (warp-uniform); both paths compute identical values for unmasked keys.
-        float r4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-        if (kb * 128 + 127 > pos_w_lo) {
+          float alpha = 1.f;
+          {
+            // causal mask: keys after the row's position become -inf (exp2 -> exact 0).  Blocks entirely at or before the warp's
+            // first position take the mask-free path (warp-uniform); both paths compute identical values for unmasked keys.
+            float r4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+            if (kb * 128 + 127 > pos_w_lo) {
 #pragma unroll
-          for (int j = 0; j < 128; j++) w[j] = (j <= lim) ? w[j] : 0xff800000u;
-        }
-#pragma unroll
-        for (int c = 0; c < 4; c++) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            r4[0] = at_max3(r4[0], __uint_as_float(w[c * 32 + j]), __uint_as_float(w[c * 32 + j + 1]));
-            r4[1] = at_max3(r4[1], __uint_as_float(w[c * 32 + j + 2]), __uint_as_float(w[c * 32 + j + 3]));
-            r4[2] = at_max3(r4[2], __uint_as_float(w[c * 32 + j + 4]), __uint_as_float(w[c * 32 + j + 5]));
-            r4[3] = at_max3(r4[3], __uint_as_float(w[c * 32 + j + 6]), __uint_as_float(w[c * 32 + j + 7]));
-          }
-        }
-        const float raw = fmaxf(fmaxf(r4[0], r4[1]), fmaxf(r4[2], r4[3])) * c_log2;
-        // lazy rescale: the running max only moves when the block's max exceeds it by more than 2^8 (p stays <= 256)
-        if (raw > m + AT_RESCALE_LOG2) {
-          alpha = at_ex2(m - raw);  // first block: ex2(-inf) = 0 (l = 0 and O is overwritten anyway)
-          m = raw;
-        }
-        const uint64_t nm2 = at_pack2(-m, -m);
-        uint64_t sa = at_pack2(0.f, 0.f), sb = sa;  // (sum of p[j], p[j+1]) over j = 0 mod 4 / j = 2 mod 4
-#pragma unroll
-        for (int c = 0; c < 4; c++) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            float a0 = __uint_as_float(w[c * 32 + j]), a1 = __uint_as_float(w[c * 32 + j + 1]), b0 = __uint_as_float(w[c * 32 + j + 2]),
-                  b1 = __uint_as_float(w[c * 32 + j + 3]);
-            at_fma2(a0, a1, c2, nm2);
-            at_fma2(b0, b1, c2, nm2);
-            a0 = at_ex2(a0);
-            a1 = at_ex2(a1);
-            b0 = at_ex2(b0);
-            b1 = at_ex2(b1);
-            sa = at_add2(sa, at_pack2(a0, a1));
-            sb = at_add2(sb, at_pack2(b0, b1));
-            __nv_bfloat162 ha = __floats2bfloat162_rn(a0, a1), hb = __floats2bfloat162_rn(b0, b1);
-            w[(c * 32 + j) >> 1] = *reinterpret_cast<uint32_t *>(&ha);
-            w[((c * 32 + j) >> 1) + 1] = *reinterpret_cast<uint32_t *>(&hb);
-          }
-        }
-        float s0, s1, s2, s3;
-        at_unpack2(sa, s0, s1);
-        at_unpack2(sb, s2, s3);
-        l = fmaf(l, alpha, (s0 + s1) + (s2 + s3));
-      }
-      // P V (g-1) must have completed before its A operand (the P columns) is overwritten and before O is rescaled
-      if (kb > 0) {
-        mbar_wait(o_full, (g - 1) & 1);
-        tc_fence_after();
-      }
-      {
-        if (kb > 0 && __any_sync(0xffffffffu, alpha != 1.f)) {  // O *= alpha in tensor memory (rows that did not ask: * 1.0f, exact)
-          uint32_t v[64];
-          tc_ld_32x32(t_o, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
-          tc_ld_32x32(t_o + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
-          tc_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 64; j++) v[j] = __float_as_uint(__uint_as_float(v[j]) * alpha);
-          tc_st_32x32(t_o, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
-          tc_st_32x32(t_o + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
-        }
-        tc_st_32x32(t_p, *reinterpret_cast<uint32_t(*)[32]>(&w[0]));
-        tc_st_32x32(t_p + 32, *reinterpret_cast<uint32_t(*)[32]>(&w[32]));
-        tc_st_wait();
-      }
-      tc_fence_before();
-      mbar_arrive(p_ready);
-      if (kb == nb - 1) {  // head finished: wait for its last P V, normalise and store the output rows
-        mbar_wait(o_full, g & 1);
-        tc_fence_after();
-        {
-          uint32_t v[64];
-          tc_ld_32x32(t_o, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
-          tc_ld_32x32(t_o + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
-          tc_ld_wait();
-          if (r < nq) {
-            const float inv = 1.0f / l;
-            const int head = STACKED ? (g / nb) * G + r : head0 + g / nb;
-            __nv_bfloat16 *dst = out + (size_t)(STACKED ? row0 : row0 + r) * (nh * 64) + head * 64;
-#pragma unroll
-            for (int j = 0; j < 64; j += 8) {
-              uint32_t w[4];
-#pragma unroll
-              for (int e = 0; e < 4; e++) {
-                __nv_bfloat162 h = __floats2bfloat162_rn(__uint_as_float(v[j + 2 * e]) * inv, __uint_as_float(v[j + 2 * e + 1]) * inv);
-                w[e] = *reinterpret_cast<uint32_t *>(&h);
-              }
-              *reinterpret_cast<uint4 *>(dst + j) = make_uint4(w[0], w[1], w[2], w[3]);
+              for (int j = 0; j < 128; j++) w[j] = (j <= lim) ? w[j] : 0xff800000u;
             }
+#pragma unroll
+            for (int j = 0; j < 128; j += 8) {
+              r4[0] = at_max3(r4[0], __uint_as_float(w[j]), __uint_as_float(w[j + 1]));
+              r4[1] = at_max3(r4[1], __uint_as_float(w[j + 2]), __uint_as_float(w[j + 3]));
+              r4[2] = at_max3(r4[2], __uint_as_float(w[j + 4]), __uint_as_float(w[j + 5]));
+              r4[3] = at_max3(r4[3], __uint_as_float(w[j + 6]), __uint_as_float(w[j + 7]));
+            }
+            const float raw = fmaxf(fmaxf(r4[0], r4[1]), fmaxf(r4[2], r4[3])) * c_log2;
+            // lazy rescale: the running max only moves when the block's max exceeds it by more than 2^8 (p stays <= 256)
+            if (raw > m + AT_RESCALE_LOG2) {
+              alpha = at_ex2(m - raw);  // first block: ex2(-inf) = 0 (l = 0 and O is overwritten anyway)
+              m = raw;
+            }
+            const uint64_t nm2 = at_pack2(-m, -m);
+            uint64_t sa = at_pack2(0.f, 0.f), sb = sa;  // (sum of p[j], p[j+1]) over j = 0 mod 4 / j = 2 mod 4
+#pragma unroll
+            for (int j = 0; j < 128; j += 4) {
+              float a0 = __uint_as_float(w[j]), a1 = __uint_as_float(w[j + 1]), b0 = __uint_as_float(w[j + 2]), b1 = __uint_as_float(w[j + 3]);
+              at_fma2(a0, a1, c2, nm2);
+              at_fma2(b0, b1, c2, nm2);
+              a0 = at_ex2(a0);
+              a1 = at_ex2(a1);
+              b0 = at_ex2(b0);
+              b1 = at_ex2(b1);
+              sa = at_add2(sa, at_pack2(a0, a1));
+              sb = at_add2(sb, at_pack2(b0, b1));
+              __nv_bfloat162 ha = __floats2bfloat162_rn(a0, a1), hb = __floats2bfloat162_rn(b0, b1);
+              w[j >> 1] = *reinterpret_cast<uint32_t *>(&ha);
+              w[(j >> 1) + 1] = *reinterpret_cast<uint32_t *>(&hb);
+            }
+            float s0, s1, s2, s3;
+            at_unpack2(sa, s0, s1);
+            at_unpack2(sb, s2, s3);
+            l = fmaf(l, alpha, (s0 + s1) + (s2 + s3));
           }
+          // The previous iteration's P V must have completed before its A operand (the P columns) is overwritten, before O is
+          // rescaled, and before a finished head's O is read out (kb == 0: the head that ended in the previous iteration).
+          if (it > 0) {
+            mbar_wait(o_full, (it - 1) & 1);
+            tc_fence_after();
+          }
+          if (owed) {  // warp-uniform
+            read_out();
+            owed = false;
+          } else if (kb > 0 && __any_sync(0xffffffffu, alpha != 1.f)) {  // O *= alpha in tensor memory (rows that did not ask: * 1.0f, exact)
+            uint32_t v[64];
+            tc_ld_32x32(t_o, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+            tc_ld_32x32(t_o + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
+            tc_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 64; j++) v[j] = __float_as_uint(__uint_as_float(v[j]) * alpha);
+            tc_st_32x32(t_o, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+            tc_st_32x32(t_o + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
+          }
+          tc_st_32x32(t_p, *reinterpret_cast<uint32_t(*)[32]>(&w[0]));
+          tc_st_32x32(t_p + 32, *reinterpret_cast<uint32_t(*)[32]>(&w[32]));
+          tc_st_wait();
+          tc_fence_before();
+          mbar_arrive(p_ready);
         }
-        tc_fence_before();
+        // head finished: its P V is still running; remember where its rows go
+        owed = true;
+        owed_inv = 1.0f / l;
+        const int head = STACKED ? hh * G + r : head0 + hh;
+        owed_dst = r < nq ? out + (size_t)(STACKED ? row0 : row0 + r) * (nh * 64) + head * 64 : nullptr;
       }
+    }
+    if (owed) {  // the last head of the last item
+      mbar_wait(o_full, (it - 1) & 1);
+      tc_fence_after();
+      read_out();
     }
   }
   tc_fence_before();
@@ -429,14 +509,26 @@ int launch_attn_tc(cz_ctx *ctx, const __nv_bfloat16 *q, int n_rows, const __nv_b
   CZ_TRY(make_q_map(&tq, q, n_rows, nh, single_rows ? nh / nkv : 1, single_rows ? 1 : 128));
   CZ_TRY(make_map_bf16(&tk, k_arena, n_slots, nkv * 64, nkv * 64, 128));
   CZ_TRY(make_map_bf16(&tv, v_arena, n_slots, nkv * 64, nkv * 64, 128));  // V rows [slot][nkv*64], same box as K
+  // persistent grid: two CTAs per SM pull (tile, KV head) items from a counter that is zeroed in stream order before the launch
+  static int *work_counter = nullptr;
+  static int n_sm = 0;
+  if (!work_counter) {
+    int dev = 0;
+    CZ_CUDA_TRY(cudaGetDevice(&dev));
+    CZ_CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+    CZ_CUDA_TRY(cudaMalloc(&work_counter, sizeof(int)));
+  }
+  CZ_CUDA_TRY(cudaMemsetAsync(work_counter, 0, sizeof(int), st));
+  const int n_items = single_rows ? n_tiles : n_tiles * nkv;
+  const unsigned grid = (unsigned)(n_items < 2 * n_sm ? n_items : 2 * n_sm);
   if (single_rows) {
-    dim3 grid((unsigned)n_tiles, 1);
     CZ_LAUNCH(ctx, CZ_K_ATTN,
-              (czk::attn_tc_kernel<true><<<grid, czk::AT_THREADS, czk::AT_SMEM, st>>>(tq, tk, tv, pos, kv_base, tile_row0, tile_n, out, nh, nkv)));
+              (czk::attn_tc_kernel<true><<<grid, czk::AT_THREADS, czk::AT_SMEM, st>>>(tq, tk, tv, pos, kv_base, tile_row0, tile_n, out, nh, nkv,
+                                                                                     n_tiles, work_counter)));
   } else {
-    dim3 grid((unsigned)n_tiles, (unsigned)nkv);
     CZ_LAUNCH(ctx, CZ_K_ATTN,
-              (czk::attn_tc_kernel<false><<<grid, czk::AT_THREADS, czk::AT_SMEM, st>>>(tq, tk, tv, pos, kv_base, tile_row0, tile_n, out, nh, nkv)));
+              (czk::attn_tc_kernel<false><<<grid, czk::AT_THREADS, czk::AT_SMEM, st>>>(tq, tk, tv, pos, kv_base, tile_row0, tile_n, out, nh, nkv,
+                                                                                      n_tiles, work_counter)));
   }
   CZ_CHECK_LAUNCH();
   return CZ_OK;
