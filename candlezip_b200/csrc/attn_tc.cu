@@ -61,6 +61,7 @@ __device__ __forceinline__ void at_fma2(float &x0, float &x1, uint64_t c2, uint6
   asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(y) : "l"(x), "l"(c2), "l"(nm2));
   asm("mov.b64 {%0, %1}, %2;" : "=f"(x0), "=f"(x1) : "l"(y));
 }
+__device__ __forceinline__ void at_unpack2(uint64_t x, float &a, float &b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(x)); }
 __device__ __forceinline__ uint64_t at_pack2(float a, float b) {
   uint64_t x;
   asm("mov.b64 %0, {%1, %2};" : "=l"(x) : "f"(a), "f"(b));
@@ -71,7 +72,32 @@ __device__ __forceinline__ uint64_t at_add2(uint64_t a, uint64_t b) {
   asm("add.rn.f32x2 %0, %1, %2;" : "=l"(y) : "l"(a), "l"(b));
   return y;
 }
-__device__ __forceinline__ void at_unpack2(uint64_t x, float &a, float &b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(x)); }
+
+// exp2 of a PAIR on the FMA pipe (no MUFU): round-to-nearest split x = n + f, f in [-0.5, 0.5] (magic-number add), degree-3
+// minimax polynomial for 2^f (max relative error 7.5e-5, far below the bf16 rounding of P), 2^n applied by adding n to the
+// exponent field.  The XU pipe (16 ex2 / clk / SM) is what bounds the softmax, so a fixed subset of the columns -- pairs
+// AT_POLY_MASK of every 8 pairs, the same for every row, tile and mode -- takes this path instead (as FlashAttention-4 does).
+constexpr uint32_t AT_POLY_MASK = 0x52;  // pairs 1, 4, 6 of every 8: 3/8 of the exponentials
+__device__ __forceinline__ void at_ex2_poly2(float &x0, float &x1) {
+  x0 = fmaxf(x0, -125.f);  // keeps 2^n a normal number; a masked key (-inf) becomes 2^-125, far below one ulp of l and of any O sum
+  x1 = fmaxf(x1, -125.f);
+  const uint64_t x = at_pack2(x0, x1);
+  const uint64_t magic = at_pack2(12582912.f, 12582912.f), nmagic = at_pack2(-12582912.f, -12582912.f), mone = at_pack2(-1.f, -1.f);
+  const uint64_t c3 = at_pack2(0x1.c3f76p-5f, 0x1.c3f76p-5f), c2 = at_pack2(0x1.f0de1ap-3f, 0x1.f0de1ap-3f),
+                 c1 = at_pack2(0x1.62f31ap-1f, 0x1.62f31ap-1f), c0 = at_pack2(0x1.fff692p-1f, 0x1.fff692p-1f);
+  const uint64_t t = at_add2(x, magic);  // low mantissa bits = round(x)
+  const uint64_t n = at_add2(t, nmagic);
+  uint64_t f, q;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(f) : "l"(n), "l"(mone), "l"(x));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(q) : "l"(f), "l"(c3), "l"(c2));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(q) : "l"(q), "l"(f), "l"(c1));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(q) : "l"(q), "l"(f), "l"(c0));
+  float t0, t1, q0, q1;
+  at_unpack2(t, t0, t1);
+  at_unpack2(q, q0, q1);
+  x0 = __int_as_float(__float_as_int(q0) + (__float_as_int(t0) << 23));
+  x1 = __int_as_float(__float_as_int(q1) + (__float_as_int(t1) << 23));
+}
 
 __device__ __forceinline__ void tc_st_32x32(uint32_t taddr, const uint32_t (&r)[32]) {
   asm volatile(
@@ -123,8 +149,11 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_tc_kernel(const __grid_con
                                                                 const int *__restrict__ kv_base, const int *__restrict__ tile_row0,
                                                                 const int *__restrict__ tile_n, __nv_bfloat16 *__restrict__ out, int nh, int nkv,
                                                                 int n_tiles, int *__restrict__ work_counter) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  // The kernel has no static shared memory, so the dynamic window starts at shared address 0 and the declared 1024-byte
+  // alignment (SWIZZLE_128B tiles) holds; every barrier / tile address is then a compile-time constant instead of a value the
+  // compiler re-derives from S2R each iteration.  Checked once below.
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
   const int G = nh / nkv;
   const int n_loop = STACKED ? nkv : G;            // heads walked per item
   const int n_items = STACKED ? n_tiles : n_tiles * nkv;
@@ -396,10 +425,18 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_tc_kernel(const __grid_con
               float a0 = __uint_as_float(w[j]), a1 = __uint_as_float(w[j + 1]), b0 = __uint_as_float(w[j + 2]), b1 = __uint_as_float(w[j + 3]);
               at_fma2(a0, a1, c2, nm2);
               at_fma2(b0, b1, c2, nm2);
-              a0 = at_ex2(a0);
-              a1 = at_ex2(a1);
-              b0 = at_ex2(b0);
-              b1 = at_ex2(b1);
+              if ((AT_POLY_MASK >> ((j >> 1) & 7)) & 1u) {
+                at_ex2_poly2(a0, a1);
+              } else {
+                a0 = at_ex2(a0);
+                a1 = at_ex2(a1);
+              }
+              if ((AT_POLY_MASK >> (((j >> 1) + 1) & 7)) & 1u) {
+                at_ex2_poly2(b0, b1);
+              } else {
+                b0 = at_ex2(b0);
+                b1 = at_ex2(b1);
+              }
               sa = at_add2(sa, at_pack2(a0, a1));
               sb = at_add2(sb, at_pack2(b0, b1));
               __nv_bfloat162 ha = __floats2bfloat162_rn(a0, a1), hb = __floats2bfloat162_rn(b0, b1);
