@@ -133,6 +133,9 @@ SIGNATURES = {
     "cz_blake3_16": (None, [u8p, C.c_size_t, u8p]),
     "cz_test_gemm": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint16), C.POINTER(C.c_uint16), C.c_int, C.c_int, _vp,
                               C.c_int]),
+    "cz_test_gemm_norm": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint16), C.POINTER(C.c_uint16), C.POINTER(C.c_uint16),
+                                   C.POINTER(C.c_float), C.c_float, C.POINTER(C.c_float), C.POINTER(C.c_uint16), C.POINTER(C.c_float),
+                                   C.POINTER(C.c_uint16)]),
     "cz_schedule_chunks": (C.c_size_t, [C.c_uint64, C.c_uint32, C.c_uint32, u64p, u32p, u64p, u32p, C.c_size_t]),
 }
 

@@ -348,7 +348,8 @@ static int encode_core(cz_model *m, const uint32_t *ids_dev, const uint32_t *ids
   const double t_begin = host_ms();
   double t_build = 0, t_flush = 0;
   const uint32_t S = sched->n_segments;
-  const size_t max_rows = sched->max_batch_tokens ? sched->max_batch_tokens : (size_t)262144;
+  static const size_t env_rows = getenv("CZ_WAVE_ROWS") ? (size_t)atoll(getenv("CZ_WAVE_ROWS")) : 0;  // tuning aid
+  const size_t max_rows = sched->max_batch_tokens ? sched->max_batch_tokens : (env_rows ? env_rows : (size_t)262144);
   GrowBuf &d_lo = m->sb[SB_LO], &d_hi = m->sb[SB_HI], &d_src = m->sb[SB_SRC], &d_extra = m->sb[SB_EXTRA], &d_lane = m->sb[SB_LANE],
           &d_raw = m->sb[SB_RAW];
   CZ_TRY(d_lo.reserve(n_tokens * 4, st));

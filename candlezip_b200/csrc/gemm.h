@@ -18,6 +18,21 @@ enum GemmEpilogue {
   EPI_RELUSQ_BF16 = 7,   // C bf16 = relu(A*B^T)^2     (RWKV-7 FFN, rwkv7.rs:426)
   EPI_QKV_ROPE = 8,      // SmolLM q/k/v projection: rotate-half RoPE on the q and k heads, bf16 q rows + K/V arena scatter
                          // (N = (nh + 2 nkv) * 64, BN = 192 = three whole heads per tile); needs GemmArgs::rope
+  EPI_ADD_NORM = 9,      // residual add WITH the next RMSNorm's inputs (tcgen05 engine only; needs GemmArgs::norm):
+                         //   x = C[M][ldc] f32 += A*B^T;  xb[M][N] bf16 = bf16(x * w_next[n]);  ssq_out[m][part] = partial sums of x^2.
+                         // The consumer GEMM takes xb as its A operand and multiplies its accumulator rows by
+                         // 1 / sqrt(sum(parts) / N + eps): RMSNorm without a separate pass over the fp32 residual.
+};
+
+// RMSNorm fusion operands (all device pointers).  Producer side: EPI_ADD_NORM.  Consumer side (any bf16-output epilogue and
+// EPI_QKV_ROPE): ssq_in != nullptr scales accumulator row m by 1 / sqrt((sum_p ssq_in[m * n_part_in + p]) * inv_d + eps).
+struct NormExt {
+  const float *w_next = nullptr;  // [N] weight of the norm that follows the residual add
+  void *xb = nullptr;             // bf16 [M][N] (ld = N)
+  float *ssq_out = nullptr;       // [M][n_part_out], n_part_out = (N / BN) * 2 (two epilogue warps per TMEM lane quadrant)
+  const float *ssq_in = nullptr;  // [M][n_part_in]
+  int n_part_in = 0;
+  float inv_d = 0.f, eps = 0.f;
 };
 
 // extra operands of EPI_QKV_ROPE (all device pointers)
@@ -39,6 +54,7 @@ struct GemmArgs {
   int fam = 0;         // profiling family (CZ_K_GEMM, CZ_K_GEMM_O, ...)
   int *aux = nullptr;  // EPI_STORE_F32_COLMAX: per-column running max, must be pre-filled with INT_MIN
   RopeExt rope;        // EPI_QKV_ROPE
+  NormExt norm;        // EPI_ADD_NORM (producer) / row scale of the consumer epilogues
 };
 
 int gemm_tcgen05(cz_ctx *ctx, const GemmArgs &g, cudaStream_t stream);

@@ -33,7 +33,9 @@ using cz::EPI_TANH_BF16;
 using cz::EPI_SIGMOID_BF16;
 using cz::EPI_RELUSQ_BF16;
 using cz::EPI_QKV_ROPE;
+using cz::EPI_ADD_NORM;
 using cz::RopeExt;
+using cz::NormExt;
 
 constexpr int BM = 128;
 constexpr int BK = 64;  // bf16 elements: 128 bytes = one swizzle row
@@ -45,21 +47,23 @@ struct GemmCfg {
   // tensor pipe at 53%, profiles/ncu_summary_r01.md): they get EIGHT epilogue warps, two per TMEM lane quadrant, each taking every
   // other 32-column chunk.  The store-only epilogues (TMA store / reduce-add) keep four warps and the deeper operand pipeline.
   static constexpr bool kHeavy = EPI == cz::EPI_SWIGLU_BF16 || EPI == cz::EPI_QKV_ROPE || EPI == cz::EPI_STORE_BF16 ||
-                                 EPI == cz::EPI_TANH_BF16 || EPI == cz::EPI_SIGMOID_BF16 || EPI == cz::EPI_RELUSQ_BF16;
+                                 EPI == cz::EPI_TANH_BF16 || EPI == cz::EPI_SIGMOID_BF16 || EPI == cz::EPI_RELUSQ_BF16 ||
+                                 EPI == cz::EPI_ADD_NORM;
   // the LM-head epilogue (TMA store + column max) keeps four warps but DOUBLE-BUFFERS its TMA patch: with a single patch every
   // 32-column chunk waited for the previous bulk store to finish reading shared memory (about 1.5 us each, 7 us per tile)
   static constexpr bool kColmax = EPI == cz::EPI_STORE_F32_COLMAX;
   static constexpr int kEpiWarps = kHeavy ? 8 : 4;
   static constexpr int kTmaPatches = kColmax ? 2 : 1;
   static constexpr int kThreads = 64 + 32 * kEpiWarps;
-  static constexpr int kStages = (BN <= 192 && (!kHeavy || EPI == cz::EPI_QKV_ROPE)) ? 5 : 4;  // RoPE stages nothing in smem
+  static constexpr int kStages = (BN <= 192 && !kHeavy) ? 5 : 4;
   static constexpr int kABytes = BM * BK * 2;
   static constexpr int kBBytes = BN * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kTmemCols = 512;  // 2 accumulator stages of BN columns, power of two >= 2*BN
   // per epilogue warp: a padded 32x33 f32 transpose patch (4224 B), two of them for the RoPE epilogue, or a dense 4 KB
   // SWIZZLE_128B TMA box (1024-aligned) for the f32 store / reduce-add epilogues
-  static constexpr int kPatchBytes = EPI == cz::EPI_QKV_ROPE ? 0 : (kHeavy ? 4224 : (kColmax ? 8192 : 5120));
+  // (EPI_QKV_ROPE: per TMEM lane quadrant three 4 KB [32 rows][64 bf16] head patches shared by its two warps = 6144 B per warp)
+  static constexpr int kPatchBytes = EPI == cz::EPI_QKV_ROPE ? 6144 : (kHeavy ? 4224 : (kColmax ? 8192 : 5120));
   static constexpr int kStagingOff = kStages * kStageBytes + 1024;  // the barriers live in the 1 KB before it
   static constexpr int kSmemBytes = kStagingOff + kEpiWarps * kPatchBytes + 1024 /*align slack*/;
   static_assert(kSmemBytes <= 232448, "shared memory budget");
@@ -72,12 +76,30 @@ __device__ __forceinline__ constexpr uint32_t make_idesc() {
 }
 
 __device__ __forceinline__ float silu_mul(float g, float u) { return __fdividef(g, 1.0f + __expf(-g)) * u; }
+// silu(g * rs) * (u * rs) with the row scale folded into the two constants nk = -rs * log2(e) and rs2 = rs * rs:
+// one multiply more than silu_mul instead of two (the SwiGLU epilogue is what bounds the gate/up GEMM)
+__device__ __forceinline__ float silu_mul_scaled(float g, float u, float nk, float rs2) {
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(g * nk));
+  return __fdividef((g * u) * rs2, 1.0f + e);
+}
+
+// RMSNorm row scale of a consumer epilogue: 1 / sqrt(mean(x^2) + eps) from the partial sums the producer (EPI_ADD_NORM or the
+// embedding kernel) left per row, added in index order; 1 when the GEMM has no fused norm.
+__device__ __forceinline__ float norm_row_scale(const NormExt &nx, int row, bool ok) {
+  if (nx.ssq_in == nullptr || !ok) return 1.0f;
+  const float *p = nx.ssq_in + (size_t)row * nx.n_part_in;
+  float s = 0.f;
+  for (int i = 0; i < nx.n_part_in; i++) s += p[i];
+  return 1.0f / sqrtf(s * nx.inv_d + nx.eps);
+}
 
 template <int BN, int EPI>
 __global__ void __launch_bounds__((GemmCfg<BN, EPI>::kThreads), 1)
     gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                    const __grid_constant__ CUtensorMap tm_c, void *__restrict__ c_ptr,
-                   int M, int N, int K, int ldc, int *__restrict__ aux, const __grid_constant__ RopeExt rx) {
+                   int M, int N, int K, int ldc, int *__restrict__ aux, const __grid_constant__ RopeExt rx,
+                   const __grid_constant__ NormExt nx) {
   using Cfg = GemmCfg<BN, EPI>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -129,6 +151,15 @@ __global__ void __launch_bounds__((GemmCfg<BN, EPI>::kThreads), 1)
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+        if constexpr (EPI == EPI_ADD_NORM) {
+          // the epilogue will read this tile's old residual a few microseconds from now: pull it into L2 (32 x 32 f32 boxes)
+          for (int rb = 0; rb < BM / 32; rb++)
+            for (int cb = 0; cb < BN / 32; cb++)
+              if (m_blk * BM + rb * 32 < M && n_blk * BN + cb * 32 < N)
+                asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(&tm_c), "r"(n_blk * BN + cb * 32),
+                             "r"(m_blk * BM + rb * 32)
+                             : "memory");
+        }
         for (int kb = 0; kb < k_blocks; kb++) {
           mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
           const uint32_t fb = smem_u32(&full_bar[stage]);
@@ -189,10 +220,14 @@ __global__ void __launch_bounds__((GemmCfg<BN, EPI>::kThreads), 1)
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, it++) {
       const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
       const int as = it & 1;
-      mbar_wait(smem_u32(&tfull_bar[as]), (it >> 1) & 1);
-      tc_fence_after();
       const int row_base = m_blk * BM + quad * 32;
       const bool row_ok = row_base + lane < M;
+      // fused RMSNorm, consumer side: this thread's row scale, fetched while the tile's MMAs are still running
+      const float rs = norm_row_scale(nx, row_base + lane, row_ok);
+      if constexpr (EPI != EPI_ADD_NORM && EPI != EPI_QKV_ROPE) {  // (those two first put their own loads in flight, then wait)
+        mbar_wait(smem_u32(&tfull_bar[as]), (it >> 1) & 1);
+        tc_fence_after();
+      }
       const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BN);
       constexpr bool kSwiglu = EPI == EPI_SWIGLU_BF16;
       constexpr bool kOutBf16 = kSwiglu || EPI == EPI_STORE_BF16 || EPI == EPI_TANH_BF16 || EPI == EPI_SIGMOID_BF16 || EPI == EPI_RELUSQ_BF16;
@@ -203,13 +238,14 @@ __global__ void __launch_bounds__((GemmCfg<BN, EPI>::kThreads), 1)
         // The tile is three whole heads (BN = 192).  tcgen05.ld hands every lane one ROW, i.e. one position: the thread loads
         // that position's cos / sin once per tile and rotates in registers (rotate-half RoPE in fp32 on the accumulators,
         // like the reference's f32 path).  The two warps of a TMEM lane quadrant split the 32 rotation pairs (j, j + 32) of a
-        // head in halves.  Stores go straight from registers: bf16 q rows, K and V arena rows at slot kv_base[row] + pos[row].
+        // head in halves.  Outputs: bf16 q rows, K and V arena rows at slot kv_base[row] + pos[row].
         const int my_row = row_base + lane;
         const bool ok = my_row < M;
         const int my_pos = ok ? rx.pos[my_row] : 0;
         const size_t my_slot = ok ? (size_t)rx.kv_base[my_row] + (size_t)my_pos : 0;
         const int dq = rx.nh * 64, dkv = rx.nkv * 64;
         const int j0 = half * 16;
+        // (fused RMSNorm: the A rows are bf16(x * w); the 1/rms factor rs is applied to the accumulators below)
         float cs[16], sn[16];
         {
           const float4 *c4 = reinterpret_cast<const float4 *>(rx.cos_tab + (size_t)my_pos * 32 + j0);
@@ -221,20 +257,27 @@ __global__ void __launch_bounds__((GemmCfg<BN, EPI>::kThreads), 1)
             sn[4 * q] = sv.x; sn[4 * q + 1] = sv.y; sn[4 * q + 2] = sv.z; sn[4 * q + 3] = sv.w;
           }
         }
+        mbar_wait(smem_u32(&tfull_bar[as]), (it >> 1) & 1);  // (the position / cos / sin loads above overlap the tile's MMAs)
+        tc_fence_after();
+        // The rotated bf16 values go through a per-quadrant shared-memory patch per head ([32 rows][128 B], 16-byte chunks XOR-ed
+        // with row & 7 so the row-per-lane writes are conflict-free) and leave as whole 128-byte row segments: a direct store from
+        // the row-per-lane layout would touch 32 rows per instruction with 16 useful bytes each.  The two warps of a quadrant
+        // fill the patches together (each its half of the rotation pairs) and then store half of the rows each.
+        const int n_heads_tile = min(BN / 64, rx.nh + 2 * rx.nkv - n_blk * (BN / 64));
+        uint8_t *qpatch = smem + Cfg::kStagingOff + quad * (3 * 4096);
 #pragma unroll 1
-        for (int hh = 0; hh < BN / 64; hh++) {
+        for (int hh = 0; hh < n_heads_tile; hh++) {
           const int head = n_blk * (BN / 64) + hh;  // 0..nh-1 q heads, then nkv k heads, then nkv v heads
-          if (head >= rx.nh + 2 * rx.nkv) break;
           uint32_t ra[16], rb[16];
           tc_ld_32x16(t_row + (uint32_t)(hh * 64 + j0), ra);
           tc_ld_32x16(t_row + (uint32_t)(hh * 64 + 32 + j0), rb);
           tc_ld_wait();
-          if (!ok) continue;
-          const bool is_q = head < rx.nh, is_v = head >= rx.nh + rx.nkv;
+          const bool is_v = head >= rx.nh + rx.nkv;
           uint32_t wa[8], wb[8];
 #pragma unroll
           for (int j = 0; j < 16; j += 2) {
-            float a0 = __uint_as_float(ra[j]), a1 = __uint_as_float(ra[j + 1]), b0 = __uint_as_float(rb[j]), b1 = __uint_as_float(rb[j + 1]);
+            float a0 = __uint_as_float(ra[j]) * rs, a1 = __uint_as_float(ra[j + 1]) * rs, b0 = __uint_as_float(rb[j]) * rs,
+                  b1 = __uint_as_float(rb[j + 1]) * rs;
             if (!is_v) {
               const float x0 = a0, y0 = b0, x1 = a1, y1 = b1;
               a0 = x0 * cs[j] - y0 * sn[j];
@@ -246,18 +289,42 @@ __global__ void __launch_bounds__((GemmCfg<BN, EPI>::kThreads), 1)
             wa[j >> 1] = *reinterpret_cast<uint32_t *>(&ha);
             wb[j >> 1] = *reinterpret_cast<uint32_t *>(&hb);
           }
-          __nv_bfloat16 *dst = is_q ? (__nv_bfloat16 *)rx.q + (size_t)my_row * dq + head * 64
-                                    : (is_v ? (__nv_bfloat16 *)rx.v_arena + my_slot * dkv + (head - rx.nh - rx.nkv) * 64
-                                            : (__nv_bfloat16 *)rx.k_arena + my_slot * dkv + (head - rx.nh) * 64);
-          uint4 *da = reinterpret_cast<uint4 *>(dst + j0), *db = reinterpret_cast<uint4 *>(dst + 32 + j0);
-          da[0] = make_uint4(wa[0], wa[1], wa[2], wa[3]);
-          da[1] = make_uint4(wa[4], wa[5], wa[6], wa[7]);
-          db[0] = make_uint4(wb[0], wb[1], wb[2], wb[3]);
-          db[1] = make_uint4(wb[4], wb[5], wb[6], wb[7]);
+          // row = lane; dims [j0, j0+16) are 16-byte chunks 2*half, 2*half+1; dims [32+j0, 32+j0+16) are chunks 4+2*half, 5+2*half
+          const uint32_t prow = smem_u32(qpatch + hh * 4096 + lane * 128);
+          const int sw = lane & 7;
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(prow + (uint32_t)(((2 * half) ^ sw) << 4)), "r"(wa[0]), "r"(wa[1]), "r"(wa[2]), "r"(wa[3]) : "memory");
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(prow + (uint32_t)(((2 * half + 1) ^ sw) << 4)), "r"(wa[4]), "r"(wa[5]), "r"(wa[6]), "r"(wa[7]) : "memory");
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(prow + (uint32_t)(((4 + 2 * half) ^ sw) << 4)), "r"(wb[0]), "r"(wb[1]), "r"(wb[2]), "r"(wb[3]) : "memory");
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(prow + (uint32_t)(((5 + 2 * half) ^ sw) << 4)), "r"(wb[4]), "r"(wb[5]), "r"(wb[6]), "r"(wb[7]) : "memory");
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[as]));
+        if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[as]));  // the accumulator has been read: the MMA warp may reuse it
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");  // both warps of the quadrant have filled the patches
+        {
+          const int chunk = lane & 7;
+#pragma unroll 1
+          for (int hh = 0; hh < n_heads_tile; hh++) {
+            const int head = n_blk * (BN / 64) + hh;
+            const bool is_q = head < rx.nh, is_v = head >= rx.nh + rx.nkv;
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+              const int rl = half * 16 + i * 4 + (lane >> 3);  // row of the quadrant handled by this lane
+              const long long slot_l = __shfl_sync(0xffffffffu, (long long)my_slot, rl);
+              const int grow = row_base + rl;
+              uint4 v;
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                           : "r"(smem_u32(qpatch + hh * 4096 + rl * 128 + ((chunk ^ (rl & 7)) << 4))) : "memory");
+              if (grow < M) {
+                __nv_bfloat16 *dst = is_q ? (__nv_bfloat16 *)rx.q + (size_t)grow * dq + head * 64
+                                          : (is_v ? (__nv_bfloat16 *)rx.v_arena + (size_t)slot_l * dkv + (head - rx.nh - rx.nkv) * 64
+                                                  : (__nv_bfloat16 *)rx.k_arena + (size_t)slot_l * dkv + (head - rx.nh) * 64);
+                *reinterpret_cast<uint4 *>(dst + chunk * 8) = v;
+              }
+            }
+          }
+        }
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");  // the patches may be overwritten by the next tile
         continue;
       } else if constexpr (kTmaF32) {
         // f32 outputs leave through TMA.  Residual add without reading the residual: the 32x32 f32 patch goes to shared memory in the TMA box layout
@@ -319,7 +386,78 @@ __global__ void __launch_bounds__((GemmCfg<BN, EPI>::kThreads), 1)
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[as]));
         continue;
+      } else if constexpr (EPI == EPI_ADD_NORM) {
+        // Residual add + the next RMSNorm's inputs.  The accumulator chunk is transposed through the warp's padded patch so that
+        // a thread owns 4 consecutive columns of 8 rows: the old residual is read and the new one written with coalesced 128-byte
+        // row segments.  All of this warp's residual loads (and the norm weights) are issued BEFORE waiting for the accumulator,
+        // so their DRAM latency overlaps the tile's MMAs.  Per row, the two warps of a TMEM lane quadrant each leave one partial
+        // sum of squares per N tile (fixed summation order: 4 columns in a thread, chunks in ascending order, then an 8-lane
+        // xor tree), which the consumer GEMM's epilogue adds in index order.
+        constexpr int kMine = BN / 64;  // 32-column chunks per warp (two warps share a quadrant)
+        float *xg = reinterpret_cast<float *>(c_ptr);
+        __nv_bfloat16 *xbg = reinterpret_cast<__nv_bfloat16 *>(nx.xb);
+        // two chunks of old residual in flight per thread (64 registers), refilled as chunks are consumed
+        float4 xo[2][8];
+        auto load_xo = [&](int k, float4(&dst)[8]) {
+          const int gcol = n_blk * BN + (half + 2 * k) * 32 + cc;
+#pragma unroll
+          for (int i = 0; i < 8; i++) {
+            const int grow = row_base + i * 4 + rr0;
+            dst[i] = (gcol < N && grow < M) ? *reinterpret_cast<const float4 *>(xg + (size_t)grow * ldc + gcol) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        };
+        load_xo(0, xo[0]);
+        if (kMine > 1) load_xo(1, xo[1]);
+        mbar_wait(smem_u32(&tfull_bar[as]), (it >> 1) & 1);
+        tc_fence_after();
+        float acc[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) acc[i] = 0.f;
+#pragma unroll
+        for (int k = 0; k < kMine; k++) {
+          const int c = half + 2 * k;
+          uint32_t r[32];
+          tc_ld_32x32(t_row + (uint32_t)(c * 32), r);
+          tc_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; j++) stg[lane * 33 + j] = __uint_as_float(r[j]);
+          __syncwarp();
+          const int gcol = n_blk * BN + c * 32 + cc;
+          if (gcol < N) {
+            const float4 wk = *reinterpret_cast<const float4 *>(nx.w_next + gcol);
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+              const int rr = i * 4 + rr0;
+              const int grow = row_base + rr;
+              if (grow >= M) continue;
+              const float *sp = stg + rr * 33 + cc;
+              const float4 o = xo[k & 1][i];
+              float4 v = make_float4(sp[0] + o.x, sp[1] + o.y, sp[2] + o.z, sp[3] + o.w);
+              *reinterpret_cast<float4 *>(xg + (size_t)grow * ldc + gcol) = v;
+              acc[i] += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+              __nv_bfloat162 h0 = __floats2bfloat162_rn(v.x * wk.x, v.y * wk.y), h1 = __floats2bfloat162_rn(v.z * wk.z, v.w * wk.w);
+              *reinterpret_cast<uint2 *>(xbg + (size_t)grow * N + gcol) = make_uint2(*reinterpret_cast<uint32_t *>(&h0), *reinterpret_cast<uint32_t *>(&h1));
+            }
+          }
+          if (k + 2 < kMine) load_xo(k + 2, xo[k & 1]);
+          __syncwarp();
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[as]));
+        const int n_part = n_tiles * kColSplit;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+          float a = acc[i];
+          a += __shfl_xor_sync(0xffffffffu, a, 4);
+          a += __shfl_xor_sync(0xffffffffu, a, 2);
+          a += __shfl_xor_sync(0xffffffffu, a, 1);
+          const int grow = row_base + i * 4 + rr0;
+          if ((lane & 7) == 0 && grow < M) nx.ssq_out[(size_t)grow * n_part + n_blk * kColSplit + half] = a;
+        }
+        continue;
       } else {
+      const float nk = -rs * 1.4426950408889634f, rs2 = rs * rs;
 #pragma unroll 1
       for (int c = half; c < kChunks; c += kColSplit) {
         uint32_t r[32];
@@ -332,11 +470,15 @@ __global__ void __launch_bounds__((GemmCfg<BN, EPI>::kThreads), 1)
           tc_ld_wait();
           col0 = n_blk * (BN / 2) + c * 32;
 #pragma unroll
-          for (int j = 0; j < 32; j++) r[j] = __float_as_uint(silu_mul(__uint_as_float(r[j]), __uint_as_float(u[j])));
+          for (int j = 0; j < 32; j++) r[j] = __float_as_uint(silu_mul_scaled(__uint_as_float(r[j]), __uint_as_float(u[j]), nk, rs2));
         } else {
           tc_ld_32x32(t_row + (uint32_t)(c * 32), r);
           tc_ld_wait();
           col0 = n_blk * BN + c * 32;
+          if (kOutBf16) {
+#pragma unroll
+            for (int j = 0; j < 32; j++) r[j] = __float_as_uint(__uint_as_float(r[j]) * rs);
+          }
         }
         if (col0 >= n_out) continue;  // warp-uniform
         if (EPI == EPI_STORE_F32_COLMAX) {
@@ -488,7 +630,7 @@ static int make_map_c(CUtensorMap *map, void *ptr, int rows, int cols, int ld_el
 
 template <int BN, int EPI>
 static int launch_tc(cz_ctx *ctx, const CUtensorMap &ta, const CUtensorMap &tb, const CUtensorMap &tc, void *c, int M, int N, int K, int ldc, int *aux,
-                     int g_fam, cudaStream_t stream, const RopeExt &rx) {
+                     int g_fam, cudaStream_t stream, const RopeExt &rx, const NormExt &nx) {
   using Cfg = czk::GemmCfg<BN, EPI>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -498,7 +640,7 @@ static int launch_tc(cz_ctx *ctx, const CUtensorMap &ta, const CUtensorMap &tb, 
   const int tiles = (int)(ceil_div(M, czk::BM) * ceil_div(N, BN));
   const int grid = tiles < ctx->sm_count ? tiles : ctx->sm_count;
   CZ_LAUNCH(ctx, g_fam,
-            (czk::gemm_tc_kernel<BN, EPI><<<grid, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(ta, tb, tc, c, M, N, K, ldc, aux, rx)));
+            (czk::gemm_tc_kernel<BN, EPI><<<grid, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(ta, tb, tc, c, M, N, K, ldc, aux, rx, nx)));
   CZ_CHECK_LAUNCH();
   return CZ_OK;
 }
@@ -528,13 +670,18 @@ int gemm_tcgen05(cz_ctx *ctx, const GemmArgs &g, cudaStream_t stream) {
     set_error("gemm_tcgen05: EPI_QKV_ROPE needs BN = 192, N = (nh + 2 nkv) * 64 and all RopeExt operands");
     return CZ_ERR_INVALID;
   }
+  if (g.epi == EPI_ADD_NORM && (g.bn != 192 || (g.N % 4) || (g.ldc % 4) || !g.norm.w_next || !g.norm.xb || !g.norm.ssq_out)) {
+    set_error("gemm_tcgen05: EPI_ADD_NORM needs BN = 192, N % 4 == 0 and the NormExt producer operands");
+    return CZ_ERR_INVALID;
+  }
   CUtensorMap ta, tb, tc;
   CZ_TRY(make_map_bf16(&ta, g.a, g.M, g.K, g.lda, czk::BM));
   CZ_TRY(make_map_bf16(&tb, g.b, g.N, g.K, g.ldb, g.bn));
-  if (g.epi == EPI_ADD_F32 || g.epi == EPI_STORE_F32 || g.epi == EPI_STORE_F32_COLMAX) CZ_TRY(make_map_c(&tc, g.c, g.M, g.N, g.ldc));
+  if (g.epi == EPI_ADD_F32 || g.epi == EPI_STORE_F32 || g.epi == EPI_STORE_F32_COLMAX || g.epi == EPI_ADD_NORM)
+    CZ_TRY(make_map_c(&tc, g.c, g.M, g.N, g.ldc));
   else tc = ta;  // unused by the other epilogues
 #define CZ_TC_CASE(BN_, EPI_) \
-  if (g.bn == BN_ && g.epi == EPI_) return launch_tc<BN_, EPI_>(ctx, ta, tb, tc, g.c, g.M, g.N, g.K, g.ldc, g.aux, g.fam, stream, g.rope)
+  if (g.bn == BN_ && g.epi == EPI_) return launch_tc<BN_, EPI_>(ctx, ta, tb, tc, g.c, g.M, g.N, g.K, g.ldc, g.aux, g.fam, stream, g.rope, g.norm)
   CZ_TC_CASE(192, EPI_STORE_F32);
   CZ_TC_CASE(192, EPI_ADD_F32);
   CZ_TC_CASE(192, EPI_SWIGLU_BF16);
@@ -548,6 +695,7 @@ int gemm_tcgen05(cz_ctx *ctx, const GemmArgs &g, cudaStream_t stream) {
   CZ_TC_CASE(256, EPI_ADD_F32);
   CZ_TC_CASE(192, EPI_QKV_ROPE);
   CZ_TC_CASE(256, EPI_SWIGLU_BF16);
+  CZ_TC_CASE(192, EPI_ADD_NORM);
 #undef CZ_TC_CASE
   set_error("gemm_tcgen05: unsupported (BN, epilogue) combination");
   return CZ_ERR_UNSUPPORTED;

@@ -19,6 +19,29 @@ __global__ void embed_kernel(const __nv_bfloat16 *__restrict__ table, const uint
   for (int i = threadIdx.x; i < d; i += blockDim.x) dst[i] = __bfloat162float(src[i]);
 }
 
+// Embedding gather that also leaves the first layer's fused-RMSNorm inputs (see EPI_ADD_NORM in gemm.h): xb = bf16(x * w),
+// ssq[row][0] = sum of x^2 (fixed order: per-lane strided partials, then an xor tree), ssq[row][1..n_part) = 0.  One warp per row.
+__global__ void __launch_bounds__(128) embed_norm_kernel(const __nv_bfloat16 *__restrict__ table, const uint32_t *__restrict__ tok,
+                                                         const float *__restrict__ w, float *__restrict__ x, __nv_bfloat16 *__restrict__ xb,
+                                                         float *__restrict__ ssq, int n_rows, int d, int n_part) {
+  const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= n_rows) return;
+  const __nv_bfloat16 *src = table + (size_t)tok[row] * d;
+  float *dst = x + (size_t)row * d;
+  __nv_bfloat16 *db = xb + (size_t)row * d;
+  float ss = 0.f;
+  for (int i = lane; i < d; i += 32) {
+    const float v = __bfloat162float(src[i]);
+    dst[i] = v;
+    db[i] = __float2bfloat16_rn(v * w[i]);
+    ss = fmaf(v, v, ss);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  if (lane < n_part) ssq[(size_t)row * n_part + lane] = lane == 0 ? ss : 0.f;
+}
+
 // One warp per output row.  src row = rows ? rows[j] : j.  y = bf16( (x * inv_rms) * w )
 __global__ void __launch_bounds__(128) rmsnorm_kernel(const float *__restrict__ x, const float *__restrict__ w,
                                                       const int *__restrict__ rows, __nv_bfloat16 *__restrict__ y, int n_out,
@@ -188,6 +211,19 @@ void llama_kernels_set_carveout() {
 int launch_embed(cz_ctx *ctx, const __nv_bfloat16 *table, const uint32_t *tok, float *x, int n_rows, int d, cudaStream_t st) {
   if (n_rows == 0) return CZ_OK;
   CZ_LAUNCH(ctx, CZ_K_ELEMWISE, (czk::embed_kernel<<<n_rows, 128, 0, st>>>(table, tok, x, n_rows, d)));
+  CZ_CHECK_LAUNCH();
+  return CZ_OK;
+}
+
+int launch_embed_norm(cz_ctx *ctx, const __nv_bfloat16 *table, const uint32_t *tok, const float *w, float *x, __nv_bfloat16 *xb,
+                      float *ssq, int n_rows, int d, int n_part, cudaStream_t st) {
+  if (n_rows == 0) return CZ_OK;
+  if (n_part < 1 || n_part > 32) {
+    set_error("embed_norm: 1 <= n_part <= 32");
+    return CZ_ERR_INVALID;
+  }
+  CZ_LAUNCH(ctx, CZ_K_ELEMWISE,
+            (czk::embed_norm_kernel<<<(unsigned)ceil_div(n_rows, 4), 128, 0, st>>>(table, tok, w, x, xb, ssq, n_rows, d, n_part)));
   CZ_CHECK_LAUNCH();
   return CZ_OK;
 }

@@ -126,6 +126,7 @@ int ensure_workspace(cz_model *m, size_t rows, size_t n_logit, size_t n_tiles) {
       return ensure_workspace(m, rows, n_logit, n_tiles);
     }
     CZ_TRY(realloc_dev(w.xn, r * D));
+    CZ_TRY(realloc_dev(w.ssq, r * 8));
     CZ_TRY(realloc_dev(w.qkv, r * QKV));
     CZ_TRY(realloc_dev(w.q, r * D));
     CZ_TRY(realloc_dev(w.attn, r * D));
@@ -271,11 +272,24 @@ int forward_trunk(cz_model *m, int n_rows, const KvView &kv, cudaStream_t st) {
   cz_ctx *ctx = m->ctx;
   Workspace &w = m->ws;
   const int D = c.d_model, F = c.d_ffn, nh = c.n_heads, nkv = c.n_kv_heads, kvd = nkv * 64, QKV = D + 2 * kvd, L = c.n_layers;
-  CZ_TRY(launch_embed(ctx, m->embed, w.tok, w.x, n_rows, D, st));
+  // Fused RMSNorm (tcgen05 engine): the residual-add epilogues of o_proj / down_proj (EPI_ADD_NORM) leave bf16(x * w_norm) and
+  // per-row partial sums of x^2 for the norm that follows, and the consuming projection scales its accumulator rows by
+  // 1/rms -- the fp32 residual is never re-read by a separate normalisation pass.  Needs D = 3 tiles of 192 (n_part = 6).
+  static const bool no_fused_norm = getenv("CZ_DEBUG_NO_FUSED_NORM") != nullptr;  // bisecting aid
+  const bool fused_norm = c.engine == CZ_ENGINE_TCGEN05 && !no_fused_norm && getenv("CZ_DEBUG_NO_FUSED_ROPE") == nullptr && D % 192 == 0 &&
+                          (D / 192) * 2 <= 8;
+  const int n_part = fused_norm ? (D / 192) * 2 : 0;
+  NormExt consume{};
+  if (fused_norm) {
+    consume.ssq_in = w.ssq; consume.n_part_in = n_part; consume.inv_d = 1.0f / (float)D; consume.eps = c.norm_eps;
+    CZ_TRY(launch_embed_norm(ctx, m->embed, w.tok, m->norms, w.x, w.xn, w.ssq, n_rows, D, n_part, st));
+  } else {
+    CZ_TRY(launch_embed(ctx, m->embed, w.tok, w.x, n_rows, D, st));
+  }
   for (int l = 0; l < L; l++) {
     const float *n1 = m->norms + (size_t)(2 * l) * D, *n2 = m->norms + (size_t)(2 * l + 1) * D;
     __nv_bfloat16 *kl = kv.k + (size_t)l * kv.layer_stride, *vl = kv.v + (size_t)l * kv.layer_stride;
-    CZ_TRY(launch_rmsnorm(ctx, w.x, n1, nullptr, w.xn, n_rows, D, c.norm_eps, st));
+    if (!fused_norm) CZ_TRY(launch_rmsnorm(ctx, w.x, n1, nullptr, w.xn, n_rows, D, c.norm_eps, st));
     GemmArgs g{};
     g.a = w.xn; g.lda = D; g.b = m->w_qkv + (size_t)l * QKV * D; g.ldb = D; g.c = w.qkv; g.ldc = QKV;
     g.M = n_rows; g.N = QKV; g.K = D; g.epi = EPI_STORE_F32; g.bn = 192; g.fam = CZ_K_GEMM;
@@ -287,8 +301,10 @@ int forward_trunk(cz_model *m, int n_rows, const KvView &kv, cudaStream_t st) {
       g.rope.pos = w.pos; g.rope.kv_base = w.kv_base; g.rope.cos_tab = m->cos_tab; g.rope.sin_tab = m->sin_tab;
       g.rope.q = w.q; g.rope.k_arena = kl; g.rope.nh = nh; g.rope.nkv = nkv;
       g.rope.v_arena = vl;  // V rows [slot][nkv*64] for both attention kernels (the tcgen05 one reads them as an MN-major operand)
+      if (fused_norm) g.norm = consume;
       CZ_TRY(gemm(ctx, c.engine, g, st));
       g.rope = RopeExt();
+      g.norm = NormExt();
     } else {
       CZ_TRY(gemm(ctx, c.engine, g, st));
       CZ_TRY(launch_rope_split(ctx, w.qkv, w.pos, w.kv_base, m->cos_tab, m->sin_tab, w.q, kl, vl, n_rows, nh, nkv, st));
@@ -303,14 +319,26 @@ int forward_trunk(cz_model *m, int n_rows, const KvView &kv, cudaStream_t st) {
       CZ_TRY(launch_attn_rows(ctx, w.q, kl, vl, w.pos, w.kv_base, w.attn, n_rows, nh, nkv, st));
     g.a = w.attn; g.lda = D; g.b = m->w_o + (size_t)l * D * D; g.ldb = D; g.c = w.x; g.ldc = D;
     g.M = n_rows; g.N = D; g.K = D; g.epi = EPI_ADD_F32; g.bn = 192; g.fam = CZ_K_GEMM_O;
+    if (fused_norm) {  // x += attn * Wo^T, and the FFN norm's inputs
+      g.epi = EPI_ADD_NORM;
+      g.norm.w_next = n2; g.norm.xb = w.xn; g.norm.ssq_out = w.ssq;
+    }
     CZ_TRY(gemm(ctx, c.engine, g, st));
-    CZ_TRY(launch_rmsnorm(ctx, w.x, n2, nullptr, w.xn, n_rows, D, c.norm_eps, st));
+    g.norm = NormExt();
+    if (!fused_norm) CZ_TRY(launch_rmsnorm(ctx, w.x, n2, nullptr, w.xn, n_rows, D, c.norm_eps, st));
     g.a = w.xn; g.lda = D; g.b = m->w_gu + (size_t)l * 2 * F * D; g.ldb = D; g.c = w.act; g.ldc = F;
     g.M = n_rows; g.N = 2 * F; g.K = D; g.epi = EPI_SWIGLU_BF16; g.bn = m->gu_bn; g.fam = CZ_K_GEMM_GU;
+    if (fused_norm) g.norm = consume;
     CZ_TRY(gemm(ctx, c.engine, g, st));
+    g.norm = NormExt();
     g.a = w.act; g.lda = F; g.b = m->w_d + (size_t)l * D * F; g.ldb = F; g.c = w.x; g.ldc = D;
     g.M = n_rows; g.N = D; g.K = F; g.epi = EPI_ADD_F32; g.bn = 192; g.fam = CZ_K_GEMM_DOWN;
+    if (fused_norm && l + 1 < L) {  // x += act * Wd^T, and the next layer's attention norm's inputs (the final norm reads fp32 x)
+      g.epi = EPI_ADD_NORM;
+      g.norm.w_next = m->norms + (size_t)(2 * (l + 1)) * D; g.norm.xb = w.xn; g.norm.ssq_out = w.ssq;
+    }
     CZ_TRY(gemm(ctx, c.engine, g, st));
+    g.norm = NormExt();
   }
   return CZ_OK;
 }

@@ -47,3 +47,53 @@ extern "C" int cz_test_gemm(cz_ctx *ctx, int engine, int M, int N, int K, const 
   cudaFree(dc);
   return rc;
 }
+
+extern "C" int cz_test_gemm_norm(cz_ctx *ctx, int M, int N, int K, int N2, const uint16_t *a_bf16, const uint16_t *b_bf16,
+                                 const uint16_t *b2_bf16, const float *w_next, float eps, float *x_inout, uint16_t *xb_out, float *ssq_out,
+                                 uint16_t *out2) {
+  CZ_TRY(require_device(ctx));
+  CZ_CUDA_TRY(cudaSetDevice(ctx->device));
+  if (N % 192 != 0 || K % 64 != 0 || N2 % 8 != 0) {
+    set_error("cz_test_gemm_norm: N % 192, K % 64, N2 % 8");
+    return CZ_ERR_INVALID;
+  }
+  const int n_part = (N / 192) * 2;
+  void *da = nullptr, *db = nullptr, *db2 = nullptr, *dx = nullptr, *dxb = nullptr, *dssq = nullptr, *dw = nullptr, *dout = nullptr;
+  CZ_CUDA_TRY(cudaMalloc(&da, (size_t)M * K * 2));
+  CZ_CUDA_TRY(cudaMalloc(&db, (size_t)N * K * 2));
+  CZ_CUDA_TRY(cudaMalloc(&db2, (size_t)N2 * N * 2));
+  CZ_CUDA_TRY(cudaMalloc(&dx, (size_t)M * N * 4));
+  CZ_CUDA_TRY(cudaMalloc(&dxb, (size_t)M * N * 2));
+  CZ_CUDA_TRY(cudaMalloc(&dssq, (size_t)M * n_part * 4));
+  CZ_CUDA_TRY(cudaMalloc(&dw, (size_t)N * 4));
+  CZ_CUDA_TRY(cudaMalloc(&dout, (size_t)M * N2 * 2));
+  CZ_CUDA_TRY(cudaMemcpy(da, a_bf16, (size_t)M * K * 2, cudaMemcpyHostToDevice));
+  CZ_CUDA_TRY(cudaMemcpy(db, b_bf16, (size_t)N * K * 2, cudaMemcpyHostToDevice));
+  CZ_CUDA_TRY(cudaMemcpy(db2, b2_bf16, (size_t)N2 * N * 2, cudaMemcpyHostToDevice));
+  CZ_CUDA_TRY(cudaMemcpy(dx, x_inout, (size_t)M * N * 4, cudaMemcpyHostToDevice));
+  CZ_CUDA_TRY(cudaMemcpy(dw, w_next, (size_t)N * 4, cudaMemcpyHostToDevice));
+  GemmArgs g{};
+  g.a = da; g.b = db; g.c = dx; g.M = M; g.N = N; g.K = K; g.lda = K; g.ldb = K; g.ldc = N; g.epi = EPI_ADD_NORM; g.bn = 192;
+  g.norm.w_next = (const float *)dw; g.norm.xb = dxb; g.norm.ssq_out = (float *)dssq;
+  int rc = gemm(ctx, CZ_ENGINE_TCGEN05, g, ctx->stream);
+  if (rc == CZ_OK) {
+    GemmArgs h{};
+    h.a = dxb; h.b = db2; h.c = dout; h.M = M; h.N = N2; h.K = N; h.lda = N; h.ldb = N; h.ldc = N2; h.epi = EPI_STORE_BF16; h.bn = 192;
+    h.norm.ssq_in = (const float *)dssq; h.norm.n_part_in = n_part; h.norm.inv_d = 1.0f / (float)N; h.norm.eps = eps;
+    rc = gemm(ctx, CZ_ENGINE_TCGEN05, h, ctx->stream);
+  }
+  if (rc == CZ_OK) {
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+      set_error(std::string("gemm execution failed: ") + cudaGetErrorString(e));
+      rc = CZ_ERR_CUDA;
+    } else {
+      cudaMemcpy(x_inout, dx, (size_t)M * N * 4, cudaMemcpyDeviceToHost);
+      cudaMemcpy(xb_out, dxb, (size_t)M * N * 2, cudaMemcpyDeviceToHost);
+      cudaMemcpy(ssq_out, dssq, (size_t)M * n_part * 4, cudaMemcpyDeviceToHost);
+      cudaMemcpy(out2, dout, (size_t)M * N2 * 2, cudaMemcpyDeviceToHost);
+    }
+  }
+  for (void *p : {da, db, db2, dx, dxb, dssq, dw, dout}) cudaFree(p);
+  return rc;
+}

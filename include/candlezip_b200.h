@@ -259,6 +259,13 @@ size_t cz_schedule_chunks(uint64_t n_tokens, uint32_t context, uint32_t reprime_
 int cz_test_gemm(cz_ctx *ctx, int engine, int M, int N, int K, const uint16_t *a_bf16, const uint16_t *b_bf16, int epi,
                  int bn, void *c_inout, int ldc);
 
+/* the fused residual-add + RMSNorm pair (tcgen05 engine, N a multiple of 192): x[M,N] += A[M,K] B[N,K]^T with
+ * xb = bf16(x * w_next) and per-row partial sums of squares (producer epilogue), then out[M,N2] = bf16(rowscale * (xb B2[N2,N]^T))
+ * with rowscale = 1 / sqrt(sum(x^2) / N + eps) (consumer epilogue).  Outputs: x (in place), xb_out [M][N], ssq_out [M][(N/192)*2],
+ * out2 [M][N2] (bf16). */
+int cz_test_gemm_norm(cz_ctx *ctx, int M, int N, int K, int N2, const uint16_t *a_bf16, const uint16_t *b_bf16, const uint16_t *b2_bf16,
+                      const float *w_next, float eps, float *x_inout, uint16_t *xb_out, float *ssq_out, uint16_t *out2);
+
 #ifdef __cplusplus
 }
 #endif

@@ -250,6 +250,51 @@ def test_gemm_tcgen05_row_invariance(gpu_ctx):
         assert np.array_equal(small.view(np.uint32), big[sel].view(np.uint32)), sel
 
 
+def _run_gemm_norm(ctx, a16, b16, b2_16, w_next, eps, x):
+    M, K = a16.shape
+    N, N2 = b16.shape[0], b2_16.shape[0]
+    x = np.ascontiguousarray(x, np.float32).copy()
+    xb = np.zeros((M, N), np.uint16)
+    ssq = np.zeros((M, (N // 192) * 2), np.float32)
+    out2 = np.zeros((M, N2), np.uint16)
+    u16p, f32p = C.POINTER(C.c_uint16), C.POINTER(C.c_float)
+    w = np.ascontiguousarray(w_next, np.float32)
+    _lib.check(_lib.lib.cz_test_gemm_norm(ctx._h, M, N, K, N2, a16.ctypes.data_as(u16p), b16.ctypes.data_as(u16p), b2_16.ctypes.data_as(u16p),
+                                          w.ctypes.data_as(f32p), eps, x.ctypes.data_as(f32p), xb.ctypes.data_as(u16p),
+                                          ssq.ctypes.data_as(f32p), out2.ctypes.data_as(u16p)))
+    return x, xb, ssq, out2
+
+
+@pytest.mark.parametrize("M", [1, 77, 300])
+def test_gemm_fused_residual_rmsnorm(gpu_ctx, M):
+    """EPI_ADD_NORM (residual add + bf16(x * w) + partial sums of squares) and the consumer's 1/rms row scale together equal
+    residual add -> RMSNorm -> projection (LLaMA block structure, candle-transformers llama.rs reached from src/models.rs:94);
+    rows are independent of the batch they are computed in (decode safety)."""
+    rng = np.random.default_rng(40 + M)
+    N, K, N2, eps = 576, 1536, 200, 1e-5
+    a16 = _bf16(rng.normal(0, 1, (M, K)))
+    b16 = _bf16(rng.normal(0, 0.05, (N, K)))
+    b2 = _bf16(rng.normal(0, 0.1, (N2, N)))
+    w = rng.uniform(0.5, 1.5, N).astype(np.float32)
+    x0 = rng.normal(0, 1, (M, N)).astype(np.float32)
+    x, xb, ssq, out2 = _run_gemm_norm(gpu_ctx, a16, b16, b2, w, eps, x0)
+    want_x = x0.astype(np.float64) + _bf16_to_f32(a16).astype(np.float64) @ _bf16_to_f32(b16).astype(np.float64).T
+    assert np.abs(x - want_x).max() < 5e-3
+    # bf16(x * w) is exact given the device's own fp32 x
+    assert np.array_equal(xb, _bf16(x * w))
+    assert np.allclose(ssq.sum(1), (x.astype(np.float64) ** 2).sum(1), rtol=1e-5)
+    rs = 1.0 / np.sqrt((x.astype(np.float64) ** 2).mean(1) + eps)
+    want2 = (_bf16_to_f32(xb).astype(np.float64) @ _bf16_to_f32(b2).astype(np.float64).T) * rs[:, None]
+    got2 = _bf16_to_f32(out2)
+    assert np.abs(got2 - want2).max() < 2e-2 * max(1.0, np.abs(want2).max())
+    if M >= 77:  # the same rows alone give the same bits
+        sel = [0, 5, 76]
+        xs, xbs, ssqs, out2s = _run_gemm_norm(gpu_ctx, np.ascontiguousarray(a16[sel]), b16, b2, w, eps, x0[sel])
+        assert np.array_equal(xs.view(np.uint32), x[sel].view(np.uint32))
+        assert np.array_equal(xbs, xb[sel]) and np.array_equal(ssqs.view(np.uint32), ssq[sel].view(np.uint32))
+        assert np.array_equal(out2s, out2[sel])
+
+
 # ------------------------------------------------------------------ SmolLM forward / encode / decode
 def _tiny(gpu_ctx, engine, seed=5, embed_std=0.05):
     return cz.Model(gpu_ctx, cz.SMOLLM_TINY, engine=engine).random_init(seed, 0.05, embed_std)
