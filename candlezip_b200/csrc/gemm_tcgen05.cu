@@ -84,16 +84,6 @@ __device__ __forceinline__ float silu_mul_scaled(float g, float u, float nk, flo
   return __fdividef((g * u) * rs2, 1.0f + e);
 }
 
-// RMSNorm row scale of a consumer epilogue: 1 / sqrt(mean(x^2) + eps) from the partial sums the producer (EPI_ADD_NORM or the
-// embedding kernel) left per row, added in index order; 1 when the GEMM has no fused norm.
-__device__ __forceinline__ float norm_row_scale(const NormExt &nx, int row, bool ok) {
-  if (nx.ssq_in == nullptr || !ok) return 1.0f;
-  const float *p = nx.ssq_in + (size_t)row * nx.n_part_in;
-  float s = 0.f;
-  for (int i = 0; i < nx.n_part_in; i++) s += p[i];
-  return 1.0f / sqrtf(s * nx.inv_d + nx.eps);
-}
-
 template <int BN, int EPI>
 __global__ void __launch_bounds__((GemmCfg<BN, EPI>::kThreads), 1)
     gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
@@ -217,13 +207,73 @@ __global__ void __launch_bounds__((GemmCfg<BN, EPI>::kThreads), 1)
     const int rr0 = lane >> 3, cc = (lane & 7) * 4;
     uint32_t n_store = 0;  // bulk stores issued by this warp so far (selects the TMA patch)
     int it = 0;
+    // Per-tile operands that do not depend on the accumulator are fetched ONE TILE AHEAD (the epilogue is the pacing stage of
+    // most of these GEMMs, so a load issued at the top of a tile's epilogue would have its whole latency exposed):
+    //   fused RMSNorm, consumer side: the partial sums of squares of this thread's row (pn);
+    //   EPI_QKV_ROPE: the row's position / KV slot base (and, below, its cos / sin rows);
+    //   EPI_ADD_NORM: the first two chunks of old residual (below).
+    float pn[8];
+    auto load_parts = [&](int tile_) {
+      const int row = (tile_ / n_tiles) * BM + quad * 32 + lane;
+      const bool ok = nx.ssq_in != nullptr && tile_ < num_tiles && row < M;
+#pragma unroll
+      for (int i = 0; i < 8; i++) pn[i] = (ok && i < nx.n_part_in) ? nx.ssq_in[(size_t)row * nx.n_part_in + i] : 0.f;
+    };
+    load_parts(blockIdx.x);
+    int pos_nx = 0, kvb_nx = 0;  // EPI_QKV_ROPE: position and KV base of this thread's row in the tile about to be processed
+    float cs[16], sn[16];         // EPI_QKV_ROPE: that row's cos / sin (this warp's half of the rotation pairs)
+    auto load_pos = [&](int tile_) {
+      const int row = (tile_ / n_tiles) * BM + quad * 32 + lane;
+      const bool ok = tile_ < num_tiles && row < M;
+      pos_nx = ok ? rx.pos[row] : 0;
+      kvb_nx = ok ? rx.kv_base[row] : 0;
+    };
+    auto load_cs = [&](int p) {
+      const float4 *c4 = reinterpret_cast<const float4 *>(rx.cos_tab + (size_t)p * 32 + half * 16);
+      const float4 *s4 = reinterpret_cast<const float4 *>(rx.sin_tab + (size_t)p * 32 + half * 16);
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        const float4 c = c4[q], sv = s4[q];
+        cs[4 * q] = c.x; cs[4 * q + 1] = c.y; cs[4 * q + 2] = c.z; cs[4 * q + 3] = c.w;
+        sn[4 * q] = sv.x; sn[4 * q + 1] = sv.y; sn[4 * q + 2] = sv.z; sn[4 * q + 3] = sv.w;
+      }
+    };
+    if constexpr (EPI == EPI_QKV_ROPE) {
+      load_pos(blockIdx.x);
+      load_cs(pos_nx);
+    }
+    // EPI_ADD_NORM: old-residual chunk k of this warp in tile tile_ (8 rows x 4 columns per thread)
+    float *xg = reinterpret_cast<float *>(c_ptr);
+    __nv_bfloat16 *xbg = reinterpret_cast<__nv_bfloat16 *>(nx.xb);
+    float4 xoA[8], xoB[8];
+    auto load_xo = [&](int tile_, int k, float4(&dst)[8]) {
+      const int gcol = (tile_ % n_tiles) * BN + (half + 2 * k) * 32 + cc;
+      const int rb = (tile_ / n_tiles) * BM + quad * 32;
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        const int grow = rb + i * 4 + rr0;
+        dst[i] = (tile_ < num_tiles && gcol < N && grow < M) ? *reinterpret_cast<const float4 *>(xg + (size_t)grow * ldc + gcol)
+                                                              : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+    if constexpr (EPI == EPI_ADD_NORM) {
+      load_xo(blockIdx.x, 0, xoA);
+      load_xo(blockIdx.x, 1, xoB);
+    }
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, it++) {
       const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
       const int as = it & 1;
       const int row_base = m_blk * BM + quad * 32;
       const bool row_ok = row_base + lane < M;
-      // fused RMSNorm, consumer side: this thread's row scale, fetched while the tile's MMAs are still running
-      const float rs = norm_row_scale(nx, row_base + lane, row_ok);
+      // fused RMSNorm, consumer side: 1 / sqrt(mean(x^2) + eps) from the partials fetched during the previous tile, added in index order
+      float rs = 1.0f;
+      if (nx.ssq_in != nullptr) {
+        float ssum = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; i++) ssum += pn[i];
+        rs = 1.0f / sqrtf(ssum * nx.inv_d + nx.eps);
+      }
+      load_parts(tile + (int)gridDim.x);
       if constexpr (EPI != EPI_ADD_NORM && EPI != EPI_QKV_ROPE) {  // (those two first put their own loads in flight, then wait)
         mbar_wait(smem_u32(&tfull_bar[as]), (it >> 1) & 1);
         tc_fence_after();
@@ -239,25 +289,12 @@ __global__ void __launch_bounds__((GemmCfg<BN, EPI>::kThreads), 1)
         // that position's cos / sin once per tile and rotates in registers (rotate-half RoPE in fp32 on the accumulators,
         // like the reference's f32 path).  The two warps of a TMEM lane quadrant split the 32 rotation pairs (j, j + 32) of a
         // head in halves.  Outputs: bf16 q rows, K and V arena rows at slot kv_base[row] + pos[row].
-        const int my_row = row_base + lane;
-        const bool ok = my_row < M;
-        const int my_pos = ok ? rx.pos[my_row] : 0;
-        const size_t my_slot = ok ? (size_t)rx.kv_base[my_row] + (size_t)my_pos : 0;
+        const size_t my_slot = (size_t)kvb_nx + (size_t)pos_nx;  // (fetched one tile ahead, like cs / sn)
         const int dq = rx.nh * 64, dkv = rx.nkv * 64;
         const int j0 = half * 16;
+        load_pos(tile + (int)gridDim.x);  // next tile's row: its position is needed for the cos / sin loads issued after the rotation
         // (fused RMSNorm: the A rows are bf16(x * w); the 1/rms factor rs is applied to the accumulators below)
-        float cs[16], sn[16];
-        {
-          const float4 *c4 = reinterpret_cast<const float4 *>(rx.cos_tab + (size_t)my_pos * 32 + j0);
-          const float4 *s4 = reinterpret_cast<const float4 *>(rx.sin_tab + (size_t)my_pos * 32 + j0);
-#pragma unroll
-          for (int q = 0; q < 4; q++) {
-            const float4 c = c4[q], sv = s4[q];
-            cs[4 * q] = c.x; cs[4 * q + 1] = c.y; cs[4 * q + 2] = c.z; cs[4 * q + 3] = c.w;
-            sn[4 * q] = sv.x; sn[4 * q + 1] = sv.y; sn[4 * q + 2] = sv.z; sn[4 * q + 3] = sv.w;
-          }
-        }
-        mbar_wait(smem_u32(&tfull_bar[as]), (it >> 1) & 1);  // (the position / cos / sin loads above overlap the tile's MMAs)
+        mbar_wait(smem_u32(&tfull_bar[as]), (it >> 1) & 1);
         tc_fence_after();
         // The rotated bf16 values go through a per-quadrant shared-memory patch per head ([32 rows][128 B], 16-byte chunks XOR-ed
         // with row & 7 so the row-per-lane writes are conflict-free) and leave as whole 128-byte row segments: a direct store from
@@ -300,6 +337,7 @@ __global__ void __launch_bounds__((GemmCfg<BN, EPI>::kThreads), 1)
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[as]));  // the accumulator has been read: the MMA warp may reuse it
+        load_cs(pos_nx);  // next tile's cos / sin: in flight during this tile's store phase
         asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");  // both warps of the quadrant have filled the patches
         {
           const int chunk = lane & 7;
@@ -389,72 +427,68 @@ __global__ void __launch_bounds__((GemmCfg<BN, EPI>::kThreads), 1)
       } else if constexpr (EPI == EPI_ADD_NORM) {
         // Residual add + the next RMSNorm's inputs.  The accumulator chunk is transposed through the warp's padded patch so that
         // a thread owns 4 consecutive columns of 8 rows: the old residual is read and the new one written with coalesced 128-byte
-        // row segments.  All of this warp's residual loads (and the norm weights) are issued BEFORE waiting for the accumulator,
-        // so their DRAM latency overlaps the tile's MMAs.  Per row, the two warps of a TMEM lane quadrant each leave one partial
-        // sum of squares per N tile (fixed summation order: 4 columns in a thread, chunks in ascending order, then an 8-lane
-        // xor tree), which the consumer GEMM's epilogue adds in index order.
-        constexpr int kMine = BN / 64;  // 32-column chunks per warp (two warps share a quadrant)
-        float *xg = reinterpret_cast<float *>(c_ptr);
-        __nv_bfloat16 *xbg = reinterpret_cast<__nv_bfloat16 *>(nx.xb);
-        // two chunks of old residual in flight per thread (64 registers), refilled as chunks are consumed
-        float4 xo[2][8];
-        auto load_xo = [&](int k, float4(&dst)[8]) {
-          const int gcol = n_blk * BN + (half + 2 * k) * 32 + cc;
+        // row segments.  Two chunks of old residual are in flight per thread (xoA / xoB, 64 registers): the first two chunks of
+        // a tile are requested while the PREVIOUS tile is still being processed (the buffers swap roles every tile), the third
+        // as soon as the first has been consumed, and the TMA producer has pulled the tile into L2 long before.  Per row, the two
+        // warps of a TMEM lane quadrant each leave one partial sum of squares per N tile (fixed summation order: 4 columns in
+        // a thread, chunks in ascending order, then an 8-lane xor tree), which the consumer GEMM's epilogue adds in index order.
+        static_assert(BN == 192, "EPI_ADD_NORM: three 32-column chunks per warp");
+        auto process = [&](float4(&bufP)[8], float4(&bufQ)[8]) {  // bufP holds chunk 0 of this tile, bufQ chunk 1
+          mbar_wait(smem_u32(&tfull_bar[as]), (it >> 1) & 1);
+          tc_fence_after();
+          float acc[8];
+#pragma unroll
+          for (int i = 0; i < 8; i++) acc[i] = 0.f;
+          auto chunk = [&](int k, float4(&xo)[8]) {
+            const int c = half + 2 * k;
+            uint32_t r[32];
+            tc_ld_32x32(t_row + (uint32_t)(c * 32), r);
+            tc_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; j++) stg[lane * 33 + j] = __uint_as_float(r[j]);
+            __syncwarp();
+            const int gcol = n_blk * BN + c * 32 + cc;
+            if (gcol < N) {
+              const float4 wk = *reinterpret_cast<const float4 *>(nx.w_next + gcol);
+#pragma unroll
+              for (int i = 0; i < 8; i++) {
+                const int rr = i * 4 + rr0;
+                const int grow = row_base + rr;
+                if (grow >= M) continue;
+                const float *sp = stg + rr * 33 + cc;
+                const float4 o = xo[i];
+                float4 v = make_float4(sp[0] + o.x, sp[1] + o.y, sp[2] + o.z, sp[3] + o.w);
+                *reinterpret_cast<float4 *>(xg + (size_t)grow * ldc + gcol) = v;
+                acc[i] += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+                __nv_bfloat162 h0 = __floats2bfloat162_rn(v.x * wk.x, v.y * wk.y), h1 = __floats2bfloat162_rn(v.z * wk.z, v.w * wk.w);
+                *reinterpret_cast<uint2 *>(xbg + (size_t)grow * N + gcol) = make_uint2(*reinterpret_cast<uint32_t *>(&h0), *reinterpret_cast<uint32_t *>(&h1));
+              }
+            }
+            __syncwarp();
+          };
+          const int next = tile + (int)gridDim.x;
+          chunk(0, bufP);
+          load_xo(tile, 2, bufP);
+          chunk(1, bufQ);
+          load_xo(next, 0, bufQ);  // (returns zeros past the last tile)
+          chunk(2, bufP);
+          load_xo(next, 1, bufP);
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[as]));
+          const int n_part = n_tiles * kColSplit;
 #pragma unroll
           for (int i = 0; i < 8; i++) {
+            float a = acc[i];
+            a += __shfl_xor_sync(0xffffffffu, a, 4);
+            a += __shfl_xor_sync(0xffffffffu, a, 2);
+            a += __shfl_xor_sync(0xffffffffu, a, 1);
             const int grow = row_base + i * 4 + rr0;
-            dst[i] = (gcol < N && grow < M) ? *reinterpret_cast<const float4 *>(xg + (size_t)grow * ldc + gcol) : make_float4(0.f, 0.f, 0.f, 0.f);
+            if ((lane & 7) == 0 && grow < M) nx.ssq_out[(size_t)grow * n_part + n_blk * kColSplit + half] = a;
           }
         };
-        load_xo(0, xo[0]);
-        if (kMine > 1) load_xo(1, xo[1]);
-        mbar_wait(smem_u32(&tfull_bar[as]), (it >> 1) & 1);
-        tc_fence_after();
-        float acc[8];
-#pragma unroll
-        for (int i = 0; i < 8; i++) acc[i] = 0.f;
-#pragma unroll
-        for (int k = 0; k < kMine; k++) {
-          const int c = half + 2 * k;
-          uint32_t r[32];
-          tc_ld_32x32(t_row + (uint32_t)(c * 32), r);
-          tc_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 32; j++) stg[lane * 33 + j] = __uint_as_float(r[j]);
-          __syncwarp();
-          const int gcol = n_blk * BN + c * 32 + cc;
-          if (gcol < N) {
-            const float4 wk = *reinterpret_cast<const float4 *>(nx.w_next + gcol);
-#pragma unroll
-            for (int i = 0; i < 8; i++) {
-              const int rr = i * 4 + rr0;
-              const int grow = row_base + rr;
-              if (grow >= M) continue;
-              const float *sp = stg + rr * 33 + cc;
-              const float4 o = xo[k & 1][i];
-              float4 v = make_float4(sp[0] + o.x, sp[1] + o.y, sp[2] + o.z, sp[3] + o.w);
-              *reinterpret_cast<float4 *>(xg + (size_t)grow * ldc + gcol) = v;
-              acc[i] += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
-              __nv_bfloat162 h0 = __floats2bfloat162_rn(v.x * wk.x, v.y * wk.y), h1 = __floats2bfloat162_rn(v.z * wk.z, v.w * wk.w);
-              *reinterpret_cast<uint2 *>(xbg + (size_t)grow * N + gcol) = make_uint2(*reinterpret_cast<uint32_t *>(&h0), *reinterpret_cast<uint32_t *>(&h1));
-            }
-          }
-          if (k + 2 < kMine) load_xo(k + 2, xo[k & 1]);
-          __syncwarp();
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[as]));
-        const int n_part = n_tiles * kColSplit;
-#pragma unroll
-        for (int i = 0; i < 8; i++) {
-          float a = acc[i];
-          a += __shfl_xor_sync(0xffffffffu, a, 4);
-          a += __shfl_xor_sync(0xffffffffu, a, 2);
-          a += __shfl_xor_sync(0xffffffffu, a, 1);
-          const int grow = row_base + i * 4 + rr0;
-          if ((lane & 7) == 0 && grow < M) nx.ssq_out[(size_t)grow * n_part + n_blk * kColSplit + half] = a;
-        }
+        if (it & 1) process(xoB, xoA);
+        else process(xoA, xoB);
         continue;
       } else {
       const float nk = -rs * 1.4426950408889634f, rs2 = rs * rs;
