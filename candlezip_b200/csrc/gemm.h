@@ -29,7 +29,7 @@ enum GemmEpilogue {
 struct NormExt {
   const float *w_next = nullptr;  // [N] weight of the norm that follows the residual add
   void *xb = nullptr;             // bf16 [M][N] (ld = N)
-  float *ssq_out = nullptr;       // [M][n_part_out], n_part_out = (N / BN) * 2 (two epilogue warps per TMEM lane quadrant)
+  float *ssq_out = nullptr;       // [M][n_part_out], n_part_out = (N / BN) * 3 (three epilogue warps per TMEM lane quadrant)
   const float *ssq_in = nullptr;  // [M][n_part_in]
   int n_part_in = 0;
   float inv_d = 0.f, eps = 0.f;

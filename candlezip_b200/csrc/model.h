@@ -18,7 +18,7 @@ struct Workspace {
   size_t cap_rows = 0, cap_logit = 0;
   float *x = nullptr;                 // [rows][D]   residual stream, fp32
   __nv_bfloat16 *xn = nullptr;        // [rows][D]   normed activations (GEMM A operand); fused-norm path: bf16(x * w_norm), unscaled
-  float *ssq = nullptr;               // [rows][8]   fused-norm path: per-row partial sums of x^2 (see EPI_ADD_NORM)
+  float *ssq = nullptr;               // [rows][12]  fused-norm path: per-row partial sums of x^2 (see EPI_ADD_NORM)
   float *qkv = nullptr;               // [rows][(nh+2nkv)*64]
   __nv_bfloat16 *q = nullptr;         // [rows][D]
   __nv_bfloat16 *attn = nullptr;      // [rows][D]

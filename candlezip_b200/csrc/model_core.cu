@@ -126,7 +126,7 @@ int ensure_workspace(cz_model *m, size_t rows, size_t n_logit, size_t n_tiles) {
       return ensure_workspace(m, rows, n_logit, n_tiles);
     }
     CZ_TRY(realloc_dev(w.xn, r * D));
-    CZ_TRY(realloc_dev(w.ssq, r * 8));
+    CZ_TRY(realloc_dev(w.ssq, r * 12));
     CZ_TRY(realloc_dev(w.qkv, r * QKV));
     CZ_TRY(realloc_dev(w.q, r * D));
     CZ_TRY(realloc_dev(w.attn, r * D));
@@ -274,11 +274,11 @@ int forward_trunk(cz_model *m, int n_rows, const KvView &kv, cudaStream_t st) {
   const int D = c.d_model, F = c.d_ffn, nh = c.n_heads, nkv = c.n_kv_heads, kvd = nkv * 64, QKV = D + 2 * kvd, L = c.n_layers;
   // Fused RMSNorm (tcgen05 engine): the residual-add epilogues of o_proj / down_proj (EPI_ADD_NORM) leave bf16(x * w_norm) and
   // per-row partial sums of x^2 for the norm that follows, and the consuming projection scales its accumulator rows by
-  // 1/rms -- the fp32 residual is never re-read by a separate normalisation pass.  Needs D = 3 tiles of 192 (n_part = 6).
+  // 1/rms -- the fp32 residual is never re-read by a separate normalisation pass.  Needs D = a multiple of 192 (SmolLM-135M: 3 N tiles, n_part = 9).
   static const bool no_fused_norm = getenv("CZ_DEBUG_NO_FUSED_NORM") != nullptr;  // bisecting aid
   const bool fused_norm = c.engine == CZ_ENGINE_TCGEN05 && !no_fused_norm && getenv("CZ_DEBUG_NO_FUSED_ROPE") == nullptr && D % 192 == 0 &&
-                          (D / 192) * 2 <= 8;
-  const int n_part = fused_norm ? (D / 192) * 2 : 0;
+                          (D / 192) * 3 <= 12;
+  const int n_part = fused_norm ? (D / 192) * 3 : 0;  // three epilogue warps per TMEM lane quadrant and N tile
   NormExt consume{};
   if (fused_norm) {
     consume.ssq_in = w.ssq; consume.n_part_in = n_part; consume.inv_d = 1.0f / (float)D; consume.eps = c.norm_eps;

@@ -57,7 +57,7 @@ extern "C" int cz_test_gemm_norm(cz_ctx *ctx, int M, int N, int K, int N2, const
     set_error("cz_test_gemm_norm: N % 192, K % 64, N2 % 8");
     return CZ_ERR_INVALID;
   }
-  const int n_part = (N / 192) * 2;
+  const int n_part = (N / 192) * 3;
   void *da = nullptr, *db = nullptr, *db2 = nullptr, *dx = nullptr, *dxb = nullptr, *dssq = nullptr, *dw = nullptr, *dout = nullptr;
   CZ_CUDA_TRY(cudaMalloc(&da, (size_t)M * K * 2));
   CZ_CUDA_TRY(cudaMalloc(&db, (size_t)N * K * 2));

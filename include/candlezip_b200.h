@@ -261,7 +261,7 @@ int cz_test_gemm(cz_ctx *ctx, int engine, int M, int N, int K, const uint16_t *a
 
 /* the fused residual-add + RMSNorm pair (tcgen05 engine, N a multiple of 192): x[M,N] += A[M,K] B[N,K]^T with
  * xb = bf16(x * w_next) and per-row partial sums of squares (producer epilogue), then out[M,N2] = bf16(rowscale * (xb B2[N2,N]^T))
- * with rowscale = 1 / sqrt(sum(x^2) / N + eps) (consumer epilogue).  Outputs: x (in place), xb_out [M][N], ssq_out [M][(N/192)*2],
+ * with rowscale = 1 / sqrt(sum(x^2) / N + eps) (consumer epilogue).  Outputs: x (in place), xb_out [M][N], ssq_out [M][(N/192)*3],
  * out2 [M][N2] (bf16). */
 int cz_test_gemm_norm(cz_ctx *ctx, int M, int N, int K, int N2, const uint16_t *a_bf16, const uint16_t *b_bf16, const uint16_t *b2_bf16,
                       const float *w_next, float eps, float *x_inout, uint16_t *xb_out, float *ssq_out, uint16_t *out2);

@@ -255,7 +255,7 @@ def _run_gemm_norm(ctx, a16, b16, b2_16, w_next, eps, x):
     N, N2 = b16.shape[0], b2_16.shape[0]
     x = np.ascontiguousarray(x, np.float32).copy()
     xb = np.zeros((M, N), np.uint16)
-    ssq = np.zeros((M, (N // 192) * 2), np.float32)
+    ssq = np.zeros((M, (N // 192) * 3), np.float32)
     out2 = np.zeros((M, N2), np.uint16)
     u16p, f32p = C.POINTER(C.c_uint16), C.POINTER(C.c_float)
     w = np.ascontiguousarray(w_next, np.float32)
