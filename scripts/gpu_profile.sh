@@ -25,8 +25,9 @@ full gemm_trunk "gemm_tc_kernel" $((G + 8)) 4          # layer 2 of the first wa
 full gemm_head "gemm_tc_kernel" $((2 * G - H)) 1       # the first LM-head launch of the timed step
 full attn "attn_tc_kernel|attn_mma_kernel" $((A + 2)) 1
 full cdf "cdf_cols_kernel" $C 1
-full elem "rmsnorm_kernel|ac_encode_lanes_kernel" 200 2
+full elem "embed_norm_kernel|rmsnorm_kernel|ac_encode_lanes_kernel" 2 3
 for r in gemm_trunk gemm_head attn cdf elem; do
   [ -f gpurun_out/${r}_$TAG.ncu-rep ] && ncu -i gpurun_out/${r}_$TAG.ncu-rep --page raw --csv > gpurun_out/${r}_${TAG}_raw.csv 2>/dev/null
 done
+[ -f gpurun_out/attn_$TAG.ncu-rep ] && ncu -i gpurun_out/attn_$TAG.ncu-rep --page source --csv > gpurun_out/attn_${TAG}_source.csv 2>/dev/null
 ls -la gpurun_out/
