@@ -71,7 +71,8 @@ struct GemmCfg {
   // operand pipeline depth: whatever fits next to the epilogue staging (the pair's smaller stages buy 5-7 stages instead of 4-5:
   // the in-flight bytes per SM over the loaded TMA latency are what bounds these GEMMs, see profiles/)
   static constexpr int kStagesFit = (232448 - 2048 - kEpiWarps * kPatchBytes) / kStageBytes;
-  static constexpr int kStages = CL == 1 ? ((BN <= 192 && !kHeavy) ? 5 : 4) : (kStagesFit > 8 ? 8 : kStagesFit);
+  static constexpr int kStagesOld = (BN <= 192 && !kHeavy) ? 5 : 4;
+  static constexpr int kStages = CL == 1 ? (kStagesFit < kStagesOld ? kStagesFit : kStagesOld) : (kStagesFit > 8 ? 8 : kStagesFit);
   static constexpr int kStagingOff = kStages * kStageBytes + 1024;  // the barriers live in the 1 KB before it
   static constexpr int kSmemBytes = kStagingOff + kEpiWarps * kPatchBytes + 1024 /*align slack*/;
   static_assert(kSmemBytes <= 232448, "shared memory budget");
