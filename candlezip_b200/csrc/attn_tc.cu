@@ -387,30 +387,45 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_tc_kernel(const __grid_con
         l = 0.f;
         for (int kb = 0; kb < nb; kb++, it++) {
           const int lim = pos_r - kb * 128;
+          // STACKED (decode): every valid row sits at the same position, so the 32-key chunks beyond it are masked for the whole
+          // tile: they are neither loaded nor exponentiated (their P is an exact zero either way), and warps without a valid row
+          // only keep the barrier protocol.  Teacher-forced tiles always walk all four chunks.
+          const int n_ch = STACKED ? min(4, ((p0 - kb * 128) >> 5) + 1) : 4;
+          const bool active = !STACKED || warp * 32 < nq;
           uint32_t w[128];  // S as raw f32 bits; the packed bf16 P overwrites w[0, 64) in place (pair (j, j+1) -> w[j/2], j/2 <= j)
           mbar_wait(s_full, it & 1);
           tc_fence_after();
+          if (active) {
 #pragma unroll
-          for (int c = 0; c < 4; c++) tc_ld_32x32(t_s + (uint32_t)(c * 32), *reinterpret_cast<uint32_t(*)[32]>(&w[c * 32]));
-          tc_ld_wait();
+            for (int c = 0; c < 4; c++)
+              if (!STACKED || c < n_ch) tc_ld_32x32(t_s + (uint32_t)(c * 32), *reinterpret_cast<uint32_t(*)[32]>(&w[c * 32]));
+            tc_ld_wait();
+          }
           tc_fence_before();
           mbar_arrive(s_free);  // S is in registers: the MMA warp may overwrite the S columns with the next S
 
           float alpha = 1.f;
-          {
-            // causal mask: keys after the row's position become -inf (exp2 -> exact 0).  Blocks entirely at or before the warp's
-            // first position take the mask-free path (warp-uniform); both paths compute identical values for unmasked keys.
+          if (active) {
+            // causal mask: keys after the row's position become -inf before the row max (exp2 -> exact 0 on the MUFU columns; the
+            // polynomial columns of P are cleared after the exponentials).  Blocks entirely at or before the warp's first position take
+            // the mask-free path (warp-uniform); both paths compute identical values for unmasked keys.
+            const bool need_mask = kb * 128 + 127 > pos_w_lo;
             float r4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-            if (kb * 128 + 127 > pos_w_lo) {
 #pragma unroll
-              for (int j = 0; j < 128; j++) w[j] = (j <= lim) ? w[j] : 0xff800000u;
-            }
+            for (int c = 0; c < 4; c++) {
+              if (!STACKED || c < n_ch) {
+                if (need_mask) {
 #pragma unroll
-            for (int j = 0; j < 128; j += 8) {
-              r4[0] = at_max3(r4[0], __uint_as_float(w[j]), __uint_as_float(w[j + 1]));
-              r4[1] = at_max3(r4[1], __uint_as_float(w[j + 2]), __uint_as_float(w[j + 3]));
-              r4[2] = at_max3(r4[2], __uint_as_float(w[j + 4]), __uint_as_float(w[j + 5]));
-              r4[3] = at_max3(r4[3], __uint_as_float(w[j + 6]), __uint_as_float(w[j + 7]));
+                  for (int j = c * 32; j < c * 32 + 32; j++) w[j] = (j <= lim) ? w[j] : 0xff800000u;
+                }
+#pragma unroll
+                for (int j = c * 32; j < c * 32 + 32; j += 8) {
+                  r4[0] = at_max3(r4[0], __uint_as_float(w[j]), __uint_as_float(w[j + 1]));
+                  r4[1] = at_max3(r4[1], __uint_as_float(w[j + 2]), __uint_as_float(w[j + 3]));
+                  r4[2] = at_max3(r4[2], __uint_as_float(w[j + 4]), __uint_as_float(w[j + 5]));
+                  r4[3] = at_max3(r4[3], __uint_as_float(w[j + 6]), __uint_as_float(w[j + 7]));
+                }
+              }
             }
             const float raw = fmaxf(fmaxf(r4[0], r4[1]), fmaxf(r4[2], r4[3])) * c_log2;
             // lazy rescale: the running max only moves when the block's max exceeds it by more than 2^8 (p stays <= 256)
@@ -421,27 +436,47 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_tc_kernel(const __grid_con
             const uint64_t nm2 = at_pack2(-m, -m);
             uint64_t sa = at_pack2(0.f, 0.f), sb = sa;  // (sum of p[j], p[j+1]) over j = 0 mod 4 / j = 2 mod 4
 #pragma unroll
-            for (int j = 0; j < 128; j += 4) {
-              float a0 = __uint_as_float(w[j]), a1 = __uint_as_float(w[j + 1]), b0 = __uint_as_float(w[j + 2]), b1 = __uint_as_float(w[j + 3]);
-              at_fma2(a0, a1, c2, nm2);
-              at_fma2(b0, b1, c2, nm2);
-              if ((AT_POLY_MASK >> ((j >> 1) & 7)) & 1u) {
-                at_ex2_poly2(a0, a1);
+            for (int c = 0; c < 4; c++) {
+              if (!STACKED || c < n_ch) {
+#pragma unroll
+                for (int j = c * 32; j < c * 32 + 32; j += 4) {
+                  float a0 = __uint_as_float(w[j]), a1 = __uint_as_float(w[j + 1]), b0 = __uint_as_float(w[j + 2]), b1 = __uint_as_float(w[j + 3]);
+                  at_fma2(a0, a1, c2, nm2);
+                  at_fma2(b0, b1, c2, nm2);
+                  if ((AT_POLY_MASK >> ((j >> 1) & 7)) & 1u) {
+                    at_ex2_poly2(a0, a1);
+                  } else {
+                    a0 = at_ex2(a0);
+                    a1 = at_ex2(a1);
+                  }
+                  if ((AT_POLY_MASK >> (((j >> 1) + 1) & 7)) & 1u) {
+                    at_ex2_poly2(b0, b1);
+                  } else {
+                    b0 = at_ex2(b0);
+                    b1 = at_ex2(b1);
+                  }
+                  sa = at_add2(sa, at_pack2(a0, a1));
+                  sb = at_add2(sb, at_pack2(b0, b1));
+                  __nv_bfloat162 ha = __floats2bfloat162_rn(a0, a1), hb = __floats2bfloat162_rn(b0, b1);
+                  w[j >> 1] = *reinterpret_cast<uint32_t *>(&ha);
+                  w[(j >> 1) + 1] = *reinterpret_cast<uint32_t *>(&hb);
+                }
               } else {
-                a0 = at_ex2(a0);
-                a1 = at_ex2(a1);
+#pragma unroll
+                for (int j = c * 16; j < c * 16 + 16; j++) w[j] = 0u;
               }
-              if ((AT_POLY_MASK >> (((j >> 1) + 1) & 7)) & 1u) {
-                at_ex2_poly2(b0, b1);
-              } else {
-                b0 = at_ex2(b0);
-                b1 = at_ex2(b1);
+            }
+            // The polynomial turns a masked key's -inf into 2^-125, not 0.  In the row sum that is far below one ulp (the sum holds
+            // a term >= 2^-8), but P must carry exact zeros for masked keys (decode skips those chunks altogether): clear the
+            // polynomial pairs of P beyond the row's position.  Only blocks that straddle the causal boundary get here.
+            if (need_mask) {
+#pragma unroll
+              for (int i = 0; i < 64; i++) {
+                if ((AT_POLY_MASK >> (i & 7)) & 1u) {
+                  const uint32_t keep = (2 * i <= lim ? 0x0000ffffu : 0u) | (2 * i + 1 <= lim ? 0xffff0000u : 0u);
+                  w[i] &= keep;
+                }
               }
-              sa = at_add2(sa, at_pack2(a0, a1));
-              sb = at_add2(sb, at_pack2(b0, b1));
-              __nv_bfloat162 ha = __floats2bfloat162_rn(a0, a1), hb = __floats2bfloat162_rn(b0, b1);
-              w[j >> 1] = *reinterpret_cast<uint32_t *>(&ha);
-              w[(j >> 1) + 1] = *reinterpret_cast<uint32_t *>(&hb);
             }
             float s0, s1, s2, s3;
             at_unpack2(sa, s0, s1);
@@ -455,9 +490,9 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_tc_kernel(const __grid_con
             tc_fence_after();
           }
           if (owed) {  // warp-uniform
-            read_out();
+            if (active) read_out();
             owed = false;
-          } else if (kb > 0 && __any_sync(0xffffffffu, alpha != 1.f)) {  // O *= alpha in tensor memory (rows that did not ask: * 1.0f, exact)
+          } else if (active && kb > 0 && __any_sync(0xffffffffu, alpha != 1.f)) {  // O *= alpha in tensor memory (rows that did not ask: * 1.0f, exact)
             uint32_t v[64];
             tc_ld_32x32(t_o, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
             tc_ld_32x32(t_o + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
@@ -467,9 +502,11 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_tc_kernel(const __grid_con
             tc_st_32x32(t_o, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
             tc_st_32x32(t_o + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
           }
-          tc_st_32x32(t_p, *reinterpret_cast<uint32_t(*)[32]>(&w[0]));
-          tc_st_32x32(t_p + 32, *reinterpret_cast<uint32_t(*)[32]>(&w[32]));
-          tc_st_wait();
+          if (active) {
+            tc_st_32x32(t_p, *reinterpret_cast<uint32_t(*)[32]>(&w[0]));
+            tc_st_32x32(t_p + 32, *reinterpret_cast<uint32_t(*)[32]>(&w[32]));
+            tc_st_wait();
+          }
           tc_fence_before();
           mbar_arrive(p_ready);
         }
@@ -483,7 +520,7 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_tc_kernel(const __grid_con
     if (owed) {  // the last head of the last item
       mbar_wait(o_full, (it - 1) & 1);
       tc_fence_after();
-      read_out();
+      if (!STACKED || owed_dst != nullptr || warp == 0) read_out();
     }
   }
   tc_fence_before();
