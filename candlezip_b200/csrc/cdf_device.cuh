@@ -32,8 +32,10 @@ __device__ __forceinline__ void exp_tab_init(uint32_t *s_lo, uint32_t *s_hi) {
   __syncthreads();
 }
 
-// Branch-free: every lane always evaluates the polynomial and the two range cases are selects at the end (a divergent
+// Branch-free: every lane always evaluates the polynomial and the underflow case is a select at the end (a divergent
 // early-out costs a BSSY/BSYNC pair per element in the unrolled column walk, profiles/ncu_summary_r01.md).
+// DOMAIN: x <= 0 or NaN.  Every caller passes logit - max(logits) (src/main.rs:786-789), so glibc's overflow branch
+// (x > 88.72 -> +inf) can never be taken and is not evaluated; +inf - +inf = NaN propagates through the polynomial.
 __device__ __forceinline__ float cz_expf(float x, const ExpTab &tab) {
   const double inv_ln2_n = 0x1.71547652b82fep+0 * 32;
   const double shift = 0x1.8p+52;
@@ -56,8 +58,7 @@ __device__ __forceinline__ float cz_expf(float x, const ExpTab &tab) {
   y = __fma_rn(p, r2, y);
   y = __dmul_rn(y, s);
   float out = __double2float_rn(y);
-  out = (x < -0x1.9fe368p6f) ? 0.0f : out;                       // underflow to zero
-  out = (x > 0x1.62e42ep6f) ? __int_as_float(0x7f800000) : out;  // overflow
+  out = (x < -0x1.9fe368p6f) ? 0.0f : out;  // underflow to zero
   return out;
 }
 
@@ -101,14 +102,24 @@ __device__ __forceinline__ void cdf_walk(const float *__restrict__ p, size_t ld,
   for (int k = 0; k < CDF_GRP; k++) cur[k] = k < n ? __ldg(p + (size_t)k * ld) : 0.f;
   bool go = true;
   int v0 = 0;
-  // main loop: the current AND the next group are entirely in range -> no per-element bounds checks
-  for (; v0 + 2 * CDF_GRP <= n; v0 += CDF_GRP) {
+  // main loop, part 1: the current and the next group AND the prefetched rows are in range -> no bounds checks at all
+  for (; v0 + CDF_PF + CDF_GRP <= n; v0 += CDF_GRP) {
 #pragma unroll
     for (int k = 0; k < CDF_GRP; k++) {
       nxt[k] = __ldg(p + (size_t)(v0 + CDF_GRP + k) * ld);
-      const int vp = min(v0 + CDF_PF + k, n - 1);
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(p + (size_t)vp * ld));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(p + (size_t)(v0 + CDF_PF + k) * ld));
     }
+#pragma unroll
+    for (int k = 0; k < CDF_GRP; k++) {
+      if (go) go = f(v0 + k, cur[k]);
+      cur[k] = nxt[k];
+    }
+    if (!__any_sync(0xffffffffu, go)) return;
+  }
+  // part 2 (the last CDF_PF rows): everything to come is already in L2 or on its way
+  for (; v0 + 2 * CDF_GRP <= n; v0 += CDF_GRP) {
+#pragma unroll
+    for (int k = 0; k < CDF_GRP; k++) nxt[k] = __ldg(p + (size_t)(v0 + CDF_GRP + k) * ld);
 #pragma unroll
     for (int k = 0; k < CDF_GRP; k++) {
       if (go) go = f(v0 + k, cur[k]);
