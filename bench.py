@@ -321,6 +321,32 @@ def run_ours(args):
     peak_tf, peak_hbm, peak_src = measured_peaks()
     gemm_ms = fam["gemm"][0] / args.steps
     achieved = gemm_flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else None
+
+    # per-kernel rooflines: algorithmic flops or bytes of ONE step over the family's live device time
+    cfgm = cz.SMOLLM_135M
+    D, F, L, V = cfgm["d_model"], cfgm["d_ffn"], cfgm["n_layers"], cfgm["vocab"]
+    qkv_n = D + 2 * cfgm["n_kv_heads"] * 64
+
+    def kern(name, fam_key, bound, work):
+        ms = fam[fam_key][0] / args.steps
+        if ms <= 0:
+            return None
+        if bound == "tensor":
+            a, pk, unit = work / (ms / 1e3) / 1e12, peak_tf, "TFLOP/s"
+        else:
+            a, pk, unit = work / (ms / 1e3) / 1e9, peak_hbm, "GB/s"
+        return {"kernel": name, "bound": bound, "achieved": a, "peak": pk, "unit": unit, "frac": a / pk, "ms_per_step": ms}
+
+    kernels = [k for k in [
+        kern("gemm_tc_kernel<256,SWIGLU,pair> gate/up", "gemm_gu", "tensor", 2.0 * rows * 2 * F * D * L),
+        kern("gemm_tc_kernel<192,ADD_NORM,pair> down_proj (+ next norm's operands)", "gemm_down", "tensor", 2.0 * rows * D * F * L),
+        # o_proj is bound by the fp32 residual: per row A 1152 B + residual read and written 4608 B + bf16 norm operand 1152 B
+        kern("gemm_tc_kernel<192,ADD_NORM,pair> o_proj (+ next norm's operands)", "gemm_o", "hbm", float(rows) * (2 * D + 8 * D + 2 * D) * L),
+        kern("gemm_tc_kernel<192,QKV_ROPE> qkv + RoPE", "gemm_qkv", "tensor", 2.0 * rows * qkv_n * D * L),
+        kern("gemm_tc_kernel<256,COLMAX> LM head", "gemm_head", "tensor", 2.0 * HEAD_PARAMS * n),
+        kern("attn_tc_kernel", "attn", "tensor", 70.57e6 * n),
+        kern("cdf_cols_kernel", "cdf", "hbm", 4.0 * V * n),
+    ] if k]
     line = {
         "metric": METRIC, "value": value, "unit": "MB/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
@@ -337,11 +363,12 @@ def run_ours(args):
                      # dram__bytes_read + dram__bytes_write per launch from the ncu --set full captures of this build
                      # (profiles/ncu_summary_r01e.md), summed over the family's launches of one step
                      "traffic": NCU_GEMM_TRAFFIC_BYTES_PER_STEP, "traffic_source": "profiles/ncu_summary_r01e.md (ncu --set full, per launch x launches per step)",
-                     "kernel": "gemm_tc_kernel (tcgen05 GEMM family: qkv+rope/o/gate-up/down/lm_head)",
+                     "kernel": "gemm_tc_kernel (tcgen05 GEMM family: qkv+rope/o/gate-up/down/lm_head; the RMSNorm passes live in the o/down epilogues)",
                      "flops_per_step": gemm_flops, "kernel_ms_per_step": gemm_ms, "peak_source": peak_src},
         # whole-path tensor roofline exactly as SURVEY 8d defines it: tokens/s x 551.0 MFLOP / measured sustained bf16 peak
         "roofline_path": {"bound": "tensor", "achieved": value * 1e6 / max(1, world) * MFLOP_PER_TOKEN * 1e6 / 1e12, "peak": peak_tf, "unit": "TFLOP/s",
                           "frac": value * 1e6 / max(1, world) * MFLOP_PER_TOKEN * 1e6 / 1e12 / peak_tf, "per_gpu": True},
+        "roofline_kernels": kernels,
         "kernel_ms_per_step": {k: v[0] / args.steps for k, v in fam.items()},
         "kernel_launches_per_step": {k: v[1] // max(1, args.steps) for k, v in fam.items()},
         "compressed_bytes_per_step": payload_bytes, "decode": decode, "rwkv7": rwkv,
