@@ -295,9 +295,10 @@ __device__ __forceinline__ void cdf_col(const float *__restrict__ p, size_t ld, 
 // warp-uniform).  Same operations in the same order as cdf_col => bit-identical results.
 // p: column base (vocab-major, element v at p[v*ld]).  Must be called by a full warp.
 template <int MODE>
+// xch: 64 doubles of shared memory private to the calling warp (16-byte aligned).
 __device__ __forceinline__ void cdf_search_warp(const float *__restrict__ p, size_t ld, int V, uint32_t value, float mx,
                                                 const ExpTab &tab, uint32_t &sym_out, uint32_t &lo_out, uint32_t &hi_out,
-                                                int &errbits) {
+                                                int &errbits, double *xch) {
   const int lane = threadIdx.x & 31;
   const int n_sym = MODE == CZ_CDF_RWKV_LITERALS ? V + 256 : V;
   const int n_grp = (V + 31) / 32;
@@ -306,21 +307,30 @@ __device__ __forceinline__ void cdf_search_warp(const float *__restrict__ p, siz
     return v < V ? p[(size_t)v * ld] : __int_as_float(0xff800000);
   };
   // generic sequential accumulation of f(x) over the vocab: acc = ((0 + f0) + f1) + ...
+  // The 32 values of a group go through the warp's shared-memory line (double-buffered: one __syncwarp per group) and every
+  // lane adds them in order from 16-byte broadcast loads: 16 LDS + 32 DADD per group instead of 64 SHFL + 32 DADD.
   auto seq_sum = [&](auto f) -> double {
     double acc = 0.0;
     float x = ld_x(0);
     for (int g = 0; g < n_grp; g++) {
       const float xn = g + 1 < n_grp ? ld_x(g + 1) : 0.f;
-      const double t = f(x);
+      double *line = xch + (g & 1) * 32;
+      line[lane] = f(x);
+      __syncwarp();
       const int cnt = V - g * 32 < 32 ? V - g * 32 : 32;
       if (cnt == 32) {
 #pragma unroll
-        for (int k = 0; k < 32; k++) acc = __dadd_rn(acc, __shfl_sync(0xffffffffu, t, k));
+        for (int k = 0; k < 32; k += 2) {
+          const double2 v = *reinterpret_cast<const double2 *>(line + k);
+          acc = __dadd_rn(acc, v.x);
+          acc = __dadd_rn(acc, v.y);
+        }
       } else {
-        for (int k = 0; k < cnt; k++) acc = __dadd_rn(acc, __shfl_sync(0xffffffffu, t, k));
+        for (int k = 0; k < cnt; k++) acc = __dadd_rn(acc, line[k]);
       }
       x = xn;
     }
+    __syncwarp();
     return acc;
   };
   const double S = seq_sum([&](float x) { return (double)cz_expf(__fsub_rn(x, mx), tab); });
@@ -353,10 +363,12 @@ __device__ __forceinline__ void cdf_search_warp(const float *__restrict__ p, siz
   float x = ld_x(0);
   for (int g = 0; g < n_grp && !done; g++) {
     const float xn = g + 1 < n_grp ? ld_x(g + 1) : 0.f;
-    const double t = pdf_vocab(x);
+    double *line = xch + (g & 1) * 32;
+    line[lane] = pdf_vocab(x);
+    __syncwarp();
     const int cnt = V - g * 32 < 32 ? V - g * 32 : 32;
     for (int k = 0; k < cnt; k++) {
-      acc = __dadd_rn(acc, __shfl_sync(0xffffffffu, t, k));
+      acc = __dadd_rn(acc, line[k]);
       const int v = g * 32 + k;
       uint32_t cur = quant(acc);
       if (cur < prev) cur = prev;

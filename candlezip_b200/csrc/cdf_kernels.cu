@@ -52,6 +52,7 @@ __global__ void __launch_bounds__(256) cdf_search_warp_kernel(const float *__res
                                                               uint32_t *__restrict__ c_lo_out, uint32_t *__restrict__ c_hi_out,
                                                               int *__restrict__ err, const int *__restrict__ colmax) {
   __shared__ uint32_t s_lo[32 * 32], s_hi[32 * 32];
+  __shared__ __align__(16) double s_xch[8 * 64];  // per warp: two 32-value exchange lines (cdf_search_warp)
   exp_tab_init(s_lo, s_hi);
   ExpTab tab{s_lo, s_hi, (int)(threadIdx.x & 31)};
   const size_t col = (size_t)blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -70,7 +71,7 @@ __global__ void __launch_bounds__(256) cdf_search_warp_kernel(const float *__res
   }
   uint32_t sym, lo, hi;
   int errbits = 0;
-  cdf_search_warp<MODE>(logits + col, ld, V, values[col], mx, tab, sym, lo, hi, errbits);
+  cdf_search_warp<MODE>(logits + col, ld, V, values[col], mx, tab, sym, lo, hi, errbits, s_xch + (threadIdx.x >> 5) * 64);
   if ((threadIdx.x & 31) == 0) {
     if (errbits) atomicOr(err, errbits);
     sym_out[col] = sym;
