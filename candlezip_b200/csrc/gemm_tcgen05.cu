@@ -107,7 +107,7 @@ __global__ void __launch_bounds__((GemmCfg<BN, EPI, 1>::kThreads), 1)
     gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                    const __grid_constant__ CUtensorMap tm_c, void *__restrict__ c_ptr,
                    int M, int N, int K, int ldc, int *__restrict__ aux, const __grid_constant__ RopeExt rx,
-                   const __grid_constant__ NormExt nx) {
+                   const __grid_constant__ NormExt nx, int raster_gw) {
   using Cfg = GemmCfg<BN, EPI, CL>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -130,7 +130,26 @@ __global__ void __launch_bounds__((GemmCfg<BN, EPI, 1>::kThreads), 1)
   const int n_tiles = (N + BN - 1) / BN;
   // work units: (group of CL vertically adjacent m tiles, n tile); CTA `rank` of a cluster takes m tile group * CL + rank (a tile
   // past the last row block is a ghost: its loads are zero-filled by TMA and every epilogue store is row-guarded)
-  const int num_tiles = ((m_tiles + CL - 1) / CL) * n_tiles;
+  // Tile order.  Default: n fastest (the CTAs running at the same time share the A rows, B -- the weights -- lives in L2).
+  // raster_gw > 0 (LM head: B = a wave's hidden states, 150 MB, A = the embedding): the n tiles are walked in groups of
+  // raster_gw, every m tile of a group before the next group, so a group's slab of B (raster_gw x BN rows) stays in L2
+  // across the m tiles instead of being streamed from DRAM once per m tile (22 GB of re-reads per launch, profiles/).
+  // Units past the last n tile of the last group are skipped by every role alike.
+  const int m_units = (m_tiles + CL - 1) / CL;
+  const int n_groups = raster_gw > 0 ? (n_tiles + raster_gw - 1) / raster_gw : 1;
+  const int num_tiles = raster_gw > 0 ? n_groups * raster_gw * m_units : m_units * n_tiles;
+  auto tile_mn = [&](int tile_, int &m_unit, int &n_blk_) -> bool {
+    if (raster_gw > 0) {
+      const int per_group = raster_gw * m_units;
+      const int g = tile_ / per_group, rem = tile_ - g * per_group;
+      m_unit = rem / raster_gw;
+      n_blk_ = g * raster_gw + (rem - m_unit * raster_gw);
+      return n_blk_ < n_tiles;
+    }
+    m_unit = tile_ / n_tiles;
+    n_blk_ = tile_ - m_unit * n_tiles;
+    return true;
+  };
   const int k_blocks = K / BK;
   uint32_t rank = 0;
   if (CL > 1) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
@@ -174,7 +193,9 @@ __global__ void __launch_bounds__((GemmCfg<BN, EPI, 1>::kThreads), 1)
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = u0; tile < num_tiles; tile += u_stride) {
-        const int m_blk = (tile / n_tiles) * CL + (int)rank, n_blk = tile % n_tiles;
+        int m_unit, n_blk;
+        if (!tile_mn(tile, m_unit, n_blk)) continue;
+        const int m_blk = m_unit * CL + (int)rank;
         if constexpr (EPI == EPI_ADD_NORM) {
           // the epilogue will read this tile's old residual a few microseconds from now: pull it into L2 (32 x 32 f32 boxes)
           for (int rb = 0; rb < BM / 32; rb++)
@@ -215,6 +236,13 @@ __global__ void __launch_bounds__((GemmCfg<BN, EPI, 1>::kThreads), 1)
       uint32_t phase = 0;
       int it = 0;
       for (int tile = u0; tile < num_tiles; tile += u_stride, it++) {
+        {
+          int mu, nb_;
+          if (!tile_mn(tile, mu, nb_)) {
+            it--;  // (skipped unit: the accumulator stage counter must not advance)
+            continue;
+          }
+        }
         const int as = it & 1;
         mbar_wait(smem_u32(&tempty_bar[as]), ((it >> 1) & 1) ^ 1);
         tc_fence_after();
@@ -268,8 +296,10 @@ __global__ void __launch_bounds__((GemmCfg<BN, EPI, 1>::kThreads), 1)
     //   EPI_ADD_NORM: the first two chunks of old residual (below).
     float pn[12];
     auto load_parts = [&](int tile_) {
-      const int row = ((tile_ / n_tiles) * CL + (int)rank) * BM + quad * 32 + lane;
-      const bool ok = nx.ssq_in != nullptr && tile_ < num_tiles && row < M;
+      int mu = 0, nb_ = 0;
+      const bool tv = tile_ < num_tiles && tile_mn(tile_, mu, nb_);
+      const int row = (mu * CL + (int)rank) * BM + quad * 32 + lane;
+      const bool ok = nx.ssq_in != nullptr && tv && row < M;
 #pragma unroll
       for (int i = 0; i < 12; i++) pn[i] = (ok && i < nx.n_part_in) ? nx.ssq_in[(size_t)row * nx.n_part_in + i] : 0.f;
     };
@@ -277,8 +307,10 @@ __global__ void __launch_bounds__((GemmCfg<BN, EPI, 1>::kThreads), 1)
     int pos_nx = 0, kvb_nx = 0;  // EPI_QKV_ROPE: position and KV base of this thread's row in the tile about to be processed
     float cs[16], sn[16];         // EPI_QKV_ROPE: that row's cos / sin (this warp's half of the rotation pairs)
     auto load_pos = [&](int tile_) {
-      const int row = ((tile_ / n_tiles) * CL + (int)rank) * BM + quad * 32 + lane;
-      const bool ok = tile_ < num_tiles && row < M;
+      int mu = 0, nb_ = 0;
+      const bool tv = tile_ < num_tiles && tile_mn(tile_, mu, nb_);
+      const int row = (mu * CL + (int)rank) * BM + quad * 32 + lane;
+      const bool ok = tv && row < M;
       pos_nx = ok ? rx.pos[row] : 0;
       kvb_nx = ok ? rx.kv_base[row] : 0;
     };
@@ -301,12 +333,14 @@ __global__ void __launch_bounds__((GemmCfg<BN, EPI, 1>::kThreads), 1)
     __nv_bfloat16 *xbg = reinterpret_cast<__nv_bfloat16 *>(nx.xb);
     float4 xoA[8], xoB[8];
     auto load_xo = [&](int tile_, int k, float4(&dst)[8]) {
-      const int gcol = (tile_ % n_tiles) * BN + (half + kColSplit * k) * 32 + cc;
-      const int rb = ((tile_ / n_tiles) * CL + (int)rank) * BM + quad * 32;
+      int mu = 0, nb_ = 0;
+      const bool tv = tile_ < num_tiles && tile_mn(tile_, mu, nb_);
+      const int gcol = nb_ * BN + (half + kColSplit * k) * 32 + cc;
+      const int rb = (mu * CL + (int)rank) * BM + quad * 32;
 #pragma unroll
       for (int i = 0; i < 8; i++) {
         const int grow = rb + i * 4 + rr0;
-        dst[i] = (tile_ < num_tiles && gcol < N && grow < M) ? *reinterpret_cast<const float4 *>(xg + (size_t)grow * ldc + gcol)
+        dst[i] = (tv && gcol < N && grow < M) ? *reinterpret_cast<const float4 *>(xg + (size_t)grow * ldc + gcol)
                                                               : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     };
@@ -315,7 +349,12 @@ __global__ void __launch_bounds__((GemmCfg<BN, EPI, 1>::kThreads), 1)
       load_xo(u0, 1, xoB);
     }
     for (int tile = u0; tile < num_tiles; tile += u_stride, it++) {
-      const int m_blk = (tile / n_tiles) * CL + (int)rank, n_blk = tile % n_tiles;
+      int m_unit, n_blk;
+      if (!tile_mn(tile, m_unit, n_blk)) {
+        it--;
+        continue;
+      }
+      const int m_blk = m_unit * CL + (int)rank;
       const int as = it & 1;
       const int row_base = m_blk * BM + quad * 32;
       const bool row_ok = row_base + lane < M;
@@ -487,17 +526,21 @@ __global__ void __launch_bounds__((GemmCfg<BN, EPI, 1>::kThreads), 1)
           __syncwarp();
           tc_ld_wait();
           if (EPI == EPI_STORE_F32_COLMAX) {
-            // per-column max over this warp's 32 rows: floats mapped to order-preserving ints, one REDUX per column,
-            // lane j keeps column j, then one coalesced atomicMax per warp.  max is exact and order-independent.
-            int mine = INT_MIN;
+            // per-column max over this warp's 32 rows: one float REDUX per column (NaN inputs are ignored, like the reference's
+            // `if v > max`, src/main.rs:786), lane j keeps column j; the 32 results are mapped to order-preserving ints and merged
+            // with one coalesced atomicMax per warp.  max is exact and order-independent.
+            float minef = __int_as_float(0xff800000);
+            const bool all_rows = row_base + 31 < M;  // warp-uniform; only the last row block has invalid rows
 #pragma unroll
             for (int j = 0; j < 32; j++) {
-              int v = (int)r[j];
-              v ^= (v >> 31) & 0x7fffffff;
-              if (!row_ok) v = INT_MIN;
-              const int mx = __reduce_max_sync(0xffffffffu, v);
-              if (lane == j) mine = mx;
+              float v = __uint_as_float(r[j]);
+              if (!all_rows && !row_ok) v = __int_as_float(0xff800000);
+              float mx;
+              asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(mx) : "f"(v));
+              if (lane == j) minef = mx;
             }
+            int mine = __float_as_int(minef);
+            mine ^= (mine >> 31) & 0x7fffffff;
             if (col0 + lane < N) atomicMax(aux + col0 + lane, mine);
           }
 #pragma unroll
@@ -789,6 +832,7 @@ template <int BN, int EPI, int CL>
 static int launch_tc_cl(cz_ctx *ctx, const CUtensorMap &ta, const CUtensorMap &tb, const CUtensorMap &tc, void *c, int M, int N, int K, int ldc,
                         int *aux, int g_fam, cudaStream_t stream, const RopeExt &rx, const NormExt &nx) {
   using Cfg = czk::GemmCfg<BN, EPI, CL>;
+  int raster_gw = 0;
   static bool attr_set = false;
   static int max_clusters = 0;  // CL > 1: clusters of CL CTAs that can be co-resident (GPCs with an odd SM count lose one SM)
   auto kern = czk::gemm_tc_kernel<BN, EPI, CL>;
@@ -817,6 +861,10 @@ static int launch_tc_cl(cz_ctx *ctx, const CUtensorMap &ta, const CUtensorMap &t
   const int units = (int)(ceil_div(ceil_div(M, czk::BM), CL) * ceil_div(N, BN));
   const int groups_max = CL > 1 ? max_clusters : ctx->sm_count;
   const int groups = units < groups_max ? units : groups_max;
+  if (EPI == EPI_STORE_F32_COLMAX) {  // LM head: keep a slab of hidden-state tiles in L2 across the vocabulary tiles (see the kernel)
+    const int n_tiles = (int)ceil_div(N, BN);
+    if (n_tiles > groups) raster_gw = (int)ceil_div(n_tiles, ceil_div(n_tiles, groups));
+  }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)(groups * CL));
   cfg.blockDim = dim3(Cfg::kThreads);
@@ -829,7 +877,7 @@ static int launch_tc_cl(cz_ctx *ctx, const CUtensorMap &ta, const CUtensorMap &t
   at[0].val.clusterDim.z = 1;
   cfg.attrs = at;
   cfg.numAttrs = 1;
-  CZ_LAUNCH(ctx, g_fam, (cudaLaunchKernelEx(&cfg, kern, ta, tb, tc, c, M, N, K, ldc, aux, rx, nx)));
+  CZ_LAUNCH(ctx, g_fam, (cudaLaunchKernelEx(&cfg, kern, ta, tb, tc, c, M, N, K, ldc, aux, rx, nx, raster_gw)));
   CZ_CHECK_LAUNCH();
   return CZ_OK;
 }

@@ -238,6 +238,19 @@ def test_gemm_tma_store_many_tiles_few_columns(gpu_ctx, epi):
     assert np.all(c[:, N:] == 0)
 
 
+def test_gemm_lm_head_grouped_raster(gpu_ctx):
+    """More column tiles than CTAs: the LM-head GEMM walks the column tiles in L2-sized groups (every vocabulary tile of a group
+    before the next group, the last group partial); every output element must still be written exactly once."""
+    rng = np.random.default_rng(77)
+    M, N, K = 300, 157 * 256 - 40, 64
+    a16 = _bf16(rng.normal(0, 1, (M, K)))
+    b16 = _bf16(rng.normal(0, 1, (N, K)))
+    ldc = (N + 3) // 4 * 4
+    c = _run_gemm(gpu_ctx, _lib.CZ_ENGINE_TCGEN05, a16, b16, 4, 256, np.full((M, ldc), -7.0, np.float32), ldc)
+    want = _bf16_to_f32(a16).astype(np.float64) @ _bf16_to_f32(b16).astype(np.float64).T
+    assert np.abs(c[:, :N] - want).max() < 2e-3
+
+
 def test_gemm_tcgen05_row_invariance(gpu_ctx):
     """decode safety: a row's result must not depend on batch size or on its position in the tile grid."""
     rng = np.random.default_rng(12)
