@@ -28,7 +28,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 METRIC = "encode_MB_per_s_smollm135m_ctx512"
-# per layer-wave launch (253k rows), dram read + written under ncu --set full (profiles/ncu_summary_r01e.md): qkv+rope 769 MB,
+# per layer-wave launch (253k rows), dram read + written under ncu --set full (profiles/ncu_summary_r01g.md): qkv+rope 769 MB,
 # o-proj (+ fused norm operands) 1791 MB, gate/up 1069 MB, down (+ fused norm operands) 2284 MB; x60 launches each, plus the
 # LM head's 51.5 GB of logits written + 0.4 GB read
 NCU_GEMM_TRAFFIC_BYTES_PER_STEP = int(60 * (769 + 1791 + 1069 + 2284) * 1e6 + 51.9e9)
@@ -361,8 +361,8 @@ def run_ours(args):
                 "d2h_bytes_per_step": int(payload_bytes + 8 * S + 16), "bitstream_equal_to_device_arm": same},
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf if achieved else None,
                      # dram__bytes_read + dram__bytes_write per launch from the ncu --set full captures of this build
-                     # (profiles/ncu_summary_r01e.md), summed over the family's launches of one step
-                     "traffic": NCU_GEMM_TRAFFIC_BYTES_PER_STEP, "traffic_source": "profiles/ncu_summary_r01e.md (ncu --set full, per launch x launches per step)",
+                     # (profiles/ncu_summary_r01g.md), summed over the family's launches of one step
+                     "traffic": NCU_GEMM_TRAFFIC_BYTES_PER_STEP, "traffic_source": "profiles/ncu_summary_r01g.md (ncu --set full, per launch x launches per step)",
                      "kernel": "gemm_tc_kernel (tcgen05 GEMM family: qkv+rope/o/gate-up/down/lm_head; the RMSNorm passes live in the o/down epilogues)",
                      "flops_per_step": gemm_flops, "kernel_ms_per_step": gemm_ms, "peak_source": peak_src},
         # whole-path tensor roofline exactly as SURVEY 8d defines it: tokens/s x 551.0 MFLOP / measured sustained bf16 peak
