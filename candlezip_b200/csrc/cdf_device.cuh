@@ -95,18 +95,21 @@ __device__ __forceinline__ float colmax_decode(int v) {
 // lane; the walk ends when every lane of the warp has stopped (keeps the warp converged for the callers' shuffles).
 constexpr int CDF_GRP = 8;
 constexpr int CDF_PF = 48;
-template <class F>
-__device__ __forceinline__ void cdf_walk(const float *__restrict__ p, size_t ld, int n, F f) {
+// NC: loads go through the read-only path (__ldg).  NC = false is for a column that this thread rewrites in place between passes
+// (RWKV literals mode caches exp(l - max) in the logit's slot): ordinary loads, which see the thread's own earlier stores.
+template <bool NC = true, class F>
+__device__ __forceinline__ void cdf_walk(const float *p, size_t ld, int n, F f) {
+  auto ldv = [&](size_t off) -> float { return NC ? __ldg(p + off) : p[off]; };
   float cur[CDF_GRP], nxt[CDF_GRP];
 #pragma unroll
-  for (int k = 0; k < CDF_GRP; k++) cur[k] = k < n ? __ldg(p + (size_t)k * ld) : 0.f;
+  for (int k = 0; k < CDF_GRP; k++) cur[k] = k < n ? ldv((size_t)k * ld) : 0.f;
   bool go = true;
   int v0 = 0;
   // main loop, part 1: the current and the next group AND the prefetched rows are in range -> no bounds checks at all
   for (; v0 + CDF_PF + CDF_GRP <= n; v0 += CDF_GRP) {
 #pragma unroll
     for (int k = 0; k < CDF_GRP; k++) {
-      nxt[k] = __ldg(p + (size_t)(v0 + CDF_GRP + k) * ld);
+      nxt[k] = ldv((size_t)(v0 + CDF_GRP + k) * ld);
       asm volatile("prefetch.global.L2 [%0];" ::"l"(p + (size_t)(v0 + CDF_PF + k) * ld));
     }
 #pragma unroll
@@ -119,7 +122,7 @@ __device__ __forceinline__ void cdf_walk(const float *__restrict__ p, size_t ld,
   // part 2 (the last CDF_PF rows): everything to come is already in L2 or on its way
   for (; v0 + 2 * CDF_GRP <= n; v0 += CDF_GRP) {
 #pragma unroll
-    for (int k = 0; k < CDF_GRP; k++) nxt[k] = __ldg(p + (size_t)(v0 + CDF_GRP + k) * ld);
+    for (int k = 0; k < CDF_GRP; k++) nxt[k] = ldv((size_t)(v0 + CDF_GRP + k) * ld);
 #pragma unroll
     for (int k = 0; k < CDF_GRP; k++) {
       if (go) go = f(v0 + k, cur[k]);
@@ -132,7 +135,7 @@ __device__ __forceinline__ void cdf_walk(const float *__restrict__ p, size_t ld,
 #pragma unroll
     for (int k = 0; k < CDF_GRP; k++) {
       const int v = v0 + CDF_GRP + k;
-      nxt[k] = v < n ? __ldg(p + (size_t)v * ld) : 0.f;
+      nxt[k] = v < n ? ldv((size_t)v * ld) : 0.f;
     }
 #pragma unroll
     for (int k = 0; k < CDF_GRP; k++) {
@@ -147,9 +150,16 @@ __device__ __forceinline__ void cdf_walk(const float *__restrict__ p, size_t ld,
 // MUST be called by all 32 lanes of a warp (inactive lanes pass a clamped, valid column and active=false).
 // p points at logits[0][col]; element v of the column is p[v * ld].
 template <int MODE, int OP>
-__device__ __forceinline__ void cdf_col(const float *__restrict__ p, size_t ld, int V, uint32_t arg, bool active,
+__device__ __forceinline__ void cdf_col(const float *__restrict__ p_in, size_t ld, int V, uint32_t arg, bool active,
                                         const ExpTab &tab, uint32_t &sym_out, uint32_t &lo_out, uint32_t &hi_out,
                                         double &xe_out, int &errbits, bool have_max = false, float known_max = 0.f) {
+  // RWKV literals mode walks the column five times (S, norm, sum2, prefix; src/main.rs:758-782): the first pass leaves
+  // e_v = expf(l_v - max) in the logit's slot (the logits are scratch, and each column belongs to one thread), so the later passes
+  // read e_v instead of re-evaluating the 24-instruction expf.  Same values, same order: bit-identical results.
+  // NOT for OP_SEARCH: the stepwise RWKV decoder keeps a stream's logits column across steps while it decodes literal bytes.
+  constexpr bool kCache = MODE == CZ_CDF_RWKV_LITERALS && OP != OP_SEARCH;
+  float *pw = const_cast<float *>(p_in);
+  const float *p = kCache ? pw : p_in;  // (cached mode: no load may go through the read-only path)
   const int n_sym = MODE == CZ_CDF_RWKV_LITERALS ? V + 256 : V;
   sym_out = 0;
   lo_out = 0;
@@ -160,18 +170,22 @@ __device__ __forceinline__ void cdf_col(const float *__restrict__ p, size_t ld, 
   if (have_max) {
     mx = known_max;
   } else {
-    cdf_walk(p, ld, V, [&](int, float x) {
+    cdf_walk<!kCache>(p, ld, V, [&](int, float x) {
       if (x > mx) mx = x;
       return true;
     });
   }
   // pass B: S = sum_i (f64)expf(l_i - max), sequential
   double S = 0.0;
-  cdf_walk(p, ld, V, [&](int, float x) {
-    S = __dadd_rn(S, (double)cz_expf(__fsub_rn(x, mx), tab));
+  cdf_walk<!kCache>(p, ld, V, [&](int v, float x) {
+    const float e = cz_expf(__fsub_rn(x, mx), tab);
+    if (kCache && active) pw[(size_t)v * ld] = e;  // (inactive lanes shadow a valid column: they must not write)
+    S = __dadd_rn(S, (double)e);
     return true;
   });
   if (!(S == S) && active) errbits |= CZ_DEVERR_NAN;
+  // e_v from a value read after pass B
+  auto ex = [&](float x) -> float { return kCache ? x : cz_expf(__fsub_rn(x, mx), tab); };
 
   double norm = 1.0, sum2 = 1.0;
   const double scale = 1.0 - 256.0 * CZ_P_FLOOR;
@@ -181,8 +195,8 @@ __device__ __forceinline__ void cdf_col(const float *__restrict__ p, size_t ld, 
   if (MODE == CZ_CDF_RWKV_LITERALS || OP == OP_XE) {
     // softmax_pdf_floor: norm = sum_i max(e_i / S, floor)   (src/main.rs:763-764)
     double acc = 0.0;
-    cdf_walk(p, ld, V, [&](int, float x) {
-      const double q = __ddiv_rn((double)cz_expf(__fsub_rn(x, mx), tab), S);
+    cdf_walk<!kCache>(p, ld, V, [&](int, float x) {
+      const double q = __ddiv_rn((double)ex(x), S);
       acc = __dadd_rn(acc, fmax(q, CZ_P_FLOOR));
       return true;
     });
@@ -191,8 +205,8 @@ __device__ __forceinline__ void cdf_col(const float *__restrict__ p, size_t ld, 
   if (MODE == CZ_CDF_RWKV_LITERALS) {
     // combined_pdf_with_literals: sum2 over V scaled entries + 256 literal entries (src/main.rs:773-779)
     double acc = 0.0;
-    cdf_walk(p, ld, V, [&](int, float x) {
-      double q = __ddiv_rn((double)cz_expf(__fsub_rn(x, mx), tab), S);
+    cdf_walk<!kCache>(p, ld, V, [&](int, float x) {
+      double q = __ddiv_rn((double)ex(x), S);
       q = __ddiv_rn(fmax(q, CZ_P_FLOOR), norm);
       acc = __dadd_rn(acc, __dmul_rn(q, scale));
       return true;
@@ -201,25 +215,25 @@ __device__ __forceinline__ void cdf_col(const float *__restrict__ p, size_t ld, 
     sum2 = acc;
   }
 
-  // final pdf entry for vocab element v (< V) with logit x
+  // final pdf entry for vocab element v (< V) with logit x (cached mode: x is already e_v)
   auto pdf_vocab = [&](float x) -> double {
     if (MODE == CZ_CDF_RWKV_LITERALS) {
-      double q = __ddiv_rn((double)cz_expf(__fsub_rn(x, mx), tab), S);
+      double q = __ddiv_rn((double)ex(x), S);
       q = __dmul_rn(__ddiv_rn(fmax(q, CZ_P_FLOOR), norm), scale);
       return sum2 > 0.0 ? __ddiv_rn(q, sum2) : q;
     } else if (OP == OP_XE) {
-      const double q = __ddiv_rn((double)cz_expf(__fsub_rn(x, mx), tab), S);
+      const double q = __ddiv_rn((double)ex(x), S);
       return __ddiv_rn(fmax(q, CZ_P_FLOOR), norm);
     } else {
       if (uniform) return uni;
-      return __ddiv_rn((double)cz_expf(__fsub_rn(x, mx), tab), S);
+      return __ddiv_rn((double)ex(x), S);
     }
   };
   const double pdf_literal = sum2 > 0.0 ? __ddiv_rn(CZ_P_FLOOR, sum2) : CZ_P_FLOOR;  // RWKV literal symbols v >= V
 
   if (OP == OP_XE) {
     double pr = CZ_P_FLOOR;  // pdf.get(sym).unwrap_or(ac_p_min())
-    if ((int)arg < V) pr = pdf_vocab(__ldg(p + (size_t)arg * ld));
+    if ((int)arg < V) pr = pdf_vocab(kCache ? p[(size_t)arg * ld] : __ldg(p + (size_t)arg * ld));
     else if ((int)arg < n_sym) pr = pdf_literal;
     pr = fmax(pr, 1e-300);
     xe_out = -log2(pr);
@@ -237,7 +251,7 @@ __device__ __forceinline__ void cdf_col(const float *__restrict__ p, size_t ld, 
     double acc = 0.0;
     uint32_t lo = 0, hi = 0;
     const int n_walk = (int)sym < V ? (int)sym + 1 : V;  // vocab part of the prefix
-    cdf_walk(p, ld, n_walk, [&](int v, float x) {
+    cdf_walk<!kCache>(p, ld, n_walk, [&](int v, float x) {
       acc = __dadd_rn(acc, pdf_vocab(x));
       if ((uint32_t)v + 1 == sym) lo = quant(acc);
       if ((uint32_t)v == sym) hi = quant(acc);
@@ -275,7 +289,7 @@ __device__ __forceinline__ void cdf_col(const float *__restrict__ p, size_t ld, 
       }
       prev = cur;
     };
-    cdf_walk(p, ld, V, [&](int v, float x) {
+    cdf_walk<!kCache>(p, ld, V, [&](int v, float x) {
       visit(v, pdf_vocab(x));
       return !done;
     });
@@ -296,9 +310,13 @@ __device__ __forceinline__ void cdf_col(const float *__restrict__ p, size_t ld, 
 // p: column base (vocab-major, element v at p[v*ld]).  Must be called by a full warp.
 template <int MODE>
 // xch: 64 doubles of shared memory private to the calling warp (16-byte aligned).
-__device__ __forceinline__ void cdf_search_warp(const float *__restrict__ p, size_t ld, int V, uint32_t value, float mx,
+__device__ __forceinline__ void cdf_search_warp(const float *__restrict__ p_in, size_t ld, int V, uint32_t value, float mx,
                                                 const ExpTab &tab, uint32_t &sym_out, uint32_t &lo_out, uint32_t &hi_out,
                                                 int &errbits, double *xch) {
+  // (No in-place caching of expf here, unlike cdf_col: the stepwise RWKV decoder keeps a stream's logits column across steps while
+  // it decodes literal bytes, so the column must stay intact.)
+  constexpr bool kCache = false;
+  float *p = const_cast<float *>(p_in);
   const int lane = threadIdx.x & 31;
   const int n_sym = MODE == CZ_CDF_RWKV_LITERALS ? V + 256 : V;
   const int n_grp = (V + 31) / 32;
@@ -333,14 +351,24 @@ __device__ __forceinline__ void cdf_search_warp(const float *__restrict__ p, siz
     __syncwarp();
     return acc;
   };
-  const double S = seq_sum([&](float x) { return (double)cz_expf(__fsub_rn(x, mx), tab); });
+  int g_store = 0;  // group counter of the first pass (the lambda is called once per group, in order)
+  const double S = seq_sum([&](float x) {
+    const float e = cz_expf(__fsub_rn(x, mx), tab);
+    if (kCache) {
+      const int v = g_store * 32 + lane;
+      if (v < V) p[(size_t)v * ld] = e;
+      g_store++;
+    }
+    return (double)e;
+  });
   if (!(S == S)) errbits |= CZ_DEVERR_NAN;
+  auto ex = [&](float x) -> float { return kCache ? x : cz_expf(__fsub_rn(x, mx), tab); };
   double norm = 1.0, sum2 = 1.0;
   const double scale = 1.0 - 256.0 * CZ_P_FLOOR;
   if (MODE == CZ_CDF_RWKV_LITERALS) {
-    norm = seq_sum([&](float x) { return fmax(__ddiv_rn((double)cz_expf(__fsub_rn(x, mx), tab), S), CZ_P_FLOOR); });
+    norm = seq_sum([&](float x) { return fmax(__ddiv_rn((double)ex(x), S), CZ_P_FLOOR); });
     double acc = seq_sum([&](float x) {
-      const double q = fmax(__ddiv_rn((double)cz_expf(__fsub_rn(x, mx), tab), S), CZ_P_FLOOR);
+      const double q = fmax(__ddiv_rn((double)ex(x), S), CZ_P_FLOOR);
       return __dmul_rn(__ddiv_rn(q, norm), scale);
     });
     for (int j = 0; j < 256; j++) acc = __dadd_rn(acc, CZ_P_FLOOR);
@@ -350,12 +378,12 @@ __device__ __forceinline__ void cdf_search_warp(const float *__restrict__ p, siz
   const double uni = 1.0 / (double)V;
   auto pdf_vocab = [&](float x) -> double {
     if (MODE == CZ_CDF_RWKV_LITERALS) {
-      double q = fmax(__ddiv_rn((double)cz_expf(__fsub_rn(x, mx), tab), S), CZ_P_FLOOR);
+      double q = fmax(__ddiv_rn((double)ex(x), S), CZ_P_FLOOR);
       q = __dmul_rn(__ddiv_rn(q, norm), scale);
       return sum2 > 0.0 ? __ddiv_rn(q, sum2) : q;
     }
     if (uniform) return uni;
-    return __ddiv_rn((double)cz_expf(__fsub_rn(x, mx), tab), S);
+    return __ddiv_rn((double)ex(x), S);
   };
   double acc = 0.0;
   uint32_t prev = 0, found = (uint32_t)(n_sym - 1), lo = 0, hi = CZ_AC_CDF_TOTAL;
