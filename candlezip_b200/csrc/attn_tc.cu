@@ -584,14 +584,9 @@ int launch_attn_tc(cz_ctx *ctx, const __nv_bfloat16 *q, int n_rows, const __nv_b
   CZ_TRY(make_map_bf16(&tk, k_arena, n_slots, nkv * 64, nkv * 64, 128));
   CZ_TRY(make_map_bf16(&tv, v_arena, n_slots, nkv * 64, nkv * 64, 128));  // V rows [slot][nkv*64], same box as K
   // persistent grid: two CTAs per SM pull (tile, KV head) items from a counter that is zeroed in stream order before the launch
-  static int *work_counter = nullptr;
-  static int n_sm = 0;
-  if (!work_counter) {
-    int dev = 0;
-    CZ_CUDA_TRY(cudaGetDevice(&dev));
-    CZ_CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-    CZ_CUDA_TRY(cudaMalloc(&work_counter, sizeof(int)));
-  }
+  // (the counter lives in the ctx's 64-byte device status block, after the error flag)
+  int *work_counter = ctx->err_flag_dev + 8;
+  const int n_sm = ctx->sm_count;
   CZ_CUDA_TRY(cudaMemsetAsync(work_counter, 0, sizeof(int), st));
   const int n_items = single_rows ? n_tiles : n_tiles * nkv;
   const unsigned grid = (unsigned)(n_items < 2 * n_sm ? n_items : 2 * n_sm);
