@@ -22,6 +22,7 @@ enum GemmEpilogue {
                          //   x = C[M][ldc] f32 += A*B^T;  xb[M][N] bf16 = bf16(x * w_next[n]);  ssq_out[m][part] = partial sums of x^2.
                          // The consumer GEMM takes xb as its A operand and multiplies its accumulator rows by
                          // 1 / sqrt(sum(parts) / N + eps): RMSNorm without a separate pass over the fp32 residual.
+  EPI_ADD_NORM_TMA = 10,  // the same contract as EPI_ADD_NORM with n_part_out = N / BN: thread-per-row epilogue, residual in and out by TMA
 };
 
 // RMSNorm fusion operands (all device pointers).  Producer side: EPI_ADD_NORM.  Consumer side (any bf16-output epilogue and

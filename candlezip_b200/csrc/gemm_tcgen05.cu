@@ -34,6 +34,7 @@ using cz::EPI_SIGMOID_BF16;
 using cz::EPI_RELUSQ_BF16;
 using cz::EPI_QKV_ROPE;
 using cz::EPI_ADD_NORM;
+using cz::EPI_ADD_NORM_TMA;
 using cz::RopeExt;
 using cz::NormExt;
 
@@ -48,7 +49,7 @@ struct GemmCfg {
   // other 32-column chunk.  The store-only epilogues (TMA store / reduce-add) keep four warps and the deeper operand pipeline.
   static constexpr bool kHeavy = EPI == cz::EPI_SWIGLU_BF16 || EPI == cz::EPI_QKV_ROPE || EPI == cz::EPI_STORE_BF16 ||
                                  EPI == cz::EPI_TANH_BF16 || EPI == cz::EPI_SIGMOID_BF16 || EPI == cz::EPI_RELUSQ_BF16 ||
-                                 EPI == cz::EPI_ADD_NORM;
+                                 EPI == cz::EPI_ADD_NORM || EPI == cz::EPI_ADD_NORM_TMA;
   // the LM-head epilogue (TMA store + column max) keeps four warps but DOUBLE-BUFFERS its TMA patch: with a single patch every
   // 32-column chunk waited for the previous bulk store to finish reading shared memory (about 1.5 us each, 7 us per tile)
   static constexpr bool kColmax = EPI == cz::EPI_STORE_F32_COLMAX;
@@ -56,7 +57,10 @@ struct GemmCfg {
   // LDTM -> exp2 / rcp -> store per chunk, about 5 cycles per instruction at two warps per scheduler) took 1.5x the tile's MMA time
   static constexpr bool kSwigluTma = EPI == cz::EPI_SWIGLU_BF16;
   // EPI_ADD_NORM: twelve warps, three per quadrant, two of the tile's six 32-column chunks each (same reason)
-  static constexpr int kEpiWarps = kSwigluTma ? 16 : (EPI == cz::EPI_ADD_NORM ? 12 : (kHeavy ? 8 : 4));
+  // EPI_ADD_NORM_TMA: four warps (thread = row): the residual goes in and out through TMA boxes, no transpose, no per-row addressing
+  static constexpr bool kNormTma = EPI == cz::EPI_ADD_NORM_TMA;
+  static constexpr int kXPatches = 4;  // residual boxes in flight per warp (look-ahead 3 chunks)
+  static constexpr int kEpiWarps = kSwigluTma ? 16 : (kNormTma ? 4 : (EPI == cz::EPI_ADD_NORM ? 12 : (kHeavy ? 8 : 4)));
   static constexpr int kTmaPatches = kColmax ? 2 : 1;
   static constexpr int kThreads = 64 + 32 * kEpiWarps;
   static constexpr int kABytes = BM * BK * 2;
@@ -67,7 +71,8 @@ struct GemmCfg {
   // SWIZZLE_128B TMA box (1024-aligned) for the f32 store / reduce-add epilogues
   // (EPI_QKV_ROPE: per TMEM lane quadrant three 4 KB [32 rows][64 bf16] head patches shared by its two warps = 6144 B per warp)
   // (EPI_SWIGLU_BF16: a dense 2 KB [32 rows][32 bf16] SWIZZLE_64B TMA box per warp)
-  static constexpr int kPatchBytes = kSwigluTma ? 2048 : (EPI == cz::EPI_QKV_ROPE ? 6144 : (kHeavy ? 4224 : (kColmax ? 8192 : 5120)));
+  // (EPI_ADD_NORM_TMA: kXPatches 4 KB [32 rows][32 f32] SWIZZLE_128B boxes + two 2 KB [32][32 bf16] SWIZZLE_64B boxes per warp)
+  static constexpr int kPatchBytes = kNormTma ? kXPatches * 4096 + 2 * 2048 : kSwigluTma ? 2048 : (EPI == cz::EPI_QKV_ROPE ? 6144 : (kHeavy ? 4224 : (kColmax ? 8192 : 5120)));
   // operand pipeline depth: whatever fits next to the epilogue staging (the pair's smaller stages buy 5-7 stages instead of 4-5:
   // the in-flight bytes per SM over the loaded TMA latency are what bounds these GEMMs, see profiles/)
   static constexpr int kStagesFit = (232448 - 2048 - kEpiWarps * kPatchBytes) / kStageBytes;
@@ -105,7 +110,7 @@ __device__ __forceinline__ float silu_mul_scaled(float g, float u, float nk, flo
 template <int BN, int EPI, int CL>
 __global__ void __launch_bounds__((GemmCfg<BN, EPI, 1>::kThreads), 1)
     gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
-                   const __grid_constant__ CUtensorMap tm_c, void *__restrict__ c_ptr,
+                   const __grid_constant__ CUtensorMap tm_c, const __grid_constant__ CUtensorMap tm_d, void *__restrict__ c_ptr,
                    int M, int N, int K, int ldc, int *__restrict__ aux, const __grid_constant__ RopeExt rx,
                    const __grid_constant__ NormExt nx, int raster_gw) {
   using Cfg = GemmCfg<BN, EPI, CL>;
@@ -119,6 +124,7 @@ __global__ void __launch_bounds__((GemmCfg<BN, EPI, 1>::kThreads), 1)
   uint64_t *tfull_bar = bars + 2 * Cfg::kStages;   // [2]
   uint64_t *tempty_bar = tfull_bar + 2;            // [2]
   uint32_t *tmem_slot = (uint32_t *)(tempty_bar + 2);
+  uint64_t *xfull_bar = bars + 32;  // EPI_ADD_NORM_TMA: [epilogue warp][kXPatches] "old residual box has landed"
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -162,6 +168,8 @@ __global__ void __launch_bounds__((GemmCfg<BN, EPI, 1>::kThreads), 1)
       mbar_init(smem_u32(&full_bar[s]), 1);
       mbar_init(smem_u32(&empty_bar[s]), 1);
     }
+    if (EPI == EPI_ADD_NORM_TMA)
+      for (int s = 0; s < Cfg::kEpiWarps * Cfg::kXPatches; s++) mbar_init(smem_u32(&xfull_bar[s]), 1);
     for (int s = 0; s < 2; s++) {
       mbar_init(smem_u32(&tfull_bar[s]), 1);
       mbar_init(smem_u32(&tempty_bar[s]), Cfg::kEpiWarps * CL);  // one arrival per epilogue warp (of both CTAs of a pair, on the leader's)
@@ -196,7 +204,7 @@ __global__ void __launch_bounds__((GemmCfg<BN, EPI, 1>::kThreads), 1)
         int m_unit, n_blk;
         if (!tile_mn(tile, m_unit, n_blk)) continue;
         const int m_blk = m_unit * CL + (int)rank;
-        if constexpr (EPI == EPI_ADD_NORM) {
+        if constexpr (EPI == EPI_ADD_NORM || EPI == EPI_ADD_NORM_TMA) {
           // the epilogue will read this tile's old residual a few microseconds from now: pull it into L2 (32 x 32 f32 boxes)
           for (int rb = 0; rb < BM / 32; rb++)
             for (int cb = 0; cb < BN / 32; cb++)
@@ -348,6 +356,31 @@ __global__ void __launch_bounds__((GemmCfg<BN, EPI, 1>::kThreads), 1)
       load_xo(u0, 0, xoA);
       load_xo(u0, 1, xoB);
     }
+    // EPI_ADD_NORM_TMA: the old residual arrives by TMA in 32 x 32 f32 boxes, kXPatches of them in flight per warp, requested three
+    // chunks ahead of their use (across tile boundaries); xseq counts the chunks this warp has consumed, (ld_tile, ld_k) is the
+    // next chunk to request.
+    constexpr int kXP = Cfg::kXPatches;
+    const uint32_t xpatch0 = smem_u32(patch);
+    uint32_t xseq = 0, ld_seq = 0;
+    int ld_tile = u0, ld_k = 0;
+    auto issue_x_load = [&]() {  // one lane
+      if (ld_tile < num_tiles) {
+        int mu = 0, nb_ = 0;
+        tile_mn(ld_tile, mu, nb_);
+        const uint32_t bar = smem_u32(&xfull_bar[warp * kXP + (int)(ld_seq % kXP)]);
+        mbar_expect_tx(bar, 4096);
+        tma_load_2d(xpatch0 + (ld_seq % kXP) * 4096, &tm_c, bar, nb_ * BN + ld_k * 32, (mu * CL + (int)rank) * BM + quad * 32);
+      }
+      ld_seq++;
+      if (++ld_k == BN / 32) {
+        ld_k = 0;
+        ld_tile += u_stride;
+      }
+    };
+    if constexpr (EPI == EPI_ADD_NORM_TMA) {
+      if (lane == 0)
+        for (int i = 0; i < kXP - 1; i++) issue_x_load();
+    }
     for (int tile = u0; tile < num_tiles; tile += u_stride, it++) {
       int m_unit, n_blk;
       if (!tile_mn(tile, m_unit, n_blk)) {
@@ -367,7 +400,7 @@ __global__ void __launch_bounds__((GemmCfg<BN, EPI, 1>::kThreads), 1)
         rs = 1.0f / sqrtf(ssum * nx.inv_d + nx.eps);
       }
       load_parts(tile + u_stride);
-      if constexpr (EPI != EPI_ADD_NORM && EPI != EPI_QKV_ROPE) {  // (those two first put their own loads in flight, then wait)
+      if constexpr (EPI != EPI_ADD_NORM && EPI != EPI_ADD_NORM_TMA && EPI != EPI_QKV_ROPE) {  // (those two first put their own loads in flight, then wait)
         mbar_wait(smem_u32(&tfull_bar[as]), (it >> 1) & 1);
         tc_fence_after();
       }
@@ -568,6 +601,66 @@ __global__ void __launch_bounds__((GemmCfg<BN, EPI, 1>::kThreads), 1)
         tc_fence_before();
         __syncwarp();
         if (lane == 0) tempty_arrive(as);
+        continue;
+      } else if constexpr (EPI == EPI_ADD_NORM_TMA) {
+        // Residual add + the next RMSNorm's inputs, thread = row (the TMEM layout), nothing transposed.  Per 32-column chunk: the
+        // old residual box (requested three chunks earlier) is read from shared memory as 8 conflict-free 16-byte pieces of the
+        // thread's row, x = old + accumulator goes back into the same box and leaves by TMA store; bf16(x * w_next) leaves
+        // through a small SWIZZLE_64B box; the row's sum of squares is thread-local: columns ascending over the tile, one
+        // partial per row and N tile, which the consumer GEMM's epilogue adds in index order.
+        mbar_wait(smem_u32(&tfull_bar[as]), (it >> 1) & 1);
+        tc_fence_after();
+        float ssq = 0.f;
+        const int sw = lane & 7, sw64 = (lane >> 1) & 3;
+#pragma unroll 1
+        for (int k = 0; k < BN / 32; k++) {
+          const uint32_t sq = xseq++;
+          const uint32_t xp = xpatch0 + (sq % kXP) * 4096, xrow = xp + (uint32_t)(lane * 128);
+          const uint32_t bp = xpatch0 + kXP * 4096 + (sq & 1) * 2048, brow = bp + (uint32_t)(lane * 64);
+          const int col0 = n_blk * BN + k * 32;
+          uint32_t r[32];
+          tc_ld_32x32(t_row + (uint32_t)(k * 32), r);
+          mbar_wait(smem_u32(&xfull_bar[warp * kXP + (int)(sq % kXP)]), (sq / kXP) & 1);
+          tc_ld_wait();
+          uint32_t pk[16];
+#pragma unroll
+          for (int q = 0; q < 8; q++) {
+            float4 o;
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(o.x), "=f"(o.y), "=f"(o.z), "=f"(o.w) : "r"(xrow + (uint32_t)((q ^ sw) << 4)) : "memory");
+            const float4 wq = *reinterpret_cast<const float4 *>(nx.w_next + col0 + 4 * q);
+            const float v0 = __uint_as_float(r[4 * q]) + o.x, v1 = __uint_as_float(r[4 * q + 1]) + o.y, v2 = __uint_as_float(r[4 * q + 2]) + o.z,
+                        v3 = __uint_as_float(r[4 * q + 3]) + o.w;
+            ssq = fmaf(v0, v0, ssq);
+            ssq = fmaf(v1, v1, ssq);
+            ssq = fmaf(v2, v2, ssq);
+            ssq = fmaf(v3, v3, ssq);
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(xrow + (uint32_t)((q ^ sw) << 4)), "f"(v0), "f"(v1), "f"(v2), "f"(v3) : "memory");
+            __nv_bfloat162 h0 = __floats2bfloat162_rn(v0 * wq.x, v1 * wq.y), h1 = __floats2bfloat162_rn(v2 * wq.z, v3 * wq.w);
+            pk[2 * q] = *reinterpret_cast<uint32_t *>(&h0);
+            pk[2 * q + 1] = *reinterpret_cast<uint32_t *>(&h1);
+          }
+#pragma unroll
+          for (int q = 0; q < 4; q++)
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(brow + (uint32_t)((q ^ sw64) << 4)), "r"(pk[4 * q]), "r"(pk[4 * q + 1]),
+                         "r"(pk[4 * q + 2]), "r"(pk[4 * q + 3])
+                         : "memory");
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) {
+            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(&tm_c), "r"(xp), "r"(col0), "r"(row_base) : "memory");
+            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(&tm_d), "r"(bp), "r"(col0), "r"(row_base) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            // every store group but this one has been read out of shared memory: the box of chunk sq - 1 takes chunk sq + 3
+            // (and the bf16 box of chunk sq - 1 is free for chunk sq + 1)
+            asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            issue_x_load();
+          }
+          __syncwarp();
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) tempty_arrive(as);
+        if (row_ok) nx.ssq_out[(size_t)(row_base + lane) * n_tiles + n_blk] = ssq;
         continue;
       } else if constexpr (EPI == EPI_ADD_NORM) {
         // Residual add + the next RMSNorm's inputs.  The accumulator chunk is transposed through the warp's padded patch so that
@@ -829,8 +922,8 @@ static int make_map_c_bf16(CUtensorMap *map, void *ptr, int rows, int cols, int 
 }
 
 template <int BN, int EPI, int CL>
-static int launch_tc_cl(cz_ctx *ctx, const CUtensorMap &ta, const CUtensorMap &tb, const CUtensorMap &tc, void *c, int M, int N, int K, int ldc,
-                        int *aux, int g_fam, cudaStream_t stream, const RopeExt &rx, const NormExt &nx) {
+static int launch_tc_cl(cz_ctx *ctx, const CUtensorMap &ta, const CUtensorMap &tb, const CUtensorMap &tc, const CUtensorMap &td, void *c, int M, int N,
+                        int K, int ldc, int *aux, int g_fam, cudaStream_t stream, const RopeExt &rx, const NormExt &nx) {
   using Cfg = czk::GemmCfg<BN, EPI, CL>;
   int raster_gw = 0;
   static bool attr_set = false;
@@ -877,16 +970,16 @@ static int launch_tc_cl(cz_ctx *ctx, const CUtensorMap &ta, const CUtensorMap &t
   at[0].val.clusterDim.z = 1;
   cfg.attrs = at;
   cfg.numAttrs = 1;
-  CZ_LAUNCH(ctx, g_fam, (cudaLaunchKernelEx(&cfg, kern, ta, tb, tc, c, M, N, K, ldc, aux, rx, nx, raster_gw)));
+  CZ_LAUNCH(ctx, g_fam, (cudaLaunchKernelEx(&cfg, kern, ta, tb, tc, td, c, M, N, K, ldc, aux, rx, nx, raster_gw)));
   CZ_CHECK_LAUNCH();
   return CZ_OK;
 }
 
 template <int BN, int EPI>
-static int launch_tc(cz_ctx *ctx, const CUtensorMap &ta, const CUtensorMap &tb, const CUtensorMap &tc, void *c, int M, int N, int K, int ldc, int *aux,
-                     int g_fam, cudaStream_t stream, const RopeExt &rx, const NormExt &nx, int cl) {
-  if (cl == 2) return launch_tc_cl<BN, EPI, 2>(ctx, ta, tb, tc, c, M, N, K, ldc, aux, g_fam, stream, rx, nx);
-  return launch_tc_cl<BN, EPI, 1>(ctx, ta, tb, tc, c, M, N, K, ldc, aux, g_fam, stream, rx, nx);
+static int launch_tc(cz_ctx *ctx, const CUtensorMap &ta, const CUtensorMap &tb, const CUtensorMap &tc, const CUtensorMap &td, void *c, int M, int N, int K,
+                     int ldc, int *aux, int g_fam, cudaStream_t stream, const RopeExt &rx, const NormExt &nx, int cl) {
+  if (cl == 2) return launch_tc_cl<BN, EPI, 2>(ctx, ta, tb, tc, td, c, M, N, K, ldc, aux, g_fam, stream, rx, nx);
+  return launch_tc_cl<BN, EPI, 1>(ctx, ta, tb, tc, td, c, M, N, K, ldc, aux, g_fam, stream, rx, nx);
 }
 
 int gemm_tcgen05(cz_ctx *ctx, const GemmArgs &g, cudaStream_t stream) {
@@ -914,7 +1007,7 @@ int gemm_tcgen05(cz_ctx *ctx, const GemmArgs &g, cudaStream_t stream) {
     set_error("gemm_tcgen05: EPI_QKV_ROPE needs BN = 192, N = (nh + 2 nkv) * 64 and all RopeExt operands");
     return CZ_ERR_INVALID;
   }
-  if (g.epi == EPI_ADD_NORM && (g.bn != 192 || (g.N % 4) || (g.ldc % 4) || !g.norm.w_next || !g.norm.xb || !g.norm.ssq_out)) {
+  if ((g.epi == EPI_ADD_NORM || g.epi == EPI_ADD_NORM_TMA) && (g.bn != 192 || (g.N % 4) || (g.ldc % 4) || !g.norm.w_next || !g.norm.xb || !g.norm.ssq_out)) {
     set_error("gemm_tcgen05: EPI_ADD_NORM needs BN = 192, N % 4 == 0 and the NormExt producer operands");
     return CZ_ERR_INVALID;
   }
@@ -922,16 +1015,18 @@ int gemm_tcgen05(cz_ctx *ctx, const GemmArgs &g, cudaStream_t stream) {
   // Measured per family (profiles/): pairs win where the main loop dominates (o_proj, gate/up, down_proj: -5 .. -13%), the
   // single-CTA kernel where the epilogue paces the tile (QKV + RoPE, LM head + column max: the leader would wait for two epilogues).
   static const int cl_env = getenv("CZ_GEMM_NO_CLUSTER") ? 1 : (getenv("CZ_GEMM_ALL_PAIRS") ? 3 : 2);
-  const int cl = cl_env == 1 ? 1 : ((cl_env == 3 || g.epi == EPI_SWIGLU_BF16 || g.epi == EPI_ADD_NORM || g.epi == EPI_ADD_F32) ? 2 : 1);
-  CUtensorMap ta, tb, tc;
+  const int cl = cl_env == 1 ? 1 : ((cl_env == 3 || g.epi == EPI_SWIGLU_BF16 || g.epi == EPI_ADD_NORM || g.epi == EPI_ADD_NORM_TMA || g.epi == EPI_ADD_F32) ? 2 : 1);
+  CUtensorMap ta, tb, tc, td;
   CZ_TRY(make_map_bf16(&ta, g.a, g.M, g.K, g.lda, czk::BM));
   CZ_TRY(make_map_bf16(&tb, g.b, g.N, g.K, g.ldb, g.bn / cl));
-  if (g.epi == EPI_ADD_F32 || g.epi == EPI_STORE_F32 || g.epi == EPI_STORE_F32_COLMAX || g.epi == EPI_ADD_NORM)
+  if (g.epi == EPI_ADD_F32 || g.epi == EPI_STORE_F32 || g.epi == EPI_STORE_F32_COLMAX || g.epi == EPI_ADD_NORM || g.epi == EPI_ADD_NORM_TMA)
     CZ_TRY(make_map_c(&tc, g.c, g.M, g.N, g.ldc));
   else if (g.epi == EPI_SWIGLU_BF16) CZ_TRY(make_map_c_bf16(&tc, g.c, g.M, g.N / 2, g.ldc));
   else tc = ta;  // unused by the other epilogues
+  if (g.epi == EPI_ADD_NORM_TMA) CZ_TRY(make_map_c_bf16(&td, g.norm.xb, g.M, g.N, g.N));  // the bf16 norm operand's store target
+  else td = ta;
 #define CZ_TC_CASE(BN_, EPI_) \
-  if (g.bn == BN_ && g.epi == EPI_) return launch_tc<BN_, EPI_>(ctx, ta, tb, tc, g.c, g.M, g.N, g.K, g.ldc, g.aux, g.fam, stream, g.rope, g.norm, cl)
+  if (g.bn == BN_ && g.epi == EPI_) return launch_tc<BN_, EPI_>(ctx, ta, tb, tc, td, g.c, g.M, g.N, g.K, g.ldc, g.aux, g.fam, stream, g.rope, g.norm, cl)
   CZ_TC_CASE(192, EPI_STORE_F32);
   CZ_TC_CASE(192, EPI_ADD_F32);
   CZ_TC_CASE(192, EPI_SWIGLU_BF16);
@@ -946,6 +1041,7 @@ int gemm_tcgen05(cz_ctx *ctx, const GemmArgs &g, cudaStream_t stream) {
   CZ_TC_CASE(192, EPI_QKV_ROPE);
   CZ_TC_CASE(256, EPI_SWIGLU_BF16);
   CZ_TC_CASE(192, EPI_ADD_NORM);
+  CZ_TC_CASE(192, EPI_ADD_NORM_TMA);
 #undef CZ_TC_CASE
   set_error("gemm_tcgen05: unsupported (BN, epilogue) combination");
   return CZ_ERR_UNSUPPORTED;

@@ -278,7 +278,11 @@ int forward_trunk(cz_model *m, int n_rows, const KvView &kv, cudaStream_t st) {
   static const bool no_fused_norm = getenv("CZ_DEBUG_NO_FUSED_NORM") != nullptr;  // bisecting aid
   const bool fused_norm = c.engine == CZ_ENGINE_TCGEN05 && !no_fused_norm && getenv("CZ_DEBUG_NO_FUSED_ROPE") == nullptr && D % 192 == 0 &&
                           (D / 192) * 3 <= 12;
-  const int n_part = fused_norm ? (D / 192) * 3 : 0;  // three epilogue warps per TMEM lane quadrant and N tile
+  // CZ_NORM_TMA=1 selects the thread-per-row residual epilogue (residual in and out by TMA, one partial per N tile); the default
+  // is the transposing epilogue (three warps per TMEM lane quadrant, three partials per N tile)
+  static const bool norm_tma = getenv("CZ_NORM_TMA") != nullptr;
+  const int epi_norm = norm_tma ? EPI_ADD_NORM_TMA : EPI_ADD_NORM;
+  const int n_part = fused_norm ? (norm_tma ? D / 192 : (D / 192) * 3) : 0;
   NormExt consume{};
   if (fused_norm) {
     consume.ssq_in = w.ssq; consume.n_part_in = n_part; consume.inv_d = 1.0f / (float)D; consume.eps = c.norm_eps;
@@ -320,7 +324,7 @@ int forward_trunk(cz_model *m, int n_rows, const KvView &kv, cudaStream_t st) {
     g.a = w.attn; g.lda = D; g.b = m->w_o + (size_t)l * D * D; g.ldb = D; g.c = w.x; g.ldc = D;
     g.M = n_rows; g.N = D; g.K = D; g.epi = EPI_ADD_F32; g.bn = 192; g.fam = CZ_K_GEMM_O;
     if (fused_norm) {  // x += attn * Wo^T, and the FFN norm's inputs
-      g.epi = EPI_ADD_NORM;
+      g.epi = epi_norm;
       g.norm.w_next = n2; g.norm.xb = w.xn; g.norm.ssq_out = w.ssq;
     }
     CZ_TRY(gemm(ctx, c.engine, g, st));
@@ -334,7 +338,7 @@ int forward_trunk(cz_model *m, int n_rows, const KvView &kv, cudaStream_t st) {
     g.a = w.act; g.lda = F; g.b = m->w_d + (size_t)l * D * F; g.ldb = F; g.c = w.x; g.ldc = D;
     g.M = n_rows; g.N = D; g.K = F; g.epi = EPI_ADD_F32; g.bn = 192; g.fam = CZ_K_GEMM_DOWN;
     if (fused_norm && l + 1 < L) {  // x += act * Wd^T, and the next layer's attention norm's inputs (the final norm reads fp32 x)
-      g.epi = EPI_ADD_NORM;
+      g.epi = epi_norm;
       g.norm.w_next = m->norms + (size_t)(2 * (l + 1)) * D; g.norm.xb = w.xn; g.norm.ssq_out = w.ssq;
     }
     CZ_TRY(gemm(ctx, c.engine, g, st));

@@ -1,5 +1,7 @@
 // Test-only entry points (declared in include/candlezip_b200.h under "test hooks"): run one dense contraction
 // through either engine on host buffers so tests can compare tcgen05 vs SIMT vs a host reference.
+#include <cstdlib>
+#include <cstring>
 #include <vector>
 
 #include "cz_common.cuh"
@@ -57,7 +59,9 @@ extern "C" int cz_test_gemm_norm(cz_ctx *ctx, int M, int N, int K, int N2, const
     set_error("cz_test_gemm_norm: N % 192, K % 64, N2 % 8");
     return CZ_ERR_INVALID;
   }
-  const int n_part = (N / 192) * 3;
+  const bool norm_tma = getenv("CZ_NORM_TMA") != nullptr;  // same switch as the model (model_core.cu)
+  const int n_part_host = (N / 192) * 3;                     // the caller's ssq_out row length
+  const int n_part = norm_tma ? N / 192 : n_part_host;
   void *da = nullptr, *db = nullptr, *db2 = nullptr, *dx = nullptr, *dxb = nullptr, *dssq = nullptr, *dw = nullptr, *dout = nullptr;
   CZ_CUDA_TRY(cudaMalloc(&da, (size_t)M * K * 2));
   CZ_CUDA_TRY(cudaMalloc(&db, (size_t)N * K * 2));
@@ -73,7 +77,7 @@ extern "C" int cz_test_gemm_norm(cz_ctx *ctx, int M, int N, int K, int N2, const
   CZ_CUDA_TRY(cudaMemcpy(dx, x_inout, (size_t)M * N * 4, cudaMemcpyHostToDevice));
   CZ_CUDA_TRY(cudaMemcpy(dw, w_next, (size_t)N * 4, cudaMemcpyHostToDevice));
   GemmArgs g{};
-  g.a = da; g.b = db; g.c = dx; g.M = M; g.N = N; g.K = K; g.lda = K; g.ldb = K; g.ldc = N; g.epi = EPI_ADD_NORM; g.bn = 192;
+  g.a = da; g.b = db; g.c = dx; g.M = M; g.N = N; g.K = K; g.lda = K; g.ldb = K; g.ldc = N; g.epi = norm_tma ? EPI_ADD_NORM_TMA : EPI_ADD_NORM; g.bn = 192;
   g.norm.w_next = (const float *)dw; g.norm.xb = dxb; g.norm.ssq_out = (float *)dssq;
   int rc = gemm(ctx, CZ_ENGINE_TCGEN05, g, ctx->stream);
   if (rc == CZ_OK) {
@@ -90,7 +94,8 @@ extern "C" int cz_test_gemm_norm(cz_ctx *ctx, int M, int N, int K, int N2, const
     } else {
       cudaMemcpy(x_inout, dx, (size_t)M * N * 4, cudaMemcpyDeviceToHost);
       cudaMemcpy(xb_out, dxb, (size_t)M * N * 2, cudaMemcpyDeviceToHost);
-      cudaMemcpy(ssq_out, dssq, (size_t)M * n_part * 4, cudaMemcpyDeviceToHost);
+      memset(ssq_out, 0, (size_t)M * n_part_host * 4);
+      cudaMemcpy2D(ssq_out, (size_t)n_part_host * 4, dssq, (size_t)n_part * 4, (size_t)n_part * 4, (size_t)M, cudaMemcpyDeviceToHost);
       cudaMemcpy(out2, dout, (size_t)M * N2 * 2, cudaMemcpyDeviceToHost);
     }
   }
