@@ -278,9 +278,9 @@ int forward_trunk(cz_model *m, int n_rows, const KvView &kv, cudaStream_t st) {
   static const bool no_fused_norm = getenv("CZ_DEBUG_NO_FUSED_NORM") != nullptr;  // bisecting aid
   const bool fused_norm = c.engine == CZ_ENGINE_TCGEN05 && !no_fused_norm && getenv("CZ_DEBUG_NO_FUSED_ROPE") == nullptr && D % 192 == 0 &&
                           (D / 192) * 3 <= 12;
-  // CZ_NORM_TMA=1 selects the thread-per-row residual epilogue (residual in and out by TMA, one partial per N tile); the default
-  // is the transposing epilogue (three warps per TMEM lane quadrant, three partials per N tile)
-  static const bool norm_tma = getenv("CZ_NORM_TMA") != nullptr;
+  // Default: the thread-per-row residual epilogue (residual in and out by TMA, one partial per N tile; 2% faster per step in
+  // A/B runs); CZ_NORM_TRANSPOSE=1 selects the transposing epilogue (three warps per TMEM lane quadrant, three partials per N tile)
+  static const bool norm_tma = getenv("CZ_NORM_TRANSPOSE") == nullptr;
   const int epi_norm = norm_tma ? EPI_ADD_NORM_TMA : EPI_ADD_NORM;
   const int n_part = fused_norm ? (norm_tma ? D / 192 : (D / 192) * 3) : 0;
   NormExt consume{};

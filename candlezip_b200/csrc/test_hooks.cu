@@ -59,7 +59,7 @@ extern "C" int cz_test_gemm_norm(cz_ctx *ctx, int M, int N, int K, int N2, const
     set_error("cz_test_gemm_norm: N % 192, K % 64, N2 % 8");
     return CZ_ERR_INVALID;
   }
-  const bool norm_tma = getenv("CZ_NORM_TMA") != nullptr;  // same switch as the model (model_core.cu)
+  const bool norm_tma = getenv("CZ_NORM_TRANSPOSE") == nullptr;  // same switch as the model (model_core.cu)
   const int n_part_host = (N / 192) * 3;                     // the caller's ssq_out row length
   const int n_part = norm_tma ? N / 192 : n_part_host;
   void *da = nullptr, *db = nullptr, *db2 = nullptr, *dx = nullptr, *dxb = nullptr, *dssq = nullptr, *dw = nullptr, *dout = nullptr;
