@@ -29,9 +29,9 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 METRIC = "encode_MB_per_s_smollm135m_ctx512"
 # per layer-wave launch (253k rows), dram read + written under ncu --set full (profiles/ncu_summary_r01g.md): qkv+rope 769 MB,
-# o-proj (+ fused norm operands) 1791 MB, gate/up 1069 MB, down (+ fused norm operands) 2284 MB; x60 launches each, plus the
+# o-proj (+ fused norm operands) 1969 MB, gate/up 1061 MB, down (+ fused norm operands) 2335 MB; x60 launches each, plus the
 # LM head's 51.5 GB of logits written + 0.4 GB read
-NCU_GEMM_TRAFFIC_BYTES_PER_STEP = int(60 * (769 + 1791 + 1069 + 2284) * 1e6 + 51.9e9)
+NCU_GEMM_TRAFFIC_BYTES_PER_STEP = int(60 * (759 + 1969 + 1061 + 2335) * 1e6 + 51.9e9)
 MFLOP_PER_TOKEN = 551.0  # trunk 423.84 + head 56.62 + attention 70.57 MFLOP per coded token at ctx 512 / reprime 512
 TRUNK_PARAMS = 106_168_320  # matmul params per token position, SURVEY 8d
 HEAD_PARAMS = 28_311_552
@@ -339,9 +339,9 @@ def run_ours(args):
 
     kernels = [k for k in [
         kern("gemm_tc_kernel<256,SWIGLU,pair> gate/up", "gemm_gu", "tensor", 2.0 * rows * 2 * F * D * L),
-        kern("gemm_tc_kernel<192,ADD_NORM,pair> down_proj (+ next norm's operands)", "gemm_down", "tensor", 2.0 * rows * D * F * L),
+        kern("gemm_tc_kernel<192,ADD_NORM_TMA,pair> down_proj (+ next norm's operands)", "gemm_down", "tensor", 2.0 * rows * D * F * L),
         # o_proj is bound by the fp32 residual: per row A 1152 B + residual read and written 4608 B + bf16 norm operand 1152 B
-        kern("gemm_tc_kernel<192,ADD_NORM,pair> o_proj (+ next norm's operands)", "gemm_o", "hbm", float(rows) * (2 * D + 8 * D + 2 * D) * L),
+        kern("gemm_tc_kernel<192,ADD_NORM_TMA,pair> o_proj (+ next norm's operands)", "gemm_o", "hbm", float(rows) * (2 * D + 8 * D + 2 * D) * L),
         kern("gemm_tc_kernel<192,QKV_ROPE> qkv + RoPE", "gemm_qkv", "tensor", 2.0 * rows * qkv_n * D * L),
         kern("gemm_tc_kernel<256,COLMAX> LM head", "gemm_head", "tensor", 2.0 * HEAD_PARAMS * n),
         kern("attn_tc_kernel", "attn", "tensor", 70.57e6 * n),
