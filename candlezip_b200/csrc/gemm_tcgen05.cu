@@ -204,7 +204,8 @@ __global__ void __launch_bounds__((GemmCfg<BN, EPI, 1>::kThreads), 1)
         int m_unit, n_blk;
         if (!tile_mn(tile, m_unit, n_blk)) continue;
         const int m_blk = m_unit * CL + (int)rank;
-        if constexpr (EPI == EPI_ADD_NORM || EPI == EPI_ADD_NORM_TMA) {
+        if constexpr (EPI == EPI_ADD_NORM) {  // (not EPI_ADD_NORM_TMA: its box loads run three chunks ahead, and a prefetch this
+                                              //  early is partly evicted again: 1120 MB read per o_proj launch against 876, profiles/)
           // the epilogue will read this tile's old residual a few microseconds from now: pull it into L2 (32 x 32 f32 boxes)
           for (int rb = 0; rb < BM / 32; rb++)
             for (int cb = 0; cb < BN / 32; cb++)
