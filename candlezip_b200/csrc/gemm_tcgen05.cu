@@ -613,16 +613,19 @@ __global__ void __launch_bounds__((GemmCfg<BN, EPI, 1>::kThreads), 1)
         tc_fence_after();
         float ssq = 0.f;
         const int sw = lane & 7, sw64 = (lane >> 1) & 3;
-#pragma unroll 1
+        // the next chunk's accumulators are already on their way from TMEM while the current chunk is processed
+        uint32_t racc[2][32];
+        tc_ld_32x32(t_row, racc[0]);
+#pragma unroll
         for (int k = 0; k < BN / 32; k++) {
           const uint32_t sq = xseq++;
           const uint32_t xp = xpatch0 + (sq % kXP) * 4096, xrow = xp + (uint32_t)(lane * 128);
           const uint32_t bp = xpatch0 + kXP * 4096 + (sq & 1) * 2048, brow = bp + (uint32_t)(lane * 64);
           const int col0 = n_blk * BN + k * 32;
-          uint32_t r[32];
-          tc_ld_32x32(t_row + (uint32_t)(k * 32), r);
+          uint32_t(&r)[32] = racc[k & 1];
           mbar_wait(smem_u32(&xfull_bar[warp * kXP + (int)(sq % kXP)]), (sq / kXP) & 1);
           tc_ld_wait();
+          if (k + 1 < BN / 32) tc_ld_32x32(t_row + (uint32_t)((k + 1) * 32), racc[(k + 1) & 1]);
           uint32_t pk[16];
 #pragma unroll
           for (int q = 0; q < 8; q++) {
