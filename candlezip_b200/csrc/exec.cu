@@ -257,8 +257,23 @@ static int stage_and_upload(cz_model *m, const Wave &w, long long *src_dev, cuda
   memcpy(h + b_src, w.pos.data(), b_i);
   memcpy(h + b_src + b_i, w.kv_base.data(), b_i);
   memcpy(h + b_src + 2 * b_i, w.logit_rows.data(), b_l);
-  memcpy(h + b_src + 2 * b_i + b_l, w.tile_row0.data(), b_t);
-  memcpy(h + b_src + 2 * b_i + b_l + b_t, w.tile_n.data(), b_t);
+  {
+    // Attention work items are pulled from a counter by persistent CTAs.  The tiles keep their natural order (the tiles of a chunk
+    // share K / V blocks, which then come out of L2), except that the short ones (at most two key blocks) go to the end of
+    // the list: the kernel then ends on 3-6 iteration items instead of a few CTAs still walking 8-block tiles.  The order of
+    // the list has no effect on the results (a tile's rows are written by whichever CTA picks it up).
+    std::vector<int> order(NT);
+    for (size_t t = 0; t < NT; t++) order[t] = (int)t;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+      const int la = w.pos[w.tile_row0[a]] + w.tile_n[a] <= 256, lb = w.pos[w.tile_row0[b]] + w.tile_n[b] <= 256;
+      return la < lb;
+    });
+    int *tr = (int *)(h + b_src + 2 * b_i + b_l), *tn = (int *)(h + b_src + 2 * b_i + b_l + b_t);
+    for (size_t t = 0; t < NT; t++) {
+      tr[t] = w.tile_row0[order[t]];
+      tn[t] = w.tile_n[order[t]];
+    }
+  }
   CZ_CUDA_TRY(cudaMemcpyAsync(src_dev, h, b_src, cudaMemcpyHostToDevice, st));
   CZ_CUDA_TRY(cudaMemcpyAsync(ws.pos, h + b_src, b_i, cudaMemcpyHostToDevice, st));
   CZ_CUDA_TRY(cudaMemcpyAsync(ws.kv_base, h + b_src + b_i, b_i, cudaMemcpyHostToDevice, st));
