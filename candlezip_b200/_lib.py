@@ -136,6 +136,8 @@ SIGNATURES = {
     "cz_test_gemm_norm": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint16), C.POINTER(C.c_uint16), C.POINTER(C.c_uint16),
                                    C.POINTER(C.c_float), C.c_float, C.POINTER(C.c_float), C.POINTER(C.c_uint16), C.POINTER(C.c_float),
                                    C.POINTER(C.c_uint16)]),
+    "cz_test_attention": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint16), C.POINTER(C.c_uint16), C.POINTER(C.c_uint16), C.c_int,
+                                   C.POINTER(C.c_uint16)]),
     "cz_schedule_chunks": (C.c_size_t, [C.c_uint64, C.c_uint32, C.c_uint32, u64p, u32p, u64p, u32p, C.c_size_t]),
 }
 

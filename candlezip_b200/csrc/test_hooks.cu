@@ -6,6 +6,7 @@
 
 #include "cz_common.cuh"
 #include "gemm.h"
+#include "llama_kernels.h"
 
 namespace cz {
 int require_device(cz_ctx *ctx);
@@ -100,5 +101,62 @@ extern "C" int cz_test_gemm_norm(cz_ctx *ctx, int M, int N, int K, int N2, const
     }
   }
   for (void *p : {da, db, db2, dx, dxb, dssq, dw, dout}) cudaFree(p);
+  return rc;
+}
+
+// One causal GQA attention pass of the tcgen05 kernel over ONE sequence of n_pos positions (the K5 kernel behind
+// src/models.rs:94,110), on host bf16 buffers: q [n_pos][nh*64], k / v [n_pos][nkv*64] (already RoPE'd -- the hook feeds the kernel
+// directly so that tests can place adversarial scores in chosen key blocks).  mode 0: teacher-forced 128-position tiles;
+// mode 1: every position as its own single-row decode tile (the stacked-GQA path of the stepwise decoder).  out [n_pos][nh*64] bf16.
+extern "C" int cz_test_attention(cz_ctx *ctx, int n_pos, int nh, int nkv, const uint16_t *q_bf16, const uint16_t *k_bf16,
+                                 const uint16_t *v_bf16, int mode, uint16_t *out_bf16) {
+  CZ_TRY(require_device(ctx));
+  CZ_CUDA_TRY(cudaSetDevice(ctx->device));
+  if (n_pos <= 0 || nh <= 0 || nkv <= 0 || nh % nkv || nh / nkv > 4 || !q_bf16 || !k_bf16 || !v_bf16 || !out_bf16) {
+    set_error("cz_test_attention: bad arguments");
+    return CZ_ERR_INVALID;
+  }
+  const size_t qn = (size_t)n_pos * nh * 64, kn = (size_t)n_pos * nkv * 64;
+  std::vector<int> pos(n_pos), base(n_pos, 0), trow, tn;
+  for (int i = 0; i < n_pos; i++) pos[i] = i;
+  if (mode == 0) {
+    for (int p = 0; p < n_pos; p += 128) {
+      trow.push_back(p);
+      tn.push_back(n_pos - p < 128 ? n_pos - p : 128);
+    }
+  } else {
+    for (int p = 0; p < n_pos; p++) {
+      trow.push_back(p);
+      tn.push_back(1);
+    }
+  }
+  const size_t nt = trow.size();
+  void *dq = nullptr, *dk = nullptr, *dv = nullptr, *dout = nullptr, *dmeta = nullptr;
+  CZ_CUDA_TRY(cudaMalloc(&dq, qn * 2));
+  CZ_CUDA_TRY(cudaMalloc(&dk, kn * 2));
+  CZ_CUDA_TRY(cudaMalloc(&dv, kn * 2));
+  CZ_CUDA_TRY(cudaMalloc(&dout, qn * 2));
+  CZ_CUDA_TRY(cudaMalloc(&dmeta, ((size_t)2 * n_pos + 2 * nt) * 4));
+  int *dpos = (int *)dmeta, *dbase = dpos + n_pos, *dtrow = dbase + n_pos, *dtn = dtrow + nt;
+  CZ_CUDA_TRY(cudaMemcpy(dq, q_bf16, qn * 2, cudaMemcpyHostToDevice));
+  CZ_CUDA_TRY(cudaMemcpy(dk, k_bf16, kn * 2, cudaMemcpyHostToDevice));
+  CZ_CUDA_TRY(cudaMemcpy(dv, v_bf16, kn * 2, cudaMemcpyHostToDevice));
+  CZ_CUDA_TRY(cudaMemset(dout, 0, qn * 2));
+  CZ_CUDA_TRY(cudaMemcpy(dpos, pos.data(), (size_t)n_pos * 4, cudaMemcpyHostToDevice));
+  CZ_CUDA_TRY(cudaMemcpy(dbase, base.data(), (size_t)n_pos * 4, cudaMemcpyHostToDevice));
+  CZ_CUDA_TRY(cudaMemcpy(dtrow, trow.data(), nt * 4, cudaMemcpyHostToDevice));
+  CZ_CUDA_TRY(cudaMemcpy(dtn, tn.data(), nt * 4, cudaMemcpyHostToDevice));
+  int rc = launch_attn_tc(ctx, (const __nv_bfloat16 *)dq, n_pos, (const __nv_bfloat16 *)dk, (const __nv_bfloat16 *)dv, n_pos, 0, dpos, dbase,
+                          dtrow, dtn, (int)nt, (__nv_bfloat16 *)dout, nh, nkv, mode != 0, ctx->stream);
+  if (rc == CZ_OK) {
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+      set_error(std::string("attention execution failed: ") + cudaGetErrorString(e));
+      rc = CZ_ERR_CUDA;
+    } else {
+      cudaMemcpy(out_bf16, dout, qn * 2, cudaMemcpyDeviceToHost);
+    }
+  }
+  for (void *p : {dq, dk, dv, dout, dmeta}) cudaFree(p);
   return rc;
 }

@@ -266,6 +266,11 @@ int cz_test_gemm(cz_ctx *ctx, int engine, int M, int N, int K, const uint16_t *a
 int cz_test_gemm_norm(cz_ctx *ctx, int M, int N, int K, int N2, const uint16_t *a_bf16, const uint16_t *b_bf16, const uint16_t *b2_bf16,
                       const float *w_next, float eps, float *x_inout, uint16_t *xb_out, float *ssq_out, uint16_t *out2);
 
+/* one causal GQA attention pass of the tcgen05 kernel over one sequence (q [n_pos][nh*64], k / v [n_pos][nkv*64], bf16, RoPE already
+ * applied): mode 0 = teacher-forced 128-position tiles, mode 1 = every position as a single-row decode tile; out [n_pos][nh*64] bf16 */
+int cz_test_attention(cz_ctx *ctx, int n_pos, int nh, int nkv, const uint16_t *q_bf16, const uint16_t *k_bf16,
+                      const uint16_t *v_bf16, int mode, uint16_t *out_bf16);
+
 #ifdef __cplusplus
 }
 #endif
