@@ -220,6 +220,17 @@ class Model:
     def session(self):
         return Session(self)
 
+    def watch_digests(self, n_tokens):
+        """f-4: BLAKE3-128 of every coded token's logits vector (blake3_f32_bin16, src/main.rs:955-961), computed on the GPU by the
+        next encode / decode calls.  Returns the uint8 array [n_tokens][16] they fill; watch_digests(0) switches it off."""
+        if not n_tokens:
+            check(lib.cz_model_set_digest_out(self._h, None, 0))
+            self._digests = None
+            return None
+        self._digests = np.zeros((n_tokens, 16), np.uint8)
+        check(lib.cz_model_set_digest_out(self._h, self._digests.ctypes.data_as(_lib.u8p), n_tokens))
+        return self._digests
+
     def _schedule(self, n_tokens, seg_start, bos, context, reprime_interval, events, max_batch_tokens):
         s = _lib.Schedule()
         seg, segp = _u64(seg_start)

@@ -13,10 +13,11 @@
       2407-2660)                                                     + AGT2 gates), BLAKE3-128 ids, orig hash VERIFIED on decode
 """
 import json
+import sys
 
 import numpy as np
 
-from . import container
+from . import _lib, container
 
 
 class ByteTokenizer:
@@ -98,7 +99,19 @@ def compress(model, data: bytes, tokenizer=None, n_segments=1, bos=0, context=51
         ids = plan_rwkv_symbols(data, tokenizer, vocab) if isinstance(tokenizer, RwkvTokenizer) else tokenizer.encode_bytes(data)
     else:
         ids = tokenizer.encode_bytes(data)
-    pays, seg = model.encode(ids, n_segments=n_segments, bos=bos, context=context, reprime_interval=reprime_interval)
+    fields = dict(bos_token_id=bos, token_count=len(ids), orig_len_bytes=len(data), model_hash16=model_hash16,
+                  tokenizer_hash16=tokenizer_hash16, orig_hash16=container.blake3_16(data), context_window=context, vocab_size=vocab,
+                  reprime_interval=reprime_interval, reserved_flags=0)
+    try:
+        pays, seg = model.encode(ids, n_segments=n_segments, bos=bos, context=context, reprime_interval=reprime_interval)
+    except _lib.CzError as e:
+        if e.code != _lib.CZ_ERR_ZERO_WIDTH:
+            raise
+        # SmolLM coding has no probability floor (src/main.rs:2295): a token whose mass quantises to a zero-width interval cannot be
+        # coded -- the reference writes a corrupt stream there.  Every input must still round-trip: store the bytes
+        # uncoded under the STORED flag (the message names the offending token index for whoever wants to know why).
+        sys.stderr.write(f"candlezip_b200: {e}; writing a STORED container\n")
+        return container.write_container(dict(fields, reserved_flags=_lib.CZ_FLAG_STORED), model_repr, [bytes(data)])
     fields = dict(bos_token_id=bos, token_count=len(ids), orig_len_bytes=len(data), model_hash16=model_hash16,
                   tokenizer_hash16=tokenizer_hash16, orig_hash16=container.blake3_16(data), context_window=context, vocab_size=vocab,
                   reprime_interval=reprime_interval, reserved_flags=0)
@@ -110,6 +123,11 @@ def decompress(model, blob: bytes, tokenizer=None, verify=True) -> bytes:
     tokenizer = tokenizer or ByteTokenizer()
     f, _, gates, _, seg_tokens, pays = container.read_container(blob)
     n = int(f["token_count"])
+    if f["reserved_flags"] & _lib.CZ_FLAG_STORED:
+        data = b"".join(pays)
+        if len(data) != int(f["orig_len_bytes"]) or (verify and container.blake3_16(data) != f["orig_hash16"]):
+            raise ValueError("stored payload does not match the header")
+        return data
     if gates is not None:
         raise ValueError("gated containers are decoded through gate.events_from_records + Model.decode(events=...)")
     seg = np.concatenate([[0], np.cumsum(seg_tokens)]).astype(np.uint64) if seg_tokens is not None else np.array([0, n], np.uint64)

@@ -101,6 +101,10 @@ def read_container(blob: bytes):
                                        C.byref(cnt))
         n += k
         engine, seg_tokens = eng.value, st
+        if int(sb.sum()) != len(blob) - n:
+            raise ValueError(f"segment table declares {int(sb.sum())} payload bytes but {len(blob) - n} follow it")
+        if int(st.sum()) != int(h.token_count):
+            raise ValueError("segment table does not add up to token_count")
         payloads = []
         for b in sb:
             payloads.append(blob[n : n + int(b)])

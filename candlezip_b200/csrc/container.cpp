@@ -222,7 +222,7 @@ size_t cz_container_read_header(const uint8_t *buf, size_t len, cz_header_v2 *h,
   h->model_file_repr_len = get_u32(buf + n + 12);
   h->reprime_interval = get_u32(buf + n + 16);
   n += 20;
-  if (len < n + h->model_file_repr_len) return 0;
+  if (h->model_file_repr_len > len - n) return 0;  // (not `len < n + repr_len`: an untrusted length must not be added to an offset)
   if (repr_off) *repr_off = n;
   return n + h->model_file_repr_len;
 }
@@ -242,15 +242,18 @@ size_t cz_container_read_gates(const uint8_t *buf, size_t len, uint8_t *records,
   size_t k = get_var(buf + 4, len - 4, &cnt);
   if (!k) return 0;
   size_t n = 4 + k;
+  // `cnt` is an untrusted 64-bit varint: compare it against what is LEFT (n <= len here), never add it to an offset -- a count
+  // near 2^64 wraps `n + cnt` / `(cnt + 7) / 8` and would let the copy loops below run past the buffer
   if (!memcmp(buf, "AGT2", 4)) {  // src/main.rs:2472-2476
-    if (len < n + cnt) return 0;
+    if (cnt > len - n) return 0;
     for (uint64_t i = 0; i < cnt && i < cap; i++) records[i] = buf[n + i] & 0x1F;
     if (n_records) *n_records = (size_t)cnt;
     return n + (size_t)cnt;
   }
   if (!memcmp(buf, "AGTB", 4)) {  // legacy bit vector, src/main.rs:2477-2482: gate bit only, candidate 0 / budget 2 (2554)
-    const size_t nbytes = (size_t)((cnt + 7) / 8);
-    if (len < n + nbytes) return 0;
+    if (cnt / 8 > len - n) return 0;
+    const size_t nbytes = (size_t)(cnt / 8 + (cnt % 8 ? 1 : 0));
+    if (nbytes > len - n) return 0;
     for (uint64_t i = 0; i < cnt && i < cap; i++) {
       uint8_t g = (buf[n + i / 8] >> (i % 8)) & 1;
       records[i] = (uint8_t)(g | (0 << 1) | (2 << 3));
@@ -286,12 +289,16 @@ size_t cz_container_read_segments(const uint8_t *buf, size_t len, int *engine, u
   k += r;
   if (!(r = get_var(buf + k, len - k, &eng))) return 0;
   k += r;
+  if (n > (len - k) / 2) return 0;  // every entry takes at least two bytes: an untrusted count cannot exceed what is left
+  uint64_t total_bytes = 0;
   for (uint64_t i = 0; i < n; i++) {
     uint64_t a, b;
     if (!(r = get_var(buf + k, len - k, &a))) return 0;
     k += r;
     if (!(r = get_var(buf + k, len - k, &b))) return 0;
     k += r;
+    if (b > len || total_bytes > len - b) return 0;  // the segments' byte counts cannot add up to more than the file holds
+    total_bytes += b;
     if (i < cap) {
       if (seg_tokens) seg_tokens[i] = a;
       if (seg_bytes) seg_bytes[i] = b;

@@ -309,8 +309,9 @@ static int run_wave_trunk(cz_model *m, const Wave &w, const uint32_t *ids_dev, c
 
 // LM head + CDF op over the wave's logit columns, in sub-batches of ws.ld_sub columns.
 // syms_dev[j] is the symbol of column j; results go to lo_out/hi_out (OP_BOUNDS) or xe_out (OP_XE), indexed by column.
+// digest_first >= 0: the model has a digest sink and column j is coded token digest_first + j (f-4, digest_kernels.cu).
 static int run_wave_head(cz_model *m, size_t n_logit, int op, int mode, const uint32_t *syms_dev, uint32_t *lo_out, uint32_t *hi_out,
-                         double *xe_out, cudaStream_t st) {
+                         double *xe_out, cudaStream_t st, long long digest_first = -1) {
   CZ_TRY(ensure_logits(m, n_logit));
   Workspace &ws = m->ws;
   const int buf = 0;
@@ -321,6 +322,9 @@ static int run_wave_head(cz_model *m, size_t n_logit, int op, int mode, const ui
     CZ_TRY(launch_cdf_cols(m->ctx, op, mode, ws.logits[buf], (size_t)m->cfg.vocab, nc, ws.ld_sub, syms_dev + c0, nullptr,
                            lo_out ? lo_out + c0 : nullptr, hi_out ? hi_out + c0 : nullptr, xe_out ? xe_out + c0 : nullptr, st,
                            have_max ? ws.colmax : nullptr));
+    if (digest_first >= 0 && m->digest_host)
+      CZ_TRY(launch_logits_digest(m->ctx, ws.logits[buf], (size_t)m->cfg.vocab, nc, ws.ld_sub, m->sb[SB_CV].p, m->sb[SB_DIGEST].as<uint8_t>(),
+                                  (unsigned long long)digest_first + c0, nullptr, nullptr, nullptr, st));
   }
   return CZ_OK;
 }
@@ -342,6 +346,31 @@ static int check_schedule(const cz_schedule *s, size_t n_tokens) {
   if (s->reprime_interval == 0 || s->context == 0) {
     set_error("schedule: context and reprime_interval must be > 0");
     return CZ_ERR_INVALID;
+  }
+  return CZ_OK;
+}
+
+// Host-side id validation: every id that can reach the embedding table is checked BEFORE anything is launched.
+// The limit is the coded alphabet: vocab for SmolLM; vocab + 256 for RWKV-7, whose literal escapes (vocab .. vocab + 255,
+// src/main.rs:833-864) never step the model -- they are coded but filtered out of every prime / history (main.rs:1763-1765).
+static int check_ids(const uint32_t *ids, size_t n, uint32_t limit, const char *what) {
+  for (size_t i = 0; i < n; i++)
+    if (ids[i] >= limit) {
+      set_error(std::string(what) + ": id " + std::to_string(ids[i]) + " at index " + std::to_string(i) + " is out of range (< " +
+                std::to_string(limit) + ")");
+      return CZ_ERR_SYMBOL_RANGE;
+    }
+  return CZ_OK;
+}
+static uint32_t coded_limit(const cz_model *m) { return (uint32_t)m->cfg.vocab + (m->cfg.arch == CZ_ARCH_RWKV7 ? 256u : 0u); }
+static int check_schedule_ids(const cz_model *m, const cz_schedule *s) {
+  CZ_TRY(check_ids(&s->bos, 1, (uint32_t)m->cfg.vocab, "schedule bos"));
+  for (uint32_t e = 0; e < s->n_events; e++) {
+    if (s->events[e].prime_len && !s->events[e].prime) {
+      set_error("schedule: prime event without tokens");
+      return CZ_ERR_INVALID;
+    }
+    CZ_TRY(check_ids(s->events[e].prime, s->events[e].prime_len, coded_limit(m), "hint prime token"));
   }
   return CZ_OK;
 }
@@ -370,6 +399,7 @@ static int encode_core(cz_model *m, const uint32_t *ids_dev, const uint32_t *ids
           &d_raw = m->sb[SB_RAW];
   CZ_TRY(d_lo.reserve(n_tokens * 4, st));
   CZ_TRY(d_hi.reserve(n_tokens * 4, st));
+  CZ_TRY(digest_begin(m, n_tokens, 262144, st));
   // explicit prime token lists of the hint events
   std::vector<uint32_t> extra;
   std::vector<size_t> ev_off(sched->n_events + 1, 0);
@@ -392,7 +422,7 @@ static int encode_core(cz_model *m, const uint32_t *ids_dev, const uint32_t *ids
     CZ_TRY(d_src.reserve(w.n_rows() * 8, st));
     CZ_TRY(run_wave_trunk(m, w, ids_dev, d_extra.as<uint32_t>(), sched->bos, d_src.as<long long>(), st));
     CZ_TRY(run_wave_head(m, w.n_logit(), czk::OP_BOUNDS, coded_mode(m), ids_dev + wave_first, d_lo.as<uint32_t>() + wave_first,
-                         d_hi.as<uint32_t>() + wave_first, nullptr, st));
+                         d_hi.as<uint32_t>() + wave_first, nullptr, st, m->digest_host ? (long long)wave_first : -1));
     wave_first += w.n_logit();
     w.clear();
     t_wave0 = host_ms();
@@ -466,6 +496,7 @@ static int encode_core(cz_model *m, const uint32_t *ids_dev, const uint32_t *ids
   CZ_CUDA_TRY(cudaMemcpyAsync(d_dst_off, seg_off_host, (S + 1) * 8, cudaMemcpyHostToDevice, st));
   CZ_LAUNCH(ctx, CZ_K_CODER, (czk::compact_payload_kernel<<<S, 128, 0, st>>>(d_raw.as<uint8_t>(), d_raw_off, d_dst_off, out_dev)));
   CZ_CHECK_LAUNCH();
+  CZ_TRY(digest_end(m, n_tokens, st));
   const double t_pre_sync = host_ms();
   CZ_CUDA_TRY(cudaStreamSynchronize(st));
   if (dbg)
@@ -505,6 +536,7 @@ static int session_forward(cz_session *s, const uint32_t *tok, size_t n, float *
     s->index_pos = reset ? n : s->index_pos + n;
     return CZ_OK;
   }
+  CZ_TRY(check_ids(tok, n, (uint32_t)m->cfg.vocab, "session token"));
   if (s->index_pos + n > (size_t)s->max_pos) {
     set_error("session: KV capacity exceeded");
     return CZ_ERR_INVALID;
@@ -545,7 +577,7 @@ static int session_forward(cz_session *s, const uint32_t *tok, size_t n, float *
   CZ_TRY(final_norm_gather(m, 1, st));
   CZ_TRY(lm_head(m, 0, 1, s->logits_dev, 4, st));
   CZ_CUDA_TRY(cudaMemcpy2DAsync(logits_out, 4, s->logits_dev, 16, 4, (size_t)m->cfg.vocab, cudaMemcpyDeviceToHost, st));
-  CZ_CUDA_TRY(cudaStreamSynchronize(st));
+  CZ_TRY(fetch_device_status(ctx, nullptr, nullptr));
   s->index_pos += n;
   return CZ_OK;
 }
@@ -605,6 +637,7 @@ int cz_encode_dev(cz_model *m, const uint32_t *ids_dev, size_t n_tokens, const c
   if (!m || !seg_off_host) return CZ_ERR_INVALID;
   CZ_TRY(require_device(m->ctx));
   CZ_TRY(check_schedule(sched, n_tokens));
+  CZ_TRY(check_schedule_ids(m, sched));  // the coded ids live on the device: the kernels check those (embed / CDF symbol range)
   CZ_TRY(model_finalize(m));
   CZ_CUDA_TRY(cudaSetDevice(m->ctx->device));
   if (n_tokens == 0) {
@@ -617,6 +650,8 @@ int cz_encode(cz_model *m, const uint32_t *ids, size_t n_tokens, const cz_schedu
   if (!m || !out || !out->data || !out->seg_off || (n_tokens && !ids)) return CZ_ERR_INVALID;
   CZ_TRY(require_device(m->ctx));
   CZ_TRY(check_schedule(sched, n_tokens));
+  CZ_TRY(check_schedule_ids(m, sched));
+  CZ_TRY(check_ids(ids, n_tokens, coded_limit(m), "coded token"));
   CZ_TRY(model_finalize(m));
   cz_ctx *ctx = m->ctx;
   CZ_CUDA_TRY(cudaSetDevice(ctx->device));
@@ -642,6 +677,7 @@ int cz_decode(cz_model *m, const uint8_t *payload, const uint64_t *seg_off, size
   if (!m || !payload || !seg_off || (n_tokens && !ids_out)) return CZ_ERR_INVALID;
   CZ_TRY(require_device(m->ctx));
   CZ_TRY(check_schedule(sched, n_tokens));
+  CZ_TRY(check_schedule_ids(m, sched));
   CZ_TRY(model_finalize(m));
   if (n_tokens == 0) return CZ_OK;
   cz_ctx *ctx = m->ctx;
@@ -676,6 +712,7 @@ int cz_decode(cz_model *m, const uint8_t *payload, const uint64_t *seg_off, size
   CZ_TRY(d_k.reserve(L * S * max_pos * kvd * 2, st));
   CZ_TRY(d_v.reserve(L * S * max_pos * kvd * 2, st));
   CZ_TRY(d_logits.reserve((size_t)c.vocab * S_pad * 4, st));
+  CZ_TRY(digest_begin(m, n_tokens, S, st));
   CZ_CUDA_TRY(cudaMemcpyAsync(d_pay.p, payload, pay_total, cudaMemcpyHostToDevice, st));
   CZ_CUDA_TRY(cudaMemcpyAsync(d_off.p, seg_off, (S + 1) * 8, cudaMemcpyHostToDevice, st));
   CZ_CUDA_TRY(cudaMemcpyAsync(d_start.p, sched->seg_start, (S + 1) * 8, cudaMemcpyHostToDevice, st));
@@ -789,6 +826,9 @@ int cz_decode(cz_model *m, const uint8_t *payload, const uint64_t *seg_off, size
     // sequence of ~250 launches is captured ONCE per chunk into a CUDA graph and replayed (the eager loop is
     // launch-bound: ~15 us of host work per launch against ~2 us of device work).
     auto decode_syms = [&]() -> int {
+      if (m->digest_host)  // f-4: digest of the logits each live stream is about to decode from, at index seg_start[g] + ctr[0]
+        CZ_TRY(launch_logits_digest(ctx, d_logits.as<float>(), (size_t)c.vocab, (size_t)n_live, S_pad, m->sb[SB_CV].p,
+                                    m->sb[SB_DIGEST].as<uint8_t>(), 0, nullptr, d_start.as<uint64_t>(), d_ctr, st));
       return launch_decode_step(ctx, coded_mode(m), d_logits.as<float>(), c.vocab, S_pad, n_live, d_pay.as<uint8_t>(), d_off.as<uint64_t>(),
                                 d_start.as<uint64_t>(), 0, d_state.p, d_ids.as<uint32_t>(), ws.tok, have_max ? ws.colmax : nullptr, st, d_ctr);
     };
@@ -842,6 +882,7 @@ int cz_decode(cz_model *m, const uint8_t *payload, const uint64_t *seg_off, size
     CZ_TRY(fetch_device_status(ctx, nullptr, nullptr));
   }
   CZ_CUDA_TRY(cudaMemcpyAsync(ids_out, d_ids.p, n_tokens * 4, cudaMemcpyDeviceToHost, st));
+  CZ_TRY(digest_end(m, n_tokens, st));
   CZ_CUDA_TRY(cudaStreamSynchronize(st));
   return CZ_OK;
 }
@@ -855,6 +896,11 @@ int cz_xe_bits(cz_model *m, const cz_xe_job *jobs, size_t n_jobs, double *bits_o
   cz_ctx *ctx = m->ctx;
   cudaStream_t st = ctx->stream;
   CZ_CUDA_TRY(cudaSetDevice(ctx->device));
+  for (size_t j = 0; j < n_jobs; j++) {
+    if ((jobs[j].prime_len && !jobs[j].prime) || (jobs[j].n_targets && !jobs[j].targets)) return CZ_ERR_INVALID;
+    CZ_TRY(check_ids(jobs[j].prime, jobs[j].prime_len, coded_limit(m), "xe prime token"));
+    CZ_TRY(check_ids(jobs[j].targets, jobs[j].n_targets, coded_limit(m), "xe target"));
+  }
   if (m->cfg.arch == CZ_ARCH_RWKV7) return rwkv_xe_bits(m, jobs, n_jobs, bits_out);
   // all tokens go to the `extra` buffer: [prime_0 | targets_0 | prime_1 | targets_1 | ...]; a parallel buffer holds
   // the targets contiguously in job order so that column j's symbol is tgt[j]
@@ -926,6 +972,9 @@ int cz_chunk_logits(cz_model *m, const uint32_t *prime, size_t prime_len, const 
   cz_ctx *ctx = m->ctx;
   cudaStream_t st = ctx->stream;
   CZ_CUDA_TRY(cudaSetDevice(ctx->device));
+  if (!targets) return CZ_ERR_INVALID;
+  CZ_TRY(check_ids(prime, prime_len, coded_limit(m), "chunk prime token"));
+  CZ_TRY(check_ids(targets, n_targets, coded_limit(m), "chunk target"));
   if (m->cfg.arch == CZ_ARCH_RWKV7) return rwkv_chunk_logits(m, prime, prime_len, targets, n_targets, logits_out);
   std::vector<uint32_t> extra(prime, prime + prime_len);
   if (n_targets > 1) extra.insert(extra.end(), targets, targets + n_targets - 1);
@@ -951,7 +1000,7 @@ int cz_chunk_logits(cz_model *m, const uint32_t *prime, size_t prime_len, const 
     for (size_t j = 0; j < nc; j++)
       for (size_t v = 0; v < V; v++) logits_out[(c0 + j) * V + v] = tmp[v * ld_c + j];
   }
-  return CZ_OK;
+  return fetch_device_status(ctx, nullptr, nullptr);
 }
 
 }  // extern "C"

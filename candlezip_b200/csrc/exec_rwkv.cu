@@ -119,6 +119,7 @@ struct RwOut {
   uint32_t *lo = nullptr, *hi = nullptr;
   double *xe = nullptr;
   float *logits_host = nullptr;  // test hook: [n_cols][V] row-major on the host (single unit)
+  bool digest = false;           // f-4: hash every column's logits into the model's digest buffer at its global coded index
 };
 
 static int rwkv_run_units(cz_model *m, std::vector<RwUnit> &units, const uint32_t *ids_dev, const uint32_t *extra_dev, uint32_t bos,
@@ -232,6 +233,9 @@ static int rwkv_run_units(cz_model *m, std::vector<RwUnit> &units, const uint32_
       CZ_TRY(launch_cdf_cols(ctx, o.op, CZ_CDF_RWKV_LITERALS, ws.logits[0], V, nc, ws.ld_sub, d_syms.as<uint32_t>() + c0, nullptr,
                              d_lo.as<uint32_t>() + c0, d_hi.as<uint32_t>() + c0, d_xe.as<double>() + c0, st,
                              have_max ? ws.colmax : nullptr));
+      if (o.digest)
+        CZ_TRY(launch_logits_digest(ctx, ws.logits[0], V, nc, ws.ld_sub, m->sb[SB_CV].p, m->sb[SB_DIGEST].as<uint8_t>(), 0,
+                                    d_oidx.as<unsigned long long>() + c0, nullptr, nullptr, st));
     }
     if (o.op == czk::OP_XE)
       CZ_LAUNCH(ctx, CZ_K_OTHER,
@@ -296,6 +300,7 @@ int rwkv_encode_bounds(cz_model *m, const uint32_t *ids_dev, const uint32_t *ids
   o.col_sym = ids_dev;
   o.lo = lo_dev;
   o.hi = hi_dev;
+  o.digest = m->digest_host != nullptr;  // (encode_core reserved the buffers: digest_begin)
   return rwkv_run_units(m, units, ids_dev, extra_dev, sched->bos, o, sched->max_batch_tokens, st);
 }
 

@@ -10,11 +10,22 @@
 
 namespace czk {
 
+// A token id >= vocab never indexes the table: it sets bit 1 of the ctx status word (-> CZ_ERR_SYMBOL_RANGE when the call
+// collects its status) and row 0 is read instead.  Callers validate host-side ids before launching; this is the second line
+// of defence for ids that only ever exist on the device (cz_encode_dev) and for anything a caller missed.
+__device__ __forceinline__ uint32_t checked_token(const uint32_t *__restrict__ tok, int row, uint32_t vocab, int *__restrict__ err,
+                                                  bool reporter) {
+  const uint32_t t = tok[row];
+  if (t < vocab) return t;
+  if (reporter && err) atomicOr(err, 2);
+  return 0u;
+}
+
 __global__ void embed_kernel(const __nv_bfloat16 *__restrict__ table, const uint32_t *__restrict__ tok, float *__restrict__ x,
-                             int n_rows, int d) {
+                             int n_rows, int d, uint32_t vocab, int *__restrict__ err) {
   const int row = blockIdx.x;
   if (row >= n_rows) return;
-  const __nv_bfloat16 *src = table + (size_t)tok[row] * d;
+  const __nv_bfloat16 *src = table + (size_t)checked_token(tok, row, vocab, err, threadIdx.x == 0) * d;
   float *dst = x + (size_t)row * d;
   for (int i = threadIdx.x; i < d; i += blockDim.x) dst[i] = __bfloat162float(src[i]);
 }
@@ -23,11 +34,12 @@ __global__ void embed_kernel(const __nv_bfloat16 *__restrict__ table, const uint
 // ssq[row][0] = sum of x^2 (fixed order: per-lane strided partials, then an xor tree), ssq[row][1..n_part) = 0.  One warp per row.
 __global__ void __launch_bounds__(128) embed_norm_kernel(const __nv_bfloat16 *__restrict__ table, const uint32_t *__restrict__ tok,
                                                          const float *__restrict__ w, float *__restrict__ x, __nv_bfloat16 *__restrict__ xb,
-                                                         float *__restrict__ ssq, int n_rows, int d, int n_part) {
+                                                         float *__restrict__ ssq, int n_rows, int d, int n_part, uint32_t vocab,
+                                                         int *__restrict__ err) {
   const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= n_rows) return;
-  const __nv_bfloat16 *src = table + (size_t)tok[row] * d;
+  const __nv_bfloat16 *src = table + (size_t)checked_token(tok, row, vocab, err, lane == 0) * d;
   float *dst = x + (size_t)row * d;
   __nv_bfloat16 *db = xb + (size_t)row * d;
   float ss = 0.f;
@@ -208,22 +220,23 @@ void llama_kernels_set_carveout() {
   prefer_max_smem(czk::rope_split_kernel);
 }
 
-int launch_embed(cz_ctx *ctx, const __nv_bfloat16 *table, const uint32_t *tok, float *x, int n_rows, int d, cudaStream_t st) {
+int launch_embed(cz_ctx *ctx, const __nv_bfloat16 *table, const uint32_t *tok, float *x, int n_rows, int d, int vocab, cudaStream_t st) {
   if (n_rows == 0) return CZ_OK;
-  CZ_LAUNCH(ctx, CZ_K_ELEMWISE, (czk::embed_kernel<<<n_rows, 128, 0, st>>>(table, tok, x, n_rows, d)));
+  CZ_LAUNCH(ctx, CZ_K_ELEMWISE, (czk::embed_kernel<<<n_rows, 128, 0, st>>>(table, tok, x, n_rows, d, (uint32_t)vocab, ctx->err_flag_dev)));
   CZ_CHECK_LAUNCH();
   return CZ_OK;
 }
 
 int launch_embed_norm(cz_ctx *ctx, const __nv_bfloat16 *table, const uint32_t *tok, const float *w, float *x, __nv_bfloat16 *xb,
-                      float *ssq, int n_rows, int d, int n_part, cudaStream_t st) {
+                      float *ssq, int n_rows, int d, int n_part, int vocab, cudaStream_t st) {
   if (n_rows == 0) return CZ_OK;
   if (n_part < 1 || n_part > 32) {
     set_error("embed_norm: 1 <= n_part <= 32");
     return CZ_ERR_INVALID;
   }
   CZ_LAUNCH(ctx, CZ_K_ELEMWISE,
-            (czk::embed_norm_kernel<<<(unsigned)ceil_div(n_rows, 4), 128, 0, st>>>(table, tok, w, x, xb, ssq, n_rows, d, n_part)));
+            (czk::embed_norm_kernel<<<(unsigned)ceil_div(n_rows, 4), 128, 0, st>>>(table, tok, w, x, xb, ssq, n_rows, d, n_part, (uint32_t)vocab,
+                                                                                   ctx->err_flag_dev)));
   CZ_CHECK_LAUNCH();
   return CZ_OK;
 }

@@ -4,9 +4,10 @@
 #include <stdint.h>
 struct cz_ctx;
 namespace cz {
-int launch_embed(cz_ctx *ctx, const __nv_bfloat16 *table, const uint32_t *tok, float *x, int n_rows, int d, cudaStream_t st);
+// token ids >= vocab read row 0 and raise bit 1 of ctx->err_flag_dev (CZ_ERR_SYMBOL_RANGE)
+int launch_embed(cz_ctx *ctx, const __nv_bfloat16 *table, const uint32_t *tok, float *x, int n_rows, int d, int vocab, cudaStream_t st);
 int launch_embed_norm(cz_ctx *ctx, const __nv_bfloat16 *table, const uint32_t *tok, const float *w, float *x, __nv_bfloat16 *xb,
-                      float *ssq, int n_rows, int d, int n_part, cudaStream_t st);
+                      float *ssq, int n_rows, int d, int n_part, int vocab, cudaStream_t st);
 int launch_rmsnorm(cz_ctx *ctx, const float *x, const float *w, const int *rows, __nv_bfloat16 *y, int n_out, int d, float eps,
                    cudaStream_t st);
 int launch_rope_split(cz_ctx *ctx, const float *qkv, const int *pos, const int *kv_base, const float *cos_tab, const float *sin_tab,

@@ -57,6 +57,7 @@ struct GrowBuf {
 };
 enum { SB_LO = 0, SB_HI, SB_SRC, SB_EXTRA, SB_LANE, SB_RAW, SB_IDS, SB_OUT, SB_PAY, SB_OFF, SB_START, SB_STATE, SB_DIDS, SB_K, SB_V,
        SB_LOGITS, SB_KVB, SB_TGT, SB_BITS, SB_JOFF, SB_XOUT, SB_RW_OIDX, SB_RW_SYMS, SB_RW_LO, SB_RW_HI, SB_RW_XE, SB_RW_FRESH,
+       SB_DIGEST, SB_CV,
        SB_COUNT };
 
 // ---- RWKV-7 (rwkv7.cu) ----
@@ -116,6 +117,10 @@ struct cz_model {
   bool attn_tc = false;  // tcgen05 attention kernel (attn_tc.cu); else the mma.sync kernel (attn_mma.cu)
   int attn_tile = 64;    // query positions per attention tile (128 with attn_tc)
   Workspace ws;
+  // f-4 watchdog digests (digest_kernels.cu): when set, every coded token's logits vector is hashed on the device during
+  // cz_encode / cz_encode_dev / cz_decode and the 16-byte digests are copied here (index = global coded index)
+  uint8_t *digest_host = nullptr;
+  size_t digest_cap = 0;
 };
 
 namespace cz {
@@ -147,6 +152,16 @@ int final_norm_gather(cz_model *m, int n_logit, cudaStream_t st);
 int lm_head(cz_model *m, int col0, int n_cols, float *logits, size_t ld, cudaStream_t st, int *colmax = nullptr,
             bool *colmax_valid = nullptr);
 
+
+// ---- f-4 logits digests (digest_kernels.cu) ----
+size_t digest_scratch_bytes(size_t V, size_t n_cols);
+int launch_logits_digest(cz_ctx *ctx, const float *logits, size_t V, size_t n_cols, size_t ld, void *scratch, uint8_t *out,
+                         unsigned long long out_first, const unsigned long long *out_index, const uint64_t *seg_start,
+                         const unsigned long long *ctr, cudaStream_t st);
+// reserves the device digest buffer (n_tokens x 16 B) + hash scratch when the model has a digest sink; no-op otherwise
+int digest_begin(cz_model *m, size_t n_tokens, size_t max_cols, cudaStream_t st);
+// copies n_tokens digests to the sink (async on st; the caller synchronises)
+int digest_end(cz_model *m, size_t n_tokens, cudaStream_t st);
 
 // ---- RWKV-7 ----
 int rwkv_finalize(cz_model *m);

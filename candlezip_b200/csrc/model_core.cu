@@ -286,9 +286,9 @@ int forward_trunk(cz_model *m, int n_rows, const KvView &kv, cudaStream_t st) {
   NormExt consume{};
   if (fused_norm) {
     consume.ssq_in = w.ssq; consume.n_part_in = n_part; consume.inv_d = 1.0f / (float)D; consume.eps = c.norm_eps;
-    CZ_TRY(launch_embed_norm(ctx, m->embed, w.tok, m->norms, w.x, w.xn, w.ssq, n_rows, D, n_part, st));
+    CZ_TRY(launch_embed_norm(ctx, m->embed, w.tok, m->norms, w.x, w.xn, w.ssq, n_rows, D, n_part, c.vocab, st));
   } else {
-    CZ_TRY(launch_embed(ctx, m->embed, w.tok, w.x, n_rows, D, st));
+    CZ_TRY(launch_embed(ctx, m->embed, w.tok, w.x, n_rows, D, c.vocab, st));
   }
   for (int l = 0; l < L; l++) {
     const float *n1 = m->norms + (size_t)(2 * l) * D, *n2 = m->norms + (size_t)(2 * l + 1) * D;

@@ -444,7 +444,7 @@ int rwkv_forward(cz_model *m, int n_rows, int n_streams, RwkvState &stt, bool in
   const size_t cap = stt.cap;
   const int pin = stt.cur, pout = in_place ? stt.cur : stt.cur ^ 1;
   const unsigned g4 = (unsigned)ceil_div(n_rows, 4);
-  CZ_TRY(launch_embed(ctx, m->embed, ws.tok, ws.x, n_rows, C, st));
+  CZ_TRY(launch_embed(ctx, m->embed, ws.tok, ws.x, n_rows, C, c.vocab, st));
   for (int l = 0; l < L; l++) {
     const float *v = m->rw.vecs + (size_t)l * RV_COUNT * C;
     const RwkvLayerW &W = m->rw.layers[l];

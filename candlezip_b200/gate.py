@@ -143,3 +143,117 @@ def scan_encode(model, ids, agent_texts, tokenize_hint, agent_chunk, n_segments=
     records, events, rows = decide(plan, bits, look, kw.get("thr_abs_bits", 0.0), kw.get("thr_pct", 0.0))
     pays, seg = model.encode(ids, n_segments=1, bos=kw.get("bos", 0), events=events or None)
     return pays, seg, records, rows, events
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Replay of a finished run (BASELINE config 4): `--reuse-scan-dir` (src/main.rs:1966-1978) loads agent_cache.jsonl and
+# proof.csv (loaders: src/main.rs:1152-1195) and never calls the agent.
+# ---------------------------------------------------------------------------------------------------------------------
+PROOF_HEADER = ["file", "chunk_index", "start_token", "end_token", "agent_text_len", "agent_duration_ms", "cross_entropy_baseline_bits",
+                "cross_entropy_conditioned_bits", "bits_saved", "percent_saved", "agent_calls", "gate", "candidate_id", "budget_id",
+                # SIMDL v1.1 columns (src/main.rs:1901-1908)
+                "gate_bits", "price_transcript_bits", "price_pointer_bits", "tool_id_best", "tool_snapshot_id", "args_hash", "output_hash",
+                "domain", "agent_id", "toolset_id", "run_id", "chunk_id"]
+
+
+def load_replay(src):
+    """src: a run directory holding agent_cache.jsonl + proof.csv (the reference's own layout), or the dict form of the
+    committed fixtures (tests/golden/corpus.py::replay).  Returns (texts, calls, decisions, proof_rows):
+      texts[chunk_index] = agent text, calls[chunk_index] = agent_calls        (load_cached_agent_results, main.rs:1152-1175)
+      decisions[chunk_index] = (gate, candidate_id, budget_id)                   (load_gate_decisions_from_csv, main.rs:1177-1195:
+                                                                                  columns 1, 11, 12, 13 of rows with >= 13 fields)
+      proof_rows = the ledger rows as lists of strings (header excluded)"""
+    import csv
+    import io
+    import json
+    import os
+
+    if isinstance(src, dict):
+        cache = {int(k): v for k, v in src["agent_cache"].items()}
+        rows = [list(r) for r in src["proof_rows"]]
+    else:
+        cache = {}
+        p = os.path.join(src, "agent_cache.jsonl")
+        if os.path.exists(p):
+            for line in open(p, encoding="utf-8"):
+                if not line.strip():
+                    continue
+                try:
+                    v = json.loads(line)
+                except ValueError:
+                    continue
+                if isinstance(v.get("chunk_index"), int) and isinstance(v.get("agent_text"), str) and isinstance(v.get("agent_calls"), int):
+                    cache[v["chunk_index"]] = {"agent_text": v["agent_text"], "agent_calls": v["agent_calls"]}  # later lines win
+        rows = []
+        p = os.path.join(src, "proof.csv")
+        if os.path.exists(p):
+            rows = list(csv.reader(io.StringIO(open(p, encoding="utf-8", newline="").read())))[1:]
+    texts = {k: v["agent_text"] for k, v in cache.items()}
+    calls = {k: int(v["agent_calls"]) for k, v in cache.items()}
+    decisions = {}
+    for r in rows:
+        if len(r) >= 13:  # the reference splits on ',' and needs parts[13]; a text-free numeric row never contains a quoted comma
+            try:
+                decisions[int(r[1])] = (int(r[11]), int(r[12]), int(r[13]))
+            except (ValueError, IndexError):
+                pass
+    return texts, calls, decisions, rows
+
+
+def events_from_decisions(ids, agent_texts, decisions, tokenize_hint, agent_chunk, scan_lookahead=512, scan_max_hint_tokens=512,
+                          max_ctx=MAX_CTX_SMOLLM):
+    """Reuse-mode encode (src/main.rs:2221-2268) and decode (2545-2614): no XE evaluation, the cached (gate, candidate, budget) of
+    each boundary is applied as-is; a gated boundary without a cached agent text primes with the history tail alone.  Returns
+    (records, events): AGT2 record bytes for every boundary and the cz_prime_event tuples."""
+    n = len(ids)
+    bud = budgets(max_ctx)
+    records, events = [], []
+    boundary = agent_chunk
+    while boundary <= n:
+        i = boundary - 1
+        chunk_index = boundary // agent_chunk
+        boundary += agent_chunk
+        gate, cid, bid = decisions.get(chunk_index, (0, 0, 2))
+        records.append((gate & 1) | ((cid & 3) << 1) | ((bid & 3) << 3))
+        if gate == 1:
+            cand = build_candidates(agent_texts.get(chunk_index, ""))[cid]
+            hint = np.asarray(tokenize_hint(cand, scan_max_hint_tokens), np.uint32)[: bud[bid]]
+            events.append((i, hint, i + scan_lookahead, min(max(max_ctx - bud[bid], 0), i + 1)))
+    return records, events
+
+
+def ledger_rows(rows, input_file, agent_texts, agent_calls=None, agent_chunk=512, domain="unknown", agent_id="replay", policy="aligned",
+                run_id="replay", price_transcript_bits=None, doc_size_bytes=0):
+    """proof.csv rows in the reference's format (src/main.rs:2177-2202): the 26 columns of PROOF_HEADER, numbers formatted
+    with six decimals exactly as `format!("{:.6}")` does.  `rows` are decide()'s dicts.  price_transcript_bits(text) -> bits
+    (the reference compresses the agent text with zstd level 19, main.rs:1031-1035; zstd is not in this image, so the column is 0
+    unless a callable is given); the pointer price is ceil(log2(n_docs)) + ceil(log2(doc bytes)) + ceil(log2(1024)) (1038-1053)."""
+    import math
+    import os
+
+    from . import container
+
+    stem = os.path.splitext(os.path.basename(input_file))[0]
+    out = []
+    for r in rows:
+        ci, i = r["chunk_index"], r["i"]
+        text = agent_texts.get(ci, "")
+        tb = text.encode("utf-8")
+        h = container.blake3_16(tb).hex()
+        ptr = (1 + (1 if doc_size_bytes <= 1 else math.ceil(math.log2(doc_size_bytes))) + 10) if text else 0
+        out.append([input_file, str(ci), str(max(0, i - agent_chunk)), str(i), str(len(tb)), "0", f"{r['baseline_bits']:.6f}",
+                    f"{r['conditioned_bits']:.6f}", f"{r['bits_saved']:.6f}", f"{r['percent_saved'] * 100.0:.6f}",
+                    str((agent_calls or {}).get(ci, 0)), str(r["gate"]), str(r["candidate_id"]), str(r["budget_id"]),
+                    "5" if r["gate"] else "0", str(price_transcript_bits(text) if (price_transcript_bits and text) else 0), str(ptr),
+                    f"cand_{r['candidate_id']}_bud_{r['budget_id']}" if r["gate"] else "none", f"snap_{ci}", h, h, domain, agent_id,
+                    f"policy_{policy}", run_id, f"{stem}:{ci}"])
+    return out
+
+
+def write_proof_csv(path, ledger):
+    import csv
+
+    with open(path, "w", newline="", encoding="utf-8") as f:
+        w = csv.writer(f, lineterminator="\n")
+        w.writerow(PROOF_HEADER)
+        w.writerows(ledger)

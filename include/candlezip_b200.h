@@ -186,13 +186,29 @@ typedef struct {
   uint64_t *seg_off;         /* [n_segments+1] filled: payload of segment g is data[seg_off[g] .. seg_off[g+1]) */
 } cz_bitstreams;
 
-/* coded tokens: ids[0..n_tokens) (BOS is NOT included; every segment is started from sched->bos) */
+/* coded tokens: ids[0..n_tokens) (BOS is NOT included; every segment is started from sched->bos).
+ * Every id is validated against the coded alphabet (vocab; vocab + 256 with RWKV-7's literal escapes) before anything is launched:
+ * CZ_ERR_SYMBOL_RANGE names the offending index.  sched->bos and the hint-prime tokens are validated the same way. */
 int cz_encode(cz_model *m, const uint32_t *ids, size_t n_tokens, const cz_schedule *sched, cz_bitstreams *out);
+/* Lock-step batched decoder: all segments advance one token per step, column g of the logits batch being segment g.
+ * PRECONDITION: segment lengths must be NON-INCREASING (longest first; cz_schedule.seg_start as produced by an even split with
+ * the remainder on the first segments) so that the live streams are always a prefix of the batch; otherwise CZ_ERR_UNSUPPORTED.
+ * Memory: the KV arenas are allocated up front, 2 * n_layers * n_segments * max_pos * n_kv_heads * 64 bf16 elements with
+ * max_pos = 1024 at --context 512 / --reprime-interval 512 (SmolLM-135M: 23.6 MB per segment, 48 GB at 2048 segments);
+ * CZ_ERR_CUDA (out of memory) if that does not fit. */
 int cz_decode(cz_model *m, const uint8_t *payload, const uint64_t *seg_off, size_t n_tokens,
               const cz_schedule *sched, uint32_t *ids_out);
-/* device-resident variant of the encode step used by bench.py for the kernel-only number: ids already in HBM */
+/* device-resident variant of the encode step used by bench.py for the kernel-only number: ids already in HBM (an id outside
+ * the coded alphabet is caught on the device: the call returns CZ_ERR_SYMBOL_RANGE and nothing is read out of bounds) */
 int cz_encode_dev(cz_model *m, const uint32_t *ids_dev, size_t n_tokens, const cz_schedule *sched,
                   uint8_t *out_dev, size_t out_cap, uint64_t *seg_off_host);
+
+/* f-4 watchdog digests: blake3_f32_bin16 (src/main.rs:955-961; enabled there by CANDLEZIP_WATCHDOG_DIGEST, :1085-1090; one
+ * `pdf_digest` per encode / decode step, :2328-2342, :2629-2647).  With a sink set, cz_encode / cz_encode_dev / cz_decode hash
+ * every coded token's logits vector (the V f32 values, little-endian) ON THE DEVICE next to the CDF pass and copy the 16-byte
+ * BLAKE3-128 digests to digests_out[i * 16 .. i * 16 + 16), i = global coded index.  Encode and decode digests of a stream are
+ * equal byte for byte (decode safety), whatever the wave size, batch size or GPU count.  NULL disables.  (RWKV-7: encode only.) */
+int cz_model_set_digest_out(cz_model *m, uint8_t *digests_out, size_t cap_tokens);
 
 typedef struct {
   const uint32_t *prime;     /* tail(history, 511-|hint|) ++ hint, built by the caller or cz_xe_make_prime */
@@ -226,6 +242,9 @@ typedef struct {
 #define CZ_FLAG_AGENT_MOCK (1u << 1)
 #define CZ_FLAG_AGENT_GATES (1u << 2)
 #define CZ_FLAG_SEGMENTS (1u << 8) /* extension: a "SEG1" table follows the gates section */
+#define CZ_FLAG_STORED (1u << 9)   /* extension: the payload is the original bytes, uncoded.  Written by the file-level compress()
+                                      when the SmolLM coder meets a symbol of mass < 2^-30 (CZ_ERR_ZERO_WIDTH: softmax_pdf has no
+                                      floor, src/main.rs:2295; the reference would emit a corrupt stream there) */
 
 size_t cz_container_header_size(const cz_header_v2 *h);
 /* writes header (+repr); returns bytes written or 0 if cap is too small */
