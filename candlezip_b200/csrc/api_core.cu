@@ -57,14 +57,14 @@ int fetch_device_status(cz_ctx *ctx, unsigned long long *err_index_dev, unsigned
   CZ_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
   if (flag) CZ_CUDA_TRY(cudaMemsetAsync(ctx->err_flag_dev, 0, sizeof(int), ctx->stream));
   if (err_index_out) *err_index_out = idx;
+  if (flag & 2) {  // (checked before the zero-width bit: an out-of-range symbol also yields an empty interval)
+    set_error("symbol id out of range for the coded alphabet");
+    return CZ_ERR_SYMBOL_RANGE;
+  }
   if (flag & 4) {
     set_error("zero-width coding interval (c_lo == c_hi) at coded index " + std::to_string(idx) +
               ": symbol mass < 2^-30; the reference would corrupt the stream here");
     return CZ_ERR_ZERO_WIDTH;
-  }
-  if (flag & 2) {
-    set_error("symbol id out of range for the coded alphabet");
-    return CZ_ERR_SYMBOL_RANGE;
   }
   if (flag & 1) {
     set_error("NaN in logits");
@@ -128,6 +128,7 @@ void cz_shutdown(cz_ctx *ctx) {
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     if (ctx->scratch) cudaFree(ctx->scratch);
+    if (ctx->cdf_stats) cudaFree(ctx->cdf_stats);
     if (ctx->err_flag_dev) cudaFree(ctx->err_flag_dev);
     if (ctx->prof_ev0) cudaEventDestroy(ctx->prof_ev0);
     if (ctx->prof_ev1) cudaEventDestroy(ctx->prof_ev1);

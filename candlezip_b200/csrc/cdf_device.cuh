@@ -21,6 +21,15 @@ struct ExpTab {
   const uint32_t *lo;
   const uint32_t *hi;
   int lane;
+  __device__ __forceinline__ uint64_t load(uint32_t entry) const {
+    const int idx = ((int)entry << 5) + lane;
+    return ((uint64_t)hi[idx] << 32) | (uint64_t)lo[idx];
+  }
+};
+// the same table as 64-bit words [entry][lane] (cdf_fast.cuh)
+struct ExpTab64 {
+  const uint64_t *t;  // base + lane
+  __device__ __forceinline__ uint64_t load(uint32_t entry) const { return t[entry << 5]; }
 };
 
 __device__ __forceinline__ void exp_tab_init(uint32_t *s_lo, uint32_t *s_hi) {
@@ -36,7 +45,8 @@ __device__ __forceinline__ void exp_tab_init(uint32_t *s_lo, uint32_t *s_hi) {
 // early-out costs a BSSY/BSYNC pair per element in the unrolled column walk, profiles/ncu_summary_r01.md).
 // DOMAIN: x <= 0 or NaN.  Every caller passes logit - max(logits) (src/main.rs:786-789), so glibc's overflow branch
 // (x > 88.72 -> +inf) can never be taken and is not evaluated; +inf - +inf = NaN propagates through the polynomial.
-__device__ __forceinline__ float cz_expf(float x, const ExpTab &tab) {
+template <class Tab>
+__device__ __forceinline__ float cz_expf(float x, const Tab &tab) {
   const double inv_ln2_n = 0x1.71547652b82fep+0 * 32;
   const double shift = 0x1.8p+52;
   const double c0 = 0x1.c6af84b912394p-5 / 32 / 32 / 32;
@@ -48,8 +58,7 @@ __device__ __forceinline__ float cz_expf(float x, const ExpTab &tab) {
   uint64_t ki = (uint64_t)__double_as_longlong(kd);
   kd = __dsub_rn(kd, shift);
   double r = __fma_rn(inv_ln2_n, xd, -kd);
-  int idx = ((int)(ki & 31) << 5) + tab.lane;
-  uint64_t t = ((uint64_t)tab.hi[idx] << 32) | (uint64_t)tab.lo[idx];
+  uint64_t t = tab.load((uint32_t)(ki & 31));
   t += ki << 47;
   double s = __longlong_as_double((long long)t);
   double p = __fma_rn(c0, r, c1);

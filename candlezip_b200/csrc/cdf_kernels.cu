@@ -12,7 +12,9 @@
 // f32::exp lowers to on Linux; every mul/add/fma is an explicit round-to-nearest intrinsic so nvcc cannot
 // re-contract.  HBM-bound by design: algorithmic bytes = 4*V per column (one read); this implementation
 // reads the column up to 3 times (max / sum / prefix), the 2nd and 3rd mostly from L2 for decode-sized M.
-#include "cdf_device.cuh"
+#include <stdlib.h>
+
+#include "cdf_fast.cuh"
 
 namespace czk {
 
@@ -43,6 +45,445 @@ __global__ void __launch_bounds__(128) cdf_cols_kernel(const float *__restrict__
     c_lo_out[col] = lo;
     c_hi_out[col] = hi;
   }
+}
+
+
+// =================================================================================================================
+// Round-2 encode-side kernels (OP_BOUNDS / OP_XE): full passes and the prefix walk are separate kernels.
+// =================================================================================================================
+
+// (double)expf(-a) for a group of values: integer-conversion fast path when every a <= CZ_EXP_FAST_MAX, otherwise the original
+// conversion path for the whole group (tiny results, -inf logits, NaN).  ef (optional) receives the f32 values.
+template <int N, bool WANT_F32>
+__device__ __forceinline__ void exp_group(const float (&a)[N], const ExpTab64 &tab, double (&d)[N], float (&ef)[N]) {
+  bool ok = true;
+#pragma unroll
+  for (int i = 0; i < N; i++) ok = ok && (a[i] <= CZ_EXP_FAST_MAX);
+  if (ok) {
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+      d[i] = cz_exp_neg_fast(a[i], tab.t);
+      if (WANT_F32) ef[i] = cz_f32_of_gridded(d[i]);
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+      const float e = cz_expf(-a[i], tab);
+      d[i] = (double)e;
+      if (WANT_F32) ef[i] = e;
+    }
+  }
+}
+
+// Full passes.  One thread owns NCOL adjacent columns (vector loads: one LDG + one address per NCOL logits); every column is still
+// summed by one thread in ascending vocab order.  MODE / OP decide which passes run:
+//   pass 1  S = sum (f64)expf(l - max)                      always            (RWKV alphabet: leaves e_v in the logit's slot)
+//   pass 2  norm = sum max(e / S, 2^-29)                    RWKV alphabet, XE
+//   pass 3  sum2 = sum RN(RN(max(e / S, 2^-29) / norm) (1 - 2^-21)) + 256 x 2^-29   RWKV alphabet
+template <int MODE, int OP, int NCOL>
+__global__ void __launch_bounds__(128) cdf_stats_kernel(float *__restrict__ logits, int V, size_t M, size_t ld, const int *__restrict__ colmax,
+                                                        CdfStats *__restrict__ stats, int *__restrict__ err) {
+  constexpr bool kLit = MODE == CZ_CDF_RWKV_LITERALS;
+  constexpr bool kNorm = kLit || OP == OP_XE;
+  constexpr int GRP = NCOL == 4 ? 4 : 8;
+  constexpr int NE = GRP * NCOL;
+  __shared__ uint64_t s_tab[32 * 32];
+  exp_tab64_init(s_tab);
+  const ExpTab64 tab{s_tab + (threadIdx.x & 31)};
+  const size_t col0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * NCOL;
+  if (col0 >= M) return;
+  float *p = logits + col0;
+  float mx[NCOL];
+  if (colmax) {
+#pragma unroll
+    for (int c = 0; c < NCOL; c++) mx[c] = col0 + c < M ? colmax_decode(colmax[col0 + c]) : 0.f;
+  } else {
+#pragma unroll
+    for (int c = 0; c < NCOL; c++) mx[c] = __int_as_float(0xff800000);
+    cdf_walk_groups<NCOL, GRP, true>(p, ld, V, [&](int, const typename CdfVec<NCOL>::T(&rows)[GRP], int cnt) {
+#pragma unroll
+      for (int k = 0; k < GRP; k++) {
+        if (k < cnt) {
+          float x[NCOL];
+          CdfVec<NCOL>::unpack(rows[k], x);
+#pragma unroll
+          for (int c = 0; c < NCOL; c++)
+            if (x[c] > mx[c]) mx[c] = x[c];  // NaN-ignoring, like `if v > max` (src/main.rs:786-788)
+        }
+      }
+    });
+  }
+  // ---- pass 1 ----
+  double S[NCOL];
+#pragma unroll
+  for (int c = 0; c < NCOL; c++) S[c] = 0.0;
+  cdf_walk_groups<NCOL, GRP, !kLit>(p, ld, V, [&](int v0, const typename CdfVec<NCOL>::T(&rows)[GRP], int cnt) {
+    float a[NE], ef[NE];
+    double d[NE];
+#pragma unroll
+    for (int k = 0; k < GRP; k++) {
+      float x[NCOL];
+      CdfVec<NCOL>::unpack(rows[k], x);
+#pragma unroll
+      for (int c = 0; c < NCOL; c++) a[k * NCOL + c] = __fsub_rn(mx[c], x[c]);  // = -(l - max), exactly
+    }
+    exp_group<NE, kLit>(a, tab, d, ef);
+#pragma unroll
+    for (int k = 0; k < GRP; k++) {
+      if (k < cnt) {
+#pragma unroll
+        for (int c = 0; c < NCOL; c++) S[c] = __dadd_rn(S[c], d[k * NCOL + c]);
+        if (kLit) {  // cache e_v for the later passes (columns beyond M are row padding: scratch)
+          typename CdfVec<NCOL>::T o;
+          float *of = reinterpret_cast<float *>(&o);
+#pragma unroll
+          for (int c = 0; c < NCOL; c++) of[c] = ef[k * NCOL + c];
+          *reinterpret_cast<typename CdfVec<NCOL>::T *>(p + (size_t)(v0 + k) * ld) = o;
+        }
+      }
+    }
+  });
+  int errbits = 0;
+#pragma unroll
+  for (int c = 0; c < NCOL; c++)
+    if (col0 + c < M && !(S[c] == S[c])) errbits |= CZ_DEVERR_NAN;
+  double norm[NCOL], sum2[NCOL];
+#pragma unroll
+  for (int c = 0; c < NCOL; c++) norm[c] = sum2[c] = 1.0;
+  if (kNorm) {
+    bool fast = true;
+    double yS[NCOL];
+#pragma unroll
+    for (int c = 0; c < NCOL; c++) {
+      fast = fast && cz_div_rcp_ok(S[c]);
+      yS[c] = __drcp_rn(S[c]);
+    }
+    // e_v (as a double) of the rows of a group: the cached f32 (RWKV alphabet) or recomputed from the logit (SmolLM XE)
+    auto e_of = [&](const typename CdfVec<NCOL>::T(&rows)[GRP], double(&d)[NE]) {
+      float a[NE], ef[NE];
+#pragma unroll
+      for (int k = 0; k < GRP; k++) {
+        float x[NCOL];
+        CdfVec<NCOL>::unpack(rows[k], x);
+#pragma unroll
+        for (int c = 0; c < NCOL; c++) {
+          if (kLit) d[k * NCOL + c] = fast ? cz_widen_pos(x[c]) : (double)x[c];  // (values below 2^-126 are floored either way)
+          else a[k * NCOL + c] = __fsub_rn(mx[c], x[c]);
+        }
+      }
+      if (!kLit) exp_group<NE, false>(a, tab, d, ef);
+    };
+    auto div_S = [&](double e, int c) { return fast ? cz_div_rcp(e, S[c], yS[c]) : __ddiv_rn(e, S[c]); };
+    // ---- pass 2 ----
+    double acc[NCOL];
+#pragma unroll
+    for (int c = 0; c < NCOL; c++) acc[c] = 0.0;
+    cdf_walk_groups<NCOL, GRP, !kLit>(p, ld, V, [&](int, const typename CdfVec<NCOL>::T(&rows)[GRP], int cnt) {
+      double d[NE];
+      e_of(rows, d);
+#pragma unroll
+      for (int k = 0; k < GRP; k++)
+        if (k < cnt) {
+#pragma unroll
+          for (int c = 0; c < NCOL; c++) acc[c] = __dadd_rn(acc[c], fmax(div_S(d[k * NCOL + c], c), CZ_P_FLOOR));
+        }
+    });
+#pragma unroll
+    for (int c = 0; c < NCOL; c++) norm[c] = acc[c];
+    if (kLit) {
+      // ---- pass 3 ----
+      const double scale = 1.0 - 256.0 * CZ_P_FLOOR;
+      double yN[NCOL];
+      bool fastn = fast;
+#pragma unroll
+      for (int c = 0; c < NCOL; c++) {
+        fastn = fastn && cz_div_rcp_ok(norm[c]);
+        yN[c] = __drcp_rn(norm[c]);
+        acc[c] = 0.0;
+      }
+      cdf_walk_groups<NCOL, GRP, false>(p, ld, V, [&](int, const typename CdfVec<NCOL>::T(&rows)[GRP], int cnt) {
+        double d[NE];
+        e_of(rows, d);
+#pragma unroll
+        for (int k = 0; k < GRP; k++)
+          if (k < cnt) {
+#pragma unroll
+            for (int c = 0; c < NCOL; c++) {
+              const double q = fmax(div_S(d[k * NCOL + c], c), CZ_P_FLOOR);
+              const double q2 = fastn ? cz_div_rcp(q, norm[c], yN[c]) : __ddiv_rn(q, norm[c]);
+              acc[c] = __dadd_rn(acc[c], __dmul_rn(q2, scale));
+            }
+          }
+      });
+#pragma unroll
+      for (int c = 0; c < NCOL; c++) {
+        for (int j = 0; j < 256; j++) acc[c] = __dadd_rn(acc[c], CZ_P_FLOOR);
+        sum2[c] = acc[c];
+      }
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < NCOL; c++)
+    if (col0 + c < M) {
+      CdfStats st;
+      st.S = S[c];
+      st.norm = norm[c];
+      st.sum2 = sum2[c];
+      st.mx = mx[c];
+      st.pad = 0;
+      stats[col0 + c] = st;
+    }
+  if (errbits) atomicOr(err, errbits);
+}
+
+// pdf entry of vocab element v from its logit (SmolLM) / cached e_v (RWKV alphabet): the same expressions as cdf_col's pdf_vocab
+template <int MODE, bool FLOORED>
+struct PdfOf {
+  double S, norm, sum2, yS, yN, y2, uni;
+  bool fast, uniform, has2;
+  __device__ __forceinline__ void init(const CdfStats &st, int V) {
+    S = st.S;
+    norm = st.norm;
+    sum2 = st.sum2;
+    fast = cz_div_rcp_ok(S) && cz_div_rcp_ok(norm) && cz_div_rcp_ok(sum2);
+    yS = __drcp_rn(S);
+    yN = __drcp_rn(norm);
+    y2 = __drcp_rn(sum2);
+    uniform = MODE == CZ_CDF_SMOLLM && !FLOORED && S <= 0.0;  // src/main.rs:794-798
+    uni = 1.0 / (double)V;
+    has2 = sum2 > 0.0;
+  }
+  __device__ __forceinline__ double dv(double a, double b, double y) const { return fast ? cz_div_rcp(a, b, y) : __ddiv_rn(a, b); }
+  __device__ __forceinline__ double operator()(double e) const {
+    if (MODE == CZ_CDF_RWKV_LITERALS) {
+      double q = fmax(dv(e, S, yS), CZ_P_FLOOR);
+      q = __dmul_rn(dv(q, norm, yN), 1.0 - 256.0 * CZ_P_FLOOR);
+      return has2 ? dv(q, sum2, y2) : q;
+    } else if (FLOORED) {
+      return dv(fmax(dv(e, S, yS), CZ_P_FLOOR), norm, yN);
+    } else {
+      return uniform ? uni : dv(e, S, yS);
+    }
+  }
+  __device__ __forceinline__ double literal() const { return has2 ? __ddiv_rn(CZ_P_FLOOR, sum2) : CZ_P_FLOOR; }
+};
+
+// Prefix walk (encode): cdf[sym], cdf[sym + 1] of every column.  A CTA takes 256 adjacent columns, sorts them by how far they have
+// to walk (the coded symbol), and warp w walks the columns of rank 32 w .. 32 w + 31: lanes of a warp finish together instead of
+// all waiting for the one column whose symbol sits at the end of the vocabulary.
+template <int MODE>
+__global__ void __launch_bounds__(256) cdf_bounds_sorted_kernel(const float *__restrict__ logits, int V, size_t M, size_t ld,
+                                                                const uint32_t *__restrict__ syms, const CdfStats *__restrict__ stats,
+                                                                uint32_t *__restrict__ c_lo_out, uint32_t *__restrict__ c_hi_out,
+                                                                int *__restrict__ err) {
+  constexpr bool kLit = MODE == CZ_CDF_RWKV_LITERALS;
+  constexpr int GRP = 8;
+  __shared__ uint64_t s_tab[32 * 32];
+  __shared__ uint32_t s_key[256];
+  __shared__ uint16_t s_perm[256];
+  exp_tab64_init(s_tab);
+  const ExpTab64 tab{s_tab + (threadIdx.x & 31)};
+  const int n_sym = kLit ? V + 256 : V;
+  const size_t c0 = (size_t)blockIdx.x * 256;
+  {
+    const size_t col = c0 + threadIdx.x;
+    uint32_t key = 0;  // columns past M and bad symbols do not walk
+    if (col < M) {
+      const uint32_t s = syms[col];
+      if ((int)s < n_sym) key = ((int)s < V ? s : (uint32_t)V - 1u) + 1u;  // rows to visit
+    }
+    s_key[threadIdx.x] = key;
+  }
+  __syncthreads();
+  {
+    const uint32_t key = s_key[threadIdx.x];
+    int rank = 0;
+    for (int u = 0; u < 256; u++) {
+      const uint32_t ku = s_key[u];
+      rank += (ku < key || (ku == key && u < (int)threadIdx.x)) ? 1 : 0;
+    }
+    s_perm[rank] = (uint16_t)threadIdx.x;
+  }
+  __syncthreads();
+  const int mine = s_perm[threadIdx.x];
+  const size_t col = c0 + mine;
+  const bool active = col < M;
+  const int n_lane = (int)s_key[mine];
+  const int n_warp = __reduce_max_sync(0xffffffffu, n_lane);
+  uint32_t sym = active ? syms[col] : 0u;
+  bool sym_bad = false;
+  if (active && (int)sym >= n_sym) {
+    sym_bad = true;
+    sym = 0;
+  }
+  CdfStats st;
+  if (active) st = stats[col];
+  else st.S = st.norm = st.sum2 = 1.0, st.mx = 0.f;
+  PdfOf<MODE, false> pdf;
+  pdf.init(st, V);
+  const float mx = st.mx;
+  const float *p = logits + (active ? col : c0);
+  double acc = 0.0;
+  uint32_t lo = 0, hi = 0;
+  // rows [0, n_lane) of this lane's column; the loop bound is the warp's maximum so that the warp stays converged
+  float cur[GRP], nxt[GRP];
+  auto ldv = [&](int v) -> float { return kLit ? p[(size_t)v * ld] : __ldg(p + (size_t)v * ld); };
+#pragma unroll
+  for (int k = 0; k < GRP; k++) cur[k] = k < n_lane ? ldv(k) : 0.f;
+  for (int v0 = 0; v0 < n_warp; v0 += GRP) {
+#pragma unroll
+    for (int k = 0; k < GRP; k++) {
+      const int v = v0 + GRP + k;
+      nxt[k] = v < n_lane ? ldv(v) : 0.f;
+      if (v0 + CDF_PF + k < n_lane) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + (size_t)(v0 + CDF_PF + k) * ld));
+    }
+    double q[GRP];
+    {
+      double d[GRP];
+      if (kLit) {
+#pragma unroll
+        for (int k = 0; k < GRP; k++) d[k] = pdf.fast ? cz_widen_pos(cur[k]) : (double)cur[k];
+      } else {
+        float a[GRP], ef[GRP];
+#pragma unroll
+        for (int k = 0; k < GRP; k++) a[k] = v0 + k < n_lane ? __fsub_rn(mx, cur[k]) : 0.f;  // rows past the lane's end: harmless exp(0)
+        exp_group<GRP, false>(a, tab, d, ef);
+      }
+#pragma unroll
+      for (int k = 0; k < GRP; k++) q[k] = pdf(d[k]);
+    }
+    if ((uint32_t)(v0 + GRP) < sym) {  // the whole group lies before cdf[sym]'s last term: no capture checks
+#pragma unroll
+      for (int k = 0; k < GRP; k++) acc = __dadd_rn(acc, q[k]);
+    } else {
+#pragma unroll
+      for (int k = 0; k < GRP; k++) {
+        acc = __dadd_rn(acc, q[k]);  // (rows past the lane's last one add garbage after both bounds were captured)
+        const uint32_t v = (uint32_t)(v0 + k);
+        if (v + 1 == sym) lo = quant(acc);
+        if (v == sym) hi = quant(acc);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < GRP; k++) cur[k] = nxt[k];
+  }
+  if (!active) return;
+  if (kLit && (int)sym >= V) {  // literal symbols follow the vocabulary: acc continues from the full vocab sum
+    const double pl = pdf.literal();
+    for (uint32_t v = (uint32_t)V; v <= sym; v++) {
+      acc = __dadd_rn(acc, pl);
+      if (v + 1 == sym) lo = quant(acc);
+      if (v == sym) hi = quant(acc);
+    }
+  }
+  if (hi < lo) hi = lo;                             // non-decreasing clamp (src/main.rs:818)
+  if ((int)sym == n_sym - 1) hi = CZ_AC_CDF_TOTAL;  // cdf[n] = total (src/main.rs:822)
+  c_lo_out[col] = sym_bad ? 0u : lo;
+  c_hi_out[col] = sym_bad ? 0u : hi;
+  if (sym_bad) atomicOr(err, CZ_DEVERR_SYM);
+}
+
+// K9 from the stats: -log2(max(p_floor(sym), 1e-300)) -- one table lookup per column (src/main.rs:1745-1747 / 1778-1781)
+template <int MODE>
+__global__ void __launch_bounds__(128) cdf_xe_final_kernel(const float *__restrict__ logits, int V, size_t M, size_t ld,
+                                                           const uint32_t *__restrict__ syms, const CdfStats *__restrict__ stats,
+                                                           double *__restrict__ xe_out) {
+  constexpr bool kLit = MODE == CZ_CDF_RWKV_LITERALS;
+  __shared__ uint64_t s_tab[32 * 32];
+  exp_tab64_init(s_tab);
+  const ExpTab64 tab{s_tab + (threadIdx.x & 31)};
+  const size_t col = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= M) return;
+  const int n_sym = kLit ? V + 256 : V;
+  const uint32_t sym = syms[col];
+  const CdfStats st = stats[col];
+  PdfOf<MODE, true> pdf;
+  pdf.init(st, V);
+  pdf.fast = false;  // a single element: the plain IEEE divisions
+  double pr = CZ_P_FLOOR;  // pdf.get(sym).unwrap_or(ac_p_min())
+  if ((int)sym < V) {
+    const float x = logits[(size_t)sym * ld + col];
+    pr = pdf(kLit ? (double)x : (double)cz_expf(__fsub_rn(x, st.mx), tab));
+  } else if ((int)sym < n_sym) {
+    pr = pdf.literal();
+  }
+  xe_out[col] = -log2(fmax(pr, 1e-300));
+}
+
+// ---- test hooks: the fast paths of cdf_fast.cuh against the originals -----------------------------------------------------------
+// every non-negative f32 bit pattern b (a = max - logit >= 0, +inf, NaNs): fast == original wherever exp_group takes the fast path,
+// and a checksum of the ORIGINAL expf over the whole domain that the CPU oracle reproduces from glibc-verified code
+__global__ void __launch_bounds__(256) expf_exhaustive_kernel(unsigned long long *__restrict__ out /* [0] mismatches [1] checksum [2] first bad */) {
+  __shared__ uint64_t s_tab[32 * 32];
+  exp_tab64_init(s_tab);
+  const ExpTab64 tab{s_tab + (threadIdx.x & 31)};
+  unsigned long long bad = 0, sum = 0, first = ~0ull;
+  for (unsigned long long b = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; b < 0x80000000ull; b += (unsigned long long)gridDim.x * blockDim.x) {
+    const float a = __uint_as_float((uint32_t)b);
+    const float ref = cz_expf(-a, tab);
+    uint32_t rb = __float_as_uint(ref);
+    if (ref != ref) rb = 0x7fc00000u;
+    sum += (unsigned long long)rb * (2ull * b + 1ull);
+    if (a <= CZ_EXP_FAST_MAX) {
+      const double f = cz_exp_neg_fast(a, tab.t);
+      if (__double_as_longlong(f) != __double_as_longlong((double)ref) || __float_as_uint(cz_f32_of_gridded(f)) != __float_as_uint(ref)) {
+        bad++;
+        if (b < first) first = b;
+      }
+    }
+  }
+  atomicAdd(&out[0], bad);
+  atomicAdd(&out[1], sum);
+  atomicMin(&out[2], first);
+}
+
+__device__ __forceinline__ unsigned long long tst_mix(unsigned long long x) {
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+// cz_div_rcp(a, b, RN(1/b)) == __ddiv_rn(a, b) on random operands of the shapes the CDF passes divide
+__global__ void __launch_bounds__(256) div_random_kernel(unsigned long long seed, int iters, unsigned long long *__restrict__ out) {
+  unsigned long long st = tst_mix(seed ^ ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) * 0xD1342543DE82EF95ull);
+  unsigned long long bad = 0;
+  auto mk = [](unsigned long long mant52, int e) { return __longlong_as_double((long long)(((unsigned long long)(e + 1023) << 52) | (mant52 & 0xFFFFFFFFFFFFFull))); };
+  for (int i = 0; i < iters; i++) {
+    const unsigned long long r0 = st = tst_mix(st), r1 = st = tst_mix(st), r2 = st = tst_mix(st);
+    double a, b;
+    switch (i & 7) {
+      case 0:
+      case 1:  // e / S: e on the f32 grid in [2^-126, 1], S in [1, 2^17)
+        a = mk(r0 & 0xFFFFFE0000000ull, -(int)(r2 % 127));
+        b = mk(r1, (int)((r2 >> 8) % 17));
+        break;
+      case 2:  // e near 1 (the tokens that carry the mass), S small
+        a = mk(r0 & 0xFFFFFE0000000ull, -(int)(r2 % 4));
+        b = mk(r1, (int)((r2 >> 8) % 6));
+        break;
+      case 3:  // floored q / norm, q / sum2: quotients of doubles near 1
+        a = mk(r0, -(int)(r2 % 30));
+        b = mk(r1, -(int)((r2 >> 8) % 2));
+        break;
+      case 4:  // divisor mantissa of all ones / nearly all ones, and just above a power of two
+        a = mk(r0, -(int)(r2 % 40));
+        b = mk((r2 & 64) ? 0xFFFFFFFFFFFFFull - (r1 & 7) : (r1 & 7), (int)((r2 >> 8) % 17));
+        break;
+      case 5:  // numerator a multiple of the divisor's leading bits: quotients with long runs of zeros / ones
+        b = mk(r1 & 0xFFFFF00000000ull, (int)((r2 >> 8) % 17));
+        a = __dmul_rn(b, mk(r0 & 0xFFF0000000000ull, -(int)(r2 % 30)));
+        a = __longlong_as_double(__double_as_longlong(a) + (long long)(r2 >> 60) - 8);
+        break;
+      default:  // anything in the exponent range cz_div_rcp_ok admits
+        a = mk(r0, (int)(r2 % 90) - 60);
+        b = mk(r1, (int)((r2 >> 8) % 120) - 60);
+        break;
+    }
+    const double y = __drcp_rn(b);
+    if (!cz_div_rcp_ok(b)) continue;
+    if (__double_as_longlong(cz_div_rcp(a, b, y)) != __double_as_longlong(__ddiv_rn(a, b))) bad++;
+  }
+  if (bad) atomicAdd(out, bad);
 }
 
 // OP_SEARCH for a small number of columns (stepwise decode): one warp per column, see cdf_search_warp
@@ -176,6 +617,74 @@ int launch_cdf_cols(cz_ctx *ctx, int op, int mode, const float *logits_dev, size
     CZ_CHECK_LAUNCH();
     return CZ_OK;
   }
+  static const bool legacy = getenv("CZ_CDF_LEGACY") != nullptr;  // bisecting aid: the round-1 single-kernel path
+  if (!legacy && (op == czk::OP_BOUNDS || op == czk::OP_XE)) {
+    // round-2 path: full passes (vectorised over adjacent columns) -> per-column stats -> sorted prefix walk / XE lookup
+    const size_t need = M * sizeof(czk::CdfStats);
+    if (need > ctx->cdf_stats_bytes) {
+      if (ctx->cdf_stats) {
+        CZ_CUDA_TRY(cudaStreamSynchronize(stream));
+        cudaFree(ctx->cdf_stats);
+        ctx->cdf_stats = nullptr;
+        ctx->cdf_stats_bytes = 0;
+      }
+      const size_t want = need + (need >> 2) + 4096;
+      CZ_CUDA_TRY(cudaMalloc(&ctx->cdf_stats, want));
+      ctx->cdf_stats_bytes = want;
+    }
+    czk::CdfStats *stats = (czk::CdfStats *)ctx->cdf_stats;
+    float *lg = const_cast<float *>(logits_dev);  // (the RWKV alphabet caches expf in place: the logits batch is scratch)
+    // adjacent columns per thread: vector loads need the alignment, and enough columns to fill the machine with fewer threads
+    const char *env_ncol = getenv("CZ_CDF_NCOL");  // (read per call: the tests switch it between calls)
+    const int force_ncol = env_ncol ? atoi(env_ncol) : 0;
+    int ncol = M >= 131072 ? 4 : (M >= 32768 ? 2 : 1);
+    if (force_ncol == 1 || force_ncol == 2 || force_ncol == 4) ncol = force_ncol;
+    while (ncol > 1 && (ld % ncol != 0 || ((uintptr_t)logits_dev & (size_t)(4 * ncol - 1)) != 0)) ncol >>= 1;
+    const unsigned g_stats = (unsigned)ceil_div(ceil_div(M, (size_t)ncol), 128);
+#define CZ_STATS(MODE, OP, NC)                                                                                                   \
+  CZ_LAUNCH(ctx, CZ_K_CDF,                                                                                                       \
+            (czk::cdf_stats_kernel<MODE, OP, NC><<<g_stats, 128, 0, stream>>>(lg, (int)V, M, ld, colmax_dev, stats, ctx->err_flag_dev)))
+#define CZ_STATS_N(MODE, OP)            \
+  do {                                  \
+    if (ncol == 4) CZ_STATS(MODE, OP, 4); \
+    else if (ncol == 2) CZ_STATS(MODE, OP, 2); \
+    else CZ_STATS(MODE, OP, 1);         \
+  } while (0)
+    if (mode == CZ_CDF_SMOLLM) {
+      if (op == czk::OP_BOUNDS) CZ_STATS_N(CZ_CDF_SMOLLM, czk::OP_BOUNDS);
+      else CZ_STATS_N(CZ_CDF_SMOLLM, czk::OP_XE);
+    } else if (mode == CZ_CDF_RWKV_LITERALS) {
+      if (op == czk::OP_BOUNDS) CZ_STATS_N(CZ_CDF_RWKV_LITERALS, czk::OP_BOUNDS);
+      else CZ_STATS_N(CZ_CDF_RWKV_LITERALS, czk::OP_XE);
+    } else {
+      set_error("cdf: unknown mode");
+      return CZ_ERR_INVALID;
+    }
+#undef CZ_STATS_N
+#undef CZ_STATS
+    CZ_CHECK_LAUNCH();
+    if (op == czk::OP_BOUNDS) {
+      const unsigned g = (unsigned)ceil_div(M, 256);
+      if (mode == CZ_CDF_SMOLLM)
+        CZ_LAUNCH(ctx, CZ_K_CDF,
+                  (czk::cdf_bounds_sorted_kernel<CZ_CDF_SMOLLM><<<g, 256, 0, stream>>>(logits_dev, (int)V, M, ld, arg_dev, stats, c_lo_dev, c_hi_dev,
+                                                                                       ctx->err_flag_dev)));
+      else
+        CZ_LAUNCH(ctx, CZ_K_CDF,
+                  (czk::cdf_bounds_sorted_kernel<CZ_CDF_RWKV_LITERALS><<<g, 256, 0, stream>>>(logits_dev, (int)V, M, ld, arg_dev, stats, c_lo_dev,
+                                                                                              c_hi_dev, ctx->err_flag_dev)));
+    } else {
+      const unsigned g = (unsigned)ceil_div(M, 128);
+      if (mode == CZ_CDF_SMOLLM)
+        CZ_LAUNCH(ctx, CZ_K_CDF,
+                  (czk::cdf_xe_final_kernel<CZ_CDF_SMOLLM><<<g, 128, 0, stream>>>(logits_dev, (int)V, M, ld, arg_dev, stats, xe_dev)));
+      else
+        CZ_LAUNCH(ctx, CZ_K_CDF,
+                  (czk::cdf_xe_final_kernel<CZ_CDF_RWKV_LITERALS><<<g, 128, 0, stream>>>(logits_dev, (int)V, M, ld, arg_dev, stats, xe_dev)));
+    }
+    CZ_CHECK_LAUNCH();
+    return CZ_OK;
+  }
   const int threads = 128;
   dim3 grid((unsigned)ceil_div(M, threads));
 #define CZ_CDF_CASE(MODE, OP)                                                                                 \
@@ -211,3 +720,45 @@ int launch_cdf_full(cz_ctx *ctx, int mode, const float *logits_dev, size_t V, ui
 }
 
 }  // namespace cz
+
+using namespace cz;
+
+extern "C" int cz_test_expf_exhaustive(cz_ctx *ctx, uint64_t *mismatches, uint64_t *checksum, uint64_t *first_bad) {
+  if (!ctx || ctx->device < 0) return CZ_ERR_NO_DEVICE;
+  CZ_CUDA_TRY(cudaSetDevice(ctx->device));
+  unsigned long long *d = nullptr, h[3] = {0, 0, ~0ull};
+  CZ_CUDA_TRY(cudaMalloc((void **)&d, 24));
+  CZ_CUDA_TRY(cudaMemcpy(d, h, 24, cudaMemcpyHostToDevice));
+  czk::expf_exhaustive_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(d);
+  cudaError_t e = cudaStreamSynchronize(ctx->stream);
+  if (e == cudaSuccess) e = cudaMemcpy(h, d, 24, cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  if (e != cudaSuccess) {
+    set_error(std::string("expf exhaustive kernel: ") + cudaGetErrorString(e));
+    return CZ_ERR_CUDA;
+  }
+  if (mismatches) *mismatches = h[0];
+  if (checksum) *checksum = h[1];
+  if (first_bad) *first_bad = h[2];
+  return CZ_OK;
+}
+
+extern "C" int cz_test_div_random(cz_ctx *ctx, uint64_t seed, uint64_t n_pairs, uint64_t *mismatches) {
+  if (!ctx || ctx->device < 0) return CZ_ERR_NO_DEVICE;
+  CZ_CUDA_TRY(cudaSetDevice(ctx->device));
+  unsigned long long *d = nullptr, h = 0;
+  CZ_CUDA_TRY(cudaMalloc((void **)&d, 8));
+  CZ_CUDA_TRY(cudaMemset(d, 0, 8));
+  const unsigned grid = (unsigned)ctx->sm_count * 8, threads = 256;
+  const uint64_t per = n_pairs / ((uint64_t)grid * threads) + 1;
+  czk::div_random_kernel<<<grid, threads, 0, ctx->stream>>>(seed, (int)(per > 0x7fffffff ? 0x7fffffff : per), d);
+  cudaError_t e = cudaStreamSynchronize(ctx->stream);
+  if (e == cudaSuccess) e = cudaMemcpy(&h, d, 8, cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  if (e != cudaSuccess) {
+    set_error(std::string("div random kernel: ") + cudaGetErrorString(e));
+    return CZ_ERR_CUDA;
+  }
+  if (mismatches) *mismatches = h;
+  return CZ_OK;
+}

@@ -56,6 +56,8 @@ struct cz_ctx {
   // scratch for the small kernels' host entry points
   void *scratch = nullptr;
   size_t scratch_bytes = 0;
+  void *cdf_stats = nullptr;  // per-column results of the CDF kernels' full passes (cdf_kernels.cu), grow-only
+  size_t cdf_stats_bytes = 0;
   int *err_flag_dev = nullptr;  // 64-byte device status block: [0] flag set by kernels on zero-width intervals etc., [8] the
                                 // attention kernel's work-item counter (attn_tc.cu)
 };

@@ -290,6 +290,13 @@ int cz_test_gemm_norm(cz_ctx *ctx, int M, int N, int K, int N2, const uint16_t *
 int cz_test_attention(cz_ctx *ctx, int n_pos, int nh, int nkv, const uint16_t *q_bf16, const uint16_t *k_bf16,
                       const uint16_t *v_bf16, int mode, uint16_t *out_bf16);
 
+/* the CDF kernels' fast paths against the originals (csrc/cdf_fast.cuh): (1) every non-negative f32 argument pattern of
+ * expf(-(max - logit)): the integer-conversion path must give the bits of the conversion path wherever it is taken; `checksum` =
+ * sum over the patterns b of bits(expf(-float(b))) * (2 b + 1) mod 2^64 (NaN results as 0x7fc00000), which the CPU oracle reproduces
+ * with its glibc-verified expf (czo_expf_checksum); (2) the reciprocal-based division against the IEEE division on random operands */
+int cz_test_expf_exhaustive(cz_ctx *ctx, uint64_t *mismatches, uint64_t *checksum, uint64_t *first_bad);
+int cz_test_div_random(cz_ctx *ctx, uint64_t seed, uint64_t n_pairs, uint64_t *mismatches);
+
 #ifdef __cplusplus
 }
 #endif

@@ -55,6 +55,25 @@ float czo_expf(float x) {
   return (float)y;
 }
 
+/* Checksum of czo_expf over the non-negative f32 bit patterns b in [b_lo, b_hi): sum of bits(expf(-float(b))) * (2 b + 1) mod 2^64,
+ * NaN results counted as 0x7fc00000.  The GPU computes the same sum with its own expf (cz_test_expf_exhaustive): equal sums over
+ * the whole domain [0, 2^31) tie the device expf to this one -- which expf_exhaustive.c ties to the host glibc expf that Rust's
+ * f32::exp calls (src/main.rs:791). */
+uint64_t czo_expf_checksum(uint64_t b_lo, uint64_t b_hi) {
+  uint64_t sum = 0;
+#pragma omp parallel for reduction(+ : sum) schedule(static)
+  for (uint64_t b = b_lo; b < b_hi; b++) {
+    uint32_t u = (uint32_t)b, r;
+    float a, e;
+    memcpy(&a, &u, 4);
+    e = czo_expf(-a);
+    memcpy(&r, &e, 4);
+    if (e != e) r = 0x7fc00000u;
+    sum += (uint64_t)r * (2ull * b + 1ull);
+  }
+  return sum;
+}
+
 double czo_ac_p_min(void) { return 2.0 * pow(2.0, -30.0); } /* src/main.rs:235-238: 2*2^-(32-2) = 2^-29 */
 
 /* src/main.rs:784-801 */

@@ -33,6 +33,7 @@ extern "C" {
 
 /* ---- numeric kernels: src/main.rs:230-238, 758-824 ---- */
 float czo_expf(float x);
+uint64_t czo_expf_checksum(uint64_t b_lo, uint64_t b_hi);
 double czo_ac_p_min(void);
 void czo_softmax_pdf(const float *logits, size_t v, double *pdf);
 void czo_softmax_pdf_floor(const float *logits, size_t v, double p_floor, double *pdf);

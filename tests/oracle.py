@@ -27,6 +27,8 @@ def _load():
     lib = C.CDLL(_SO)
     lib.czo_expf.restype = C.c_float
     lib.czo_expf.argtypes = [C.c_float]
+    lib.czo_expf_checksum.restype = C.c_uint64
+    lib.czo_expf_checksum.argtypes = [C.c_uint64, C.c_uint64]
     lib.czo_ac_p_min.restype = C.c_double
     lib.czo_softmax_pdf.argtypes = [f32p, C.c_size_t, f64p]
     lib.czo_softmax_pdf_floor.argtypes = [f32p, C.c_size_t, C.c_double, f64p]

@@ -321,3 +321,56 @@ def test_zero_width_symbol_falls_back_to_a_stored_container(gpu_ctx):
     bad[-1] ^= 1
     with pytest.raises(ValueError):
         codec.decompress(model, bytes(bad))
+
+
+def test_cdf_fast_paths_equal_the_originals_exhaustively(gpu_ctx):
+    """csrc/cdf_fast.cuh: (1) expf through integer conversions == expf through F2F conversions for EVERY argument the fast path
+    accepts (all 2^31 non-negative f32 patterns are visited), and the device expf's checksum over the whole domain equals the
+    oracle's (whose expf is verified exhaustively against the host glibc expf, the one Rust's f32::exp calls, src/main.rs:791);
+    (2) the reciprocal-based division (Markstein) == IEEE division on 2^34 random operand pairs."""
+    bad, chk, first = C.c_uint64(), C.c_uint64(), C.c_uint64()
+    _lib.check(_lib.lib.cz_test_expf_exhaustive(gpu_ctx._h, C.byref(bad), C.byref(chk), C.byref(first)))
+    assert bad.value == 0, f"{bad.value} arguments differ, first bit pattern {first.value:#x}"
+    assert chk.value == oracle.lib.czo_expf_checksum(0, 1 << 31)
+    for seed in (1, 2):
+        m = C.c_uint64()
+        _lib.check(_lib.lib.cz_test_div_random(gpu_ctx._h, seed, 1 << 33, C.byref(m)))
+        assert m.value == 0, m.value
+
+
+@pytest.mark.parametrize("ncol", [1, 2, 4])
+@pytest.mark.parametrize("mode", [0, 1])
+def test_cdf_bounds_and_xe_new_kernels_all_vector_widths(gpu_ctx, mode, ncol):
+    """the round-2 stats / sorted-prefix / XE kernels against the oracle for 1, 2 and 4 adjacent columns per thread (forced through
+    CZ_CDF_NCOL; by default the width follows the column count), with symbols at both ends of the alphabet, literal escapes,
+    logits more than 87 below the maximum (the conversion fallback), -inf entries and exact ties; then a model-level encode whose
+    ragged column counts go through the same width, checked against the oracle coder on the GPU's own logits."""
+    import test_gpu_parity as tgp
+
+    os.environ["CZ_CDF_NCOL"] = str(ncol)
+    try:
+        rng = np.random.default_rng(100 + mode)
+        v = 2304
+        n_sym = v + 256 if mode else v
+        for m in (40, 260, 1024):
+            logits = tgp._adversarial_logits(rng, v, m)
+            logits[:, m // 2] = rng.normal(0, 30, v)      # most entries > 87 below the max: slow conversion path, tiny / zero terms
+            syms = rng.integers(0, n_sym, m).astype(np.uint32)
+            syms[:6] = [0, n_sym - 1, 1, v - 1, min(v, n_sym - 1), n_sym - 2]
+            lo, hi = gpu_ctx.cdf_bounds(logits, syms, mode)
+            xe = gpu_ctx.xe_bits_cols(logits, syms, mode)
+            for j in range(m):
+                cdf = oracle.logits_to_cdf(logits[:, j], mode)
+                assert (int(lo[j]), int(hi[j])) == (int(cdf[syms[j]]), int(cdf[syms[j] + 1])), (m, j, syms[j])
+                pdf = oracle.combined_pdf_with_literals(logits[:, j]) if mode else oracle.softmax_pdf_floor(logits[:, j])
+                want = -np.log2(max(pdf[syms[j]], 1e-300))
+                assert abs(xe[j] - want) <= 1e-12 * max(1.0, abs(want)), (m, j)
+        if mode == 0:
+            model = _tiny(gpu_ctx)
+            ids = rng.integers(0, 1024, 701).astype(np.uint32)
+            pays, seg = model.encode(ids, n_segments=1)
+            lg = np.concatenate([model.chunk_logits([0], ids[:512]), model.chunk_logits(np.concatenate([[0], ids])[2:513], ids[512:])])
+            bounds = [tuple(int(x) for x in oracle.logits_to_cdf(lg[j], 0)[[ids[j], ids[j] + 1]]) for j in range(701)]
+            assert oracle.ac_encode(bounds) == pays[0]
+    finally:
+        os.environ.pop("CZ_CDF_NCOL", None)
