@@ -461,8 +461,10 @@ def run_ours(args):
         kern("gemm_tc_kernel<192,QKV_ROPE> qkv + RoPE", "gemm_qkv", "tensor", 2.0 * rows * qkv_n * Dm * L),
         kern("gemm_tc_kernel<256,COLMAX> LM head", "gemm_head", "tensor", 2.0 * HEAD_PARAMS * n),
         kern("attn_tc_kernel", "attn", "tensor", 70.57e6 * n),
-        # CDF: one full read of the column for the sum + the prefix walk up to the coded symbol: 4V (1 + E[sym]/V) bytes per token
-        kern("cdf_cols_kernel", "cdf", "hbm", 4.0 * V * n * (1.0 + mean_sym_over_v)),
+        # CDF: one full read of the column for the sum (cdf_stats_kernel) + the prefix walk up to the coded symbol
+        # (cdf_bounds_sorted_kernel): 4V and 4V E[sym]/V bytes per token
+        kern("cdf_stats_kernel (max given by the LM head; sequential f64 sum)", "cdf", "hbm", 4.0 * V * n),
+        kern("cdf_bounds_sorted_kernel (prefix walk to the coded symbol)", "cdf_prefix", "hbm", 4.0 * V * n * mean_sym_over_v),
     ] if k]
     line = {
         "metric": METRIC, "value": value, "unit": "MB/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

@@ -28,7 +28,7 @@ CZ_DTYPE_F32, CZ_DTYPE_BF16, CZ_DTYPE_F16 = 0, 1, 2
 CZ_ENGINE_TCGEN05, CZ_ENGINE_SIMT = 0, 1
 CZ_FLAG_SEGMENTS = 1 << 8
 CZ_FLAG_STORED = 1 << 9
-K_FAMILIES = ("gemm_qkv", "attn", "elemwise", "cdf", "coder", "other", "gemm_o", "gemm_gu", "gemm_down", "gemm_head")
+K_FAMILIES = ("gemm_qkv", "attn", "elemwise", "cdf", "coder", "other", "gemm_o", "gemm_gu", "gemm_down", "gemm_head", "cdf_prefix")
 
 
 class CzError(RuntimeError):

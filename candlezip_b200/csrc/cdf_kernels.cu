@@ -666,11 +666,11 @@ int launch_cdf_cols(cz_ctx *ctx, int op, int mode, const float *logits_dev, size
     if (op == czk::OP_BOUNDS) {
       const unsigned g = (unsigned)ceil_div(M, 256);
       if (mode == CZ_CDF_SMOLLM)
-        CZ_LAUNCH(ctx, CZ_K_CDF,
+        CZ_LAUNCH(ctx, CZ_K_CDF_PREFIX,
                   (czk::cdf_bounds_sorted_kernel<CZ_CDF_SMOLLM><<<g, 256, 0, stream>>>(logits_dev, (int)V, M, ld, arg_dev, stats, c_lo_dev, c_hi_dev,
                                                                                        ctx->err_flag_dev)));
       else
-        CZ_LAUNCH(ctx, CZ_K_CDF,
+        CZ_LAUNCH(ctx, CZ_K_CDF_PREFIX,
                   (czk::cdf_bounds_sorted_kernel<CZ_CDF_RWKV_LITERALS><<<g, 256, 0, stream>>>(logits_dev, (int)V, M, ld, arg_dev, stats, c_lo_dev,
                                                                                               c_hi_dev, ctx->err_flag_dev)));
     } else {

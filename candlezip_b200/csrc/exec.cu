@@ -319,12 +319,12 @@ static int run_wave_head(cz_model *m, size_t n_logit, int op, int mode, const ui
     const size_t nc = std::min(ws.ld_sub, n_logit - c0);
     bool have_max = false;
     CZ_TRY(lm_head(m, (int)c0, (int)nc, ws.logits[buf], ws.ld_sub, st, ws.colmax, &have_max));
+    if (digest_first >= 0 && m->digest_host)  // (before the CDF pass: the RWKV alphabet's pass overwrites the logits with expf values)
+      CZ_TRY(launch_logits_digest(m->ctx, ws.logits[buf], (size_t)m->cfg.vocab, nc, ws.ld_sub, m->sb[SB_CV].p, m->sb[SB_DIGEST].as<uint8_t>(),
+                                  (unsigned long long)digest_first + c0, nullptr, nullptr, nullptr, st));
     CZ_TRY(launch_cdf_cols(m->ctx, op, mode, ws.logits[buf], (size_t)m->cfg.vocab, nc, ws.ld_sub, syms_dev + c0, nullptr,
                            lo_out ? lo_out + c0 : nullptr, hi_out ? hi_out + c0 : nullptr, xe_out ? xe_out + c0 : nullptr, st,
                            have_max ? ws.colmax : nullptr));
-    if (digest_first >= 0 && m->digest_host)
-      CZ_TRY(launch_logits_digest(m->ctx, ws.logits[buf], (size_t)m->cfg.vocab, nc, ws.ld_sub, m->sb[SB_CV].p, m->sb[SB_DIGEST].as<uint8_t>(),
-                                  (unsigned long long)digest_first + c0, nullptr, nullptr, nullptr, st));
   }
   return CZ_OK;
 }

@@ -230,12 +230,12 @@ static int rwkv_run_units(cz_model *m, std::vector<RwUnit> &units, const uint32_
       const size_t nc = std::min(ws.ld_sub, NL - c0);
       bool have_max = false;
       CZ_TRY(lm_head(m, (int)c0, (int)nc, ws.logits[0], ws.ld_sub, st, ws.colmax, &have_max));
+      if (o.digest)  // (before the CDF pass, which caches expf values in the logits' slots)
+        CZ_TRY(launch_logits_digest(ctx, ws.logits[0], V, nc, ws.ld_sub, m->sb[SB_CV].p, m->sb[SB_DIGEST].as<uint8_t>(), 0,
+                                    d_oidx.as<unsigned long long>() + c0, nullptr, nullptr, st));
       CZ_TRY(launch_cdf_cols(ctx, o.op, CZ_CDF_RWKV_LITERALS, ws.logits[0], V, nc, ws.ld_sub, d_syms.as<uint32_t>() + c0, nullptr,
                              d_lo.as<uint32_t>() + c0, d_hi.as<uint32_t>() + c0, d_xe.as<double>() + c0, st,
                              have_max ? ws.colmax : nullptr));
-      if (o.digest)
-        CZ_TRY(launch_logits_digest(ctx, ws.logits[0], V, nc, ws.ld_sub, m->sb[SB_CV].p, m->sb[SB_DIGEST].as<uint8_t>(), 0,
-                                    d_oidx.as<unsigned long long>() + c0, nullptr, nullptr, st));
     }
     if (o.op == czk::OP_XE)
       CZ_LAUNCH(ctx, CZ_K_OTHER,

@@ -63,7 +63,8 @@ enum {
   CZ_K_GEMM = 0, /* qkv projection (and generic GEMM calls) */
   CZ_K_ATTN = 1, CZ_K_ELEMWISE = 2, CZ_K_CDF = 3, CZ_K_CODER = 4, CZ_K_OTHER = 5,
   CZ_K_GEMM_O = 6, CZ_K_GEMM_GU = 7, CZ_K_GEMM_DOWN = 8, CZ_K_GEMM_HEAD = 9,
-  CZ_K_FAMILIES = 10
+  CZ_K_CDF_PREFIX = 10, /* the encode-side prefix walk (CZ_K_CDF keeps the full passes and the decode-side search) */
+  CZ_K_FAMILIES = 11
 };
 /* mode 0 off; 1 synchronous (sync after every launch: exact per-launch times, perturbs the step); 2 deferred
  * (event pairs recorded around every launch, read back in cz_profile_read: does not perturb the timed region) */

@@ -16,10 +16,17 @@ ctx = cz.Context(0)
 cfg = cz.SMOLLM_135M if arch == "smollm" else cz.RWKV7_0P1B
 model = cz.Model(ctx, cfg).random_init(0, 0.02, 0.02)
 rng = np.random.default_rng(0)
-ids = rng.integers(97, 123, n).astype(np.uint32)
+if len(sys.argv) > 4 and sys.argv[4] == "corpus":  # real bytes, ids spread over the vocabulary like real token ids (the CDF search walks further)
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import corpus
+
+    d = corpus.load("enwik8_3mib")
+    ids = corpus.byte_ids((d * (n // len(d) + 1))[:n], cfg["vocab"], True)
+else:
+    ids = rng.integers(97, 123, n).astype(np.uint32)
 pays, seg = model.encode(ids, n_segments=segs)
 model.decode(pays, seg)  # warm (allocations)
-res = {"arch": arch, "tokens": n, "segments": segs}
+res = {"arch": arch, "tokens": n, "segments": segs, "ids": sys.argv[4] if len(sys.argv) > 4 else "a-z"}
 for graph in (1, 0):
     os.environ.pop("CZ_DECODE_NO_GRAPH", None)
     if not graph:
