@@ -389,21 +389,16 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_tc_kernel(const __grid_con
           const int lim = pos_r - kb * 128;
           // STACKED (decode): every valid row sits at the same position, so the 32-key chunks beyond it are masked for the whole
           // tile: they are neither loaded nor exponentiated (their P is an exact zero either way), and warps without a valid row
-          // only keep the barrier protocol.
-          // Teacher-forced tiles: in the diagonal block the 32-key chunks beyond the WARP's last position are masked for all of its
-          // rows, so they get the same treatment (warp w of the diagonal block walks w + 1 chunks: 3/8 of the block's exponentials
-          // are never evaluated); a skipped chunk's P is the exact zero the masked path produces, and the 2^-125 a masked
-          // polynomial column adds to the row sum is absorbed by it, so a row's bits do not change.  Warps without a valid row
-          // (ragged last tile) only keep the barrier protocol.
-          const int n_ch = min(4, (((STACKED ? p0 : pos_w_lo + 31) - kb * 128) >> 5) + 1);
-          const bool active = warp * 32 < nq;
+          // only keep the barrier protocol.  Teacher-forced tiles always walk all four chunks.
+          const int n_ch = STACKED ? min(4, ((p0 - kb * 128) >> 5) + 1) : 4;
+          const bool active = !STACKED || warp * 32 < nq;
           uint32_t w[128];  // S as raw f32 bits; the packed bf16 P overwrites w[0, 64) in place (pair (j, j+1) -> w[j/2], j/2 <= j)
           mbar_wait(s_full, it & 1);
           tc_fence_after();
           if (active) {
 #pragma unroll
             for (int c = 0; c < 4; c++)
-              if (c < n_ch) tc_ld_32x32(t_s + (uint32_t)(c * 32), *reinterpret_cast<uint32_t(*)[32]>(&w[c * 32]));
+              if (!STACKED || c < n_ch) tc_ld_32x32(t_s + (uint32_t)(c * 32), *reinterpret_cast<uint32_t(*)[32]>(&w[c * 32]));
             tc_ld_wait();
           }
           tc_fence_before();
@@ -418,7 +413,7 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_tc_kernel(const __grid_con
             float r4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
             for (int c = 0; c < 4; c++) {
-              if (c < n_ch) {
+              if (!STACKED || c < n_ch) {
                 if (need_mask) {
 #pragma unroll
                   for (int j = c * 32; j < c * 32 + 32; j++) w[j] = (j <= lim) ? w[j] : 0xff800000u;
@@ -442,7 +437,7 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_tc_kernel(const __grid_con
             uint64_t sa = at_pack2(0.f, 0.f), sb = sa;  // (sum of p[j], p[j+1]) over j = 0 mod 4 / j = 2 mod 4
 #pragma unroll
             for (int c = 0; c < 4; c++) {
-              if (c < n_ch) {
+              if (!STACKED || c < n_ch) {
 #pragma unroll
                 for (int j = c * 32; j < c * 32 + 32; j += 4) {
                   float a0 = __uint_as_float(w[j]), a1 = __uint_as_float(w[j + 1]), b0 = __uint_as_float(w[j + 2]), b1 = __uint_as_float(w[j + 3]);

@@ -394,8 +394,13 @@ __device__ __forceinline__ void cdf_search_warp(const float *__restrict__ p_in, 
     if (uniform) return uni;
     return __ddiv_rn((double)ex(x), S);
   };
-  double acc = 0.0;
-  uint32_t prev = 0, found = (uint32_t)(n_sym - 1), lo = 0, hi = CZ_AC_CDF_TOTAL;
+  // Search: the first v with value < cdf[v + 1].  cdf[v + 1] = floor(acc_v * 2^30) (clamped, made non-decreasing -- which a
+  // non-decreasing acc already is), so  value < cdf[v + 1]  <=>  acc_v * 2^30 >= value + 1  <=>  acc_v >= (value + 1) * 2^-30: the
+  // scaling by a power of two is exact on both sides, so the per-element test is ONE f64 compare against a constant instead of a
+  // quantisation (multiply, clamp, convert) per element; the two bounds are quantised once, from acc_{v-1} and acc_v.
+  const double thr = __dmul_rn((double)value + 1.0, 0x1p-30);
+  double acc = 0.0, acc_prev = 0.0;
+  uint32_t found = (uint32_t)(n_sym - 1);
   bool done = false;
   float x = ld_x(0);
   for (int g = 0; g < n_grp && !done; g++) {
@@ -405,38 +410,38 @@ __device__ __forceinline__ void cdf_search_warp(const float *__restrict__ p_in, 
     __syncwarp();
     const int cnt = V - g * 32 < 32 ? V - g * 32 : 32;
     for (int k = 0; k < cnt; k++) {
-      acc = __dadd_rn(acc, line[k]);
+      const double a2 = __dadd_rn(acc, line[k]);
       const int v = g * 32 + k;
-      uint32_t cur = quant(acc);
-      if (cur < prev) cur = prev;
-      if (v == n_sym - 1) cur = CZ_AC_CDF_TOTAL;
-      if (value < cur) {
+      if (a2 >= thr || v == n_sym - 1) {
         found = (uint32_t)v;
-        lo = prev;
-        hi = cur;
+        acc_prev = acc;
+        acc = a2;
         done = true;
         break;
       }
-      prev = cur;
+      acc = a2;
     }
     x = xn;
   }
   if (MODE == CZ_CDF_RWKV_LITERALS && !done) {
     const double pl = sum2 > 0.0 ? __ddiv_rn(CZ_P_FLOOR, sum2) : CZ_P_FLOOR;
     for (int v = V; v < n_sym; v++) {
-      acc = __dadd_rn(acc, pl);
-      uint32_t cur = quant(acc);
-      if (cur < prev) cur = prev;
-      if (v == n_sym - 1) cur = CZ_AC_CDF_TOTAL;
-      if (value < cur) {
+      const double a2 = __dadd_rn(acc, pl);
+      if (a2 >= thr || v == n_sym - 1) {
         found = (uint32_t)v;
-        lo = prev;
-        hi = cur;
+        acc_prev = acc;
+        acc = a2;
+        done = true;
         break;
       }
-      prev = cur;
+      acc = a2;
     }
   }
+  // (done is always true here: the last symbol ends the search)
+  uint32_t lo = found == 0 ? 0u : quant(acc_prev);
+  uint32_t hi = quant(acc);
+  if (hi < lo) hi = lo;
+  if ((int)found == n_sym - 1) hi = CZ_AC_CDF_TOTAL;
   sym_out = found;
   lo_out = lo;
   hi_out = hi;

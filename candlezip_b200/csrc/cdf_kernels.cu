@@ -637,7 +637,9 @@ int launch_cdf_cols(cz_ctx *ctx, int op, int mode, const float *logits_dev, size
     // adjacent columns per thread: vector loads need the alignment, and enough columns to fill the machine with fewer threads
     const char *env_ncol = getenv("CZ_CDF_NCOL");  // (read per call: the tests switch it between calls)
     const int force_ncol = env_ncol ? atoi(env_ncol) : 0;
-    int ncol = M >= 131072 ? 4 : (M >= 32768 ? 2 : 1);
+    // (measured on B200, scripts/cdf_bench.py: 1 column per thread is the fastest at every batch size -- 131,072 columns: 13.9 ms
+    // against 14.0 / 16.5 ms for 2 / 4; the RWKV alphabet 28 / 37 / 65 ms: the wider variants leave too few warps per scheduler)
+    int ncol = 1;
     if (force_ncol == 1 || force_ncol == 2 || force_ncol == 4) ncol = force_ncol;
     while (ncol > 1 && (ld % ncol != 0 || ((uintptr_t)logits_dev & (size_t)(4 * ncol - 1)) != 0)) ncol >>= 1;
     const unsigned g_stats = (unsigned)ceil_div(ceil_div(M, (size_t)ncol), 128);
