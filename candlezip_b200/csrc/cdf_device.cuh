@@ -80,6 +80,17 @@ __device__ __forceinline__ uint32_t quant(double acc) {
   return (uint32_t)__double2ll_rd(f);
 }
 
+// a / b correctly rounded, given y = __drcp_rn(b); a >= 0, b > 0, all quantities (and the residuals) in the normal range.
+__device__ __forceinline__ double cz_div_rcp(double a, double b, double y) {
+  const double q0 = __dmul_rn(a, y);
+  const double r0 = __fma_rn(-b, q0, a);
+  const double q1 = __fma_rn(r0, y, q0);
+  const double r1 = __fma_rn(-b, q1, a);
+  return __fma_rn(r1, y, q1);
+}
+// divisors for which cz_div_rcp is used: finite, and far from the ends of the exponent range (S in [1, V], norm and sum2 near 1)
+__device__ __forceinline__ bool cz_div_rcp_ok(double b) { return b >= 0x1p-64 && b <= 0x1p64; }
+
 enum { OP_BOUNDS = 0, OP_SEARCH = 1, OP_XE = 2 };
 
 #define CZ_P_FLOOR 0x1p-29 /* ac_p_min(): src/main.rs:235-238 */
@@ -385,14 +396,18 @@ __device__ __forceinline__ void cdf_search_warp(const float *__restrict__ p_in, 
   }
   const bool uniform = MODE == CZ_CDF_SMOLLM && S <= 0.0;
   const double uni = 1.0 / (double)V;
+  // the divisors are per-column constants: correctly rounded quotients from their reciprocals (cz_div_rcp, proof in cdf_fast.cuh)
+  const bool fastd = cz_div_rcp_ok(S) && cz_div_rcp_ok(norm) && cz_div_rcp_ok(sum2);
+  const double yS = __drcp_rn(S), yN = __drcp_rn(norm), y2 = __drcp_rn(sum2);
+  auto dv = [&](double a, double b, double y) { return fastd ? cz_div_rcp(a, b, y) : __ddiv_rn(a, b); };
   auto pdf_vocab = [&](float x) -> double {
     if (MODE == CZ_CDF_RWKV_LITERALS) {
-      double q = fmax(__ddiv_rn((double)ex(x), S), CZ_P_FLOOR);
-      q = __dmul_rn(__ddiv_rn(q, norm), scale);
-      return sum2 > 0.0 ? __ddiv_rn(q, sum2) : q;
+      double q = fmax(dv((double)ex(x), S, yS), CZ_P_FLOOR);
+      q = __dmul_rn(dv(q, norm, yN), scale);
+      return sum2 > 0.0 ? dv(q, sum2, y2) : q;
     }
     if (uniform) return uni;
-    return __ddiv_rn((double)ex(x), S);
+    return dv((double)ex(x), S, yS);
   };
   // Search: the first v with value < cdf[v + 1].  cdf[v + 1] = floor(acc_v * 2^30) (clamped, made non-decreasing -- which a
   // non-decreasing acc already is), so  value < cdf[v + 1]  <=>  acc_v * 2^30 >= value + 1  <=>  acc_v >= (value + 1) * 2^-30: the

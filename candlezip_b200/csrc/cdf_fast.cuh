@@ -75,16 +75,7 @@ __device__ __forceinline__ double cz_widen_pos(float e) {
   return __longlong_as_double((long long)((uint64_t)__float_as_uint(e) * 0x20000000ull + 0x3800000000000000ull));
 }
 
-// a / b correctly rounded, given y = __drcp_rn(b); a >= 0, b > 0, all quantities (and the residuals) in the normal range.
-__device__ __forceinline__ double cz_div_rcp(double a, double b, double y) {
-  const double q0 = __dmul_rn(a, y);
-  const double r0 = __fma_rn(-b, q0, a);
-  const double q1 = __fma_rn(r0, y, q0);
-  const double r1 = __fma_rn(-b, q1, a);
-  return __fma_rn(r1, y, q1);
-}
-// divisors for which cz_div_rcp is used: finite, and far from the ends of the exponent range (S in [1, V], norm and sum2 near 1)
-__device__ __forceinline__ bool cz_div_rcp_ok(double b) { return b >= 0x1p-64 && b <= 0x1p64; }
+// (cz_div_rcp / cz_div_rcp_ok: cdf_device.cuh -- the decode-side search uses them too)
 
 // ---- vectorised full-column walk: NCOL adjacent columns per thread ------------------------------------------------------------
 template <int NCOL>

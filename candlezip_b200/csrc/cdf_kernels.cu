@@ -15,6 +15,7 @@
 #include <stdlib.h>
 
 #include "cdf_fast.cuh"
+#include "tc_ptx.cuh"
 
 namespace czk {
 
@@ -56,16 +57,17 @@ __global__ void __launch_bounds__(128) cdf_cols_kernel(const float *__restrict__
 // conversion path for the whole group (tiny results, -inf logits, NaN).  ef (optional) receives the f32 values.
 template <int N, bool WANT_F32>
 __device__ __forceinline__ void exp_group(const float (&a)[N], const ExpTab64 &tab, double (&d)[N], float (&ef)[N]) {
+  // The fast path is evaluated unconditionally (garbage, but harmless, for arguments it does not cover) and a group that holds
+  // such an argument is redone on the conversion path afterwards: the common case stays one straight-line block, which lets the
+  // compiler interleave it with the caller's sequential f64 chains.
   bool ok = true;
 #pragma unroll
-  for (int i = 0; i < N; i++) ok = ok && (a[i] <= CZ_EXP_FAST_MAX);
-  if (ok) {
-#pragma unroll
-    for (int i = 0; i < N; i++) {
-      d[i] = cz_exp_neg_fast(a[i], tab.t);
-      if (WANT_F32) ef[i] = cz_f32_of_gridded(d[i]);
-    }
-  } else {
+  for (int i = 0; i < N; i++) {
+    ok = ok && (a[i] <= CZ_EXP_FAST_MAX);
+    d[i] = cz_exp_neg_fast(a[i], tab.t);
+    if (WANT_F32) ef[i] = cz_f32_of_gridded(d[i]);
+  }
+  if (!ok) {
 #pragma unroll
     for (int i = 0; i < N; i++) {
       const float e = cz_expf(-a[i], tab);
@@ -236,6 +238,195 @@ __global__ void __launch_bounds__(128) cdf_stats_kernel(float *__restrict__ logi
   if (errbits) atomicOr(err, errbits);
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------------------
+// Full passes with the logits STAGED THROUGH SHARED MEMORY BY TMA.  cdf_stats_kernel spends a third of its issue slots on getting
+// the data: per logit one LDG, one L2 prefetch and four 64-bit address adds (rows are ld * 4 bytes apart, nothing folds into an
+// immediate), and its top stall is the load scoreboard (ncu, profiles/ncu_summary_r02.md).  Here one elected thread per CTA streams
+// [16 rows] x [256 columns] boxes (16 KB, 1 KB contiguous per row) into a 4-stage shared-memory ring with cp.async.bulk.tensor;
+// the 256 consumer threads (thread = column) read their values with immediate-offset LDS, so the per-logit cost is the arithmetic
+// alone and the loads run arbitrarily far ahead of it.  Same values, same order per column: bit-identical to cdf_stats_kernel.
+// Needs ld % 4 == 0 and a 16-byte aligned base (tensor-map strides); otherwise the launcher keeps cdf_stats_kernel.
+// ---------------------------------------------------------------------------------------------------------------------------------
+constexpr int ST_COLS = 256, ST_ROWS = 16, ST_STAGES = 4, ST_TILE_BYTES = ST_COLS * ST_ROWS * 4;
+constexpr int ST_SMEM = ST_STAGES * ST_TILE_BYTES + 32 * 32 * 8 + 128;  // tiles | exp table | barriers
+
+template <int MODE, int OP>
+__global__ void __launch_bounds__(ST_COLS + 32, 3) cdf_stats_tma_kernel(const __grid_constant__ CUtensorMap tm, float *__restrict__ logits, int V,
+                                                                       size_t M, size_t ld, const int *__restrict__ colmax,
+                                                                       CdfStats *__restrict__ stats, int *__restrict__ err) {
+  constexpr bool kLit = MODE == CZ_CDF_RWKV_LITERALS;
+  constexpr bool kNorm = kLit || OP == OP_XE;
+  extern __shared__ __align__(1024) uint8_t st_smem[];
+  float *tiles = reinterpret_cast<float *>(st_smem);
+  uint64_t *s_tab = reinterpret_cast<uint64_t *>(st_smem + ST_STAGES * ST_TILE_BYTES);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(st_smem + ST_STAGES * ST_TILE_BYTES + 32 * 32 * 8);
+  const uint32_t full_bar = smem_u32(&bars[0]), empty_bar = smem_u32(&bars[ST_STAGES]);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    for (int s2 = 0; s2 < ST_STAGES; s2++) {
+      mbar_init(full_bar + 8 * s2, 1);
+      mbar_init(empty_bar + 8 * s2, ST_COLS / 32);  // one arrival per consumer warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  exp_tab64_init(s_tab);  // (__syncthreads inside)
+  const int n_tiles = (V + ST_ROWS - 1) / ST_ROWS;
+  const bool need_max = colmax == nullptr;
+  const int n_pass = (need_max ? 1 : 0) + 1 + (kNorm ? 1 : 0) + (kLit ? 1 : 0);
+  const int c0 = blockIdx.x * ST_COLS;
+
+  if (warp == ST_COLS / 32) {
+    // ===================== producer warp: lane 0 issues the box loads =====================
+    int it = 0;
+    for (int pass = 0; pass < n_pass; pass++) {
+      if (lane == 0) {
+        if (pass == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&tm) : "memory");
+        for (int t = 0; t < n_tiles; t++, it++) {
+          const int st = it % ST_STAGES;
+          mbar_wait(empty_bar + 8 * st, ((it / ST_STAGES) & 1) ^ 1);
+          mbar_expect_tx(full_bar + 8 * st, ST_TILE_BYTES);
+          tma_load_2d(smem_u32(tiles + (size_t)st * ST_COLS * ST_ROWS), &tm, full_bar + 8 * st, c0, t * ST_ROWS);
+        }
+      }
+      __syncwarp();
+      // the RWKV alphabet's first pass rewrites the batch in place (expf cache): its stores must be complete and visible to the
+      // async proxy before the next pass's boxes are requested
+      if (kLit && pass == (need_max ? 1 : 0)) asm volatile("bar.sync 1, %0;" ::"n"(ST_COLS + 32) : "memory");
+    }
+    return;
+  }
+  // ===================== consumers: thread = column =====================
+  const ExpTab64 tab{s_tab + lane};
+  const size_t col = (size_t)c0 + tid;
+  const bool active = col < M;
+  float mx = need_max ? __int_as_float(0xff800000) : (active ? colmax_decode(colmax[col]) : 0.f);
+  int it = 0;
+  // walks one pass: f(v0, x[8], cnt) per group of 8 rows, in ascending row order
+  auto run_pass = [&](auto f) {
+    for (int t = 0; t < n_tiles; t++, it++) {
+      const int st = it % ST_STAGES;
+      mbar_wait(full_bar + 8 * st, (it / ST_STAGES) & 1);
+      const float *src = tiles + (size_t)st * ST_COLS * ST_ROWS + tid;
+      float x[ST_ROWS];
+#pragma unroll
+      for (int k = 0; k < ST_ROWS; k++) x[k] = src[k * ST_COLS];
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty_bar + 8 * st);  // the values are in registers: the slot can be refilled
+      if (t + 1 < n_tiles || V % ST_ROWS == 0) {  // a full tile: the group size is a compile-time 8 (no per-element predicates)
+#pragma unroll
+        for (int g = 0; g < ST_ROWS / 8; g++) {
+          float xg[8];
+#pragma unroll
+          for (int k = 0; k < 8; k++) xg[k] = x[g * 8 + k];
+          f(t * ST_ROWS + g * 8, xg, 8);
+        }
+      } else {  // the ragged last tile
+        const int rows = V - t * ST_ROWS;
+#pragma unroll
+        for (int g = 0; g < ST_ROWS / 8; g++) {
+          const int cnt = rows - g * 8;
+          if (cnt > 0) {
+            float xg[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) xg[k] = x[g * 8 + k];
+            f(t * ST_ROWS + g * 8, xg, cnt < 8 ? cnt : 8);
+          }
+        }
+      }
+    }
+  };
+  auto pass_barrier = [&]() {
+    if (kLit) {
+      asm volatile("fence.proxy.async.global;" ::: "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(ST_COLS + 32) : "memory");
+    }
+  };
+  if (need_max) {
+    run_pass([&](int, const float(&x)[8], int cnt) {
+#pragma unroll
+      for (int k = 0; k < 8; k++)
+        if (k < cnt && x[k] > mx) mx = x[k];  // NaN-ignoring, like `if v > max` (src/main.rs:786-788)
+    });
+  }
+  // ---- pass 1: S ----
+  double S = 0.0;
+  run_pass([&](int v0, const float(&x)[8], int cnt) {
+    float a[8], ef[8];
+    double d[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) a[k] = __fsub_rn(mx, x[k]);  // = -(l - max), exactly
+    exp_group<8, kLit>(a, tab, d, ef);
+#pragma unroll
+    for (int k = 0; k < 8; k++)
+      if (k < cnt) {
+        S = __dadd_rn(S, d[k]);
+        if (kLit && active) logits[(size_t)(v0 + k) * ld + col] = ef[k];  // cache e_v for the later passes
+      }
+  });
+  int errbits = 0;
+  if (active && !(S == S)) errbits |= CZ_DEVERR_NAN;
+  double norm = 1.0, sum2 = 1.0;
+  if (kNorm) {
+    pass_barrier();
+    const bool fast = cz_div_rcp_ok(S);
+    const double yS = __drcp_rn(S);
+    auto e_of = [&](const float(&x)[8], double(&d)[8]) {
+      if (kLit) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) d[k] = fast ? cz_widen_pos(x[k]) : (double)x[k];  // (values below 2^-126 are floored either way)
+      } else {
+        float a[8], ef[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) a[k] = __fsub_rn(mx, x[k]);
+        exp_group<8, false>(a, tab, d, ef);
+      }
+    };
+    auto div_S = [&](double e) { return fast ? cz_div_rcp(e, S, yS) : __ddiv_rn(e, S); };
+    // ---- pass 2: norm ----
+    double acc = 0.0;
+    run_pass([&](int, const float(&x)[8], int cnt) {
+      double d[8];
+      e_of(x, d);
+#pragma unroll
+      for (int k = 0; k < 8; k++)
+        if (k < cnt) acc = __dadd_rn(acc, fmax(div_S(d[k]), CZ_P_FLOOR));
+    });
+    norm = acc;
+    if (kLit) {
+      // ---- pass 3: sum2 ----  (no stores since pass 1: no barrier needed, the producer may already be ahead)
+      const double scale = 1.0 - 256.0 * CZ_P_FLOOR;
+      const bool fastn = fast && cz_div_rcp_ok(norm);
+      const double yN = __drcp_rn(norm);
+      acc = 0.0;
+      run_pass([&](int, const float(&x)[8], int cnt) {
+        double d[8];
+        e_of(x, d);
+#pragma unroll
+        for (int k = 0; k < 8; k++)
+          if (k < cnt) {
+            const double q = fmax(div_S(d[k]), CZ_P_FLOOR);
+            const double q2 = fastn ? cz_div_rcp(q, norm, yN) : __ddiv_rn(q, norm);
+            acc = __dadd_rn(acc, __dmul_rn(q2, scale));
+          }
+      });
+      for (int j = 0; j < 256; j++) acc = __dadd_rn(acc, CZ_P_FLOOR);
+      sum2 = acc;
+    }
+  }
+  if (active) {
+    CdfStats st;
+    st.S = S;
+    st.norm = norm;
+    st.sum2 = sum2;
+    st.mx = mx;
+    st.pad = 0;
+    stats[col] = st;
+    if (errbits) atomicOr(err, errbits);
+  }
+}
+
 // pdf entry of vocab element v from its logit (SmolLM) / cached e_v (RWKV alphabet): the same expressions as cdf_col's pdf_vocab
 template <int MODE, bool FLOORED>
 struct PdfOf {
@@ -323,53 +514,71 @@ __global__ void __launch_bounds__(256) cdf_bounds_sorted_kernel(const float *__r
   pdf.init(st, V);
   const float mx = st.mx;
   const float *p = logits + (active ? col : c0);
-  double acc = 0.0;
+  double acc = 0.0, acc_end = 0.0;
   uint32_t lo = 0, hi = 0;
-  // rows [0, n_lane) of this lane's column; the loop bound is the warp's maximum so that the warp stays converged
-  float cur[GRP], nxt[GRP];
+  // Rows [0, n_lane) of this lane's column; the loop bound is the warp's maximum so that the warp stays converged.  The only truly
+  // sequential part is acc += q_v: the pdf entries of the NEXT group (expf, divisions) are computed in the same straight-line
+  // block as the current group's chain of adds, so that the chain's latency hides behind them -- the walk of the one column per
+  // CTA whose symbol sits at the end of the vocabulary is what the kernel's duration comes down to.
   auto ldv = [&](int v) -> float { return kLit ? p[(size_t)v * ld] : __ldg(p + (size_t)v * ld); };
+  auto pdf_group = [&](const float(&rows)[GRP], int v0, double(&q)[GRP]) {
+    double d[GRP];
+    if (kLit) {
 #pragma unroll
-  for (int k = 0; k < GRP; k++) cur[k] = k < n_lane ? ldv(k) : 0.f;
+      for (int k = 0; k < GRP; k++) d[k] = pdf.fast ? cz_widen_pos(rows[k]) : (double)rows[k];
+    } else {
+      float a[GRP], ef[GRP];
+#pragma unroll
+      for (int k = 0; k < GRP; k++) a[k] = v0 + k < n_lane ? __fsub_rn(mx, rows[k]) : 0.f;  // rows past the lane's end: harmless exp(0)
+      exp_group<GRP, false>(a, tab, d, ef);
+    }
+#pragma unroll
+    for (int k = 0; k < GRP; k++) q[k] = pdf(d[k]);
+  };
+  float r1[GRP], r2[GRP];  // rows of groups g + 1 and g + 2
+  double q[GRP];
+  {
+    float r0[GRP];
+#pragma unroll
+    for (int k = 0; k < GRP; k++) {
+      r0[k] = k < n_lane ? ldv(k) : 0.f;
+      r1[k] = GRP + k < n_lane ? ldv(GRP + k) : 0.f;
+    }
+    pdf_group(r0, 0, q);
+  }
   for (int v0 = 0; v0 < n_warp; v0 += GRP) {
 #pragma unroll
     for (int k = 0; k < GRP; k++) {
-      const int v = v0 + GRP + k;
-      nxt[k] = v < n_lane ? ldv(v) : 0.f;
+      const int v = v0 + 2 * GRP + k;
+      r2[k] = v < n_lane ? ldv(v) : 0.f;
       if (v0 + CDF_PF + k < n_lane) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + (size_t)(v0 + CDF_PF + k) * ld));
     }
-    double q[GRP];
-    {
-      double d[GRP];
-      if (kLit) {
+    double qn[GRP], a[GRP];
+    pdf_group(r1, v0 + GRP, qn);
+    a[0] = __dadd_rn(acc, q[0]);
 #pragma unroll
-        for (int k = 0; k < GRP; k++) d[k] = pdf.fast ? cz_widen_pos(cur[k]) : (double)cur[k];
-      } else {
-        float a[GRP], ef[GRP];
-#pragma unroll
-        for (int k = 0; k < GRP; k++) a[k] = v0 + k < n_lane ? __fsub_rn(mx, cur[k]) : 0.f;  // rows past the lane's end: harmless exp(0)
-        exp_group<GRP, false>(a, tab, d, ef);
-      }
-#pragma unroll
-      for (int k = 0; k < GRP; k++) q[k] = pdf(d[k]);
-    }
-    if ((uint32_t)(v0 + GRP) < sym) {  // the whole group lies before cdf[sym]'s last term: no capture checks
-#pragma unroll
-      for (int k = 0; k < GRP; k++) acc = __dadd_rn(acc, q[k]);
-    } else {
+    for (int k = 1; k < GRP; k++) a[k] = __dadd_rn(a[k - 1], q[k]);  // (rows past the lane's last one add garbage after both bounds were captured)
+    acc = a[GRP - 1];
+    // cdf[sym] or cdf[sym + 1] ends inside this group, or (literal symbols) the vocabulary does: rare, at most twice per column
+    if (sym - (uint32_t)v0 <= (uint32_t)GRP || (kLit && (uint32_t)(n_lane - v0) <= (uint32_t)GRP)) {
 #pragma unroll
       for (int k = 0; k < GRP; k++) {
-        acc = __dadd_rn(acc, q[k]);  // (rows past the lane's last one add garbage after both bounds were captured)
         const uint32_t v = (uint32_t)(v0 + k);
-        if (v + 1 == sym) lo = quant(acc);
-        if (v == sym) hi = quant(acc);
+        if (v + 1 == sym) lo = quant(a[k]);
+        if (v == sym) hi = quant(a[k]);
+        if (kLit && v + 1 == (uint32_t)n_lane) acc_end = a[k];  // the sum over exactly the vocabulary: the literal symbols continue from it
       }
     }
 #pragma unroll
-    for (int k = 0; k < GRP; k++) cur[k] = nxt[k];
+    for (int k = 0; k < GRP; k++) {
+      q[k] = qn[k];
+      r1[k] = r2[k];
+    }
   }
   if (!active) return;
   if (kLit && (int)sym >= V) {  // literal symbols follow the vocabulary: acc continues from the full vocab sum
     const double pl = pdf.literal();
+    acc = acc_end;
     for (uint32_t v = (uint32_t)V; v <= sym; v++) {
       acc = __dadd_rn(acc, pl);
       if (v + 1 == sym) lo = quant(acc);
@@ -591,6 +800,35 @@ int launch_fill_i32(cz_ctx *ctx, int *p, int v, size_t n, cudaStream_t stream) {
   return CZ_OK;
 }
 
+// logits [V][ld] f32 as a 2D tensor, box = ST_COLS columns x ST_ROWS rows, no swizzle (thread t reads word t of a row: conflict-free);
+// rows beyond V and columns beyond ld are zero-filled
+static int make_logits_map(CUtensorMap *map, const float *logits, size_t V, size_t ld) {
+  typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                               const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                               CUtensorMapFloatOOBfill);
+  static EncodeFn fn = nullptr;
+  if (!fn) {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) != cudaSuccess || qr != cudaDriverEntryPointSuccess) {
+      set_error("cuTensorMapEncodeTiled entry point not available");
+      return CZ_ERR_CUDA;
+    }
+    fn = (EncodeFn)p;
+  }
+  cuuint64_t gdim[2] = {(cuuint64_t)ld, (cuuint64_t)V};
+  cuuint64_t gstride[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {(cuuint32_t)czk::ST_COLS, (cuuint32_t)czk::ST_ROWS};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(logits), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (logits) failed with CUresult " + std::to_string((int)r));
+    return CZ_ERR_CUDA;
+  }
+  return CZ_OK;
+}
+
 // Device-pointer launchers (used by the executor and by the host-buffer C-ABI wrappers in api.cu)
 int launch_cdf_cols(cz_ctx *ctx, int op, int mode, const float *logits_dev, size_t V, size_t M, size_t ld,
                     const uint32_t *arg_dev, uint32_t *sym_out_dev, uint32_t *c_lo_dev, uint32_t *c_hi_dev,
@@ -642,7 +880,43 @@ int launch_cdf_cols(cz_ctx *ctx, int op, int mode, const float *logits_dev, size
     int ncol = 1;
     if (force_ncol == 1 || force_ncol == 2 || force_ncol == 4) ncol = force_ncol;
     while (ncol > 1 && (ld % ncol != 0 || ((uintptr_t)logits_dev & (size_t)(4 * ncol - 1)) != 0)) ncol >>= 1;
+    // TMA-staged variant: needs tensor-map-compatible strides / alignment and enough columns to fill the machine with 256-column CTAs
+    static const bool no_tma = getenv("CZ_CDF_NO_TMA") != nullptr;  // bisecting aid
+    const bool tma_ok = !no_tma && force_ncol == 0 && ld % 4 == 0 && ((uintptr_t)logits_dev & 15) == 0 && M >= 256 && V >= 64;
+    if (tma_ok) {
+      CUtensorMap tm;
+      CZ_TRY(make_logits_map(&tm, logits_dev, V, ld));
+      static bool attr = false;
+      if (!attr) {
+#define CZ_TMA_ATTR(MODE, OP) \
+  CZ_CUDA_TRY(cudaFuncSetAttribute(czk::cdf_stats_tma_kernel<MODE, OP>, cudaFuncAttributeMaxDynamicSharedMemorySize, czk::ST_SMEM))
+        CZ_TMA_ATTR(CZ_CDF_SMOLLM, czk::OP_BOUNDS);
+        CZ_TMA_ATTR(CZ_CDF_SMOLLM, czk::OP_XE);
+        CZ_TMA_ATTR(CZ_CDF_RWKV_LITERALS, czk::OP_BOUNDS);
+        CZ_TMA_ATTR(CZ_CDF_RWKV_LITERALS, czk::OP_XE);
+#undef CZ_TMA_ATTR
+        attr = true;
+      }
+      const unsigned g = (unsigned)ceil_div(M, (size_t)czk::ST_COLS);
+#define CZ_TMA_STATS(MODE, OP)                                                                                                        \
+  CZ_LAUNCH(ctx, CZ_K_CDF,                                                                                                            \
+            (czk::cdf_stats_tma_kernel<MODE, OP><<<g, czk::ST_COLS + 32, czk::ST_SMEM, stream>>>(tm, lg, (int)V, M, ld, colmax_dev, stats, \
+                                                                                                 ctx->err_flag_dev)))
+      if (mode == CZ_CDF_SMOLLM) {
+        if (op == czk::OP_BOUNDS) CZ_TMA_STATS(CZ_CDF_SMOLLM, czk::OP_BOUNDS);
+        else CZ_TMA_STATS(CZ_CDF_SMOLLM, czk::OP_XE);
+      } else if (mode == CZ_CDF_RWKV_LITERALS) {
+        if (op == czk::OP_BOUNDS) CZ_TMA_STATS(CZ_CDF_RWKV_LITERALS, czk::OP_BOUNDS);
+        else CZ_TMA_STATS(CZ_CDF_RWKV_LITERALS, czk::OP_XE);
+      } else {
+        set_error("cdf: unknown mode");
+        return CZ_ERR_INVALID;
+      }
+#undef CZ_TMA_STATS
+      CZ_CHECK_LAUNCH();
+    }
     const unsigned g_stats = (unsigned)ceil_div(ceil_div(M, (size_t)ncol), 128);
+    if (!tma_ok) {
 #define CZ_STATS(MODE, OP, NC)                                                                                                   \
   CZ_LAUNCH(ctx, CZ_K_CDF,                                                                                                       \
             (czk::cdf_stats_kernel<MODE, OP, NC><<<g_stats, 128, 0, stream>>>(lg, (int)V, M, ld, colmax_dev, stats, ctx->err_flag_dev)))
@@ -665,6 +939,7 @@ int launch_cdf_cols(cz_ctx *ctx, int op, int mode, const float *logits_dev, size
 #undef CZ_STATS_N
 #undef CZ_STATS
     CZ_CHECK_LAUNCH();
+    }
     if (op == czk::OP_BOUNDS) {
       const unsigned g = (unsigned)ceil_div(M, 256);
       if (mode == CZ_CDF_SMOLLM)
