@@ -84,8 +84,12 @@ __device__ __forceinline__ void exp_group(const float (&a)[N], const ExpTab64 &t
 //   pass 3  sum2 = sum RN(RN(max(e / S, 2^-29) / norm) (1 - 2^-21)) + 256 x 2^-29   RWKV alphabet
 template <int MODE, int OP, int NCOL>
 __global__ void __launch_bounds__(128) cdf_stats_kernel(float *__restrict__ logits, int V, size_t M, size_t ld, const int *__restrict__ colmax,
-                                                        CdfStats *__restrict__ stats, int *__restrict__ err) {
+                                                        CdfStats *__restrict__ stats, int *__restrict__ err,
+                                                        const uint32_t *__restrict__ syms) {
   constexpr bool kLit = MODE == CZ_CDF_RWKV_LITERALS;
+  // SmolLM bounds: the prefix walk needs e_v = expf(l_v - max) for v <= the coded symbol again.  They are left in the logits' slots
+  // (the batch is scratch once the digests are taken), so that walk costs a load and a division per element instead of an expf.
+  constexpr bool kCacheToSym = !kLit && OP == OP_BOUNDS;
   constexpr bool kNorm = kLit || OP == OP_XE;
   constexpr int GRP = NCOL == 4 ? 4 : 8;
   constexpr int NE = GRP * NCOL;
@@ -117,9 +121,15 @@ __global__ void __launch_bounds__(128) cdf_stats_kernel(float *__restrict__ logi
   }
   // ---- pass 1 ----
   double S[NCOL];
+  uint32_t symc[NCOL], sym_hi = 0;
 #pragma unroll
-  for (int c = 0; c < NCOL; c++) S[c] = 0.0;
-  cdf_walk_groups<NCOL, GRP, !kLit>(p, ld, V, [&](int v0, const typename CdfVec<NCOL>::T(&rows)[GRP], int cnt) {
+  for (int c = 0; c < NCOL; c++) {
+    S[c] = 0.0;
+    symc[c] = (kCacheToSym && col0 + c < M) ? syms[col0 + c] : 0u;
+    if ((int)symc[c] >= V) symc[c] = 0;  // (a bad symbol is reported by the prefix kernel)
+    sym_hi = symc[c] > sym_hi ? symc[c] : sym_hi;
+  }
+  cdf_walk_groups<NCOL, GRP, !(kLit || kCacheToSym)>(p, ld, V, [&](int v0, const typename CdfVec<NCOL>::T(&rows)[GRP], int cnt) {
     float a[NE], ef[NE];
     double d[NE];
 #pragma unroll
@@ -129,7 +139,14 @@ __global__ void __launch_bounds__(128) cdf_stats_kernel(float *__restrict__ logi
 #pragma unroll
       for (int c = 0; c < NCOL; c++) a[k * NCOL + c] = __fsub_rn(mx[c], x[c]);  // = -(l - max), exactly
     }
-    exp_group<NE, kLit>(a, tab, d, ef);
+    exp_group<NE, kLit || kCacheToSym>(a, tab, d, ef);
+    if (kCacheToSym && (uint32_t)v0 <= sym_hi) {  // rows up to the coded symbol (per thread: the store path is skipped beyond it)
+#pragma unroll
+      for (int k = 0; k < GRP; k++)
+#pragma unroll
+        for (int c = 0; c < NCOL; c++)
+          if (k < cnt && (uint32_t)(v0 + k) <= symc[c] && col0 + c < M) p[(size_t)(v0 + k) * ld + c] = ef[k * NCOL + c];
+    }
 #pragma unroll
     for (int k = 0; k < GRP; k++) {
       if (k < cnt) {
@@ -254,9 +271,11 @@ constexpr int ST_SMEM = ST_STAGES * ST_TILE_BYTES + 32 * 32 * 8 + 128;  // tiles
 template <int MODE, int OP>
 __global__ void __launch_bounds__(ST_COLS + 32, 3) cdf_stats_tma_kernel(const __grid_constant__ CUtensorMap tm, float *__restrict__ logits, int V,
                                                                        size_t M, size_t ld, const int *__restrict__ colmax,
-                                                                       CdfStats *__restrict__ stats, int *__restrict__ err) {
+                                                                       CdfStats *__restrict__ stats, int *__restrict__ err,
+                                                                       const uint32_t *__restrict__ syms) {
   constexpr bool kLit = MODE == CZ_CDF_RWKV_LITERALS;
   constexpr bool kNorm = kLit || OP == OP_XE;
+  constexpr bool kCacheToSym = !kLit && OP == OP_BOUNDS;  // see cdf_stats_kernel
   extern __shared__ __align__(1024) uint8_t st_smem[];
   float *tiles = reinterpret_cast<float *>(st_smem);
   uint64_t *s_tab = reinterpret_cast<uint64_t *>(st_smem + ST_STAGES * ST_TILE_BYTES);
@@ -352,12 +371,20 @@ __global__ void __launch_bounds__(ST_COLS + 32, 3) cdf_stats_tma_kernel(const __
   }
   // ---- pass 1: S ----
   double S = 0.0;
+  uint32_t symc = (kCacheToSym && active) ? syms[col] : 0u;
+  if ((int)symc >= V) symc = 0;  // (a bad symbol is reported by the prefix kernel)
+  float *const pcol = logits + col;
   run_pass([&](int v0, const float(&x)[8], int cnt) {
     float a[8], ef[8];
     double d[8];
 #pragma unroll
     for (int k = 0; k < 8; k++) a[k] = __fsub_rn(mx, x[k]);  // = -(l - max), exactly
-    exp_group<8, kLit>(a, tab, d, ef);
+    exp_group<8, kLit || kCacheToSym>(a, tab, d, ef);
+    if (kCacheToSym && active && (uint32_t)v0 <= symc) {  // rows up to the coded symbol: e_v stays in the logit's slot for the prefix walk
+#pragma unroll
+      for (int k = 0; k < 8; k++)
+        if (k < cnt && (uint32_t)(v0 + k) <= symc) pcol[(size_t)(v0 + k) * ld] = ef[k];
+    }
 #pragma unroll
     for (int k = 0; k < 8; k++)
       if (k < cnt) {
@@ -462,12 +489,14 @@ struct PdfOf {
 // Prefix walk (encode): cdf[sym], cdf[sym + 1] of every column.  A CTA takes 256 adjacent columns, sorts them by how far they have
 // to walk (the coded symbol), and warp w walks the columns of rank 32 w .. 32 w + 31: lanes of a warp finish together instead of
 // all waiting for the one column whose symbol sits at the end of the vocabulary.
-template <int MODE>
+// CACHED: rows [0, sym] of the column hold e_v (left there by the stats kernel) instead of the logits.
+template <int MODE, bool CACHED>
 __global__ void __launch_bounds__(256) cdf_bounds_sorted_kernel(const float *__restrict__ logits, int V, size_t M, size_t ld,
                                                                 const uint32_t *__restrict__ syms, const CdfStats *__restrict__ stats,
                                                                 uint32_t *__restrict__ c_lo_out, uint32_t *__restrict__ c_hi_out,
                                                                 int *__restrict__ err) {
   constexpr bool kLit = MODE == CZ_CDF_RWKV_LITERALS;
+  constexpr bool kE = kLit || CACHED;  // the rows hold e_v
   constexpr int GRP = 8;
   __shared__ uint64_t s_tab[32 * 32];
   __shared__ uint32_t s_key[256];
@@ -520,12 +549,25 @@ __global__ void __launch_bounds__(256) cdf_bounds_sorted_kernel(const float *__r
   // sequential part is acc += q_v: the pdf entries of the NEXT group (expf, divisions) are computed in the same straight-line
   // block as the current group's chain of adds, so that the chain's latency hides behind them -- the walk of the one column per
   // CTA whose symbol sits at the end of the vocabulary is what the kernel's duration comes down to.
-  auto ldv = [&](int v) -> float { return kLit ? p[(size_t)v * ld] : __ldg(p + (size_t)v * ld); };
+  auto ldv = [&](int v) -> float { return kE ? p[(size_t)v * ld] : __ldg(p + (size_t)v * ld); };
   auto pdf_group = [&](const float(&rows)[GRP], int v0, double(&q)[GRP]) {
     double d[GRP];
     if (kLit) {
 #pragma unroll
-      for (int k = 0; k < GRP; k++) d[k] = pdf.fast ? cz_widen_pos(rows[k]) : (double)rows[k];
+      for (int k = 0; k < GRP; k++) d[k] = pdf.fast ? cz_widen_pos(rows[k]) : (double)rows[k];  // (values below 2^-126 are floored either way)
+    } else if (CACHED) {
+      // no floor in the SmolLM pdf: a zero / subnormal e_v must be widened exactly.  They only occur more than 87 below the
+      // maximum: the integer widening for the group when every value is a normal float, the conversion otherwise.
+      bool ok = true;
+#pragma unroll
+      for (int k = 0; k < GRP; k++) {
+        ok = ok && (__float_as_uint(rows[k]) >= 0x00800000u);
+        d[k] = cz_widen_pos(rows[k]);
+      }
+      if (!ok) {
+#pragma unroll
+        for (int k = 0; k < GRP; k++) d[k] = (double)rows[k];
+      }
     } else {
       float a[GRP], ef[GRP];
 #pragma unroll
@@ -535,23 +577,25 @@ __global__ void __launch_bounds__(256) cdf_bounds_sorted_kernel(const float *__r
 #pragma unroll
     for (int k = 0; k < GRP; k++) q[k] = pdf(d[k]);
   };
+  // Loads and prefetches are unconditional on a row index clamped to the lane's last row (a lane that is done re-reads that row
+  // out of L1 while the warp's longest column finishes): no per-element branches in the loop.
+  const int v_last = n_lane > 0 ? n_lane - 1 : 0;
   float r1[GRP], r2[GRP];  // rows of groups g + 1 and g + 2
   double q[GRP];
   {
     float r0[GRP];
 #pragma unroll
     for (int k = 0; k < GRP; k++) {
-      r0[k] = k < n_lane ? ldv(k) : 0.f;
-      r1[k] = GRP + k < n_lane ? ldv(GRP + k) : 0.f;
+      r0[k] = ldv(min(k, v_last));
+      r1[k] = ldv(min(GRP + k, v_last));
     }
     pdf_group(r0, 0, q);
   }
   for (int v0 = 0; v0 < n_warp; v0 += GRP) {
 #pragma unroll
     for (int k = 0; k < GRP; k++) {
-      const int v = v0 + 2 * GRP + k;
-      r2[k] = v < n_lane ? ldv(v) : 0.f;
-      if (v0 + CDF_PF + k < n_lane) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + (size_t)(v0 + CDF_PF + k) * ld));
+      r2[k] = ldv(min(v0 + 2 * GRP + k, v_last));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(p + (size_t)min(v0 + CDF_PF + k, v_last) * ld));
     }
     double qn[GRP], a[GRP];
     pdf_group(r1, v0 + GRP, qn);
@@ -901,7 +945,7 @@ int launch_cdf_cols(cz_ctx *ctx, int op, int mode, const float *logits_dev, size
 #define CZ_TMA_STATS(MODE, OP)                                                                                                        \
   CZ_LAUNCH(ctx, CZ_K_CDF,                                                                                                            \
             (czk::cdf_stats_tma_kernel<MODE, OP><<<g, czk::ST_COLS + 32, czk::ST_SMEM, stream>>>(tm, lg, (int)V, M, ld, colmax_dev, stats, \
-                                                                                                 ctx->err_flag_dev)))
+                                                                                                 ctx->err_flag_dev, arg_dev)))
       if (mode == CZ_CDF_SMOLLM) {
         if (op == czk::OP_BOUNDS) CZ_TMA_STATS(CZ_CDF_SMOLLM, czk::OP_BOUNDS);
         else CZ_TMA_STATS(CZ_CDF_SMOLLM, czk::OP_XE);
@@ -919,7 +963,7 @@ int launch_cdf_cols(cz_ctx *ctx, int op, int mode, const float *logits_dev, size
     if (!tma_ok) {
 #define CZ_STATS(MODE, OP, NC)                                                                                                   \
   CZ_LAUNCH(ctx, CZ_K_CDF,                                                                                                       \
-            (czk::cdf_stats_kernel<MODE, OP, NC><<<g_stats, 128, 0, stream>>>(lg, (int)V, M, ld, colmax_dev, stats, ctx->err_flag_dev)))
+            (czk::cdf_stats_kernel<MODE, OP, NC><<<g_stats, 128, 0, stream>>>(lg, (int)V, M, ld, colmax_dev, stats, ctx->err_flag_dev, arg_dev)))
 #define CZ_STATS_N(MODE, OP)            \
   do {                                  \
     if (ncol == 4) CZ_STATS(MODE, OP, 4); \
@@ -942,14 +986,15 @@ int launch_cdf_cols(cz_ctx *ctx, int op, int mode, const float *logits_dev, size
     }
     if (op == czk::OP_BOUNDS) {
       const unsigned g = (unsigned)ceil_div(M, 256);
+      // (both stats kernels leave e_v in rows [0, sym] of a SmolLM column: the prefix walk reads them back)
       if (mode == CZ_CDF_SMOLLM)
         CZ_LAUNCH(ctx, CZ_K_CDF_PREFIX,
-                  (czk::cdf_bounds_sorted_kernel<CZ_CDF_SMOLLM><<<g, 256, 0, stream>>>(logits_dev, (int)V, M, ld, arg_dev, stats, c_lo_dev, c_hi_dev,
-                                                                                       ctx->err_flag_dev)));
+                  (czk::cdf_bounds_sorted_kernel<CZ_CDF_SMOLLM, true><<<g, 256, 0, stream>>>(logits_dev, (int)V, M, ld, arg_dev, stats, c_lo_dev,
+                                                                                             c_hi_dev, ctx->err_flag_dev)));
       else
         CZ_LAUNCH(ctx, CZ_K_CDF_PREFIX,
-                  (czk::cdf_bounds_sorted_kernel<CZ_CDF_RWKV_LITERALS><<<g, 256, 0, stream>>>(logits_dev, (int)V, M, ld, arg_dev, stats, c_lo_dev,
-                                                                                              c_hi_dev, ctx->err_flag_dev)));
+                  (czk::cdf_bounds_sorted_kernel<CZ_CDF_RWKV_LITERALS, false><<<g, 256, 0, stream>>>(logits_dev, (int)V, M, ld, arg_dev, stats,
+                                                                                                     c_lo_dev, c_hi_dev, ctx->err_flag_dev)));
     } else {
       const unsigned g = (unsigned)ceil_div(M, 128);
       if (mode == CZ_CDF_SMOLLM)
