@@ -84,12 +84,8 @@ __device__ __forceinline__ void exp_group(const float (&a)[N], const ExpTab64 &t
 //   pass 3  sum2 = sum RN(RN(max(e / S, 2^-29) / norm) (1 - 2^-21)) + 256 x 2^-29   RWKV alphabet
 template <int MODE, int OP, int NCOL>
 __global__ void __launch_bounds__(128) cdf_stats_kernel(float *__restrict__ logits, int V, size_t M, size_t ld, const int *__restrict__ colmax,
-                                                        CdfStats *__restrict__ stats, int *__restrict__ err,
-                                                        const uint32_t *__restrict__ syms) {
+                                                        CdfStats *__restrict__ stats, int *__restrict__ err) {
   constexpr bool kLit = MODE == CZ_CDF_RWKV_LITERALS;
-  // SmolLM bounds: the prefix walk needs e_v = expf(l_v - max) for v <= the coded symbol again.  They are left in the logits' slots
-  // (the batch is scratch once the digests are taken), so that walk costs a load and a division per element instead of an expf.
-  constexpr bool kCacheToSym = !kLit && OP == OP_BOUNDS;
   constexpr bool kNorm = kLit || OP == OP_XE;
   constexpr int GRP = NCOL == 4 ? 4 : 8;
   constexpr int NE = GRP * NCOL;
@@ -121,15 +117,9 @@ __global__ void __launch_bounds__(128) cdf_stats_kernel(float *__restrict__ logi
   }
   // ---- pass 1 ----
   double S[NCOL];
-  uint32_t symc[NCOL], sym_hi = 0;
 #pragma unroll
-  for (int c = 0; c < NCOL; c++) {
-    S[c] = 0.0;
-    symc[c] = (kCacheToSym && col0 + c < M) ? syms[col0 + c] : 0u;
-    if ((int)symc[c] >= V) symc[c] = 0;  // (a bad symbol is reported by the prefix kernel)
-    sym_hi = symc[c] > sym_hi ? symc[c] : sym_hi;
-  }
-  cdf_walk_groups<NCOL, GRP, !(kLit || kCacheToSym)>(p, ld, V, [&](int v0, const typename CdfVec<NCOL>::T(&rows)[GRP], int cnt) {
+  for (int c = 0; c < NCOL; c++) S[c] = 0.0;
+  cdf_walk_groups<NCOL, GRP, !kLit>(p, ld, V, [&](int v0, const typename CdfVec<NCOL>::T(&rows)[GRP], int cnt) {
     float a[NE], ef[NE];
     double d[NE];
 #pragma unroll
@@ -139,14 +129,7 @@ __global__ void __launch_bounds__(128) cdf_stats_kernel(float *__restrict__ logi
 #pragma unroll
       for (int c = 0; c < NCOL; c++) a[k * NCOL + c] = __fsub_rn(mx[c], x[c]);  // = -(l - max), exactly
     }
-    exp_group<NE, kLit || kCacheToSym>(a, tab, d, ef);
-    if (kCacheToSym && (uint32_t)v0 <= sym_hi) {  // rows up to the coded symbol (per thread: the store path is skipped beyond it)
-#pragma unroll
-      for (int k = 0; k < GRP; k++)
-#pragma unroll
-        for (int c = 0; c < NCOL; c++)
-          if (k < cnt && (uint32_t)(v0 + k) <= symc[c] && col0 + c < M) p[(size_t)(v0 + k) * ld + c] = ef[k * NCOL + c];
-    }
+    exp_group<NE, kLit>(a, tab, d, ef);
 #pragma unroll
     for (int k = 0; k < GRP; k++) {
       if (k < cnt) {
@@ -271,11 +254,9 @@ constexpr int ST_SMEM = ST_STAGES * ST_TILE_BYTES + 32 * 32 * 8 + 128;  // tiles
 template <int MODE, int OP>
 __global__ void __launch_bounds__(ST_COLS + 32, 3) cdf_stats_tma_kernel(const __grid_constant__ CUtensorMap tm, float *__restrict__ logits, int V,
                                                                        size_t M, size_t ld, const int *__restrict__ colmax,
-                                                                       CdfStats *__restrict__ stats, int *__restrict__ err,
-                                                                       const uint32_t *__restrict__ syms) {
+                                                                       CdfStats *__restrict__ stats, int *__restrict__ err) {
   constexpr bool kLit = MODE == CZ_CDF_RWKV_LITERALS;
   constexpr bool kNorm = kLit || OP == OP_XE;
-  constexpr bool kCacheToSym = !kLit && OP == OP_BOUNDS;  // see cdf_stats_kernel
   extern __shared__ __align__(1024) uint8_t st_smem[];
   float *tiles = reinterpret_cast<float *>(st_smem);
   uint64_t *s_tab = reinterpret_cast<uint64_t *>(st_smem + ST_STAGES * ST_TILE_BYTES);
@@ -371,20 +352,12 @@ __global__ void __launch_bounds__(ST_COLS + 32, 3) cdf_stats_tma_kernel(const __
   }
   // ---- pass 1: S ----
   double S = 0.0;
-  uint32_t symc = (kCacheToSym && active) ? syms[col] : 0u;
-  if ((int)symc >= V) symc = 0;  // (a bad symbol is reported by the prefix kernel)
-  float *const pcol = logits + col;
   run_pass([&](int v0, const float(&x)[8], int cnt) {
     float a[8], ef[8];
     double d[8];
 #pragma unroll
     for (int k = 0; k < 8; k++) a[k] = __fsub_rn(mx, x[k]);  // = -(l - max), exactly
-    exp_group<8, kLit || kCacheToSym>(a, tab, d, ef);
-    if (kCacheToSym && active && (uint32_t)v0 <= symc) {  // rows up to the coded symbol: e_v stays in the logit's slot for the prefix walk
-#pragma unroll
-      for (int k = 0; k < 8; k++)
-        if (k < cnt && (uint32_t)(v0 + k) <= symc) pcol[(size_t)(v0 + k) * ld] = ef[k];
-    }
+    exp_group<8, kLit>(a, tab, d, ef);
 #pragma unroll
     for (int k = 0; k < 8; k++)
       if (k < cnt) {
@@ -486,143 +459,97 @@ struct PdfOf {
   __device__ __forceinline__ double literal() const { return has2 ? __ddiv_rn(CZ_P_FLOOR, sum2) : CZ_P_FLOOR; }
 };
 
-// Prefix walk (encode): cdf[sym], cdf[sym + 1] of every column.  A CTA takes 256 adjacent columns, sorts them by how far they have
-// to walk (the coded symbol), and warp w walks the columns of rank 32 w .. 32 w + 31: lanes of a warp finish together instead of
-// all waiting for the one column whose symbol sits at the end of the vocabulary.
-// CACHED: rows [0, sym] of the column hold e_v (left there by the stats kernel) instead of the logits.
-template <int MODE, bool CACHED>
-__global__ void __launch_bounds__(256) cdf_bounds_sorted_kernel(const float *__restrict__ logits, int V, size_t M, size_t ld,
-                                                                const uint32_t *__restrict__ syms, const CdfStats *__restrict__ stats,
-                                                                uint32_t *__restrict__ c_lo_out, uint32_t *__restrict__ c_hi_out,
-                                                                int *__restrict__ err) {
+// Prefix walk (encode): cdf[sym], cdf[sym + 1] of every column -- ONE WARP PER COLUMN.
+//
+// The walk is a strictly sequential f64 sum of sym + 1 terms, and symbols are heavy-tailed (mean id / V = 0.1 for real text, but
+// one column in twenty needs more than half of the vocabulary).  With a thread per column a warp walks until its slowest lane is
+// done, and even with the columns of a CTA sorted by symbol the kernel's duration was the latency of the lone warps left walking
+// the longest columns (ncu, profiles/ncu_summary_r02.md: 1.2 warps per scheduler, 4,000 cycles per 8 rows, 9-13 ms per 131,072
+// columns).  Here the 32 lanes of a warp evaluate the pdf entries of 32 consecutive vocab entries of ONE column in parallel (expf,
+// divisions: the expensive part) and only the order-dependent accumulation is serial -- every lane performs it redundantly on the
+// shared-memory line the values were exchanged through (cdf_search_warp's scheme), so all lanes hold the same acc and every branch
+// is warp-uniform.  Columns are independent warps of very different lengths, thousands per SM over the kernel's life: the machine
+// stays full until the end, and the longest column costs V / 32 short iterations.  The 8 warps of a CTA take 8 adjacent columns =
+// one 32-byte sector per vocab row, so a row's sector is fetched from DRAM once and the other seven warps find it in L1 / L2.
+// Same operations in the same order as cdf_col's OP_BOUNDS: bit-identical results.
+template <int MODE>
+__global__ void __launch_bounds__(256) cdf_bounds_warp_kernel(const float *__restrict__ logits, int V, size_t M, size_t ld,
+                                                              const uint32_t *__restrict__ syms, const CdfStats *__restrict__ stats,
+                                                              uint32_t *__restrict__ c_lo_out, uint32_t *__restrict__ c_hi_out,
+                                                              int *__restrict__ err) {
   constexpr bool kLit = MODE == CZ_CDF_RWKV_LITERALS;
-  constexpr bool kE = kLit || CACHED;  // the rows hold e_v
-  constexpr int GRP = 8;
   __shared__ uint64_t s_tab[32 * 32];
-  __shared__ uint32_t s_key[256];
-  __shared__ uint16_t s_perm[256];
+  __shared__ __align__(16) double s_xch[8 * 64];  // per warp: two 32-value exchange lines
   exp_tab64_init(s_tab);
-  const ExpTab64 tab{s_tab + (threadIdx.x & 31)};
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const ExpTab64 tab{s_tab + lane};
+  const size_t col = (size_t)blockIdx.x * 8 + warp;
+  if (col >= M) return;
   const int n_sym = kLit ? V + 256 : V;
-  const size_t c0 = (size_t)blockIdx.x * 256;
-  {
-    const size_t col = c0 + threadIdx.x;
-    uint32_t key = 0;  // columns past M and bad symbols do not walk
-    if (col < M) {
-      const uint32_t s = syms[col];
-      if ((int)s < n_sym) key = ((int)s < V ? s : (uint32_t)V - 1u) + 1u;  // rows to visit
+  uint32_t sym = syms[col];
+  if ((int)sym >= n_sym) {
+    if (lane == 0) {
+      atomicOr(err, CZ_DEVERR_SYM);
+      c_lo_out[col] = 0u;
+      c_hi_out[col] = 0u;
     }
-    s_key[threadIdx.x] = key;
+    return;
   }
-  __syncthreads();
-  {
-    const uint32_t key = s_key[threadIdx.x];
-    int rank = 0;
-    for (int u = 0; u < 256; u++) {
-      const uint32_t ku = s_key[u];
-      rank += (ku < key || (ku == key && u < (int)threadIdx.x)) ? 1 : 0;
-    }
-    s_perm[rank] = (uint16_t)threadIdx.x;
-  }
-  __syncthreads();
-  const int mine = s_perm[threadIdx.x];
-  const size_t col = c0 + mine;
-  const bool active = col < M;
-  const int n_lane = (int)s_key[mine];
-  const int n_warp = __reduce_max_sync(0xffffffffu, n_lane);
-  uint32_t sym = active ? syms[col] : 0u;
-  bool sym_bad = false;
-  if (active && (int)sym >= n_sym) {
-    sym_bad = true;
-    sym = 0;
-  }
-  CdfStats st;
-  if (active) st = stats[col];
-  else st.S = st.norm = st.sum2 = 1.0, st.mx = 0.f;
+  const CdfStats st = stats[col];
   PdfOf<MODE, false> pdf;
   pdf.init(st, V);
   const float mx = st.mx;
-  const float *p = logits + (active ? col : c0);
-  double acc = 0.0, acc_end = 0.0;
-  uint32_t lo = 0, hi = 0;
-  // Rows [0, n_lane) of this lane's column; the loop bound is the warp's maximum so that the warp stays converged.  The only truly
-  // sequential part is acc += q_v: the pdf entries of the NEXT group (expf, divisions) are computed in the same straight-line
-  // block as the current group's chain of adds, so that the chain's latency hides behind them -- the walk of the one column per
-  // CTA whose symbol sits at the end of the vocabulary is what the kernel's duration comes down to.
-  auto ldv = [&](int v) -> float { return kE ? p[(size_t)v * ld] : __ldg(p + (size_t)v * ld); };
-  auto pdf_group = [&](const float(&rows)[GRP], int v0, double(&q)[GRP]) {
-    double d[GRP];
-    if (kLit) {
-#pragma unroll
-      for (int k = 0; k < GRP; k++) d[k] = pdf.fast ? cz_widen_pos(rows[k]) : (double)rows[k];  // (values below 2^-126 are floored either way)
-    } else if (CACHED) {
-      // no floor in the SmolLM pdf: a zero / subnormal e_v must be widened exactly.  They only occur more than 87 below the
-      // maximum: the integer widening for the group when every value is a normal float, the conversion otherwise.
-      bool ok = true;
-#pragma unroll
-      for (int k = 0; k < GRP; k++) {
-        ok = ok && (__float_as_uint(rows[k]) >= 0x00800000u);
-        d[k] = cz_widen_pos(rows[k]);
-      }
-      if (!ok) {
-#pragma unroll
-        for (int k = 0; k < GRP; k++) d[k] = (double)rows[k];
-      }
-    } else {
-      float a[GRP], ef[GRP];
-#pragma unroll
-      for (int k = 0; k < GRP; k++) a[k] = v0 + k < n_lane ? __fsub_rn(mx, rows[k]) : 0.f;  // rows past the lane's end: harmless exp(0)
-      exp_group<GRP, false>(a, tab, d, ef);
-    }
-#pragma unroll
-    for (int k = 0; k < GRP; k++) q[k] = pdf(d[k]);
+  const float *p = logits + col;
+  double *xch = s_xch + warp * 64;
+  const int n = (int)sym < V ? (int)sym + 1 : V;  // vocab rows to add
+  const int n_grp = (n + 31) >> 5;
+  // the rows hold logits (SmolLM) or the e_v the stats kernel's first pass left there (RWKV alphabet)
+  auto ld_x = [&](int g) -> float {
+    const int v = g * 32 + lane;
+    return v < n ? (kLit ? p[(size_t)v * ld] : __ldg(p + (size_t)v * ld)) : 0.f;
   };
-  // Loads and prefetches are unconditional on a row index clamped to the lane's last row (a lane that is done re-reads that row
-  // out of L1 while the warp's longest column finishes): no per-element branches in the loop.
-  const int v_last = n_lane > 0 ? n_lane - 1 : 0;
-  float r1[GRP], r2[GRP];  // rows of groups g + 1 and g + 2
-  double q[GRP];
-  {
-    float r0[GRP];
-#pragma unroll
-    for (int k = 0; k < GRP; k++) {
-      r0[k] = ldv(min(k, v_last));
-      r1[k] = ldv(min(GRP + k, v_last));
+  auto q_of = [&](float x) -> double {
+    double d;
+    if (kLit) {
+      d = pdf.fast ? cz_widen_pos(x) : (double)x;  // (values below 2^-126 are floored either way)
+    } else {
+      const float a1[1] = {__fsub_rn(mx, x)};
+      double d1[1];
+      float e1[1];
+      exp_group<1, false>(a1, tab, d1, e1);
+      d = d1[0];
     }
-    pdf_group(r0, 0, q);
-  }
-  for (int v0 = 0; v0 < n_warp; v0 += GRP) {
+    return pdf(d);
+  };
+  double acc = 0.0;
+  uint32_t lo = 0, hi = 0;
+  float x = ld_x(0);
+  for (int g = 0; g < n_grp; g++) {
+    const float xn = g + 1 < n_grp ? ld_x(g + 1) : 0.f;
+    double *line = xch + (g & 1) * 32;
+    line[lane] = q_of(x);
+    __syncwarp();
+    const int v0 = g * 32;
+    if (v0 + 32 < (int)sym && v0 + 32 <= n) {  // (warp-uniform) a full group that ends before cdf[sym]'s last term: 32 plain adds
 #pragma unroll
-    for (int k = 0; k < GRP; k++) {
-      r2[k] = ldv(min(v0 + 2 * GRP + k, v_last));
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(p + (size_t)min(v0 + CDF_PF + k, v_last) * ld));
-    }
-    double qn[GRP], a[GRP];
-    pdf_group(r1, v0 + GRP, qn);
-    a[0] = __dadd_rn(acc, q[0]);
-#pragma unroll
-    for (int k = 1; k < GRP; k++) a[k] = __dadd_rn(a[k - 1], q[k]);  // (rows past the lane's last one add garbage after both bounds were captured)
-    acc = a[GRP - 1];
-    // cdf[sym] or cdf[sym + 1] ends inside this group, or (literal symbols) the vocabulary does: rare, at most twice per column
-    if (sym - (uint32_t)v0 <= (uint32_t)GRP || (kLit && (uint32_t)(n_lane - v0) <= (uint32_t)GRP)) {
-#pragma unroll
-      for (int k = 0; k < GRP; k++) {
+      for (int k = 0; k < 32; k += 2) {
+        const double2 t = *reinterpret_cast<const double2 *>(line + k);
+        acc = __dadd_rn(acc, t.x);
+        acc = __dadd_rn(acc, t.y);
+      }
+    } else {  // at most the last two groups of a column
+      const int cnt = n - v0 < 32 ? n - v0 : 32;
+      for (int k = 0; k < cnt; k++) {
+        acc = __dadd_rn(acc, line[k]);
         const uint32_t v = (uint32_t)(v0 + k);
-        if (v + 1 == sym) lo = quant(a[k]);
-        if (v == sym) hi = quant(a[k]);
-        if (kLit && v + 1 == (uint32_t)n_lane) acc_end = a[k];  // the sum over exactly the vocabulary: the literal symbols continue from it
+        if (v + 1 == sym) lo = quant(acc);
+        if (v == sym) hi = quant(acc);
       }
     }
-#pragma unroll
-    for (int k = 0; k < GRP; k++) {
-      q[k] = qn[k];
-      r1[k] = r2[k];
-    }
+    x = xn;
   }
-  if (!active) return;
-  if (kLit && (int)sym >= V) {  // literal symbols follow the vocabulary: acc continues from the full vocab sum
+  if (kLit && (int)sym >= V) {  // literal symbols follow the vocabulary
     const double pl = pdf.literal();
-    acc = acc_end;
     for (uint32_t v = (uint32_t)V; v <= sym; v++) {
       acc = __dadd_rn(acc, pl);
       if (v + 1 == sym) lo = quant(acc);
@@ -631,9 +558,10 @@ __global__ void __launch_bounds__(256) cdf_bounds_sorted_kernel(const float *__r
   }
   if (hi < lo) hi = lo;                             // non-decreasing clamp (src/main.rs:818)
   if ((int)sym == n_sym - 1) hi = CZ_AC_CDF_TOTAL;  // cdf[n] = total (src/main.rs:822)
-  c_lo_out[col] = sym_bad ? 0u : lo;
-  c_hi_out[col] = sym_bad ? 0u : hi;
-  if (sym_bad) atomicOr(err, CZ_DEVERR_SYM);
+  if (lane == 0) {
+    c_lo_out[col] = lo;
+    c_hi_out[col] = hi;
+  }
 }
 
 // K9 from the stats: -log2(max(p_floor(sym), 1e-300)) -- one table lookup per column (src/main.rs:1745-1747 / 1778-1781)
@@ -945,7 +873,7 @@ int launch_cdf_cols(cz_ctx *ctx, int op, int mode, const float *logits_dev, size
 #define CZ_TMA_STATS(MODE, OP)                                                                                                        \
   CZ_LAUNCH(ctx, CZ_K_CDF,                                                                                                            \
             (czk::cdf_stats_tma_kernel<MODE, OP><<<g, czk::ST_COLS + 32, czk::ST_SMEM, stream>>>(tm, lg, (int)V, M, ld, colmax_dev, stats, \
-                                                                                                 ctx->err_flag_dev, arg_dev)))
+                                                                                                 ctx->err_flag_dev)))
       if (mode == CZ_CDF_SMOLLM) {
         if (op == czk::OP_BOUNDS) CZ_TMA_STATS(CZ_CDF_SMOLLM, czk::OP_BOUNDS);
         else CZ_TMA_STATS(CZ_CDF_SMOLLM, czk::OP_XE);
@@ -963,7 +891,7 @@ int launch_cdf_cols(cz_ctx *ctx, int op, int mode, const float *logits_dev, size
     if (!tma_ok) {
 #define CZ_STATS(MODE, OP, NC)                                                                                                   \
   CZ_LAUNCH(ctx, CZ_K_CDF,                                                                                                       \
-            (czk::cdf_stats_kernel<MODE, OP, NC><<<g_stats, 128, 0, stream>>>(lg, (int)V, M, ld, colmax_dev, stats, ctx->err_flag_dev, arg_dev)))
+            (czk::cdf_stats_kernel<MODE, OP, NC><<<g_stats, 128, 0, stream>>>(lg, (int)V, M, ld, colmax_dev, stats, ctx->err_flag_dev)))
 #define CZ_STATS_N(MODE, OP)            \
   do {                                  \
     if (ncol == 4) CZ_STATS(MODE, OP, 4); \
@@ -985,16 +913,15 @@ int launch_cdf_cols(cz_ctx *ctx, int op, int mode, const float *logits_dev, size
     CZ_CHECK_LAUNCH();
     }
     if (op == czk::OP_BOUNDS) {
-      const unsigned g = (unsigned)ceil_div(M, 256);
-      // (both stats kernels leave e_v in rows [0, sym] of a SmolLM column: the prefix walk reads them back)
+      const unsigned g = (unsigned)ceil_div(M, 8);
       if (mode == CZ_CDF_SMOLLM)
         CZ_LAUNCH(ctx, CZ_K_CDF_PREFIX,
-                  (czk::cdf_bounds_sorted_kernel<CZ_CDF_SMOLLM, true><<<g, 256, 0, stream>>>(logits_dev, (int)V, M, ld, arg_dev, stats, c_lo_dev,
-                                                                                             c_hi_dev, ctx->err_flag_dev)));
+                  (czk::cdf_bounds_warp_kernel<CZ_CDF_SMOLLM><<<g, 256, 0, stream>>>(logits_dev, (int)V, M, ld, arg_dev, stats, c_lo_dev, c_hi_dev,
+                                                                                     ctx->err_flag_dev)));
       else
         CZ_LAUNCH(ctx, CZ_K_CDF_PREFIX,
-                  (czk::cdf_bounds_sorted_kernel<CZ_CDF_RWKV_LITERALS, false><<<g, 256, 0, stream>>>(logits_dev, (int)V, M, ld, arg_dev, stats,
-                                                                                                     c_lo_dev, c_hi_dev, ctx->err_flag_dev)));
+                  (czk::cdf_bounds_warp_kernel<CZ_CDF_RWKV_LITERALS><<<g, 256, 0, stream>>>(logits_dev, (int)V, M, ld, arg_dev, stats, c_lo_dev,
+                                                                                            c_hi_dev, ctx->err_flag_dev)));
     } else {
       const unsigned g = (unsigned)ceil_div(M, 128);
       if (mode == CZ_CDF_SMOLLM)

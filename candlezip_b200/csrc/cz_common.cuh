@@ -41,6 +41,7 @@ struct cz_ctx {
   int sm_count = 0;
   cudaStream_t stream = nullptr;
   cudaStream_t stream2 = nullptr;
+  cudaStream_t prof_stream = nullptr;  // stream the next launches go to when it is not `stream` (profiling events are recorded there)
   uint64_t launches = 0;
   // per-family profiling: mode 1 = synchronous (event pair + sync per launch), mode 2 = deferred (event pairs are
   // pooled and only read in cz_profile_read, so the timed region is not perturbed by host syncs)
@@ -71,7 +72,8 @@ struct LaunchScope {
   cz_ctx *ctx;
   int fam;
   size_t slot = 0;
-  LaunchScope(cz_ctx *c, int f) : ctx(c), fam(f) {
+  cudaStream_t st;
+  LaunchScope(cz_ctx *c, int f) : ctx(c), fam(f), st(c->prof_stream ? c->prof_stream : c->stream) {
     if (ctx->capturing) return;
     if (ctx->prof_mode == 2) {
       slot = ctx->ev_used++;
@@ -84,9 +86,9 @@ struct LaunchScope {
         ctx->ev_fam.push_back(f);
       }
       ctx->ev_fam[slot] = f;
-      cudaEventRecord(ctx->ev_pool[2 * slot], ctx->stream);
+      cudaEventRecord(ctx->ev_pool[2 * slot], st);
     } else if (ctx->prof_on) {
-      cudaEventRecord(ctx->prof_ev0, ctx->stream);
+      cudaEventRecord(ctx->prof_ev0, st);
     }
   }
   ~LaunchScope() {
@@ -94,9 +96,9 @@ struct LaunchScope {
     ctx->prof_launches[fam]++;
     if (ctx->capturing) return;
     if (ctx->prof_mode == 2) {
-      cudaEventRecord(ctx->ev_pool[2 * slot + 1], ctx->stream);
+      cudaEventRecord(ctx->ev_pool[2 * slot + 1], st);
     } else if (ctx->prof_on) {
-      cudaEventRecord(ctx->prof_ev1, ctx->stream);
+      cudaEventRecord(ctx->prof_ev1, st);
       cudaEventSynchronize(ctx->prof_ev1);
       float ms = 0.f;
       cudaEventElapsedTime(&ms, ctx->prof_ev0, ctx->prof_ev1);

@@ -314,17 +314,45 @@ static int run_wave_head(cz_model *m, size_t n_logit, int op, int mode, const ui
                          double *xe_out, cudaStream_t st, long long digest_first = -1) {
   CZ_TRY(ensure_logits(m, n_logit));
   Workspace &ws = m->ws;
-  const int buf = 0;
+  cz_ctx *ctx = m->ctx;
+  // The CDF pass of a sub-batch (FP64 / integer issue-bound, with a latency-bound tail) runs on the side stream while the main
+  // stream goes on with the next sub-batch's LM head or the next wave's trunk (tensor / TMA-bound): different pipes, so part of
+  // its time disappears behind them.  Two logits buffers; an event pair per buffer orders LM head -> CDF -> (the LM head that
+  // reuses the buffer).  join_cdf() before anything consumes the bounds.
+  static const bool no_overlap = getenv("CZ_NO_OVERLAP") != nullptr;  // bisecting aid
+  const bool overlap = !no_overlap && ctx->stream2 && !ctx->capturing && ctx->prof_mode != 1;
   for (size_t c0 = 0; c0 < n_logit; c0 += ws.ld_sub) {
     const size_t nc = std::min(ws.ld_sub, n_logit - c0);
+    const int buf = ws.head_buf;
+    ws.head_buf ^= 1;
+    int *colmax = ws.colmax + (size_t)buf * ws.ld_sub;
+    if (ws.cdf_pending[buf]) {  // the CDF pass that last used this buffer must be done before the LM head overwrites it
+      CZ_CUDA_TRY(cudaStreamWaitEvent(st, ws.ev_cdf[buf], 0));
+      ws.cdf_pending[buf] = false;
+    }
     bool have_max = false;
-    CZ_TRY(lm_head(m, (int)c0, (int)nc, ws.logits[buf], ws.ld_sub, st, ws.colmax, &have_max));
+    CZ_TRY(lm_head(m, (int)c0, (int)nc, ws.logits[buf], ws.ld_sub, st, colmax, &have_max));
+    cudaStream_t cst = st;
+    if (overlap) {
+      cst = ctx->stream2;
+      CZ_CUDA_TRY(cudaEventRecord(ws.ev_head[buf], st));
+      CZ_CUDA_TRY(cudaStreamWaitEvent(cst, ws.ev_head[buf], 0));
+      ctx->prof_stream = cst;
+    }
+    int rc = CZ_OK;
     if (digest_first >= 0 && m->digest_host)  // (before the CDF pass: the RWKV alphabet's pass overwrites the logits with expf values)
-      CZ_TRY(launch_logits_digest(m->ctx, ws.logits[buf], (size_t)m->cfg.vocab, nc, ws.ld_sub, m->sb[SB_CV].p, m->sb[SB_DIGEST].as<uint8_t>(),
-                                  (unsigned long long)digest_first + c0, nullptr, nullptr, nullptr, st));
-    CZ_TRY(launch_cdf_cols(m->ctx, op, mode, ws.logits[buf], (size_t)m->cfg.vocab, nc, ws.ld_sub, syms_dev + c0, nullptr,
-                           lo_out ? lo_out + c0 : nullptr, hi_out ? hi_out + c0 : nullptr, xe_out ? xe_out + c0 : nullptr, st,
-                           have_max ? ws.colmax : nullptr));
+      rc = launch_logits_digest(ctx, ws.logits[buf], (size_t)m->cfg.vocab, nc, ws.ld_sub, m->sb[SB_CV].p, m->sb[SB_DIGEST].as<uint8_t>(),
+                                (unsigned long long)digest_first + c0, nullptr, nullptr, nullptr, cst);
+    if (rc == CZ_OK)
+      rc = launch_cdf_cols(ctx, op, mode, ws.logits[buf], (size_t)m->cfg.vocab, nc, ws.ld_sub, syms_dev + c0, nullptr,
+                           lo_out ? lo_out + c0 : nullptr, hi_out ? hi_out + c0 : nullptr, xe_out ? xe_out + c0 : nullptr, cst,
+                           have_max ? colmax : nullptr);
+    ctx->prof_stream = nullptr;
+    CZ_TRY(rc);
+    if (overlap) {
+      CZ_CUDA_TRY(cudaEventRecord(ws.ev_cdf[buf], cst));
+      ws.cdf_pending[buf] = true;
+    }
   }
   return CZ_OK;
 }
@@ -470,6 +498,7 @@ static int encode_core(cz_model *m, const uint32_t *ids_dev, const uint32_t *ids
     set_error("internal: schedule did not cover every token");
     return CZ_ERR_INVALID;
   }
+  CZ_TRY(join_cdf(m, st));
   // ---- arithmetic-coder lanes: one per segment ----
   std::vector<uint64_t> lane_off(sched->seg_start, sched->seg_start + S + 1), raw_off(S + 1);
   for (uint32_t g = 0; g <= S; g++) raw_off[g] = 4 * lane_off[g] + 8 * (uint64_t)g;
@@ -956,6 +985,7 @@ int cz_xe_bits(cz_model *m, const cz_xe_job *jobs, size_t n_jobs, double *bits_o
     w.add_chunk(jobs[j].prime_len, jobs[j].n_targets, [&](uint32_t k) { return -2 - (p0 + k); }, [&](uint32_t q) { return -2 - (t0 + q); });
   }
   CZ_TRY(flush());
+  CZ_TRY(join_cdf(m, st));
   CZ_LAUNCH(ctx, CZ_K_OTHER,
             (czk::sum_bits_kernel<<<(unsigned)ceil_div(n_jobs, 128), 128, 0, st>>>(d_bits.as<double>(), d_joff.as<uint64_t>(),
                                                                                   d_out.as<double>(), (int)n_jobs)));

@@ -37,9 +37,13 @@ struct Workspace {
   __nv_bfloat16 *xn_logit = nullptr;  // [cap_logit][D]
   uint32_t *lo_tmp = nullptr, *hi_tmp = nullptr;  // [sub] per-sub-batch CDF outputs before the scatter
   double *xe_tmp = nullptr;
-  int *colmax = nullptr;              // [ld_sub] per-column max of the current logits sub-batch
-  float *logits[2] = {nullptr, nullptr};  // [V][ld_sub] vocab-major, double-buffered
+  int *colmax = nullptr;              // [ld_sub] per-column max of the current logits sub-batch (buffer 0; buffer 1 follows it)
+  float *logits[2] = {nullptr, nullptr};  // [V][ld_sub] vocab-major, double-buffered: the CDF pass of one sub-batch runs on the
+                                          // side stream while the main stream already computes the next wave / sub-batch
   size_t ld_sub = 0;
+  int head_buf = 0;                   // logits buffer the next LM-head launch writes
+  cudaEvent_t ev_head[2] = {nullptr, nullptr}, ev_cdf[2] = {nullptr, nullptr};
+  bool cdf_pending[2] = {false, false};  // a CDF pass on the side stream still owns that buffer
   // pinned host staging for row metadata
   void *h_stage = nullptr;
   size_t h_stage_bytes = 0;
@@ -129,6 +133,8 @@ int model_finalize(cz_model *m);
 int ensure_workspace(cz_model *m, size_t rows, size_t n_logit, size_t n_tiles = 0);
 int ensure_stage(cz_model *m, size_t bytes);
 int ensure_logits(cz_model *m, size_t n_cols);
+// makes `st` wait for the CDF passes still running on the side stream (their results / the logits buffers are about to be used)
+int join_cdf(cz_model *m, cudaStream_t st);
 
 // KV arena view: element (layer l, slot s) lives at base + l*layer_stride + s*kvd
 struct KvView {

@@ -164,21 +164,41 @@ int ensure_logits(cz_model *m, size_t n_cols) {
   Workspace &w = m->ws;
   const cz_model_config &c = m->cfg;
   size_t want = (std::max<size_t>(n_cols, 256) + 1023) & ~(size_t)1023;
-  size_t max_ld = 262144;
+  // two buffers of up to 131,072 columns (25.8 GB each for V = 49152): wide enough for the thread-per-column CDF kernels to fill
+  // the machine, and one can go through its CDF pass while the LM head fills the other
+  size_t max_ld = 131072;
   if (const char *e = getenv("CZ_LOGITS_COLS")) max_ld = std::max<size_t>(256, (size_t)atoll(e));
   want = std::min(want, max_ld);
   if (want <= w.ld_sub) return CZ_OK;
   CZ_CUDA_TRY(cudaSetDevice(m->ctx->device));
   CZ_CUDA_TRY(cudaStreamSynchronize(m->ctx->stream));
+  CZ_CUDA_TRY(cudaStreamSynchronize(m->ctx->stream2));
+  w.cdf_pending[0] = w.cdf_pending[1] = false;
   CZ_TRY(realloc_dev(w.logits[0], 0));
+  CZ_TRY(realloc_dev(w.logits[1], 0));
   CZ_TRY(realloc_dev(w.colmax, 0));
   w.ld_sub = 0;
   size_t free_b = 0, total_b = 0;
   CZ_CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
-  while (want > 256 && want * (size_t)c.vocab * 4 > free_b * 60 / 100) want >>= 1;
+  while (want > 256 && 2 * want * (size_t)c.vocab * 4 > free_b * 60 / 100) want >>= 1;
   CZ_TRY(realloc_dev(w.logits[0], want * (size_t)c.vocab));
-  CZ_TRY(realloc_dev(w.colmax, want));
+  CZ_TRY(realloc_dev(w.logits[1], want * (size_t)c.vocab));
+  CZ_TRY(realloc_dev(w.colmax, 2 * want));
   w.ld_sub = want;
+  for (int b = 0; b < 2; b++) {
+    if (!w.ev_head[b]) CZ_CUDA_TRY(cudaEventCreateWithFlags(&w.ev_head[b], cudaEventDisableTiming));
+    if (!w.ev_cdf[b]) CZ_CUDA_TRY(cudaEventCreateWithFlags(&w.ev_cdf[b], cudaEventDisableTiming));
+  }
+  return CZ_OK;
+}
+
+int join_cdf(cz_model *m, cudaStream_t st) {
+  Workspace &w = m->ws;
+  for (int b = 0; b < 2; b++)
+    if (w.cdf_pending[b]) {
+      CZ_CUDA_TRY(cudaStreamWaitEvent(st, w.ev_cdf[b], 0));
+      w.cdf_pending[b] = false;
+    }
   return CZ_OK;
 }
 
