@@ -416,6 +416,34 @@ def run_ours(args):
                  "note": "random-init weights: bits/byte is not a compression figure; the size is compared with the CPU reference in cpu_baseline"}
     D.barrier()
 
+    # ---- BASELINE config 4: the agentic gate scan replayed from the shipped asyoulik run (agent_cache.jsonl + proof.csv), rank 0 ----
+    gate_scan = None
+    if args.gate and rank == 0:
+        from candlezip_b200 import gate
+
+        gids = np.load(os.path.join(ROOT, "tests", "golden", "reference_fixtures.npz"))["run_asyoulik_syms"].astype(np.uint32)
+        texts, calls, decisions, shipped = gate.load_replay(corpus.replay("asyoulik"))
+        smap = corpus.spread_map(V_SMOLLM)
+        tok = lambda text, mx: smap[np.frombuffer(text.encode("utf-8"), np.uint8)][:mx]  # noqa: E731
+        jobs, plan = gate.plan_scan(gids, texts, tok, 512, 512)
+        model.xe_bits(jobs[:64])  # warm-up (buffers)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        bits = model.xe_bits(jobs)
+        t1 = time.perf_counter()
+        records, events, rows = gate.decide(plan, bits, 512)
+        gp, _ = model.encode(gids, n_segments=1, events=events or None)
+        t2 = time.perf_counter()
+        xe_rows = int(sum(len(p_) + len(t_) - 1 for p_, t_ in jobs))
+        gate_scan = {"input": "asyoulik.txt as the shipped SmolLM2 token ids (39,915 ids, watchdog_decode_steps.jsonl) + the shipped agent_cache.jsonl "
+                              "(30 agent texts, byte-level hint tokens: no tokenizer.json offline), --scan-lookahead 512, chunk 512",
+                     "boundaries": len(plan), "xe_jobs": len(jobs), "xe_rows": xe_rows, "scan_s": t1 - t0, "xe_jobs_per_s": len(jobs) / (t1 - t0),
+                     "xe_tokens_per_s": xe_rows / (t1 - t0), "gated": int(sum(r & 1 for r in records)), "gated_in_shipped_ledger": int(sum(g for g, _, _ in decisions.values())),
+                     "encode_with_primes_s": t2 - t1, "payload_bytes": len(gp[0]),
+                     "note": "all baseline / hint-conditioned passes of all 77 boundaries as ONE batch of paired streams (the reference runs them one after the "
+                             "other on a second session, src/main.rs:2043-2054); random-init weights, so which hints gate is not comparable with the shipped ledger"}
+    D.barrier()
+
     # ---- RWKV-7 0.1B (BASELINE config 3) on the enwik8 stand-in, sharded over the ranks; random-init weights ----
     rwkv = None
     if args.rwkv_bytes > 0:
@@ -490,7 +518,7 @@ def run_ours(args):
         "roofline_kernels": kernels,
         "kernel_ms_per_step": {k: v[0] / prof_steps for k, v in fam.items()},
         "kernel_launches_per_step": {k: v[1] // prof_steps for k, v in fam.items()},
-        "compressed_bytes_per_step": payload_bytes, "sharded": sharded, "alice29": alice, "rwkv7": rwkv,
+        "compressed_bytes_per_step": payload_bytes, "sharded": sharded, "alice29": alice, "gate_scan": gate_scan, "rwkv7": rwkv,
     }
     if rwkv:
         rwkv["kernel_ms_total"] = {k: round(v[0], 2) for k, v in rfam.items()}
@@ -569,6 +597,7 @@ def main():
                     help="segments of the whole-file strong-scaling / decode figure (1536 x 2048 tokens = 3 MiB: 3 reprimes per stream); 0 = skip")
     ap.add_argument("--sharded-bytes", type=int, default=3145728)
     ap.add_argument("--no-alice", dest="alice", action="store_false")
+    ap.add_argument("--no-gate", dest="gate", action="store_false")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-tokens", type=int, default=4096, help="prefix of alice29.txt the CPU reference codes (>= 7 reprimes)")
     ap.add_argument("--rwkv-bytes", type=int, default=1048576, help="RWKV-7 figures on this prefix of the enwik8 stand-in (0 = skip)")

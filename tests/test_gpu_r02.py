@@ -376,3 +376,28 @@ def test_cdf_bounds_and_xe_new_kernels_all_vector_widths(gpu_ctx, mode, ncol):
             assert oracle.ac_encode(bounds) == pays[0]
     finally:
         os.environ.pop("CZ_CDF_NCOL", None)
+
+
+def test_cli_twin_gate_scan_replay_self_test(gpu_ctx, tmp_path):
+    """`python -m candlezip_b200 self-test FILE --reuse-scan-dir DIR` (src/main.rs:156-221 with --reuse-scan-dir, :1966-1978): the gate
+    scan replayed from an agent_cache.jsonl in the reference's format; AGT2 container, proof.csv ledger, byte-exact round trip."""
+    import json
+    import subprocess
+
+    import corpus
+
+    data = corpus.load("alice29.txt")[:2600]
+    src = tmp_path / "alice_head.txt"
+    src.write_bytes(data)
+    rdir = tmp_path / "run"
+    rdir.mkdir()
+    with open(rdir / "agent_cache.jsonl", "w", encoding="utf-8") as f:
+        f.write(json.dumps({"chunk_index": 1, "agent_text": data[512:1400].decode("latin-1"), "agent_calls": 3}) + "\n")
+        f.write(json.dumps({"chunk_index": 3, "agent_text": "Alice 1865 Rabbit-Hole\nDown the 2nd well", "agent_calls": 1}) + "\n")
+    out_dir = tmp_path / "scan_out"
+    r = subprocess.run([sys.executable, "-m", "candlezip_b200", "self-test", str(src), "--reuse-scan-dir", str(rdir), "--scan-output-dir", str(out_dir),
+                        "--scan-lookahead", "300"], cwd=ROOT, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "roundtrip OK" in r.stdout and "scan: 5 boundaries" in r.stdout, (r.stdout, r.stderr[-800:])
+    rows = open(out_dir / "proof.csv").read().strip().split("\n")
+    assert len(rows) == 6 and rows[0].startswith("file,chunk_index,start_token,end_token,agent_text_len")
+    assert [x.split(",")[1:4] for x in rows[1:]] == [[str(k), str(max(0, 512 * k - 1 - 512)), str(512 * k - 1)] for k in range(1, 6)]
