@@ -431,7 +431,7 @@ def run_ours(args):
         t0 = time.perf_counter()
         bits = model.xe_bits(jobs)
         t1 = time.perf_counter()
-        records, events, rows = gate.decide(plan, bits, 512)
+        records, events, gate_rows = gate.decide(plan, bits, 512)
         gp, _ = model.encode(gids, n_segments=1, events=events or None)
         t2 = time.perf_counter()
         xe_rows = int(sum(len(p_) + len(t_) - 1 for p_, t_ in jobs))
