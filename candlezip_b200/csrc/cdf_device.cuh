@@ -347,14 +347,19 @@ __device__ __forceinline__ void cdf_search_warp(const float *__restrict__ p_in, 
   // generic sequential accumulation of f(x) over the vocab: acc = ((0 + f0) + f1) + ...
   // The 32 values of a group go through the warp's shared-memory line (double-buffered: one __syncwarp per group) and every
   // lane adds them in order from 16-byte broadcast loads: 16 LDS + 32 DADD per group instead of 64 SHFL + 32 DADD.
+  // The next group's values (expf, divisions: a long dependent chain per lane) are computed before the current group's adds are
+  // issued: nothing in them depends on the running sum, so they fill the adds' latency instead of preceding it.
   auto seq_sum = [&](auto f) -> double {
     double acc = 0.0;
-    float x = ld_x(0);
+    double q = f(ld_x(0));
+    float x1 = n_grp > 1 ? ld_x(1) : 0.f;
     for (int g = 0; g < n_grp; g++) {
-      const float xn = g + 1 < n_grp ? ld_x(g + 1) : 0.f;
+      const float x2 = g + 2 < n_grp ? ld_x(g + 2) : 0.f;
       double *line = xch + (g & 1) * 32;
-      line[lane] = f(x);
+      line[lane] = q;
       __syncwarp();
+      q = g + 1 < n_grp ? f(x1) : 0.0;
+      x1 = x2;
       const int cnt = V - g * 32 < 32 ? V - g * 32 : 32;
       if (cnt == 32) {
 #pragma unroll
@@ -366,7 +371,6 @@ __device__ __forceinline__ void cdf_search_warp(const float *__restrict__ p_in, 
       } else {
         for (int k = 0; k < cnt; k++) acc = __dadd_rn(acc, line[k]);
       }
-      x = xn;
     }
     __syncwarp();
     return acc;
@@ -417,14 +421,51 @@ __device__ __forceinline__ void cdf_search_warp(const float *__restrict__ p_in, 
   double acc = 0.0, acc_prev = 0.0;
   uint32_t found = (uint32_t)(n_sym - 1);
   bool done = false;
-  float x = ld_x(0);
+  double qv = pdf_vocab(ld_x(0));
+  float x1 = n_grp > 1 ? ld_x(1) : 0.f;
   for (int g = 0; g < n_grp && !done; g++) {
-    const float xn = g + 1 < n_grp ? ld_x(g + 1) : 0.f;
+    const float x2 = g + 2 < n_grp ? ld_x(g + 2) : 0.f;
     double *line = xch + (g & 1) * 32;
-    line[lane] = pdf_vocab(x);
+    line[lane] = qv;
     __syncwarp();
+    qv = g + 1 < n_grp ? pdf_vocab(x1) : 0.0;  // (ahead of this group's adds, see seq_sum)
+    x1 = x2;
     const int cnt = V - g * 32 < 32 ? V - g * 32 : 32;
-    for (int k = 0; k < cnt; k++) {
+    // acc never decreases, so a group of adds holds the crossing iff its LAST partial sum has reached the threshold: a full
+    // group that does not end the alphabet is 32 straight adds (eight at a time out of 16-byte broadcast loads) and four compares;
+    // only the eight adds around the crossing are looked at one by one.
+    int k0 = 0;
+    if (cnt == 32 && g * 32 + 32 < n_sym) {
+#pragma unroll
+      for (int o = 0; o < 32 && !done; o += 8) {
+        double a[8];
+        const double2 t0 = *reinterpret_cast<const double2 *>(line + o), t1 = *reinterpret_cast<const double2 *>(line + o + 2),
+                      t2 = *reinterpret_cast<const double2 *>(line + o + 4), t3 = *reinterpret_cast<const double2 *>(line + o + 6);
+        a[0] = __dadd_rn(acc, t0.x);
+        a[1] = __dadd_rn(a[0], t0.y);
+        a[2] = __dadd_rn(a[1], t1.x);
+        a[3] = __dadd_rn(a[2], t1.y);
+        a[4] = __dadd_rn(a[3], t2.x);
+        a[5] = __dadd_rn(a[4], t2.y);
+        a[6] = __dadd_rn(a[5], t3.x);
+        a[7] = __dadd_rn(a[6], t3.y);
+        if (a[7] >= thr) {  // (warp-uniform: every lane holds the same sums)
+#pragma unroll
+          for (int k = 0; k < 8; k++) {
+            if (!done && a[k] >= thr) {
+              found = (uint32_t)(g * 32 + o + k);
+              acc_prev = k ? a[k - 1] : acc;
+              acc = a[k];
+              done = true;
+            }
+          }
+        } else {
+          acc = a[7];
+        }
+      }
+      k0 = 32;
+    }
+    for (int k = k0; k < cnt && !done; k++) {  // the alphabet's last group / a ragged one: element by element
       const double a2 = __dadd_rn(acc, line[k]);
       const int v = g * 32 + k;
       if (a2 >= thr || v == n_sym - 1) {
@@ -436,7 +477,6 @@ __device__ __forceinline__ void cdf_search_warp(const float *__restrict__ p_in, 
       }
       acc = a2;
     }
-    x = xn;
   }
   if (MODE == CZ_CDF_RWKV_LITERALS && !done) {
     const double pl = sum2 > 0.0 ? __ddiv_rn(CZ_P_FLOOR, sum2) : CZ_P_FLOOR;

@@ -14,6 +14,8 @@
 // reads the column up to 3 times (max / sum / prefix), the 2nd and 3rd mostly from L2 for decode-sized M.
 #include <stdlib.h>
 
+#include <algorithm>
+
 #include "cdf_fast.cuh"
 #include "tc_ptx.cuh"
 
@@ -472,95 +474,109 @@ struct PdfOf {
 // stays full until the end, and the longest column costs V / 32 short iterations.  The 8 warps of a CTA take 8 adjacent columns =
 // one 32-byte sector per vocab row, so a row's sector is fetched from DRAM once and the other seven warps find it in L1 / L2.
 // Same operations in the same order as cdf_col's OP_BOUNDS: bit-identical results.
+// Columns are handed out one at a time from a global counter (persistent warps): a warp that finishes a short column takes the
+// next one instead of idling until the longest column of its CTA is done, and columns c .. c + 7 -- which share a 32-byte sector
+// per vocab row -- are in flight at about the same time, so the sector is fetched from DRAM once and found in L2 by the others.
 template <int MODE>
 __global__ void __launch_bounds__(256) cdf_bounds_warp_kernel(const float *__restrict__ logits, int V, size_t M, size_t ld,
                                                               const uint32_t *__restrict__ syms, const CdfStats *__restrict__ stats,
                                                               uint32_t *__restrict__ c_lo_out, uint32_t *__restrict__ c_hi_out,
-                                                              int *__restrict__ err) {
+                                                              int *__restrict__ err, unsigned int *__restrict__ work_counter) {
   constexpr bool kLit = MODE == CZ_CDF_RWKV_LITERALS;
+  constexpr int DEPTH = 4;  // groups of 32 rows whose loads are in flight ahead of the group being added
   __shared__ uint64_t s_tab[32 * 32];
   __shared__ __align__(16) double s_xch[8 * 64];  // per warp: two 32-value exchange lines
   exp_tab64_init(s_tab);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const ExpTab64 tab{s_tab + lane};
-  const size_t col = (size_t)blockIdx.x * 8 + warp;
-  if (col >= M) return;
-  const int n_sym = kLit ? V + 256 : V;
-  uint32_t sym = syms[col];
-  if ((int)sym >= n_sym) {
-    if (lane == 0) {
-      atomicOr(err, CZ_DEVERR_SYM);
-      c_lo_out[col] = 0u;
-      c_hi_out[col] = 0u;
-    }
-    return;
-  }
-  const CdfStats st = stats[col];
-  PdfOf<MODE, false> pdf;
-  pdf.init(st, V);
-  const float mx = st.mx;
-  const float *p = logits + col;
   double *xch = s_xch + warp * 64;
-  const int n = (int)sym < V ? (int)sym + 1 : V;  // vocab rows to add
-  const int n_grp = (n + 31) >> 5;
-  // the rows hold logits (SmolLM) or the e_v the stats kernel's first pass left there (RWKV alphabet)
-  auto ld_x = [&](int g) -> float {
-    const int v = g * 32 + lane;
-    return v < n ? (kLit ? p[(size_t)v * ld] : __ldg(p + (size_t)v * ld)) : 0.f;
-  };
-  auto q_of = [&](float x) -> double {
-    double d;
-    if (kLit) {
-      d = pdf.fast ? cz_widen_pos(x) : (double)x;  // (values below 2^-126 are floored either way)
-    } else {
-      const float a1[1] = {__fsub_rn(mx, x)};
-      double d1[1];
-      float e1[1];
-      exp_group<1, false>(a1, tab, d1, e1);
-      d = d1[0];
-    }
-    return pdf(d);
-  };
-  double acc = 0.0;
-  uint32_t lo = 0, hi = 0;
-  float x = ld_x(0);
-  for (int g = 0; g < n_grp; g++) {
-    const float xn = g + 1 < n_grp ? ld_x(g + 1) : 0.f;
-    double *line = xch + (g & 1) * 32;
-    line[lane] = q_of(x);
-    __syncwarp();
-    const int v0 = g * 32;
-    if (v0 + 32 < (int)sym && v0 + 32 <= n) {  // (warp-uniform) a full group that ends before cdf[sym]'s last term: 32 plain adds
-#pragma unroll
-      for (int k = 0; k < 32; k += 2) {
-        const double2 t = *reinterpret_cast<const double2 *>(line + k);
-        acc = __dadd_rn(acc, t.x);
-        acc = __dadd_rn(acc, t.y);
+  const int n_sym = kLit ? V + 256 : V;
+  for (;;) {
+    unsigned int c = 0;
+    if (lane == 0) c = atomicAdd(work_counter, 1u);
+    c = __shfl_sync(0xffffffffu, c, 0);
+    if ((size_t)c >= M) return;
+    const size_t col = c;
+    const uint32_t sym = syms[col];
+    if ((int)sym >= n_sym) {
+      if (lane == 0) {
+        atomicOr(err, CZ_DEVERR_SYM);
+        c_lo_out[col] = 0u;
+        c_hi_out[col] = 0u;
       }
-    } else {  // at most the last two groups of a column
-      const int cnt = n - v0 < 32 ? n - v0 : 32;
-      for (int k = 0; k < cnt; k++) {
-        acc = __dadd_rn(acc, line[k]);
-        const uint32_t v = (uint32_t)(v0 + k);
+      continue;
+    }
+    const CdfStats st = stats[col];
+    PdfOf<MODE, false> pdf;
+    pdf.init(st, V);
+    const float mx = st.mx;
+    const float *p = logits + col;
+    const int n = (int)sym < V ? (int)sym + 1 : V;  // vocab rows to add
+    const int n_grp = (n + 31) >> 5;
+    // the rows hold logits (SmolLM) or the e_v the stats kernel's first pass left there (RWKV alphabet)
+    auto ld_x = [&](int g) -> float {
+      const int v = g * 32 + lane;
+      return v < n ? (kLit ? p[(size_t)v * ld] : __ldg(p + (size_t)v * ld)) : 0.f;
+    };
+    auto q_of = [&](float x) -> double {
+      double d;
+      if (kLit) {
+        d = pdf.fast ? cz_widen_pos(x) : (double)x;  // (values below 2^-126 are floored either way)
+      } else {
+        const float a1[1] = {__fsub_rn(mx, x)};
+        double d1[1];
+        float e1[1];
+        exp_group<1, false>(a1, tab, d1, e1);
+        d = d1[0];
+      }
+      return pdf(d);
+    };
+    double acc = 0.0;
+    uint32_t lo = 0, hi = 0;
+    float xr[DEPTH];
+#pragma unroll
+    for (int k = 0; k < DEPTH; k++) xr[k] = ld_x(k);
+    for (int g = 0; g < n_grp; g++) {
+      const float x = xr[0];
+#pragma unroll
+      for (int k = 0; k + 1 < DEPTH; k++) xr[k] = xr[k + 1];
+      xr[DEPTH - 1] = ld_x(g + DEPTH);
+      double *line = xch + (g & 1) * 32;
+      line[lane] = q_of(x);
+      __syncwarp();
+      const int v0 = g * 32;
+      if (v0 + 32 < (int)sym && v0 + 32 <= n) {  // (warp-uniform) a full group that ends before cdf[sym]'s last term: 32 plain adds
+#pragma unroll
+        for (int k = 0; k < 32; k += 2) {
+          const double2 t = *reinterpret_cast<const double2 *>(line + k);
+          acc = __dadd_rn(acc, t.x);
+          acc = __dadd_rn(acc, t.y);
+        }
+      } else {  // at most the last two groups of a column
+        const int cnt = n - v0 < 32 ? n - v0 : 32;
+        for (int k = 0; k < cnt; k++) {
+          acc = __dadd_rn(acc, line[k]);
+          const uint32_t v = (uint32_t)(v0 + k);
+          if (v + 1 == sym) lo = quant(acc);
+          if (v == sym) hi = quant(acc);
+        }
+      }
+    }
+    __syncwarp();  // (the next column's first group reuses line 0)
+    if (kLit && (int)sym >= V) {  // literal symbols follow the vocabulary
+      const double pl = pdf.literal();
+      for (uint32_t v = (uint32_t)V; v <= sym; v++) {
+        acc = __dadd_rn(acc, pl);
         if (v + 1 == sym) lo = quant(acc);
         if (v == sym) hi = quant(acc);
       }
     }
-    x = xn;
-  }
-  if (kLit && (int)sym >= V) {  // literal symbols follow the vocabulary
-    const double pl = pdf.literal();
-    for (uint32_t v = (uint32_t)V; v <= sym; v++) {
-      acc = __dadd_rn(acc, pl);
-      if (v + 1 == sym) lo = quant(acc);
-      if (v == sym) hi = quant(acc);
+    if (hi < lo) hi = lo;                             // non-decreasing clamp (src/main.rs:818)
+    if ((int)sym == n_sym - 1) hi = CZ_AC_CDF_TOTAL;  // cdf[n] = total (src/main.rs:822)
+    if (lane == 0) {
+      c_lo_out[col] = lo;
+      c_hi_out[col] = hi;
     }
-  }
-  if (hi < lo) hi = lo;                             // non-decreasing clamp (src/main.rs:818)
-  if ((int)sym == n_sym - 1) hi = CZ_AC_CDF_TOTAL;  // cdf[n] = total (src/main.rs:822)
-  if (lane == 0) {
-    c_lo_out[col] = lo;
-    c_hi_out[col] = hi;
   }
 }
 
@@ -913,15 +929,19 @@ int launch_cdf_cols(cz_ctx *ctx, int op, int mode, const float *logits_dev, size
     CZ_CHECK_LAUNCH();
     }
     if (op == czk::OP_BOUNDS) {
-      const unsigned g = (unsigned)ceil_div(M, 8);
+      // persistent warps pulling columns from a counter in the ctx's status block (word 12; the attention kernel's is word 8)
+      unsigned int *counter = reinterpret_cast<unsigned int *>(ctx->err_flag_dev + 12);
+      CZ_CUDA_TRY(cudaMemsetAsync(counter, 0, sizeof(unsigned int), stream));
+      const size_t want_ctas = ceil_div(M, 8);
+      const unsigned g = (unsigned)std::min<size_t>(want_ctas, (size_t)ctx->sm_count * 8);
       if (mode == CZ_CDF_SMOLLM)
         CZ_LAUNCH(ctx, CZ_K_CDF_PREFIX,
                   (czk::cdf_bounds_warp_kernel<CZ_CDF_SMOLLM><<<g, 256, 0, stream>>>(logits_dev, (int)V, M, ld, arg_dev, stats, c_lo_dev, c_hi_dev,
-                                                                                     ctx->err_flag_dev)));
+                                                                                     ctx->err_flag_dev, counter)));
       else
         CZ_LAUNCH(ctx, CZ_K_CDF_PREFIX,
                   (czk::cdf_bounds_warp_kernel<CZ_CDF_RWKV_LITERALS><<<g, 256, 0, stream>>>(logits_dev, (int)V, M, ld, arg_dev, stats, c_lo_dev,
-                                                                                            c_hi_dev, ctx->err_flag_dev)));
+                                                                                            c_hi_dev, ctx->err_flag_dev, counter)));
     } else {
       const unsigned g = (unsigned)ceil_div(M, 128);
       if (mode == CZ_CDF_SMOLLM)
