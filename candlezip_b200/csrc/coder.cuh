@@ -9,10 +9,13 @@ namespace czk {
 struct AcEncoder {
   uint64_t low, high, carry_run;
   uint8_t *out;      // lane's output region (global)
-  uint64_t n_bytes;  // bytes_out, including bytes still in the staging buffer
-  uint32_t bit_buffer;
-  uint32_t bit_count;
-  uint8_t *stage;    // optional shared-memory staging buffer (nullptr: write straight to `out`)
+  uint64_t n_bytes;  // bytes emitted so far (whole 32-bit words until finish()), including bytes still in the staging buffer
+  // Bit packer (src/main.rs:299-318 emits one bit at a time into a byte): here the bits queue up in a 64-bit accumulator (fewer
+  // than 32 pending between calls) and leave as big-endian 32-bit words -- MSB-first within the stream, so the byte sequence is the
+  // same -- one store per 32 bits instead of a shift / compare / store per byte on the single thread that owns the stream.
+  uint64_t bit_acc;
+  uint32_t n_bits;
+  uint8_t *stage;    // optional shared-memory staging buffer, 4-byte aligned (nullptr: write straight to `out`)
   uint32_t stage_cap, stage_n;
 
   __device__ __forceinline__ void init(uint8_t *o) {
@@ -21,8 +24,8 @@ struct AcEncoder {
     carry_run = 0;
     out = o;
     n_bytes = 0;
-    bit_buffer = 0;
-    bit_count = 0;
+    bit_acc = 0;
+    n_bits = 0;
     stage = nullptr;
     stage_cap = stage_n = 0;
   }
@@ -32,46 +35,44 @@ struct AcEncoder {
     for (uint32_t i = 0; i < stage_n; i++) out[b0 + i] = stage[i];
     stage_n = 0;
   }
-  __device__ __forceinline__ void put_bit_internal(uint32_t bit) {
-    bit_buffer = (bit_buffer << 1) | (bit & 1u);
-    if (++bit_count == 8) {
-      if (stage) {
-        if (stage_n == stage_cap) flush_stage_serial();
-        stage[stage_n++] = (uint8_t)bit_buffer;
-        n_bytes++;
-      } else {
-        out[n_bytes++] = (uint8_t)bit_buffer;
-      }
-      bit_buffer = 0;
-      bit_count = 0;
+  __device__ __forceinline__ void emit_byte(uint32_t v) {
+    if (stage) {
+      if (stage_n == stage_cap) flush_stage_serial();
+      stage[stage_n++] = (uint8_t)v;
+    } else {
+      out[n_bytes] = (uint8_t)v;
+    }
+    n_bytes++;
+  }
+  __device__ __forceinline__ void emit_word(uint32_t w) {  // the next four bytes of the stream, first byte = top byte of w
+    if (stage) {
+      if (stage_n + 4 > stage_cap) flush_stage_serial();
+      *reinterpret_cast<uint32_t *>(stage + stage_n) = __byte_perm(w, 0u, 0x0123);  // (stage_n stays a multiple of 4 until finish())
+      stage_n += 4;
+    } else {
+      out[n_bytes] = (uint8_t)(w >> 24);
+      out[n_bytes + 1] = (uint8_t)(w >> 16);
+      out[n_bytes + 2] = (uint8_t)(w >> 8);
+      out[n_bytes + 3] = (uint8_t)w;
+    }
+    n_bytes += 4;
+  }
+  // append the low `n` (1..32) bits of `bits`, MSB first, to the byte stream
+  __device__ __forceinline__ void put_bits_plain(uint32_t bits, uint32_t n) {
+    const uint64_t v = n >= 32 ? (uint64_t)bits : ((uint64_t)bits & ((1ull << n) - 1ull));
+    bit_acc = (bit_acc << n) | v;
+    n_bits += n;
+    if (n_bits >= 32) {
+      n_bits -= 32;
+      emit_word((uint32_t)(bit_acc >> n_bits));
     }
   }
+  __device__ __forceinline__ void put_bit_internal(uint32_t bit) { put_bits_plain(bit & 1u, 1); }
   __device__ __forceinline__ void put_bit(uint32_t bit) {
     put_bit_internal(bit);
     while (carry_run > 0) {
       put_bit_internal((~bit) & 1u);
       carry_run--;
-    }
-  }
-  // append the low `n` (<= 32) bits of `bits`, MSB first, to the byte stream
-  __device__ __forceinline__ void put_bits_plain(uint32_t bits, uint32_t n) {
-    while (n > 0) {
-      const uint32_t take = (8 - bit_count) < n ? (8 - bit_count) : n;
-      const uint32_t chunk = (bits >> (n - take)) & ((1u << take) - 1u);
-      bit_buffer = (bit_buffer << take) | chunk;
-      bit_count += take;
-      n -= take;
-      if (bit_count == 8) {
-        if (stage) {
-          if (stage_n == stage_cap) flush_stage_serial();
-          stage[stage_n++] = (uint8_t)bit_buffer;
-          n_bytes++;
-        } else {
-          out[n_bytes++] = (uint8_t)bit_buffer;
-        }
-        bit_buffer = 0;
-        bit_count = 0;
-      }
     }
   }
   // total is fixed at 2^30 (AC_CDF_TOTAL), so floor(range*c/total) is a shift. Caller guarantees c_lo < c_hi <= 2^30.
@@ -150,9 +151,10 @@ struct AcEncoder {
   __device__ __forceinline__ uint64_t finish() {  // src/main.rs:387-399
     carry_run++;
     put_bit(low < 0x40000000ull ? 0u : 1u);
-    if (bit_count > 0) {
-      uint32_t remaining = 8 - bit_count;
-      for (uint32_t i = 0; i < remaining; i++) put_bit_internal(0);
+    if (n_bits & 7u) put_bits_plain(0u, 8u - (n_bits & 7u));  // zero-pad to a byte
+    while (n_bits > 0) {                                      // the pending whole bytes (at most three)
+      n_bits -= 8;
+      emit_byte((uint32_t)(bit_acc >> n_bits) & 0xFFu);
     }
     return n_bytes;
   }

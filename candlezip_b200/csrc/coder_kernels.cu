@@ -20,7 +20,7 @@ __global__ void __launch_bounds__(32) ac_encode_lanes_kernel(const uint32_t *__r
                                                              uint64_t *__restrict__ out_len, int *__restrict__ err,
                                                              unsigned long long *__restrict__ err_index) {
   __shared__ uint32_t s_lo[AC_BATCH], s_hi[AC_BATCH];
-  __shared__ uint8_t s_stage[AC_STAGE];
+  __shared__ __align__(16) uint8_t s_stage[AC_STAGE];
   const size_t lane = blockIdx.x;
   if (lane >= n_lanes) return;
   const int tid = threadIdx.x;
