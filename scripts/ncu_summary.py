@@ -11,6 +11,8 @@ COLS = [
     ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram%"),
     ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed", "tensor%"),
     ("sm__inst_executed_pipe_tc.avg.pct_of_peak_sustained_active", "tc_inst%"),
+    ("sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active", "fp64%"),
+    ("sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "xu%"),
     ("sm__warps_active.avg.pct_of_peak_sustained_active", "warps%"),
     ("sm__issue_active.avg.pct_of_peak_sustained_elapsed", "issue%"),
     ("launch__registers_per_thread", "regs"),
@@ -30,8 +32,8 @@ def to_us(v, unit):
     return v * {"ns": 1e-3, "us": 1, "ms": 1e3, "s": 1e6}.get(unit, 1)
 
 
-print("| file | kernel | time us | dram rd MB | dram wr MB | dram GB/s | dram% | tensor% | tc_inst% | warps% | issue% | regs | grid | block |")
-print("|---|---|---|---|---|---|---|---|---|---|---|---|---|---|")
+print("| file | kernel | time us | dram rd MB | dram wr MB | dram GB/s | dram% | tensor% | tc_inst% | fp64% | xu% | warps% | issue% | regs | grid | block |")
+print("|---|---|---|---|---|---|---|---|---|---|---|---|---|---|---|---|")
 for path in sys.argv[1:]:
     rows = list(csv.reader(open(path)))
     hdr, units = rows[0], rows[1]
