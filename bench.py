@@ -489,10 +489,10 @@ def run_ours(args):
         kern("gemm_tc_kernel<192,QKV_ROPE> qkv + RoPE", "gemm_qkv", "tensor", 2.0 * rows * qkv_n * Dm * L),
         kern("gemm_tc_kernel<256,COLMAX> LM head", "gemm_head", "tensor", 2.0 * HEAD_PARAMS * n),
         kern("attn_tc_kernel", "attn", "tensor", 70.57e6 * n),
-        # CDF: one full read of the column for the sum (cdf_stats_kernel) + the prefix walk up to the coded symbol
-        # (cdf_bounds_sorted_kernel): 4V and 4V E[sym]/V bytes per token
-        kern("cdf_stats_kernel (max given by the LM head; sequential f64 sum)", "cdf", "hbm", 4.0 * V * n),
-        kern("cdf_bounds_sorted_kernel (prefix walk to the coded symbol)", "cdf_prefix", "hbm", 4.0 * V * n * mean_sym_over_v),
+        # CDF: one full read of the column for the sum (cdf_stats_tma_kernel, which also leaves e_v, v <= sym, in the e-cache) + the
+        # prefix walk up to the coded symbol (cdf_bounds_warp_kernel): algorithmic 4V and 4V E[sym]/V bytes per token
+        kern("cdf_stats_tma_kernel (max given by the LM head; sequential f64 sum; fills the e-cache)", "cdf", "hbm", 4.0 * V * n),
+        kern("cdf_bounds_warp_kernel<cached> (prefix walk to the coded symbol)", "cdf_prefix", "hbm", 4.0 * V * n * mean_sym_over_v),
     ] if k]
     line = {
         "metric": METRIC, "value": value, "unit": "MB/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -511,7 +511,7 @@ def run_ours(args):
                      "traffic": NCU_GEMM_TRAFFIC_BYTES_PER_STEP, "traffic_source": "profiles/ncu_summary_r01g.md (ncu --set full, per launch x launches per step)",
                      "kernel": "gemm_tc_kernel (tcgen05 GEMM family: qkv+rope/o/gate-up/down/lm_head; the RMSNorm passes live in the o/down epilogues)",
                      "flops_per_step": gemm_flops, "kernel_ms_per_step": gemm_ms, "peak_source": peak_src,
-                     "timing": f"separate profiled pass ({prof_steps} steps, CUDA-event pairs around every launch; that pass ran at {prof_ms_per_step:.1f} ms/step)"},
+                     "timing": f"separate profiled pass ({prof_steps} steps, CUDA-event pairs around every launch, the CDF pass on the main stream instead of overlapped on the side stream; that pass ran at {prof_ms_per_step:.1f} ms/step)"},
         # whole-path tensor roofline exactly as SURVEY 8d defines it: tokens/s x 551.0 MFLOP / measured sustained bf16 peak
         "roofline_path": {"bound": "tensor", "achieved": value * 1e6 / max(1, world) * MFLOP_PER_TOKEN * 1e6 / 1e12, "peak": peak_tf, "unit": "TFLOP/s",
                           "frac": value * 1e6 / max(1, world) * MFLOP_PER_TOKEN * 1e6 / 1e12 / peak_tf, "per_gpu": True},

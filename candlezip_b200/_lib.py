@@ -145,6 +145,7 @@ SIGNATURES = {
                                    C.POINTER(C.c_uint16)]),
     "cz_test_expf_exhaustive": (C.c_int, [_vp, u64p, u64p, u64p]),
     "cz_test_div_random": (C.c_int, [_vp, C.c_uint64, C.c_uint64, u64p]),
+    "cz_test_cdf_ecache_state": (C.c_int, [_vp, C.POINTER(C.c_int), u64p]),
     "cz_schedule_chunks": (C.c_size_t, [C.c_uint64, C.c_uint32, C.c_uint32, u64p, u32p, u64p, u32p, C.c_size_t]),
 }
 

@@ -129,6 +129,8 @@ void cz_shutdown(cz_ctx *ctx) {
     cudaDeviceSynchronize();
     if (ctx->scratch) cudaFree(ctx->scratch);
     if (ctx->cdf_stats) cudaFree(ctx->cdf_stats);
+    if (ctx->cdf_ecache) cudaFree(ctx->cdf_ecache);
+    if (ctx->cdf_eoff) cudaFree(ctx->cdf_eoff);
     if (ctx->err_flag_dev) cudaFree(ctx->err_flag_dev);
     if (ctx->prof_ev0) cudaEventDestroy(ctx->prof_ev0);
     if (ctx->prof_ev1) cudaEventDestroy(ctx->prof_ev1);

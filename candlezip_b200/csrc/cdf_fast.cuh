@@ -50,7 +50,10 @@ __device__ __forceinline__ double cz_exp_neg_fast(float a, const uint64_t *__res
   const uint32_t ki = (uint32_t)__double2loint(kd);
   kd = __dsub_rn(kd, shift);
   const double r = __fma_rn(ninv, ad, -kd);
-  const uint64_t t = tab_lane[(ki & 31u) << 5];
+  // (explicit shared-window address: lane slot + entry * 256 bytes is one LOP3 + one IMAD; through the generic pointer the compiler
+  // rebuilds the lane part of the index for every lookup)
+  uint64_t t;
+  asm("ld.shared.u64 %0, [%1];" : "=l"(t) : "r"((uint32_t)__cvta_generic_to_shared(tab_lane) + ((ki & 31u) << 8)));
   const double s = __hiloint2double((int)((uint32_t)(t >> 32) + (ki << 15)), (int)(uint32_t)t);  // t += ki << 47
   const double p = __fma_rn(c0, r, c1);
   const double r2 = __dmul_rn(r, r);

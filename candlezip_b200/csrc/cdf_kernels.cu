@@ -15,6 +15,7 @@
 #include <stdlib.h>
 
 #include <algorithm>
+#include <type_traits>
 
 #include "cdf_fast.cuh"
 #include "tc_ptx.cuh"
@@ -242,23 +243,96 @@ __global__ void __launch_bounds__(128) cdf_stats_kernel(float *__restrict__ logi
 
 
 // ---------------------------------------------------------------------------------------------------------------------------------
+// The e-cache: what the prefix walk needs, laid out for it.
+// The prefix walk of column c adds e_v / S for v = 0 .. sym_c.  Reading those e_v (or the logits they come from) out of the
+// vocab-major batch costs a whole 32-byte sector -- a 64-byte DRAM fetch -- per 4-byte value, because the walk lengths of adjacent
+// columns have nothing to do with each other (ncu, profiles/ncu_summary_r02.md: 38 GB of DRAM reads per 131,072 columns against
+// 2.6 GB of values used, the kernel sits at 72% of DRAM bandwidth).  The stats pass has every e_v in a register anyway, so the
+// thread that owns column c also stores e_v (as the f64 it adds to S), for v <= sym_c only, CONTIGUOUSLY per column: groups of 8
+// rows = 64 bytes, at a per-column offset from an exclusive scan of ceil((sym_c + 1) / 8).  The prefix walk then reads 256
+// coalesced bytes per 32 rows and no longer evaluates expf.  Capacity is a fraction of the batch (real text: mean sym / V = 0.1);
+// if a batch needs more, the flag stays 0 and the prefix walk reads the logits as before -- same values either way.
+// ---------------------------------------------------------------------------------------------------------------------------------
+constexpr int EC_GRP = 8;  // rows per cache group (64 bytes of f64)
+
+__global__ void __launch_bounds__(1024) ecache_offsets_kernel(const uint32_t *__restrict__ syms, size_t M, int V, int n_sym,
+                                                              uint32_t *__restrict__ eoff, unsigned long long cap_groups,
+                                                              int *__restrict__ flag) {
+  __shared__ unsigned long long s_warp[32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const size_t per = (M + 1023) / 1024, b = (size_t)tid * per, e = b + per < M ? b + per : M;
+  auto groups = [&](size_t c) -> unsigned {
+    const uint32_t sym = syms[c];
+    if ((int)sym >= n_sym) return 0u;  // (reported by the prefix kernel)
+    const int n = (int)sym < V ? (int)sym + 1 : V;
+    return (unsigned)((n + EC_GRP - 1) / EC_GRP);
+  };
+  unsigned long long mine = 0;
+  for (size_t c = b; c < e; c++) mine += groups(c);
+  unsigned long long incl = mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) s_warp[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    unsigned long long w = s_warp[lane];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned long long t = __shfl_up_sync(0xffffffffu, w, o);
+      if (lane >= o) w += t;
+    }
+    s_warp[lane] = w;
+  }
+  __syncthreads();
+  const unsigned long long total = s_warp[31];
+  const bool fits = total <= cap_groups && total <= 0xffffffffull;
+  if (tid == 0) {
+    *flag = fits ? 1 : 0;
+    eoff[M] = fits ? (uint32_t)total : 0u;
+  }
+  if (!fits) return;
+  unsigned long long run = incl - mine + (warp ? s_warp[warp - 1] : 0ull);
+  for (size_t c = b; c < e; c++) {
+    eoff[c] = (uint32_t)run;
+    run += groups(c);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------------
 // Full passes with the logits STAGED THROUGH SHARED MEMORY BY TMA.  cdf_stats_kernel spends a third of its issue slots on getting
 // the data: per logit one LDG, one L2 prefetch and four 64-bit address adds (rows are ld * 4 bytes apart, nothing folds into an
 // immediate), and its top stall is the load scoreboard (ncu, profiles/ncu_summary_r02.md).  Here one elected thread per CTA streams
-// [16 rows] x [256 columns] boxes (16 KB, 1 KB contiguous per row) into a 4-stage shared-memory ring with cp.async.bulk.tensor;
+// [16 or 32 rows] x [256 columns] boxes (1 KB contiguous per row) into a shared-memory ring (StCfg) with cp.async.bulk.tensor;
 // the 256 consumer threads (thread = column) read their values with immediate-offset LDS, so the per-logit cost is the arithmetic
 // alone and the loads run arbitrarily far ahead of it.  Same values, same order per column: bit-identical to cdf_stats_kernel.
 // Needs ld % 4 == 0 and a 16-byte aligned base (tensor-map strides); otherwise the launcher keeps cdf_stats_kernel.
 // ---------------------------------------------------------------------------------------------------------------------------------
-constexpr int ST_COLS = 256, ST_ROWS = 16, ST_STAGES = 4, ST_TILE_BYTES = ST_COLS * ST_ROWS * 4;
-constexpr int ST_SMEM = ST_STAGES * ST_TILE_BYTES + 32 * 32 * 8 + 128;  // tiles | exp table | barriers
+// Tile shape per alphabet, two CTAs per SM (measured on B200, scripts/cdf_bench.py, 131,072 columns, stats pass alone; three CTAs per SM
+// cap the kernel at 75 registers and the compiler then re-materialises the polynomial's constants in every group of 8 rows):
+//   SmolLM  16 rows x 4 stages x 3 CTAs 13.5 ms | 16 x 4 x 2 CTAs 12.0 | 16 x 6 x 2 12.0 | 32 x 3 x 2 11.6 | 32 x 2 x 2 11.9 | 8 x 8 x 2 12.7
+//   RWKV    16 x 4 x 3 CTAs 53.1 ms | 16 x 4 x 2 50.5 | 16 x 6 x 2 50.2 | 32 x 3 x 2 52.1   (its first pass stores e_v in place, a barrier per pass)
+constexpr int ST_COLS = 256;
+template <int MODE>
+struct StCfg {
+  static constexpr int ROWS = MODE == CZ_CDF_RWKV_LITERALS ? 16 : 32;
+  static constexpr int STAGES = MODE == CZ_CDF_RWKV_LITERALS ? 6 : 3;
+  static constexpr int TILE_BYTES = ST_COLS * ROWS * 4;
+  static constexpr int SMEM = STAGES * TILE_BYTES + 32 * 32 * 8 + 128;  // tiles | exp table | barriers
+};
 
 template <int MODE, int OP>
-__global__ void __launch_bounds__(ST_COLS + 32, 3) cdf_stats_tma_kernel(const __grid_constant__ CUtensorMap tm, float *__restrict__ logits, int V,
+__global__ void __launch_bounds__(ST_COLS + 32, 2) cdf_stats_tma_kernel(const __grid_constant__ CUtensorMap tm, float *__restrict__ logits, int V,
                                                                        size_t M, size_t ld, const int *__restrict__ colmax,
-                                                                       CdfStats *__restrict__ stats, int *__restrict__ err) {
+                                                                       CdfStats *__restrict__ stats, int *__restrict__ err,
+                                                                       const uint32_t *__restrict__ syms, const uint32_t *__restrict__ eoff,
+                                                                       double *__restrict__ ecache, const int *__restrict__ eflag) {
   constexpr bool kLit = MODE == CZ_CDF_RWKV_LITERALS;
   constexpr bool kNorm = kLit || OP == OP_XE;
+  constexpr bool kSpill = OP == OP_BOUNDS;  // (ecache may still be null: no e-cache for this batch)
+  constexpr int ST_ROWS = StCfg<MODE>::ROWS, ST_STAGES = StCfg<MODE>::STAGES, ST_TILE_BYTES = StCfg<MODE>::TILE_BYTES;
   extern __shared__ __align__(1024) uint8_t st_smem[];
   float *tiles = reinterpret_cast<float *>(st_smem);
   uint64_t *s_tab = reinterpret_cast<uint64_t *>(st_smem + ST_STAGES * ST_TILE_BYTES);
@@ -311,32 +385,33 @@ __global__ void __launch_bounds__(ST_COLS + 32, 3) cdf_stats_tma_kernel(const __
       const int st = it % ST_STAGES;
       mbar_wait(full_bar + 8 * st, (it / ST_STAGES) & 1);
       const float *src = tiles + (size_t)st * ST_COLS * ST_ROWS + tid;
-      float x[ST_ROWS];
-#pragma unroll
-      for (int k = 0; k < ST_ROWS; k++) x[k] = src[k * ST_COLS];
-      __syncwarp();
-      if (lane == 0) mbar_arrive(empty_bar + 8 * st);  // the values are in registers: the slot can be refilled
-      if (t + 1 < n_tiles || V % ST_ROWS == 0) {  // a full tile: the group size is a compile-time 8 (no per-element predicates)
+      if (t + 1 < n_tiles || V % ST_ROWS == 0) {
+        // a full tile: compile-time groups of 8 rows (no per-element predicates), read 8 at a time (the registers of a whole tile
+        // are better spent on keeping the polynomial's constants resident); the slot is handed back once its last group is read
 #pragma unroll
         for (int g = 0; g < ST_ROWS / 8; g++) {
           float xg[8];
 #pragma unroll
-          for (int k = 0; k < 8; k++) xg[k] = x[g * 8 + k];
+          for (int k = 0; k < 8; k++) xg[k] = src[(g * 8 + k) * ST_COLS];
+          if (g == ST_ROWS / 8 - 1) {
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty_bar + 8 * st);
+          }
           f(t * ST_ROWS + g * 8, xg, 8);
         }
-      } else {  // the ragged last tile
-        const int rows = V - t * ST_ROWS;
-#pragma unroll
-        for (int g = 0; g < ST_ROWS / 8; g++) {
-          const int cnt = rows - g * 8;
-          if (cnt > 0) {
-            float xg[8];
-#pragma unroll
-            for (int k = 0; k < 8; k++) xg[k] = x[g * 8 + k];
-            f(t * ST_ROWS + g * 8, xg, cnt < 8 ? cnt : 8);
-          }
-        }
+        continue;
       }
+      // the ragged last tile (rows beyond V are zero-filled by the tensor map; f ignores them)
+      const int rows = V - t * ST_ROWS;
+      for (int g = 0; g * 8 < rows; g++) {
+        float xg[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) xg[k] = src[(g * 8 + k) * ST_COLS];
+        const int cnt = rows - g * 8;
+        f(t * ST_ROWS + g * 8, xg, cnt < 8 ? cnt : 8);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty_bar + 8 * st);
     }
   };
   auto pass_barrier = [&]() {
@@ -353,6 +428,15 @@ __global__ void __launch_bounds__(ST_COLS + 32, 3) cdf_stats_tma_kernel(const __
     });
   }
   // ---- pass 1: S ----
+  // e-cache: this column's rows 0 .. sym go to ecache[eoff[col] * 8 ...] (see ecache_offsets_kernel)
+  int n_spill = 0;
+  double *edst = nullptr;
+  if (kSpill && ecache != nullptr && active && *eflag != 0) {
+    const uint32_t sym = syms[col];
+    const int n_sym = kLit ? V + 256 : V;
+    if ((int)sym < n_sym) n_spill = (int)sym < V ? (int)sym + 1 : V;
+    edst = ecache + (size_t)eoff[col] * EC_GRP;
+  }
   double S = 0.0;
   run_pass([&](int v0, const float(&x)[8], int cnt) {
     float a[8], ef[8];
@@ -366,6 +450,11 @@ __global__ void __launch_bounds__(ST_COLS + 32, 3) cdf_stats_tma_kernel(const __
         S = __dadd_rn(S, d[k]);
         if (kLit && active) logits[(size_t)(v0 + k) * ld + col] = ef[k];  // cache e_v for the later passes
       }
+    if (kSpill && v0 < n_spill) {  // (rows of the group beyond sym, or beyond V in the ragged tile, are never read)
+      double2 *q = reinterpret_cast<double2 *>(edst + v0);
+#pragma unroll
+      for (int k = 0; k < 8; k += 2) q[k >> 1] = make_double2(d[k], d[k + 1]);
+    }
   });
   int errbits = 0;
   if (active && !(S == S)) errbits |= CZ_DEVERR_NAN;
@@ -477,18 +566,24 @@ struct PdfOf {
 // Columns are handed out one at a time from a global counter (persistent warps): a warp that finishes a short column takes the
 // next one instead of idling until the longest column of its CTA is done, and columns c .. c + 7 -- which share a 32-byte sector
 // per vocab row -- are in flight at about the same time, so the sector is fetched from DRAM once and found in L2 by the others.
-template <int MODE>
+// CACHED: the e_v come from the e-cache the stats pass filled (f64, contiguous per column: 256 coalesced bytes per 32 rows, no
+// expf); the kernel is a no-op when the batch did not fit the cache (*eflag == 0).  !CACHED: from the vocab-major logits; a no-op
+// when eflag is given and set.  The launcher issues both, exactly one of them works.
+template <int MODE, bool CACHED>
 __global__ void __launch_bounds__(256) cdf_bounds_warp_kernel(const float *__restrict__ logits, int V, size_t M, size_t ld,
                                                               const uint32_t *__restrict__ syms, const CdfStats *__restrict__ stats,
                                                               uint32_t *__restrict__ c_lo_out, uint32_t *__restrict__ c_hi_out,
-                                                              int *__restrict__ err, unsigned int *__restrict__ work_counter) {
+                                                              int *__restrict__ err, unsigned int *__restrict__ work_counter,
+                                                              const uint32_t *__restrict__ eoff, const double *__restrict__ ecache,
+                                                              const int *__restrict__ eflag) {
   constexpr bool kLit = MODE == CZ_CDF_RWKV_LITERALS;
   constexpr int DEPTH = 4;  // groups of 32 rows whose loads are in flight ahead of the group being added
-  __shared__ uint64_t s_tab[32 * 32];
+  __shared__ uint64_t s_tab[CACHED ? 32 : 32 * 32];
   __shared__ __align__(16) double s_xch[8 * 64];  // per warp: two 32-value exchange lines
-  exp_tab64_init(s_tab);
+  if (CACHED ? *eflag == 0 : (eflag != nullptr && *eflag != 0)) return;
+  if (!CACHED) exp_tab64_init(s_tab);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const ExpTab64 tab{s_tab + lane};
+  const ExpTab64 tab{s_tab + (CACHED ? 0 : lane)};
   double *xch = s_xch + warp * 64;
   const int n_sym = kLit ? V + 256 : V;
   for (;;) {
@@ -514,13 +609,18 @@ __global__ void __launch_bounds__(256) cdf_bounds_warp_kernel(const float *__res
     const int n = (int)sym < V ? (int)sym + 1 : V;  // vocab rows to add
     const int n_grp = (n + 31) >> 5;
     // the rows hold logits (SmolLM) or the e_v the stats kernel's first pass left there (RWKV alphabet)
-    auto ld_x = [&](int g) -> float {
+    using X = typename std::conditional<CACHED, double, float>::type;
+    const double *pe = CACHED ? ecache + (size_t)eoff[col] * EC_GRP : nullptr;
+    auto ld_x = [&](int g) -> X {
       const int v = g * 32 + lane;
+      if (CACHED) return v < n ? __ldg(pe + v) : 0.0;
       return v < n ? (kLit ? p[(size_t)v * ld] : __ldg(p + (size_t)v * ld)) : 0.f;
     };
-    auto q_of = [&](float x) -> double {
+    auto q_of = [&](X x) -> double {
       double d;
-      if (kLit) {
+      if (CACHED) {
+        d = (double)x;
+      } else if (kLit) {
         d = pdf.fast ? cz_widen_pos(x) : (double)x;  // (values below 2^-126 are floored either way)
       } else {
         const float a1[1] = {__fsub_rn(mx, x)};
@@ -533,11 +633,11 @@ __global__ void __launch_bounds__(256) cdf_bounds_warp_kernel(const float *__res
     };
     double acc = 0.0;
     uint32_t lo = 0, hi = 0;
-    float xr[DEPTH];
+    X xr[DEPTH];
 #pragma unroll
     for (int k = 0; k < DEPTH; k++) xr[k] = ld_x(k);
     for (int g = 0; g < n_grp; g++) {
-      const float x = xr[0];
+      const X x = xr[0];
 #pragma unroll
       for (int k = 0; k + 1 < DEPTH; k++) xr[k] = xr[k + 1];
       xr[DEPTH - 1] = ld_x(g + DEPTH);
@@ -788,9 +888,9 @@ int launch_fill_i32(cz_ctx *ctx, int *p, int v, size_t n, cudaStream_t stream) {
   return CZ_OK;
 }
 
-// logits [V][ld] f32 as a 2D tensor, box = ST_COLS columns x ST_ROWS rows, no swizzle (thread t reads word t of a row: conflict-free);
+// logits [V][ld] f32 as a 2D tensor, box = ST_COLS columns x StCfg<MODE>::ROWS rows, no swizzle (thread t reads word t of a row: conflict-free);
 // rows beyond V and columns beyond ld are zero-filled
-static int make_logits_map(CUtensorMap *map, const float *logits, size_t V, size_t ld) {
+static int make_logits_map(CUtensorMap *map, const float *logits, size_t V, size_t ld, int box_rows) {
   typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                                const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
                                CUtensorMapFloatOOBfill);
@@ -806,7 +906,7 @@ static int make_logits_map(CUtensorMap *map, const float *logits, size_t V, size
   }
   cuuint64_t gdim[2] = {(cuuint64_t)ld, (cuuint64_t)V};
   cuuint64_t gstride[1] = {(cuuint64_t)ld * 4};
-  cuuint32_t box[2] = {(cuuint32_t)czk::ST_COLS, (cuuint32_t)czk::ST_ROWS};
+  cuuint32_t box[2] = {(cuuint32_t)czk::ST_COLS, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(logits), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -871,13 +971,64 @@ int launch_cdf_cols(cz_ctx *ctx, int op, int mode, const float *logits_dev, size
     // TMA-staged variant: needs tensor-map-compatible strides / alignment and enough columns to fill the machine with 256-column CTAs
     static const bool no_tma = getenv("CZ_CDF_NO_TMA") != nullptr;  // bisecting aid
     const bool tma_ok = !no_tma && force_ncol == 0 && ld % 4 == 0 && ((uintptr_t)logits_dev & 15) == 0 && M >= 256 && V >= 64;
+    // e-cache for the prefix walk (see ecache_offsets_kernel): only with the TMA-staged stats kernel, which fills it
+    uint32_t *eoff = nullptr;
+    double *ecache = nullptr;
+    int *eflag = nullptr;
+    if (op == czk::OP_BOUNDS) ctx->cdf_eflag_last = nullptr;
+    if (tma_ok && op == czk::OP_BOUNDS && !ctx->cdf_ecache_failed && getenv("CZ_CDF_NO_ECACHE") == nullptr) {
+      const char *env_frac = getenv("CZ_CDF_ECACHE_FRAC");  // (read per call: the tests switch it between calls)
+      double frac = env_frac ? atof(env_frac) : 0.25;       // capacity as a fraction of the batch's rows (real text needs 0.1)
+      frac = frac < 0.0 ? 0.0 : frac > 1.0 ? 1.0 : frac;
+      const size_t grp_per_col = ceil_div(V, (size_t)czk::EC_GRP);
+      size_t cap_groups = std::min<size_t>((size_t)((double)M * (double)grp_per_col * frac) + 1, 0xffffffffull);
+      const size_t need_e = cap_groups * czk::EC_GRP * sizeof(double), need_o = (M + 2) * sizeof(uint32_t);
+      bool ok = true;
+      if (need_o > ctx->cdf_eoff_bytes || need_e > ctx->cdf_ecache_bytes) {
+        if (ctx->capturing) {
+          ok = false;  // no allocation inside a graph capture
+        } else {
+          CZ_CUDA_TRY(cudaStreamSynchronize(stream));
+          if (need_o > ctx->cdf_eoff_bytes) {
+            if (ctx->cdf_eoff) cudaFree(ctx->cdf_eoff);
+            ctx->cdf_eoff = nullptr;
+            ctx->cdf_eoff_bytes = 0;
+            const size_t want = need_o + (need_o >> 2) + 4096;
+            CZ_CUDA_TRY(cudaMalloc(&ctx->cdf_eoff, want));
+            ctx->cdf_eoff_bytes = want;
+          }
+          if (need_e > ctx->cdf_ecache_bytes) {
+            if (ctx->cdf_ecache) cudaFree(ctx->cdf_ecache);
+            ctx->cdf_ecache = nullptr;
+            ctx->cdf_ecache_bytes = 0;
+            if (cudaMalloc(&ctx->cdf_ecache, need_e) != cudaSuccess) {
+              cudaGetLastError();  // out of memory: the prefix walk keeps reading the logits, for good
+              ctx->cdf_ecache = nullptr;
+              ctx->cdf_ecache_failed = true;
+              ok = false;
+            } else {
+              ctx->cdf_ecache_bytes = need_e;
+            }
+          }
+        }
+      }
+      if (ok) {
+        eoff = (uint32_t *)ctx->cdf_eoff;
+        eflag = (int *)(eoff + M + 1);
+        ecache = (double *)ctx->cdf_ecache;
+        const int n_sym = mode == CZ_CDF_RWKV_LITERALS ? (int)V + 256 : (int)V;
+        CZ_LAUNCH(ctx, CZ_K_CDF, (czk::ecache_offsets_kernel<<<1, 1024, 0, stream>>>(arg_dev, M, (int)V, n_sym, eoff, (unsigned long long)cap_groups, eflag)));
+        CZ_CHECK_LAUNCH();
+        ctx->cdf_eflag_last = eflag;
+      }
+    }
     if (tma_ok) {
       CUtensorMap tm;
-      CZ_TRY(make_logits_map(&tm, logits_dev, V, ld));
+      CZ_TRY(make_logits_map(&tm, logits_dev, V, ld, mode == CZ_CDF_RWKV_LITERALS ? czk::StCfg<CZ_CDF_RWKV_LITERALS>::ROWS : czk::StCfg<CZ_CDF_SMOLLM>::ROWS));
       static bool attr = false;
       if (!attr) {
 #define CZ_TMA_ATTR(MODE, OP) \
-  CZ_CUDA_TRY(cudaFuncSetAttribute(czk::cdf_stats_tma_kernel<MODE, OP>, cudaFuncAttributeMaxDynamicSharedMemorySize, czk::ST_SMEM))
+  CZ_CUDA_TRY(cudaFuncSetAttribute(czk::cdf_stats_tma_kernel<MODE, OP>, cudaFuncAttributeMaxDynamicSharedMemorySize, czk::StCfg<MODE>::SMEM))
         CZ_TMA_ATTR(CZ_CDF_SMOLLM, czk::OP_BOUNDS);
         CZ_TMA_ATTR(CZ_CDF_SMOLLM, czk::OP_XE);
         CZ_TMA_ATTR(CZ_CDF_RWKV_LITERALS, czk::OP_BOUNDS);
@@ -888,8 +1039,8 @@ int launch_cdf_cols(cz_ctx *ctx, int op, int mode, const float *logits_dev, size
       const unsigned g = (unsigned)ceil_div(M, (size_t)czk::ST_COLS);
 #define CZ_TMA_STATS(MODE, OP)                                                                                                        \
   CZ_LAUNCH(ctx, CZ_K_CDF,                                                                                                            \
-            (czk::cdf_stats_tma_kernel<MODE, OP><<<g, czk::ST_COLS + 32, czk::ST_SMEM, stream>>>(tm, lg, (int)V, M, ld, colmax_dev, stats, \
-                                                                                                 ctx->err_flag_dev)))
+            (czk::cdf_stats_tma_kernel<MODE, OP><<<g, czk::ST_COLS + 32, czk::StCfg<MODE>::SMEM, stream>>>(tm, lg, (int)V, M, ld, colmax_dev, stats, \
+                                                                                                 ctx->err_flag_dev, arg_dev, eoff, ecache, eflag)))
       if (mode == CZ_CDF_SMOLLM) {
         if (op == czk::OP_BOUNDS) CZ_TMA_STATS(CZ_CDF_SMOLLM, czk::OP_BOUNDS);
         else CZ_TMA_STATS(CZ_CDF_SMOLLM, czk::OP_XE);
@@ -934,14 +1085,19 @@ int launch_cdf_cols(cz_ctx *ctx, int op, int mode, const float *logits_dev, size
       CZ_CUDA_TRY(cudaMemsetAsync(counter, 0, sizeof(unsigned int), stream));
       const size_t want_ctas = ceil_div(M, 8);
       const unsigned g = (unsigned)std::min<size_t>(want_ctas, (size_t)ctx->sm_count * 8);
-      if (mode == CZ_CDF_SMOLLM)
-        CZ_LAUNCH(ctx, CZ_K_CDF_PREFIX,
-                  (czk::cdf_bounds_warp_kernel<CZ_CDF_SMOLLM><<<g, 256, 0, stream>>>(logits_dev, (int)V, M, ld, arg_dev, stats, c_lo_dev, c_hi_dev,
-                                                                                     ctx->err_flag_dev, counter)));
-      else
-        CZ_LAUNCH(ctx, CZ_K_CDF_PREFIX,
-                  (czk::cdf_bounds_warp_kernel<CZ_CDF_RWKV_LITERALS><<<g, 256, 0, stream>>>(logits_dev, (int)V, M, ld, arg_dev, stats, c_lo_dev,
-                                                                                            c_hi_dev, ctx->err_flag_dev, counter)));
+#define CZ_PREFIX(MODE, CACHED)                                                                                                          \
+  CZ_LAUNCH(ctx, CZ_K_CDF_PREFIX,                                                                                                        \
+            (czk::cdf_bounds_warp_kernel<MODE, CACHED><<<g, 256, 0, stream>>>(logits_dev, (int)V, M, ld, arg_dev, stats, c_lo_dev, c_hi_dev, \
+                                                                              ctx->err_flag_dev, counter, eoff, ecache, eflag)))
+      // with an e-cache both variants are issued: the flag the offsets kernel wrote decides on the device which one works
+      if (mode == CZ_CDF_SMOLLM) {
+        if (ecache) CZ_PREFIX(CZ_CDF_SMOLLM, true);
+        CZ_PREFIX(CZ_CDF_SMOLLM, false);
+      } else {
+        if (ecache) CZ_PREFIX(CZ_CDF_RWKV_LITERALS, true);
+        CZ_PREFIX(CZ_CDF_RWKV_LITERALS, false);
+      }
+#undef CZ_PREFIX
     } else {
       const unsigned g = (unsigned)ceil_div(M, 128);
       if (mode == CZ_CDF_SMOLLM)
@@ -991,6 +1147,21 @@ int launch_cdf_full(cz_ctx *ctx, int mode, const float *logits_dev, size_t V, ui
 }  // namespace cz
 
 using namespace cz;
+
+extern "C" int cz_test_cdf_ecache_state(cz_ctx *ctx, int *state, uint64_t *groups) {
+  if (!ctx || ctx->device < 0) return CZ_ERR_NO_DEVICE;
+  CZ_CUDA_TRY(cudaSetDevice(ctx->device));
+  CZ_CUDA_TRY(cudaDeviceSynchronize());
+  int st = -1;
+  uint32_t total = 0;
+  if (ctx->cdf_eflag_last) {
+    CZ_CUDA_TRY(cudaMemcpy(&st, ctx->cdf_eflag_last, sizeof(int), cudaMemcpyDeviceToHost));
+    CZ_CUDA_TRY(cudaMemcpy(&total, (const uint32_t *)ctx->cdf_eflag_last - 1, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+  }
+  if (state) *state = st;
+  if (groups) *groups = total;
+  return CZ_OK;
+}
 
 extern "C" int cz_test_expf_exhaustive(cz_ctx *ctx, uint64_t *mismatches, uint64_t *checksum, uint64_t *first_bad) {
   if (!ctx || ctx->device < 0) return CZ_ERR_NO_DEVICE;

@@ -59,6 +59,13 @@ struct cz_ctx {
   size_t scratch_bytes = 0;
   void *cdf_stats = nullptr;  // per-column results of the CDF kernels' full passes (cdf_kernels.cu), grow-only
   size_t cdf_stats_bytes = 0;
+  // compact per-column copy of e_v for v <= coded symbol, written by the stats pass and read by the prefix walk (cdf_kernels.cu)
+  void *cdf_ecache = nullptr;
+  size_t cdf_ecache_bytes = 0;
+  void *cdf_eoff = nullptr;  // u32 offsets [M + 1] (units of 8 doubles) + the "cache in use" flag
+  size_t cdf_eoff_bytes = 0;
+  const void *cdf_eflag_last = nullptr;  // device address of the last batch's flag; the total follows the offsets right before it
+  bool cdf_ecache_failed = false;  // the allocation did not fit once: the prefix walk reads the logits from then on
   int *err_flag_dev = nullptr;  // 64-byte device status block: [0] flag set by kernels on zero-width intervals etc., [8] the
                                 // attention kernel's work-item counter (attn_tc.cu)
 };

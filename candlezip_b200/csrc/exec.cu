@@ -320,7 +320,8 @@ static int run_wave_head(cz_model *m, size_t n_logit, int op, int mode, const ui
   // its time disappears behind them.  Two logits buffers; an event pair per buffer orders LM head -> CDF -> (the LM head that
   // reuses the buffer).  join_cdf() before anything consumes the bounds.
   static const bool no_overlap = getenv("CZ_NO_OVERLAP") != nullptr;  // bisecting aid
-  const bool overlap = !no_overlap && ctx->stream2 && !ctx->capturing && ctx->prof_mode != 1;
+  // (per-launch profiling runs everything on one stream: a kernel timed while another one shares the machine says nothing about either)
+  const bool overlap = !no_overlap && ctx->stream2 && !ctx->capturing && ctx->prof_mode == 0;
   for (size_t c0 = 0; c0 < n_logit; c0 += ws.ld_sub) {
     const size_t nc = std::min(ws.ld_sub, n_logit - c0);
     const int buf = ws.head_buf;

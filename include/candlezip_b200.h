@@ -297,6 +297,10 @@ int cz_test_attention(cz_ctx *ctx, int n_pos, int nh, int nkv, const uint16_t *q
  * with its glibc-verified expf (czo_expf_checksum); (2) the reciprocal-based division against the IEEE division on random operands */
 int cz_test_expf_exhaustive(cz_ctx *ctx, uint64_t *mismatches, uint64_t *checksum, uint64_t *first_bad);
 int cz_test_div_random(cz_ctx *ctx, uint64_t seed, uint64_t n_pairs, uint64_t *mismatches);
+/* what the last encode-side CDF batch (cz_cdf_bounds or the executor) did with the e-cache -- the compact copy of e_v, v <= coded
+ * symbol, that the stats pass leaves for the prefix walk (csrc/cdf_kernels.cu): *state = 1 the prefix walk read the cache, 0 the batch
+ * did not fit its capacity and the walk read the logits, -1 no cache was set up for that batch; *groups = 64-byte groups used */
+int cz_test_cdf_ecache_state(cz_ctx *ctx, int *state, uint64_t *groups);
 
 #ifdef __cplusplus
 }

@@ -34,9 +34,14 @@ data = corpus.load("enwik8_3mib")
 ids = corpus.byte_ids((data * (M // len(data) + 1))[:M], V, True)
 cases = {"sym0": np.zeros(M, np.uint32), "spread_ids": ids, "uniform": np.random.default_rng(0).integers(0, V, M).astype(np.uint32)}
 res = {"mode": mode, "V": V, "cols": M, "legacy": bool(os.environ.get("CZ_CDF_LEGACY"))}
-variants = ("legacy",) if res["legacy"] else ("tma", "ncol1")
+variants = ("legacy",) if res["legacy"] else ("tma", "tma_noecache", "ncol1")
+if os.environ.get("CDF_BENCH_VARIANTS"):
+    variants = tuple(os.environ["CDF_BENCH_VARIANTS"].split(","))
 for ncol in variants:
     os.environ.pop("CZ_CDF_NCOL", None)
+    os.environ.pop("CZ_CDF_NO_ECACHE", None)
+    if ncol == "tma_noecache":  # the prefix walk reads the vocab-major logits instead of the e-cache the stats pass fills
+        os.environ["CZ_CDF_NO_ECACHE"] = "1"
     if ncol == "ncol1":  # the direct-load kernel (a forced column width keeps the TMA-staged variant off)
         os.environ["CZ_CDF_NCOL"] = "1"
     for name, syms in cases.items():

@@ -3,6 +3,8 @@
 # Every ncu run is preceded by the identical plain command (B200_PROFILING.md).  Usage: scripts/gpu_profile.sh [tag]
 TAG=${1:-r02}
 mkdir -p gpurun_out
+REP=${CZ_NCU_REP_DIR:-/tmp/cz_ncu}
+mkdir -p $REP
 CMD="python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-alice --no-gate --sharded-segments 0 --rwkv-bytes 0"
 $CMD > gpurun_out/prof_plain_$TAG.json 2> gpurun_out/prof_plain_$TAG.err || { echo "plain run failed"; tail -5 gpurun_out/prof_plain_$TAG.err; exit 1; }
 # launch list of the SECOND (timed) step: skip the warm-up step's launches
@@ -13,8 +15,9 @@ echo "launch list rc=$?"
 # full captures. -k filters by function base name; --launch-skip counts MATCHING launches.
 full() { # name kernel-regex skip count [command]
   local cmd="${5:-$CMD}"
-  ncu --set full --clock-control none --import-source on -k regex:"$2" -s $3 -c $4 -o gpurun_out/$1_$TAG -f $cmd > gpurun_out/ncu_$1_$TAG.log 2>&1
-  echo "full capture $1 rc=$? $(ls -la gpurun_out/$1_$TAG.ncu-rep 2>/dev/null | awk '{print $5}') bytes"
+  # the .ncu-rep files stay on the box (gpurun merges at most 64 MiB back): only the raw / source CSV exports travel
+  ncu --set full --clock-control none --import-source on -k regex:"$2" -s $3 -c $4 -o $REP/$1_$TAG -f $cmd > gpurun_out/ncu_$1_$TAG.log 2>&1
+  echo "full capture $1 rc=$? $(ls -la $REP/$1_$TAG.ncu-rep 2>/dev/null | awk '{print $5}') bytes"
 }
 J() { python -c "import json;d=json.load(open('gpurun_out/prof_plain_$TAG.json'))['kernel_launches_per_step'];print($1)"; }
 G=$(J "d['gemm']"); H=$(J "d['gemm_head']"); A=$(J "d['attn']"); C=$(J "d['cdf']"); P=$(J "d['cdf_prefix']")
@@ -32,7 +35,11 @@ DCMD="python scripts/decode_profile.py smollm 98304 384 corpus"
 full decode_step "decode_step_kernel" 300 1 "$DCMD"
 full decode_attn "attn_tc_kernel" 9000 1 "$DCMD"
 for r in gemm_trunk gemm_head attn cdf_stats cdf_prefix elem rwkv decode_step decode_attn; do
-  [ -f gpurun_out/${r}_$TAG.ncu-rep ] && ncu -i gpurun_out/${r}_$TAG.ncu-rep --page raw --csv > gpurun_out/${r}_${TAG}_raw.csv 2>/dev/null
+  [ -f $REP/${r}_$TAG.ncu-rep ] && ncu -i $REP/${r}_$TAG.ncu-rep --page raw --csv > gpurun_out/${r}_${TAG}_raw.csv 2>/dev/null
+done
+for r in attn cdf_stats cdf_prefix; do
+  [ -f $REP/${r}_$TAG.ncu-rep ] && ncu -i $REP/${r}_$TAG.ncu-rep --page source --csv > gpurun_out/${r}_${TAG}_source.csv 2>/dev/null
 done
 python scripts/ncu_summary.py gpurun_out/*_${TAG}_raw.csv > gpurun_out/ncu_table_$TAG.md 2>/dev/null
-ls -la gpurun_out/ | tail -40
+cat gpurun_out/ncu_table_$TAG.md
+du -sh gpurun_out

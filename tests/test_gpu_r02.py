@@ -378,6 +378,56 @@ def test_cdf_bounds_and_xe_new_kernels_all_vector_widths(gpu_ctx, mode, ncol):
         os.environ.pop("CZ_CDF_NCOL", None)
 
 
+@pytest.mark.parametrize("mode", [0, 1])
+def test_cdf_prefix_walk_through_the_ecache_and_its_fallback(gpu_ctx, mode):
+    """csrc/cdf_kernels.cu (e-cache): the stats pass leaves e_v, v <= coded symbol, contiguously per column and the prefix walk reads
+    that instead of the vocab-major logits.  Same bounds as the oracle (src/main.rs:784-824 / 758-782) (a) through the cache
+    (heavy-tailed symbols at the default capacity; uniform symbols with the capacity raised to the whole batch), (b) when the batch
+    does not fit (uniform symbols at the default capacity: the flag computed on the device sends the walk back to the logits) and
+    (c) with the cache disabled; the state hook says which of the three ran."""
+    import test_gpu_parity as tgp
+
+    def state():
+        st, g = C.c_int(), C.c_uint64()
+        _lib.check(_lib.lib.cz_test_cdf_ecache_state(gpu_ctx._h, C.byref(st), C.byref(g)))
+        return st.value, g.value
+
+    rng = np.random.default_rng(300 + mode)
+    v = 2309 if mode else 2304  # (2309: a ragged last 16-row tile and a ragged last cache group)
+    n_sym = v + 256 if mode else v
+    try:
+        for m in (260, 1031 // 4 * 4, 2048):
+            logits = tgp._adversarial_logits(rng, v, m)
+            logits[:, m // 3] = rng.normal(0, 30, v)  # entries > 87 below the max: the conversion path inside a cached column
+            heavy = np.minimum((rng.random(m) ** 6 * n_sym).astype(np.uint32), n_sym - 1)  # mean id / alphabet = 1/7
+            heavy[:8] = [0, 1, 7, 8, 9, v - 1, min(v, n_sym - 1), n_sym - 1]
+            heavy[m // 3] = v - 2
+            uniform = rng.integers(0, n_sym, m).astype(np.uint32)
+            want = {}
+            for name, syms in (("heavy", heavy), ("uniform", uniform)):
+                cdfs = [oracle.logits_to_cdf(logits[:, j], mode) for j in range(m)]
+                want[name] = (np.array([c[s] for c, s in zip(cdfs, syms)], np.uint32), np.array([c[s + 1] for c, s in zip(cdfs, syms)], np.uint32))
+            runs = [("heavy", None, 1), ("uniform", None, 0), ("uniform", "1.0", 1), ("heavy", "off", -1)]
+            for name, frac, expect in runs:
+                os.environ.pop("CZ_CDF_ECACHE_FRAC", None)
+                os.environ.pop("CZ_CDF_NO_ECACHE", None)
+                if frac == "off":
+                    os.environ["CZ_CDF_NO_ECACHE"] = "1"
+                elif frac:
+                    os.environ["CZ_CDF_ECACHE_FRAC"] = frac
+                syms = heavy if name == "heavy" else uniform
+                lo, hi = gpu_ctx.cdf_bounds(logits, syms, mode)
+                st, groups = state()
+                assert st == expect, (m, name, frac, st, groups)
+                if st == 1:
+                    need = sum((min(int(x) + 1, v) + 7) // 8 for x in syms)
+                    assert groups == need, (groups, need)
+                assert np.array_equal(lo, want[name][0]) and np.array_equal(hi, want[name][1]), (m, name, frac)
+    finally:
+        os.environ.pop("CZ_CDF_ECACHE_FRAC", None)
+        os.environ.pop("CZ_CDF_NO_ECACHE", None)
+
+
 def test_cli_twin_gate_scan_replay_self_test(gpu_ctx, tmp_path):
     """`python -m candlezip_b200 self-test FILE --reuse-scan-dir DIR` (src/main.rs:156-221 with --reuse-scan-dir, :1966-1978): the gate
     scan replayed from an agent_cache.jsonl in the reference's format; AGT2 container, proof.csv ledger, byte-exact round trip."""
