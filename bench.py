@@ -39,10 +39,10 @@ import corpus  # noqa: E402  (tests/golden/corpus.py: committed corpora, stdlib 
 
 METRIC = "encode_MB_per_s_smollm135m_ctx512"
 V_SMOLLM = 49152
-# dram__bytes_read + dram__bytes_write per launch under ncu --set full (profiles/ncu_summary_r01g.md; 253k-row layer-wave launches):
-# qkv+rope 769 MB, o-proj (+ fused norm operands) 1969 MB, gate/up 1061 MB, down (+ fused norm operands) 2335 MB; x60 launches each,
-# plus the LM head's 51.5 GB of logits written + 0.4 GB read
-NCU_GEMM_TRAFFIC_BYTES_PER_STEP = int(60 * (759 + 1969 + 1061 + 2335) * 1e6 + 51.9e9)
+# dram__bytes_read + dram__bytes_write per launch under ncu --set full (profiles/ncu_summary_r02.md; 253k-row layer-wave launches):
+# qkv+rope 763 MB, o-proj (+ fused norm operands) 1754 MB, gate/up 1063 MB, down (+ fused norm operands) 2267 MB; x60 launches each,
+# plus the LM head: 51.5 GB of logits written and 0.31 bytes read per byte written (operand re-reads, 7.8 GB per 127k-column launch)
+NCU_GEMM_TRAFFIC_BYTES_PER_STEP = int(60 * (763 + 1754 + 1063 + 2267) * 1e6 + 51.54e9 * (1 + 7.77 / 24.94))
 MFLOP_PER_TOKEN = 551.0  # trunk 423.84 + head 56.62 + attention 70.57 MFLOP per coded token at ctx 512 / reprime 512
 TRUNK_PARAMS = 106_168_320  # matmul params per token position, SURVEY 8d
 HEAD_PARAMS = 28_311_552
@@ -508,7 +508,7 @@ def run_ours(args):
                 "d2h_bytes_per_step": int(payload_bytes + 8 * S + 16), "bitstream_equal_to_device_arm": same},
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf if achieved else None,
                      # dram__bytes_read + dram__bytes_write per launch from the ncu --set full captures (profiles/), summed over one step
-                     "traffic": NCU_GEMM_TRAFFIC_BYTES_PER_STEP, "traffic_source": "profiles/ncu_summary_r01g.md (ncu --set full, per launch x launches per step)",
+                     "traffic": NCU_GEMM_TRAFFIC_BYTES_PER_STEP, "traffic_source": "profiles/ncu_summary_r02.md (ncu --set full, per launch x launches per step)",
                      "kernel": "gemm_tc_kernel (tcgen05 GEMM family: qkv+rope/o/gate-up/down/lm_head; the RMSNorm passes live in the o/down epilogues)",
                      "flops_per_step": gemm_flops, "kernel_ms_per_step": gemm_ms, "peak_source": peak_src,
                      "timing": f"separate profiled pass ({prof_steps} steps, CUDA-event pairs around every launch, the CDF pass on the main stream instead of overlapped on the side stream; that pass ran at {prof_ms_per_step:.1f} ms/step)"},
