@@ -321,185 +321,4 @@ __device__ __forceinline__ void cdf_col(const float *__restrict__ p_in, size_t l
   }
 }
 
-// ---------------------------------------------------------------------------------------------------------------
-// Warp-per-column search for the stepwise decoder.  With only B (hundreds) columns per step the thread-per-column
-// walk above is a ~10^5-deep dependent chain per thread with nothing to overlap.  Here the 32 lanes evaluate expf /
-// the pdf for 32 consecutive vocab entries in parallel and only the order-dependent f64 accumulation is serial
-// (every lane performs it redundantly on shuffled values, so all lanes hold the same S / acc and branches stay
-// warp-uniform).  Same operations in the same order as cdf_col => bit-identical results.
-// p: column base (vocab-major, element v at p[v*ld]).  Must be called by a full warp.
-template <int MODE>
-// xch: 64 doubles of shared memory private to the calling warp (16-byte aligned).
-__device__ __forceinline__ void cdf_search_warp(const float *__restrict__ p_in, size_t ld, int V, uint32_t value, float mx,
-                                                const ExpTab &tab, uint32_t &sym_out, uint32_t &lo_out, uint32_t &hi_out,
-                                                int &errbits, double *xch) {
-  // (No in-place caching of expf here, unlike cdf_col: the stepwise RWKV decoder keeps a stream's logits column across steps while
-  // it decodes literal bytes, so the column must stay intact.)
-  constexpr bool kCache = false;
-  float *p = const_cast<float *>(p_in);
-  const int lane = threadIdx.x & 31;
-  const int n_sym = MODE == CZ_CDF_RWKV_LITERALS ? V + 256 : V;
-  const int n_grp = (V + 31) / 32;
-  auto ld_x = [&](int g) -> float {
-    const int v = g * 32 + lane;
-    return v < V ? p[(size_t)v * ld] : __int_as_float(0xff800000);
-  };
-  // generic sequential accumulation of f(x) over the vocab: acc = ((0 + f0) + f1) + ...
-  // The 32 values of a group go through the warp's shared-memory line (double-buffered: one __syncwarp per group) and every
-  // lane adds them in order from 16-byte broadcast loads: 16 LDS + 32 DADD per group instead of 64 SHFL + 32 DADD.
-  // The next group's values (expf, divisions: a long dependent chain per lane) are computed before the current group's adds are
-  // issued: nothing in them depends on the running sum, so they fill the adds' latency instead of preceding it.
-  auto seq_sum = [&](auto f) -> double {
-    double acc = 0.0;
-    double q = f(ld_x(0));
-    float x1 = n_grp > 1 ? ld_x(1) : 0.f;
-    for (int g = 0; g < n_grp; g++) {
-      const float x2 = g + 2 < n_grp ? ld_x(g + 2) : 0.f;
-      double *line = xch + (g & 1) * 32;
-      line[lane] = q;
-      __syncwarp();
-      q = g + 1 < n_grp ? f(x1) : 0.0;
-      x1 = x2;
-      const int cnt = V - g * 32 < 32 ? V - g * 32 : 32;
-      if (cnt == 32) {
-#pragma unroll
-        for (int k = 0; k < 32; k += 2) {
-          const double2 v = *reinterpret_cast<const double2 *>(line + k);
-          acc = __dadd_rn(acc, v.x);
-          acc = __dadd_rn(acc, v.y);
-        }
-      } else {
-        for (int k = 0; k < cnt; k++) acc = __dadd_rn(acc, line[k]);
-      }
-    }
-    __syncwarp();
-    return acc;
-  };
-  int g_store = 0;  // group counter of the first pass (the lambda is called once per group, in order)
-  const double S = seq_sum([&](float x) {
-    const float e = cz_expf(__fsub_rn(x, mx), tab);
-    if (kCache) {
-      const int v = g_store * 32 + lane;
-      if (v < V) p[(size_t)v * ld] = e;
-      g_store++;
-    }
-    return (double)e;
-  });
-  if (!(S == S)) errbits |= CZ_DEVERR_NAN;
-  auto ex = [&](float x) -> float { return kCache ? x : cz_expf(__fsub_rn(x, mx), tab); };
-  double norm = 1.0, sum2 = 1.0;
-  const double scale = 1.0 - 256.0 * CZ_P_FLOOR;
-  if (MODE == CZ_CDF_RWKV_LITERALS) {
-    norm = seq_sum([&](float x) { return fmax(__ddiv_rn((double)ex(x), S), CZ_P_FLOOR); });
-    double acc = seq_sum([&](float x) {
-      const double q = fmax(__ddiv_rn((double)ex(x), S), CZ_P_FLOOR);
-      return __dmul_rn(__ddiv_rn(q, norm), scale);
-    });
-    for (int j = 0; j < 256; j++) acc = __dadd_rn(acc, CZ_P_FLOOR);
-    sum2 = acc;
-  }
-  const bool uniform = MODE == CZ_CDF_SMOLLM && S <= 0.0;
-  const double uni = 1.0 / (double)V;
-  // the divisors are per-column constants: correctly rounded quotients from their reciprocals (cz_div_rcp, proof in cdf_fast.cuh)
-  const bool fastd = cz_div_rcp_ok(S) && cz_div_rcp_ok(norm) && cz_div_rcp_ok(sum2);
-  const double yS = __drcp_rn(S), yN = __drcp_rn(norm), y2 = __drcp_rn(sum2);
-  auto dv = [&](double a, double b, double y) { return fastd ? cz_div_rcp(a, b, y) : __ddiv_rn(a, b); };
-  auto pdf_vocab = [&](float x) -> double {
-    if (MODE == CZ_CDF_RWKV_LITERALS) {
-      double q = fmax(dv((double)ex(x), S, yS), CZ_P_FLOOR);
-      q = __dmul_rn(dv(q, norm, yN), scale);
-      return sum2 > 0.0 ? dv(q, sum2, y2) : q;
-    }
-    if (uniform) return uni;
-    return dv((double)ex(x), S, yS);
-  };
-  // Search: the first v with value < cdf[v + 1].  cdf[v + 1] = floor(acc_v * 2^30) (clamped, made non-decreasing -- which a
-  // non-decreasing acc already is), so  value < cdf[v + 1]  <=>  acc_v * 2^30 >= value + 1  <=>  acc_v >= (value + 1) * 2^-30: the
-  // scaling by a power of two is exact on both sides, so the per-element test is ONE f64 compare against a constant instead of a
-  // quantisation (multiply, clamp, convert) per element; the two bounds are quantised once, from acc_{v-1} and acc_v.
-  const double thr = __dmul_rn((double)value + 1.0, 0x1p-30);
-  double acc = 0.0, acc_prev = 0.0;
-  uint32_t found = (uint32_t)(n_sym - 1);
-  bool done = false;
-  double qv = pdf_vocab(ld_x(0));
-  float x1 = n_grp > 1 ? ld_x(1) : 0.f;
-  for (int g = 0; g < n_grp && !done; g++) {
-    const float x2 = g + 2 < n_grp ? ld_x(g + 2) : 0.f;
-    double *line = xch + (g & 1) * 32;
-    line[lane] = qv;
-    __syncwarp();
-    qv = g + 1 < n_grp ? pdf_vocab(x1) : 0.0;  // (ahead of this group's adds, see seq_sum)
-    x1 = x2;
-    const int cnt = V - g * 32 < 32 ? V - g * 32 : 32;
-    // acc never decreases, so a group of adds holds the crossing iff its LAST partial sum has reached the threshold: a full
-    // group that does not end the alphabet is 32 straight adds (eight at a time out of 16-byte broadcast loads) and four compares;
-    // only the eight adds around the crossing are looked at one by one.
-    int k0 = 0;
-    if (cnt == 32 && g * 32 + 32 < n_sym) {
-#pragma unroll
-      for (int o = 0; o < 32 && !done; o += 8) {
-        double a[8];
-        const double2 t0 = *reinterpret_cast<const double2 *>(line + o), t1 = *reinterpret_cast<const double2 *>(line + o + 2),
-                      t2 = *reinterpret_cast<const double2 *>(line + o + 4), t3 = *reinterpret_cast<const double2 *>(line + o + 6);
-        a[0] = __dadd_rn(acc, t0.x);
-        a[1] = __dadd_rn(a[0], t0.y);
-        a[2] = __dadd_rn(a[1], t1.x);
-        a[3] = __dadd_rn(a[2], t1.y);
-        a[4] = __dadd_rn(a[3], t2.x);
-        a[5] = __dadd_rn(a[4], t2.y);
-        a[6] = __dadd_rn(a[5], t3.x);
-        a[7] = __dadd_rn(a[6], t3.y);
-        if (a[7] >= thr) {  // (warp-uniform: every lane holds the same sums)
-#pragma unroll
-          for (int k = 0; k < 8; k++) {
-            if (!done && a[k] >= thr) {
-              found = (uint32_t)(g * 32 + o + k);
-              acc_prev = k ? a[k - 1] : acc;
-              acc = a[k];
-              done = true;
-            }
-          }
-        } else {
-          acc = a[7];
-        }
-      }
-      k0 = 32;
-    }
-    for (int k = k0; k < cnt && !done; k++) {  // the alphabet's last group / a ragged one: element by element
-      const double a2 = __dadd_rn(acc, line[k]);
-      const int v = g * 32 + k;
-      if (a2 >= thr || v == n_sym - 1) {
-        found = (uint32_t)v;
-        acc_prev = acc;
-        acc = a2;
-        done = true;
-        break;
-      }
-      acc = a2;
-    }
-  }
-  if (MODE == CZ_CDF_RWKV_LITERALS && !done) {
-    const double pl = sum2 > 0.0 ? __ddiv_rn(CZ_P_FLOOR, sum2) : CZ_P_FLOOR;
-    for (int v = V; v < n_sym; v++) {
-      const double a2 = __dadd_rn(acc, pl);
-      if (a2 >= thr || v == n_sym - 1) {
-        found = (uint32_t)v;
-        acc_prev = acc;
-        acc = a2;
-        done = true;
-        break;
-      }
-      acc = a2;
-    }
-  }
-  // (done is always true here: the last symbol ends the search)
-  uint32_t lo = found == 0 ? 0u : quant(acc_prev);
-  uint32_t hi = quant(acc);
-  if (hi < lo) hi = lo;
-  if ((int)found == n_sym - 1) hi = CZ_AC_CDF_TOTAL;
-  sym_out = found;
-  lo_out = lo;
-  hi_out = hi;
-}
-
 }  // namespace czk

@@ -56,30 +56,6 @@ __global__ void __launch_bounds__(128) cdf_cols_kernel(const float *__restrict__
 // Round-2 encode-side kernels (OP_BOUNDS / OP_XE): full passes and the prefix walk are separate kernels.
 // =================================================================================================================
 
-// (double)expf(-a) for a group of values: integer-conversion fast path when every a <= CZ_EXP_FAST_MAX, otherwise the original
-// conversion path for the whole group (tiny results, -inf logits, NaN).  ef (optional) receives the f32 values.
-template <int N, bool WANT_F32>
-__device__ __forceinline__ void exp_group(const float (&a)[N], const ExpTab64 &tab, double (&d)[N], float (&ef)[N]) {
-  // The fast path is evaluated unconditionally (garbage, but harmless, for arguments it does not cover) and a group that holds
-  // such an argument is redone on the conversion path afterwards: the common case stays one straight-line block, which lets the
-  // compiler interleave it with the caller's sequential f64 chains.
-  bool ok = true;
-#pragma unroll
-  for (int i = 0; i < N; i++) {
-    ok = ok && (a[i] <= CZ_EXP_FAST_MAX);
-    d[i] = cz_exp_neg_fast(a[i], tab.t);
-    if (WANT_F32) ef[i] = cz_f32_of_gridded(d[i]);
-  }
-  if (!ok) {
-#pragma unroll
-    for (int i = 0; i < N; i++) {
-      const float e = cz_expf(-a[i], tab);
-      d[i] = (double)e;
-      if (WANT_F32) ef[i] = e;
-    }
-  }
-}
-
 // Full passes.  One thread owns NCOL adjacent columns (vector loads: one LDG + one address per NCOL logits); every column is still
 // summed by one thread in ascending vocab order.  MODE / OP decide which passes run:
 //   pass 1  S = sum (f64)expf(l - max)                      always            (RWKV alphabet: leaves e_v in the logit's slot)
@@ -789,10 +765,10 @@ __global__ void __launch_bounds__(256) cdf_search_warp_kernel(const float *__res
                                                               const uint32_t *__restrict__ values, uint32_t *__restrict__ sym_out,
                                                               uint32_t *__restrict__ c_lo_out, uint32_t *__restrict__ c_hi_out,
                                                               int *__restrict__ err, const int *__restrict__ colmax) {
-  __shared__ uint32_t s_lo[32 * 32], s_hi[32 * 32];
-  __shared__ __align__(16) double s_xch[8 * 64];  // per warp: two 32-value exchange lines (cdf_search_warp)
-  exp_tab_init(s_lo, s_hi);
-  ExpTab tab{s_lo, s_hi, (int)(threadIdx.x & 31)};
+  __shared__ uint64_t s_tab[32 * 32];
+  __shared__ __align__(16) double s_xch[8 * 128];  // per warp: two 32-value exchange lines + the row ring (cdf_search_warp)
+  exp_tab64_init(s_tab);
+  const ExpTab64 tab{s_tab + (threadIdx.x & 31)};
   const size_t col = (size_t)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (col >= M) return;
   float mx;
@@ -809,7 +785,7 @@ __global__ void __launch_bounds__(256) cdf_search_warp_kernel(const float *__res
   }
   uint32_t sym, lo, hi;
   int errbits = 0;
-  cdf_search_warp<MODE>(logits + col, ld, V, values[col], mx, tab, sym, lo, hi, errbits, s_xch + (threadIdx.x >> 5) * 64);
+  cdf_search_warp<MODE>(logits + col, ld, V, values[col], mx, tab, sym, lo, hi, errbits, s_xch + (threadIdx.x >> 5) * 128);
   if ((threadIdx.x & 31) == 0) {
     if (errbits) atomicOr(err, errbits);
     sym_out[col] = sym;

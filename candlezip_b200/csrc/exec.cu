@@ -9,7 +9,7 @@
 #include <algorithm>
 #include <vector>
 
-#include "cdf_device.cuh"
+#include "cdf_fast.cuh"
 #include "coder.cuh"
 #include "model.h"
 #include "schedule.h"
@@ -70,10 +70,10 @@ __global__ void __launch_bounds__(256) decode_step_kernel(const float *__restric
                                                           uint32_t *__restrict__ next_tok, int *__restrict__ err,
                                                           const int *__restrict__ colmax, const unsigned long long *__restrict__ ctr) {
   if (ctr) coded_index = ctr[0];  // device-resident step counter: lets one captured CUDA graph serve every step
-  __shared__ uint32_t s_lo[32 * 32], s_hi[32 * 32];
-  __shared__ __align__(16) double s_xch[8 * 64];  // per warp: two 32-value exchange lines (cdf_search_warp)
-  exp_tab_init(s_lo, s_hi);
-  ExpTab tab{s_lo, s_hi, (int)(threadIdx.x & 31)};
+  __shared__ uint64_t s_tab[32 * 32];
+  __shared__ __align__(16) double s_xch[8 * 128];  // per warp: two 32-value exchange lines + the row ring (cdf_search_warp)
+  exp_tab64_init(s_tab);
+  const ExpTab64 tab{s_tab + (threadIdx.x & 31)};
   const int lane = blockIdx.x * 8 + (threadIdx.x >> 5);  // stream index (warp-uniform)
   if (lane >= n_lanes) return;
   const uint64_t seg_len = seg_start[lane + 1] - seg_start[lane];
@@ -95,7 +95,7 @@ __global__ void __launch_bounds__(256) decode_step_kernel(const float *__restric
   }
   uint32_t sym, lo, hi;
   int errbits = 0;
-  cdf_search_warp<MODE>(logits + lane, ld, V, value, mx, tab, sym, lo, hi, errbits, s_xch + (threadIdx.x >> 5) * 64);
+  cdf_search_warp<MODE>(logits + lane, ld, V, value, mx, tab, sym, lo, hi, errbits, s_xch + (threadIdx.x >> 5) * 128);
   if ((threadIdx.x & 31) == 0) {
     if (errbits) atomicOr(err, errbits);
     d.consume(lo, hi);

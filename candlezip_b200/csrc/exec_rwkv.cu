@@ -14,7 +14,7 @@
 #include <algorithm>
 #include <vector>
 
-#include "cdf_device.cuh"
+#include "cdf_fast.cuh"
 #include "coder.cuh"
 #include "model.h"
 
