@@ -178,237 +178,307 @@ __device__ __forceinline__ void exp_group(const float (&a)[N], const ExpTab64 &t
 
 
 // ---------------------------------------------------------------------------------------------------------------
-// Warp-per-column search for the stepwise decoder.  With only B (hundreds) columns per step the thread-per-column
-// walk is a ~10^5-deep dependent chain per thread with nothing to overlap.  Here the 32 lanes evaluate expf / the pdf
-// for 32 consecutive vocab entries in parallel and only the order-dependent f64 accumulation is serial (every lane
-// performs it redundantly on values exchanged through a shared-memory line, so all lanes hold the same S / acc and
-// branches stay warp-uniform).  Same operations in the same order as cdf_col => bit-identical results.
+// Warp-level search for the stepwise decoder: one warp walks NC columns (streams) at once.  With only hundreds of columns per
+// step a thread-per-column walk is a ~10^5-deep dependent chain per thread with nothing to overlap.  Here the 32 lanes evaluate
+// expf / the pdf for 32 consecutive vocab entries in parallel and only the order-dependent f64 accumulation is serial (every lane
+// performs it redundantly on values exchanged through a shared-memory line, so all lanes hold the same S / acc and branches stay
+// warp-uniform).  Same operations in the same order per column as cdf_col => bit-identical results.
 //
 // What a step costs is the latency of one warp's instruction stream (one or two warps per scheduler), so the loop is built for
-// the in-order issue of a single warp (ncu, profiles/ncu_summary_r02.md: before, 1,240 cycles per group of 32 rows against the
-// 262 of its 32 dependent adds -- 38% `wait`, 35% `long_scoreboard`, issue 16%):
-//   * the column's rows arrive through a per-warp shared-memory ring filled by cp.async four groups ahead: no register ring (whose
+// the in-order issue of a single warp (ncu, profiles/ncu_summary_r02.md: the first version took 1,240 cycles per group of 32 rows
+// against the 262 of its 32 dependent adds -- 38% `wait`, 35% `long_scoreboard`, issue 16%):
+//   * the columns' rows arrive through a per-warp shared-memory ring filled by cp.async four groups ahead: no register ring (whose
 //     rotating moves wait for the newest load), and a decode batch's logits (V x streams x 4 bytes) come from DRAM;
 //   * the next group's pdf entries are evaluated by a BRANCH-FREE fast path placed in the same basic block as the current group's
-//     32 unconditional adds, so the scheduler interleaves the two dependent chains; whether a lane's argument was outside the fast
+//     unconditional adds, so the scheduler interleaves the dependent chains; whether a lane's argument was outside the fast
 //     path's domain is looked at after the adds, and only then is the value redone on the general path;
-//   * the search adds whole groups and compares once per group (acc never decreases); the group that holds the crossing is
+//   * NC = 2 columns per warp: their two add chains are independent, so each fills the other's 8-cycle DADD latency;
+//   * the search adds whole groups and compares once per group (acc never decreases); the group that holds a column's crossing is
 //     re-walked element by element.
-// p: column base (vocab-major, element v at p[v*ld]).  Must be called by a full warp.
-// xch: 128 doubles (1 KB) of shared memory private to the calling warp, 16-byte aligned: two exchange lines + the row ring.
-template <int MODE>
-__device__ __forceinline__ void cdf_search_warp(const float *__restrict__ p, size_t ld, int V, uint32_t value, float mx,
-                                                const ExpTab64 &tab, uint32_t &sym_out, uint32_t &lo_out, uint32_t &hi_out,
-                                                int &errbits, double *xch) {
+// p[c]: column base (vocab-major, element v at p[c][v*ld]).  Must be called by a full warp; columns may repeat (a warp with one
+// live stream passes it twice and ignores the second result).
+// xch: NC * 128 doubles (NC KB) of shared memory private to the calling warp, 16-byte aligned: exchange lines + the row rings.
+template <int MODE, int NC>
+__device__ __forceinline__ void cdf_search_warp_n(const float *const (&p)[NC], size_t ld, int V, const uint32_t (&value)[NC],
+                                                  const float (&mx)[NC], const ExpTab64 &tab, uint32_t (&sym_out)[NC],
+                                                  uint32_t (&lo_out)[NC], uint32_t (&hi_out)[NC], int &errbits, double *xch) {
   // (No in-place caching of expf here, unlike cdf_col: the stepwise RWKV decoder keeps a stream's logits column across steps while
   // it decodes literal bytes, so the column must stay intact.)
   const int lane = threadIdx.x & 31;
   const int n_sym = MODE == CZ_CDF_RWKV_LITERALS ? V + 256 : V;
   const int n_full = V / 32, n_grp = (V + 31) / 32;
   constexpr int SR_DEPTH = 4;  // groups in flight (power of two)
-  float *ring = reinterpret_cast<float *>(xch + 64);
+  float *ring = reinterpret_cast<float *>(xch + NC * 64);
   const uint32_t ring_u32 = (uint32_t)__cvta_generic_to_shared(ring) + (uint32_t)lane * 4u;
-  auto issue = [&](int g) {  // this lane's row of group g -> ring slot g % SR_DEPTH; always one commit group per call
+  auto line_of = [&](int c, int buf) -> double * { return xch + (c * 2 + buf) * 32; };
+  auto issue = [&](int g) {  // this lane's row of group g of every column -> ring slot g % SR_DEPTH; one commit group per call
     const int v = g * 32 + lane;
-    if (v < V)
-      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(ring_u32 + (uint32_t)((g & (SR_DEPTH - 1)) * 128)), "l"(p + (size_t)v * ld)
-                   : "memory");
+    if (v < V) {
+#pragma unroll
+      for (int c = 0; c < NC; c++)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(ring_u32 + (uint32_t)((c * SR_DEPTH + (g & (SR_DEPTH - 1))) * 128)),
+                     "l"(p[c] + (size_t)v * ld)
+                     : "memory");
+    }
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
-  auto take = [&](int g) -> float {  // (after issue(g + SR_DEPTH - 1): at most SR_DEPTH - 1 younger groups may still be pending)
+  auto take = [&](int g, float (&x)[NC]) {  // (after issue(g + SR_DEPTH - 1): at most SR_DEPTH - 1 younger groups may still be pending)
     asm volatile("cp.async.wait_group %0;" ::"n"(SR_DEPTH - 1) : "memory");
     const int v = g * 32 + lane;
-    return v < V ? ring[(g & (SR_DEPTH - 1)) * 32 + lane] : mx;  // rows beyond V are never added: any finite value
+#pragma unroll
+    for (int c = 0; c < NC; c++) x[c] = v < V ? ring[(c * SR_DEPTH + (g & (SR_DEPTH - 1))) * 32 + lane] : mx[c];  // rows beyond V are never added
   };
   auto drain = [&]() { asm volatile("cp.async.wait_all;" ::: "memory"); };
-  // One in-order pass: acc = ((0 + f(x_0)) + f(x_1)) + ...   ffast(x, ok): branch-free, its value is only used if ok;
-  // fslow(x): the general path, same value wherever ffast is ok.
-  auto seq_sum = [&](auto ffast, auto fslow) -> double {
-    double acc = 0.0;
-#pragma unroll
-    for (int k = 0; k < SR_DEPTH - 1; k++) issue(k);
-    issue(SR_DEPTH - 1);
-    double q = fslow(take(0));
-    for (int g = 0; g < n_full; g++) {
-      issue(g + SR_DEPTH);
-      const float xn = take(g + 1);
-      double *line = xch + (g & 1) * 32;
-      line[lane] = q;
-      __syncwarp();
-      bool ok;
-      double qn = ffast(xn, ok);
-#pragma unroll
-      for (int k = 0; k < 32; k += 2) {
-        const double2 v = *reinterpret_cast<const double2 *>(line + k);
-        acc = __dadd_rn(acc, v.x);
-        acc = __dadd_rn(acc, v.y);
-      }
-      if (!ok) qn = fslow(xn);
-      q = qn;
-    }
-    if (n_full < n_grp) {  // the ragged last group
-      double *line = xch + (n_full & 1) * 32;
-      line[lane] = q;
-      __syncwarp();
-      const int cnt = V - n_full * 32;
-      for (int k = 0; k < cnt; k++) acc = __dadd_rn(acc, line[k]);
-    }
-    __syncwarp();
-    drain();
-    return acc;
-  };
-  // (double)expf(x - max): integer-conversion fast path for max - x <= 87 (cz_exp_neg_fast), else the original conversion path
-  auto ex_fast = [&](float x, bool &ok) -> double {
-    const float a = __fsub_rn(mx, x);
-    ok = a <= CZ_EXP_FAST_MAX;  // (false for NaN)
-    return cz_exp_neg_fast(a, tab.t);
-  };
-  auto ex_slow = [&](float x) -> double { return (double)cz_expf(__fsub_rn(x, mx), tab); };
-  const double S = seq_sum(ex_fast, ex_slow);
-  if (!(S == S)) errbits |= CZ_DEVERR_NAN;
-  double norm = 1.0, sum2 = 1.0;
-  const double scale = 1.0 - 256.0 * CZ_P_FLOOR;
-  // every division by a per-column constant: correctly rounded quotient from the constant's reciprocal (cz_div_rcp, proof above)
-  // when the constant is in the proven range, else the IEEE division -- decided once per column, outside the loops
-  const double yS = __drcp_rn(S);
-  if (MODE == CZ_CDF_RWKV_LITERALS) {
-    if (cz_div_rcp_ok(S)) {
-      norm = seq_sum([&](float x, bool &ok) { return fmax(cz_div_rcp(ex_fast(x, ok), S, yS), CZ_P_FLOOR); },
-                     [&](float x) { return fmax(cz_div_rcp(ex_slow(x), S, yS), CZ_P_FLOOR); });
-    } else {
-      norm = seq_sum([&](float x, bool &ok) { return fmax(__ddiv_rn(ex_fast(x, ok), S), CZ_P_FLOOR); },
-                     [&](float x) { return fmax(__ddiv_rn(ex_slow(x), S), CZ_P_FLOOR); });
-    }
-    const double yN1 = __drcp_rn(norm);
-    double acc;
-    if (cz_div_rcp_ok(S) && cz_div_rcp_ok(norm)) {
-      auto g = [&](double e) { return __dmul_rn(cz_div_rcp(fmax(cz_div_rcp(e, S, yS), CZ_P_FLOOR), norm, yN1), scale); };
-      acc = seq_sum([&](float x, bool &ok) { return g(ex_fast(x, ok)); }, [&](float x) { return g(ex_slow(x)); });
-    } else {
-      auto g = [&](double e) { return __dmul_rn(__ddiv_rn(fmax(__ddiv_rn(e, S), CZ_P_FLOOR), norm), scale); };
-      acc = seq_sum([&](float x, bool &ok) { return g(ex_fast(x, ok)); }, [&](float x) { return g(ex_slow(x)); });
-    }
-    for (int j = 0; j < 256; j++) acc = __dadd_rn(acc, CZ_P_FLOOR);
-    sum2 = acc;
-  }
-  const bool uniform = MODE == CZ_CDF_SMOLLM && S <= 0.0;  // src/main.rs:794-798
-  const double uni = 1.0 / (double)V;
-  const bool fastd = cz_div_rcp_ok(S) && cz_div_rcp_ok(norm) && cz_div_rcp_ok(sum2);
-  const double yN = __drcp_rn(norm), y2 = __drcp_rn(sum2);
-  const bool has2 = sum2 > 0.0;
-  // Search: the first v with value < cdf[v + 1].  cdf[v + 1] = floor(acc_v * 2^30) (clamped, made non-decreasing -- which a
-  // non-decreasing acc already is), so  value < cdf[v + 1]  <=>  acc_v * 2^30 >= value + 1  <=>  acc_v >= (value + 1) * 2^-30: the
-  // scaling by a power of two is exact on both sides, so the test is ONE f64 compare against a constant instead of a quantisation
-  // (multiply, clamp, convert) per element; the two bounds are quantised once, from acc_{v-1} and acc_v.
-  const double thr = __dmul_rn((double)value + 1.0, 0x1p-30);
-  double acc = 0.0, acc_prev = 0.0;
-  uint32_t found = (uint32_t)(n_sym - 1);
-  bool done = false;
-  // walks the vocabulary with pdf = pfast / pslow (same contract as seq_sum's pair) until the crossing
-  auto search = [&](auto pfast, auto pslow) {
+  // One in-order pass per column: out[c] = ((0 + f(c, x_0)) + f(c, x_1)) + ...   ffast(c, x, ok): branch-free, its value is only
+  // used if ok; fslow(c, x): the general path, same value wherever ffast is ok.
+  auto seq_sum = [&](auto ffast, auto fslow, double (&out)[NC]) {
+    double acc[NC], q[NC];
+    float xn[NC], x2[NC];
 #pragma unroll
     for (int k = 0; k < SR_DEPTH; k++) issue(k);
-    double q = pslow(take(0));
-    int g = 0;
-    for (; g < n_full && !done; g++) {
-      issue(g + SR_DEPTH);
-      const float xn = take(g + 1);
-      double *line = xch + (g & 1) * 32;
-      line[lane] = q;
+    take(0, xn);
+#pragma unroll
+    for (int c = 0; c < NC; c++) {
+      acc[c] = 0.0;
+      q[c] = fslow(c, xn[c]);
+    }
+    issue(SR_DEPTH);
+    take(1, xn);  // group g + 1's rows are read out of the ring one iteration before they are used
+    for (int g = 0; g < n_full; g++) {
+      issue(g + 1 + SR_DEPTH);
+      take(g + 2, x2);
+#pragma unroll
+      for (int c = 0; c < NC; c++) line_of(c, g & 1)[lane] = q[c];
       __syncwarp();
-      bool ok;
-      double qn = pfast(xn, ok);
-      double a = acc;
+      bool ok[NC];
+      double qn[NC];
+#pragma unroll
+      for (int c = 0; c < NC; c++) qn[c] = ffast(c, xn[c], ok[c]);
 #pragma unroll
       for (int k = 0; k < 32; k += 2) {
-        const double2 v = *reinterpret_cast<const double2 *>(line + k);
-        a = __dadd_rn(a, v.x);
-        a = __dadd_rn(a, v.y);
-      }
-      if (!ok) qn = pslow(xn);
-      q = qn;
-      if (a >= thr || g * 32 + 32 >= n_sym) {  // (warp-uniform) the crossing, or the alphabet's last symbol, is in this group
-        for (int k = 0; k < 32; k++) {
-          const double a2 = __dadd_rn(acc, line[k]);
-          const int v = g * 32 + k;
-          if (a2 >= thr || v == n_sym - 1) {
-            found = (uint32_t)v;
-            acc_prev = acc;
-            acc = a2;
-            done = true;
-            break;
-          }
-          acc = a2;
+#pragma unroll
+        for (int c = 0; c < NC; c++) {
+          const double2 v = *reinterpret_cast<const double2 *>(line_of(c, g & 1) + k);
+          acc[c] = __dadd_rn(acc[c], v.x);
+          acc[c] = __dadd_rn(acc[c], v.y);
         }
-      } else {
-        acc = a;
+      }
+#pragma unroll
+      for (int c = 0; c < NC; c++) {
+        if (!ok[c]) qn[c] = fslow(c, xn[c]);
+        q[c] = qn[c];
+        xn[c] = x2[c];
       }
     }
-    if (!done && n_full < n_grp) {  // the ragged last group of the vocabulary: element by element (g == n_full here)
-      double *line = xch + (n_full & 1) * 32;
-      line[lane] = q;
+    if (n_full < n_grp) {  // the ragged last group
+#pragma unroll
+      for (int c = 0; c < NC; c++) line_of(c, n_full & 1)[lane] = q[c];
       __syncwarp();
       const int cnt = V - n_full * 32;
       for (int k = 0; k < cnt; k++) {
-        const double a2 = __dadd_rn(acc, line[k]);
-        const int v = n_full * 32 + k;
-        if (a2 >= thr || v == n_sym - 1) {
-          found = (uint32_t)v;
-          acc_prev = acc;
-          acc = a2;
-          done = true;
-          break;
-        }
-        acc = a2;
+#pragma unroll
+        for (int c = 0; c < NC; c++) acc[c] = __dadd_rn(acc[c], line_of(c, n_full & 1)[k]);
       }
     }
     __syncwarp();
     drain();
+#pragma unroll
+    for (int c = 0; c < NC; c++) out[c] = acc[c];
   };
-  if (uniform) {
-    search([&](float, bool &ok) { ok = true; return uni; }, [&](float) { return uni; });
-  } else if (MODE == CZ_CDF_RWKV_LITERALS) {
-    if (fastd) {
-      auto g = [&](double e) {
-        // (fastd => sum2 is in cz_div_rcp's range, in particular > 0: no `has2` case here, the block stays branch-free)
-        return cz_div_rcp(__dmul_rn(cz_div_rcp(fmax(cz_div_rcp(e, S, yS), CZ_P_FLOOR), norm, yN), scale), sum2, y2);
-      };
-      search([&](float x, bool &ok) { return g(ex_fast(x, ok)); }, [&](float x) { return g(ex_slow(x)); });
-    } else {
-      auto g = [&](double e) {
-        const double q = __dmul_rn(__ddiv_rn(fmax(__ddiv_rn(e, S), CZ_P_FLOOR), norm), scale);
-        return has2 ? __ddiv_rn(q, sum2) : q;
-      };
-      search([&](float x, bool &ok) { return g(ex_fast(x, ok)); }, [&](float x) { return g(ex_slow(x)); });
-    }
-  } else {
-    if (fastd)
-      search([&](float x, bool &ok) { return cz_div_rcp(ex_fast(x, ok), S, yS); }, [&](float x) { return cz_div_rcp(ex_slow(x), S, yS); });
-    else
-      search([&](float x, bool &ok) { return __ddiv_rn(ex_fast(x, ok), S); }, [&](float x) { return __ddiv_rn(ex_slow(x), S); });
+  // (double)expf(x - max): integer-conversion fast path for max - x <= 87 (cz_exp_neg_fast), else the original conversion path
+  auto ex_fast = [&](int c, float x, bool &ok) -> double {
+    const float a = __fsub_rn(mx[c], x);
+    ok = a <= CZ_EXP_FAST_MAX;  // (false for NaN)
+    return cz_exp_neg_fast(a, tab.t);
+  };
+  auto ex_slow = [&](int c, float x) -> double { return (double)cz_expf(__fsub_rn(x, mx[c]), tab); };
+  double S[NC], norm[NC], sum2[NC], yS[NC], yN[NC], y2[NC];
+  seq_sum(ex_fast, ex_slow, S);
+  const double scale = 1.0 - 256.0 * CZ_P_FLOOR;
+  // every division by a per-column constant: correctly rounded quotient from the constant's reciprocal (cz_div_rcp, proof above)
+  // when the constant is in the proven range, else the IEEE division (the same value) -- decided once, for all NC columns, outside
+  // the loops
+  bool okS = true, any_uniform = false;
+#pragma unroll
+  for (int c = 0; c < NC; c++) {
+    if (!(S[c] == S[c])) errbits |= CZ_DEVERR_NAN;
+    okS = okS && cz_div_rcp_ok(S[c]);
+    yS[c] = __drcp_rn(S[c]);
+    norm[c] = 1.0;
+    sum2[c] = 1.0;
+    any_uniform = any_uniform || (MODE == CZ_CDF_SMOLLM && S[c] <= 0.0);  // src/main.rs:794-798
   }
-  if (MODE == CZ_CDF_RWKV_LITERALS && !done) {
-    const double pl = sum2 > 0.0 ? __ddiv_rn(CZ_P_FLOOR, sum2) : CZ_P_FLOOR;
-    for (int v = V; v < n_sym; v++) {
-      const double a2 = __dadd_rn(acc, pl);
-      if (a2 >= thr || v == n_sym - 1) {
-        found = (uint32_t)v;
-        acc_prev = acc;
-        acc = a2;
-        done = true;
+  if (MODE == CZ_CDF_RWKV_LITERALS) {
+    if (okS) {
+      auto g = [&](int c, double e) { return fmax(cz_div_rcp(e, S[c], yS[c]), CZ_P_FLOOR); };
+      seq_sum([&](int c, float x, bool &ok) { return g(c, ex_fast(c, x, ok)); }, [&](int c, float x) { return g(c, ex_slow(c, x)); }, norm);
+    } else {
+      auto g = [&](int c, double e) { return fmax(__ddiv_rn(e, S[c]), CZ_P_FLOOR); };
+      seq_sum([&](int c, float x, bool &ok) { return g(c, ex_fast(c, x, ok)); }, [&](int c, float x) { return g(c, ex_slow(c, x)); }, norm);
+    }
+    bool okN = okS;
+#pragma unroll
+    for (int c = 0; c < NC; c++) {
+      okN = okN && cz_div_rcp_ok(norm[c]);
+      yN[c] = __drcp_rn(norm[c]);
+    }
+    if (okN) {
+      auto g = [&](int c, double e) { return __dmul_rn(cz_div_rcp(fmax(cz_div_rcp(e, S[c], yS[c]), CZ_P_FLOOR), norm[c], yN[c]), scale); };
+      seq_sum([&](int c, float x, bool &ok) { return g(c, ex_fast(c, x, ok)); }, [&](int c, float x) { return g(c, ex_slow(c, x)); }, sum2);
+    } else {
+      auto g = [&](int c, double e) { return __dmul_rn(__ddiv_rn(fmax(__ddiv_rn(e, S[c]), CZ_P_FLOOR), norm[c]), scale); };
+      seq_sum([&](int c, float x, bool &ok) { return g(c, ex_fast(c, x, ok)); }, [&](int c, float x) { return g(c, ex_slow(c, x)); }, sum2);
+    }
+#pragma unroll
+    for (int c = 0; c < NC; c++)
+      for (int j = 0; j < 256; j++) sum2[c] = __dadd_rn(sum2[c], CZ_P_FLOOR);
+  }
+  bool fastd = okS;
+#pragma unroll
+  for (int c = 0; c < NC; c++) {
+    fastd = fastd && cz_div_rcp_ok(norm[c]) && cz_div_rcp_ok(sum2[c]);
+    yN[c] = __drcp_rn(norm[c]);
+    y2[c] = __drcp_rn(sum2[c]);
+  }
+  const double uni = 1.0 / (double)V;
+  // Search: per column the first v with value < cdf[v + 1].  cdf[v + 1] = floor(acc_v * 2^30) (clamped, made non-decreasing --
+  // which a non-decreasing acc already is), so  value < cdf[v + 1]  <=>  acc_v * 2^30 >= value + 1  <=>  acc_v >= (value + 1) * 2^-30:
+  // the scaling by a power of two is exact on both sides, so the test is ONE f64 compare against a constant instead of a
+  // quantisation (multiply, clamp, convert) per element; the two bounds are quantised once, from acc_{v-1} and acc_v.
+  double thr[NC], acc[NC], acc_prev[NC];
+  uint32_t found[NC];
+  bool done[NC];
+#pragma unroll
+  for (int c = 0; c < NC; c++) {
+    thr[c] = __dmul_rn((double)value[c] + 1.0, 0x1p-30);
+    acc[c] = 0.0;
+    acc_prev[c] = 0.0;
+    found[c] = (uint32_t)(n_sym - 1);
+    done[c] = false;
+  }
+  auto all_done = [&]() {
+    bool d = true;
+#pragma unroll
+    for (int c = 0; c < NC; c++) d = d && done[c];
+    return d;
+  };
+  // re-walks one group of `cnt` values of column c element by element from acc[c] (the crossing, or the alphabet's end, is in it)
+  auto scan_group = [&](int c, const double *line, int v0, int cnt) {
+    for (int k = 0; k < cnt; k++) {
+      const double a2 = __dadd_rn(acc[c], line[k]);
+      const int v = v0 + k;
+      if (a2 >= thr[c] || v == n_sym - 1) {
+        found[c] = (uint32_t)v;
+        acc_prev[c] = acc[c];
+        acc[c] = a2;
+        done[c] = true;
         break;
       }
-      acc = a2;
+      acc[c] = a2;
     }
+  };
+  // walks the vocabulary with pdf = pfast / pslow (same contract as seq_sum's pair) until every column has its crossing
+  auto search = [&](auto pfast, auto pslow) {
+    double q[NC];
+    float xn[NC], x2[NC];
+#pragma unroll
+    for (int k = 0; k < SR_DEPTH; k++) issue(k);
+    take(0, xn);
+#pragma unroll
+    for (int c = 0; c < NC; c++) q[c] = pslow(c, xn[c]);
+    issue(SR_DEPTH);
+    take(1, xn);
+    int g = 0;
+    for (; g < n_full && !all_done(); g++) {
+      issue(g + 1 + SR_DEPTH);
+      take(g + 2, x2);
+#pragma unroll
+      for (int c = 0; c < NC; c++) line_of(c, g & 1)[lane] = q[c];
+      __syncwarp();
+      bool ok[NC];
+      double qn[NC], a[NC];
+#pragma unroll
+      for (int c = 0; c < NC; c++) {
+        qn[c] = pfast(c, xn[c], ok[c]);
+        a[c] = acc[c];
+      }
+#pragma unroll
+      for (int k = 0; k < 32; k += 2) {
+#pragma unroll
+        for (int c = 0; c < NC; c++) {
+          const double2 v = *reinterpret_cast<const double2 *>(line_of(c, g & 1) + k);
+          a[c] = __dadd_rn(a[c], v.x);
+          a[c] = __dadd_rn(a[c], v.y);
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < NC; c++) {
+        if (!ok[c]) qn[c] = pslow(c, xn[c]);
+        q[c] = qn[c];
+        xn[c] = x2[c];
+        if (!done[c]) {  // (warp-uniform)
+          if (a[c] >= thr[c] || g * 32 + 32 >= n_sym) scan_group(c, line_of(c, g & 1), g * 32, 32);
+          else acc[c] = a[c];
+        }
+      }
+    }
+    if (n_full < n_grp && !all_done()) {  // the ragged last group of the vocabulary (only reached with g == n_full)
+#pragma unroll
+      for (int c = 0; c < NC; c++) line_of(c, n_full & 1)[lane] = q[c];
+      __syncwarp();
+#pragma unroll
+      for (int c = 0; c < NC; c++)
+        if (!done[c]) scan_group(c, line_of(c, n_full & 1), n_full * 32, V - n_full * 32);
+    }
+    __syncwarp();
+    drain();
+  };
+  if (any_uniform || !fastd) {
+    // degenerate columns (S <= 0: the reference's uniform pdf; constants outside the reciprocal's proven range): everything on the
+    // general path, per-column branches and IEEE divisions
+    auto g = [&](int c, double e) -> double {
+      if (MODE == CZ_CDF_RWKV_LITERALS) {
+        const double q = __dmul_rn(__ddiv_rn(fmax(__ddiv_rn(e, S[c]), CZ_P_FLOOR), norm[c]), scale);
+        return sum2[c] > 0.0 ? __ddiv_rn(q, sum2[c]) : q;
+      }
+      return S[c] <= 0.0 ? uni : __ddiv_rn(e, S[c]);
+    };
+    search([&](int, float, bool &ok) { ok = false; return 0.0; }, [&](int c, float x) { return g(c, ex_slow(c, x)); });
+  } else if (MODE == CZ_CDF_RWKV_LITERALS) {
+    // (fastd => sum2 is in cz_div_rcp's range, in particular > 0: the reference's `sum2 > 0` case, the block stays branch-free)
+    auto g = [&](int c, double e) {
+      return cz_div_rcp(__dmul_rn(cz_div_rcp(fmax(cz_div_rcp(e, S[c], yS[c]), CZ_P_FLOOR), norm[c], yN[c]), scale), sum2[c], y2[c]);
+    };
+    search([&](int c, float x, bool &ok) { return g(c, ex_fast(c, x, ok)); }, [&](int c, float x) { return g(c, ex_slow(c, x)); });
+  } else {
+    search([&](int c, float x, bool &ok) { return cz_div_rcp(ex_fast(c, x, ok), S[c], yS[c]); },
+           [&](int c, float x) { return cz_div_rcp(ex_slow(c, x), S[c], yS[c]); });
   }
-  // (done is always true here: the last symbol ends the search)
-  uint32_t lo = found == 0 ? 0u : quant(acc_prev);
-  uint32_t hi = quant(acc);
-  if (hi < lo) hi = lo;
-  if ((int)found == n_sym - 1) hi = CZ_AC_CDF_TOTAL;
-  sym_out = found;
-  lo_out = lo;
-  hi_out = hi;
+#pragma unroll
+  for (int c = 0; c < NC; c++) {
+    if (MODE == CZ_CDF_RWKV_LITERALS && !done[c]) {  // literal symbols follow the vocabulary
+      const double pl = sum2[c] > 0.0 ? __ddiv_rn(CZ_P_FLOOR, sum2[c]) : CZ_P_FLOOR;
+      for (int v = V; v < n_sym; v++) {
+        const double a2 = __dadd_rn(acc[c], pl);
+        if (a2 >= thr[c] || v == n_sym - 1) {
+          found[c] = (uint32_t)v;
+          acc_prev[c] = acc[c];
+          acc[c] = a2;
+          done[c] = true;
+          break;
+        }
+        acc[c] = a2;
+      }
+    }
+    // (done[c] is always true here: the last symbol ends the search)
+    uint32_t lo = found[c] == 0 ? 0u : quant(acc_prev[c]);
+    uint32_t hi = quant(acc[c]);
+    if (hi < lo) hi = lo;
+    if ((int)found[c] == n_sym - 1) hi = CZ_AC_CDF_TOTAL;
+    sym_out[c] = found[c];
+    lo_out[c] = lo;
+    hi_out[c] = hi;
+  }
 }
 
 }  // namespace czk

@@ -759,38 +759,56 @@ __global__ void __launch_bounds__(256) div_random_kernel(unsigned long long seed
   if (bad) atomicAdd(out, bad);
 }
 
-// OP_SEARCH for a small number of columns (stepwise decode): one warp per column, see cdf_search_warp
+// OP_SEARCH for a small number of columns (what the stepwise decoder does per step): cdf_search_warp_n with NC columns per warp
+// (2 here, so that the multi-column form stays covered by the kernel-level parity tests; the decoder itself uses 1, exec.cu)
 template <int MODE>
-__global__ void __launch_bounds__(256) cdf_search_warp_kernel(const float *__restrict__ logits, int V, size_t M, size_t ld,
+__global__ void __launch_bounds__(128) cdf_search_warp_kernel(const float *__restrict__ logits, int V, size_t M, size_t ld,
                                                               const uint32_t *__restrict__ values, uint32_t *__restrict__ sym_out,
                                                               uint32_t *__restrict__ c_lo_out, uint32_t *__restrict__ c_hi_out,
                                                               int *__restrict__ err, const int *__restrict__ colmax) {
+  constexpr int NC = 2;
   __shared__ uint64_t s_tab[32 * 32];
-  __shared__ __align__(16) double s_xch[8 * 128];  // per warp: two 32-value exchange lines + the row ring (cdf_search_warp)
+  __shared__ __align__(16) double s_xch[4 * NC * 128];  // per warp and column: exchange lines + row ring
   exp_tab64_init(s_tab);
   const ExpTab64 tab{s_tab + (threadIdx.x & 31)};
-  const size_t col = (size_t)blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (col >= M) return;
-  float mx;
-  if (colmax) {
-    mx = colmax_decode(colmax[col]);
-  } else {
-    mx = __int_as_float(0xff800000);
-    for (int v = threadIdx.x & 31; v < V; v += 32) {
-      const float x = logits[(size_t)v * ld + col];
-      if (x > mx) mx = x;
-    }
+  const int warp = threadIdx.x >> 5;
+  const size_t col0 = ((size_t)blockIdx.x * 4 + warp) * NC;
+  if (col0 >= M) return;
+  const float *cp[NC];
+  uint32_t value[NC];
+  float mx[NC];
+  size_t cols[NC];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  for (int c = 0; c < NC; c++) {
+    const size_t col = col0 + c < M ? col0 + c : col0;  // an odd last column is walked twice
+    cols[c] = col;
+    cp[c] = logits + col;
+    value[c] = values[col];
+    if (colmax) {
+      mx[c] = colmax_decode(colmax[col]);
+    } else {
+      float m = __int_as_float(0xff800000);
+      for (int v = threadIdx.x & 31; v < V; v += 32) {
+        const float x = logits[(size_t)v * ld + col];
+        if (x > m) m = x;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+      mx[c] = m;
+    }
   }
-  uint32_t sym, lo, hi;
+  uint32_t sym[NC], lo[NC], hi[NC];
   int errbits = 0;
-  cdf_search_warp<MODE>(logits + col, ld, V, values[col], mx, tab, sym, lo, hi, errbits, s_xch + (threadIdx.x >> 5) * 128);
+  cdf_search_warp_n<MODE, NC>(cp, ld, V, value, mx, tab, sym, lo, hi, errbits, s_xch + warp * (NC * 128));
   if ((threadIdx.x & 31) == 0) {
     if (errbits) atomicOr(err, errbits);
-    sym_out[col] = sym;
-    c_lo_out[col] = lo;
-    c_hi_out[col] = hi;
+#pragma unroll
+    for (int c = 0; c < NC; c++) {
+      if (col0 + c >= M) continue;
+      sym_out[cols[c]] = sym[c];
+      c_lo_out[cols[c]] = lo[c];
+      c_hi_out[cols[c]] = hi[c];
+    }
   }
 }
 
@@ -903,14 +921,14 @@ int launch_cdf_cols(cz_ctx *ctx, int op, int mode, const float *logits_dev, size
     return CZ_ERR_INVALID;
   }
   if (op == czk::OP_SEARCH && M <= 8192) {  // decode-sized: warp per column
-    const unsigned g = (unsigned)ceil_div(M, 8);
+    const unsigned g = (unsigned)ceil_div(M, 8);  // 4 warps x 2 columns
     if (mode == CZ_CDF_SMOLLM)
       CZ_LAUNCH(ctx, CZ_K_CDF,
-                (czk::cdf_search_warp_kernel<CZ_CDF_SMOLLM><<<g, 256, 0, stream>>>(logits_dev, (int)V, M, ld, arg_dev, sym_out_dev, c_lo_dev,
+                (czk::cdf_search_warp_kernel<CZ_CDF_SMOLLM><<<g, 128, 0, stream>>>(logits_dev, (int)V, M, ld, arg_dev, sym_out_dev, c_lo_dev,
                                                                                    c_hi_dev, ctx->err_flag_dev, colmax_dev)));
     else if (mode == CZ_CDF_RWKV_LITERALS)
       CZ_LAUNCH(ctx, CZ_K_CDF,
-                (czk::cdf_search_warp_kernel<CZ_CDF_RWKV_LITERALS><<<g, 256, 0, stream>>>(logits_dev, (int)V, M, ld, arg_dev, sym_out_dev,
+                (czk::cdf_search_warp_kernel<CZ_CDF_RWKV_LITERALS><<<g, 128, 0, stream>>>(logits_dev, (int)V, M, ld, arg_dev, sym_out_dev,
                                                                                           c_lo_dev, c_hi_dev, ctx->err_flag_dev, colmax_dev)));
     else {
       set_error("cdf: unknown mode");

@@ -59,49 +59,76 @@ __global__ void ac_decoder_init_kernel(const uint8_t *__restrict__ payload, cons
   st[lane] = d.s;
 }
 
-// One WARP per stream: AC target value -> CDF search over its logits column -> symbol -> AC state update.
-// (src/main.rs:2622-2626: to_vec1 + softmax_pdf + quantize_pdf_to_cdf + decode_symbol_counts, fused, on device.)
+// One WARP per DS_NC adjacent streams: AC target values -> CDF search over their logits columns (cdf_search_warp_n) -> symbols ->
+// AC state updates.  (src/main.rs:2622-2626: to_vec1 + softmax_pdf + quantize_pdf_to_cdf + decode_symbol_counts, fused, on device.)
 // 8 warps per CTA take 8 adjacent columns so that the 32-byte sectors of the vocab-major logits are shared through L1.
+// DS_NC = 1: two columns per warp (their add chains could fill each other's latency) measured SLOWER on B200 -- 3.18 against 2.87 ms
+// per step for the RWKV alphabet at 1,024 streams, 1.70 against 1.44 ms for SmolLM at 1,536 (253 registers, half as many warps).
+constexpr int DS_NC = 1, DS_WARPS = 8;
 template <int MODE>
-__global__ void __launch_bounds__(256) decode_step_kernel(const float *__restrict__ logits, int V, size_t ld, int n_lanes,
-                                                          const uint8_t *__restrict__ payload, const uint64_t *__restrict__ seg_off,
-                                                          const uint64_t *__restrict__ seg_start, uint64_t coded_index,
-                                                          AcDecoderState *__restrict__ st, uint32_t *__restrict__ ids_out,
-                                                          uint32_t *__restrict__ next_tok, int *__restrict__ err,
-                                                          const int *__restrict__ colmax, const unsigned long long *__restrict__ ctr) {
+__global__ void __launch_bounds__(DS_WARPS * 32) decode_step_kernel(const float *__restrict__ logits, int V, size_t ld, int n_lanes,
+                                                                   const uint8_t *__restrict__ payload, const uint64_t *__restrict__ seg_off,
+                                                                   const uint64_t *__restrict__ seg_start, uint64_t coded_index,
+                                                                   AcDecoderState *__restrict__ st, uint32_t *__restrict__ ids_out,
+                                                                   uint32_t *__restrict__ next_tok, int *__restrict__ err,
+                                                                   const int *__restrict__ colmax, const unsigned long long *__restrict__ ctr) {
   if (ctr) coded_index = ctr[0];  // device-resident step counter: lets one captured CUDA graph serve every step
   __shared__ uint64_t s_tab[32 * 32];
-  __shared__ __align__(16) double s_xch[8 * 128];  // per warp: two 32-value exchange lines + the row ring (cdf_search_warp)
+  __shared__ __align__(16) double s_xch[DS_WARPS * DS_NC * 128];  // per warp and column: exchange lines + row ring (cdf_search_warp_n)
   exp_tab64_init(s_tab);
   const ExpTab64 tab{s_tab + (threadIdx.x & 31)};
-  const int lane = blockIdx.x * 8 + (threadIdx.x >> 5);  // stream index (warp-uniform)
-  if (lane >= n_lanes) return;
-  const uint64_t seg_len = seg_start[lane + 1] - seg_start[lane];
-  if (coded_index >= seg_len) return;  // streams past their end idle (ragged last segments)
-  AcDecoder d;
-  d.resume(st[lane], payload + seg_off[lane], seg_off[lane + 1] - seg_off[lane]);
-  const uint32_t value = d.peek_value();
-  float mx;
-  if (colmax) {
-    mx = colmax_decode(colmax[lane]);
-  } else {  // engines without the fused column max: parallel max (exact, order-independent)
-    mx = __int_as_float(0xff800000);
-    for (int v = threadIdx.x & 31; v < V; v += 32) {
-      const float x = logits[(size_t)v * ld + lane];
-      if (x > mx) mx = x;
-    }
+  const int warp = threadIdx.x >> 5;
+  const int lane0 = (blockIdx.x * DS_WARPS + warp) * DS_NC;  // first stream of this warp (warp-uniform)
+  // streams past the batch or past their own end idle (ragged last segments); an idle slot repeats a live stream of the warp
+  bool live[DS_NC];
+  int stream[DS_NC];
+  int any = -1;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  for (int c = 0; c < DS_NC; c++) {
+    const int l = lane0 + c;
+    live[c] = l < n_lanes && coded_index < seg_start[l + 1] - seg_start[l];
+    stream[c] = l;
+    if (live[c] && any < 0) any = l;
   }
-  uint32_t sym, lo, hi;
+  if (any < 0) return;
+  AcDecoder d[DS_NC];
+  uint32_t value[DS_NC];
+  float mx[DS_NC];
+  const float *col[DS_NC];
+#pragma unroll
+  for (int c = 0; c < DS_NC; c++) {
+    if (!live[c]) stream[c] = any;
+    const int l = stream[c];
+    d[c].resume(st[l], payload + seg_off[l], seg_off[l + 1] - seg_off[l]);
+    value[c] = d[c].peek_value();
+    col[c] = logits + l;
+    if (colmax) {
+      mx[c] = colmax_decode(colmax[l]);
+    } else {  // engines without the fused column max: parallel max (exact, order-independent)
+      float m = __int_as_float(0xff800000);
+      for (int v = threadIdx.x & 31; v < V; v += 32) {
+        const float x = logits[(size_t)v * ld + l];
+        if (x > m) m = x;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+      mx[c] = m;
+    }
+  }
+  uint32_t sym[DS_NC], lo[DS_NC], hi[DS_NC];
   int errbits = 0;
-  cdf_search_warp<MODE>(logits + lane, ld, V, value, mx, tab, sym, lo, hi, errbits, s_xch + (threadIdx.x >> 5) * 128);
+  cdf_search_warp_n<MODE, DS_NC>(col, ld, V, value, mx, tab, sym, lo, hi, errbits, s_xch + warp * (DS_NC * 128));
   if ((threadIdx.x & 31) == 0) {
     if (errbits) atomicOr(err, errbits);
-    d.consume(lo, hi);
-    st[lane] = d.s;
-    ids_out[seg_start[lane] + coded_index] = sym;
-    next_tok[lane] = sym;
+#pragma unroll
+    for (int c = 0; c < DS_NC; c++) {
+      if (!live[c]) continue;
+      const int l = stream[c];
+      d[c].consume(lo[c], hi[c]);
+      st[l] = d[c].s;
+      ids_out[seg_start[l] + coded_index] = sym[c];
+      next_tok[l] = sym[c];
+    }
   }
 }
 
@@ -169,15 +196,15 @@ int launch_decoder_init(cz_ctx *ctx, const uint8_t *payload, const uint64_t *seg
 int launch_decode_step(cz_ctx *ctx, int mode, const float *logits, int V, size_t ld, int n_lanes, const uint8_t *payload,
                        const uint64_t *seg_off, const uint64_t *seg_start, uint64_t coded_index, void *decoder_state, uint32_t *ids_out,
                        uint32_t *next_tok, const int *colmax, cudaStream_t st, const unsigned long long *ctr) {
-  const unsigned grid = (unsigned)ceil_div(n_lanes, 8);
+  const unsigned grid = (unsigned)ceil_div(n_lanes, czk::DS_NC * czk::DS_WARPS);
   czk::AcDecoderState *ds = (czk::AcDecoderState *)decoder_state;
   if (mode == CZ_CDF_SMOLLM)
     CZ_LAUNCH(ctx, CZ_K_CDF,
-              (czk::decode_step_kernel<CZ_CDF_SMOLLM><<<grid, 256, 0, st>>>(logits, V, ld, n_lanes, payload, seg_off, seg_start, coded_index, ds,
+              (czk::decode_step_kernel<CZ_CDF_SMOLLM><<<grid, czk::DS_WARPS * 32, 0, st>>>(logits, V, ld, n_lanes, payload, seg_off, seg_start, coded_index, ds,
                                                                             ids_out, next_tok, ctx->err_flag_dev, colmax, ctr)));
   else
     CZ_LAUNCH(ctx, CZ_K_CDF,
-              (czk::decode_step_kernel<CZ_CDF_RWKV_LITERALS><<<grid, 256, 0, st>>>(logits, V, ld, n_lanes, payload, seg_off, seg_start, coded_index,
+              (czk::decode_step_kernel<CZ_CDF_RWKV_LITERALS><<<grid, czk::DS_WARPS * 32, 0, st>>>(logits, V, ld, n_lanes, payload, seg_off, seg_start, coded_index,
                                                                                    ds, ids_out, next_tok, ctx->err_flag_dev, colmax, ctr)));
   CZ_CHECK_LAUNCH();
   return CZ_OK;
