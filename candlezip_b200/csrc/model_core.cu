@@ -164,9 +164,11 @@ int ensure_logits(cz_model *m, size_t n_cols) {
   Workspace &w = m->ws;
   const cz_model_config &c = m->cfg;
   size_t want = (std::max<size_t>(n_cols, 256) + 1023) & ~(size_t)1023;
-  // two buffers of up to 131,072 columns (25.8 GB each for V = 49152): wide enough for the thread-per-column CDF kernels to fill
-  // the machine, and one can go through its CDF pass while the LM head fills the other
-  size_t max_ld = 131072;
+  // two buffers of up to sm_count x 1,024 columns (151,552 on B200: 29.8 GB each for V = 49152): wide enough for the
+  // thread-per-column CDF kernels to fill the machine, and one can go through its CDF pass while the LM head fills the other.  The
+  // width is two full waves of the stats kernel (256-column CTAs, two per SM): with 131,072 columns its second wave was 73% full
+  // (26.8 -> 23.1 ms per bench step, profiles/ab_cols.log); halving it under memory pressure (below) leaves one full wave.
+  size_t max_ld = (size_t)std::max(1, m->ctx->sm_count) * 1024;
   if (const char *e = getenv("CZ_LOGITS_COLS")) max_ld = std::max<size_t>(256, (size_t)atoll(e));
   want = std::min(want, max_ld);
   if (want <= w.ld_sub) return CZ_OK;
