@@ -111,6 +111,96 @@ __global__ void __launch_bounds__(128) rwkv_ln_mix_kernel(const float *__restric
   }
 }
 
+// The same operator with 8 CONTIGUOUS elements per lane and chunk (C = NCH * 256: the 0.1B model's 768 = 3 chunks): 16-byte loads
+// and 16-byte bf16 stores.  The element-per-lane form above issues 24 four-byte loads per operand and 144 two-byte stores per row
+// for NMIX = 6 and moved 1.3 TB/s (ncu, profiles/ncu_summary_r02.md: issue 23%, 8.4 long-scoreboard stalls per issue); this one
+// issues 6 + 18.  (Different lane -> element assignment, so the LayerNorm sums round differently: a model width takes one form or
+// the other for good, encode and decode alike.)
+template <int NCH>
+__device__ __forceinline__ void warp_layer_norm_v8(const float *__restrict__ xr, const float *__restrict__ w, const float *__restrict__ b,
+                                                   float eps, int lane, float (&out)[NCH][8]) {
+  constexpr int C = NCH * 256;
+  float s = 0.f;
+#pragma unroll
+  for (int c = 0; c < NCH; c++) {
+    const float4 *src = reinterpret_cast<const float4 *>(xr + (c * 32 + lane) * 8);
+    const float4 a = src[0], d = src[1];
+    out[c][0] = a.x; out[c][1] = a.y; out[c][2] = a.z; out[c][3] = a.w;
+    out[c][4] = d.x; out[c][5] = d.y; out[c][6] = d.z; out[c][7] = d.w;
+#pragma unroll
+    for (int j = 0; j < 8; j++) s += out[c][j];
+  }
+  const float mean = warp_sum(s) / (float)C;
+  float q = 0.f;
+#pragma unroll
+  for (int c = 0; c < NCH; c++)
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      const float d = out[c][j] - mean;
+      out[c][j] = d;
+      q = fmaf(d, d, q);
+    }
+  const float inv = 1.0f / sqrtf(warp_sum(q) / (float)C + eps);
+#pragma unroll
+  for (int c = 0; c < NCH; c++) {
+    const float4 *wp = reinterpret_cast<const float4 *>(w + (c * 32 + lane) * 8), *bp = reinterpret_cast<const float4 *>(b + (c * 32 + lane) * 8);
+    const float4 w0 = __ldg(wp), w1 = __ldg(wp + 1), b0 = __ldg(bp), b1 = __ldg(bp + 1);
+    const float ww[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w}, bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+    for (int j = 0; j < 8; j++) out[c][j] = out[c][j] * inv * ww[j] + bb[j];
+  }
+}
+
+template <int NMIX, int NCH>
+__global__ void __launch_bounds__(128) rwkv_ln_mix_v8_kernel(const float *__restrict__ x, const float *__restrict__ lnw,
+                                                             const float *__restrict__ lnb, MixMu mu, const int *__restrict__ prev_row,
+                                                             const int *__restrict__ slot, const int *__restrict__ flags,
+                                                             const float *__restrict__ state_in, float *__restrict__ state_out,
+                                                             MixOut out, int n_rows, float eps) {
+  constexpr int C = NCH * 256;
+  const int row = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= n_rows) return;
+  float xn[NCH][8], pv[NCH][8];
+  warp_layer_norm_v8<NCH>(x + (size_t)row * C, lnw, lnb, eps, lane, xn);
+  const int pr = prev_row[row], sl = slot[row], fl = flags[row];
+  if (pr >= 0) {
+    warp_layer_norm_v8<NCH>(x + (size_t)pr * C, lnw, lnb, eps, lane, pv);
+  } else {
+#pragma unroll
+    for (int c = 0; c < NCH; c++) {
+      const float4 *src = reinterpret_cast<const float4 *>(state_in + (size_t)sl * C + (c * 32 + lane) * 8);
+      const float4 a = src[0], d = src[1];
+      pv[c][0] = a.x; pv[c][1] = a.y; pv[c][2] = a.z; pv[c][3] = a.w;
+      pv[c][4] = d.x; pv[c][5] = d.y; pv[c][6] = d.z; pv[c][7] = d.w;
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < NCH; c++) {
+    const int base = (c * 32 + lane) * 8;
+    float xx[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) xx[j] = pv[c][j] - xn[c][j];
+#pragma unroll
+    for (int q = 0; q < NMIX; q++) {
+      const float4 *mp = reinterpret_cast<const float4 *>(mu.p[q] + base);
+      const float4 m0 = __ldg(mp), m1 = __ldg(mp + 1);
+      const float mm[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+      uint32_t pk[4];
+#pragma unroll
+      for (int j = 0; j < 8; j += 2) {
+        const __nv_bfloat162 h = __floats2bfloat162_rn(xn[c][j] + xx[j] * mm[j], xn[c][j + 1] + xx[j + 1] * mm[j + 1]);
+        pk[j >> 1] = *reinterpret_cast<const uint32_t *>(&h);
+      }
+      *reinterpret_cast<uint4 *>(out.p[q] + (size_t)row * C + base) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    }
+    if ((fl & 1) && !(fl & 2)) {
+      float4 *dst = reinterpret_cast<float4 *>(state_out + (size_t)sl * C + base);
+      dst[0] = make_float4(xn[c][0], xn[c][1], xn[c][2], xn[c][3]);
+      dst[1] = make_float4(xn[c][4], xn[c][5], xn[c][6], xn[c][7]);
+    }
+  }
+}
+
 // final LayerNorm of the gathered logit rows -> bf16 (rwkv7.rs:515)
 __global__ void __launch_bounds__(128) rwkv_ln_gather_kernel(const float *__restrict__ x, const float *__restrict__ w,
                                                              const float *__restrict__ b, const int *__restrict__ rows,
@@ -435,6 +525,30 @@ void rwkv_free(cz_model *m) {
 // Forward of one slab.  Row metadata (ws.tok; rws.prev_row/slot/flags; rws.row_begin/row_end/stream_slot) is already on the
 // device.  in_place: T = 1 decode steps read and write the same token-shift buffers; slabs ping-pong them.
 // stream_active (device, nullable): per-stream flag for the stepwise decoder.
+
+// rwkv_ln_mix: the 8-elements-per-lane kernel when the width is a multiple of 256 (<= 1024) and every operand is 16-byte aligned
+template <int NMIX>
+static int launch_ln_mix(cz_ctx *ctx, cudaStream_t st, unsigned grid, const float *x, const float *lnw, const float *lnb, const czk::MixMu &mu,
+                         const int *prev_row, const int *slot, const int *flags, const float *state_in, float *state_out, const czk::MixOut &out,
+                         int n_rows, int C, float eps) {
+  bool vec = C % 256 == 0 && C <= 1024 && (((uintptr_t)x | (uintptr_t)lnw | (uintptr_t)lnb | (uintptr_t)state_in | (uintptr_t)state_out) & 15) == 0;
+  for (int q = 0; q < NMIX; q++) vec = vec && (((uintptr_t)mu.p[q] | (uintptr_t)out.p[q]) & 15) == 0;
+#define CZ_LNMIX_V8(NCH)                                                                                                                       \
+  CZ_LAUNCH(ctx, CZ_K_ELEMWISE,                                                                                                                \
+            (czk::rwkv_ln_mix_v8_kernel<NMIX, NCH><<<grid, 128, 0, st>>>(x, lnw, lnb, mu, prev_row, slot, flags, state_in, state_out, out, n_rows, \
+                                                                        eps)))
+  if (vec && C == 256) CZ_LNMIX_V8(1);
+  else if (vec && C == 512) CZ_LNMIX_V8(2);
+  else if (vec && C == 768) CZ_LNMIX_V8(3);
+  else if (vec && C == 1024) CZ_LNMIX_V8(4);
+  else
+    CZ_LAUNCH(ctx, CZ_K_ELEMWISE,
+              (czk::rwkv_ln_mix_kernel<NMIX><<<grid, 128, 0, st>>>(x, lnw, lnb, mu, prev_row, slot, flags, state_in, state_out, out, n_rows, C, eps)));
+#undef CZ_LNMIX_V8
+  CZ_CHECK_LAUNCH();
+  return CZ_OK;
+}
+
 int rwkv_forward(cz_model *m, int n_rows, int n_streams, RwkvState &stt, bool in_place, const int *stream_active, cudaStream_t st) {
   const cz_model_config &c = m->cfg;
   cz_ctx *ctx = m->ctx;
@@ -459,11 +573,8 @@ int rwkv_forward(cz_model *m, int n_rows, int n_streams, RwkvState &stt, bool in
       mu.p[q] = v + (size_t)(RV_XR + q) * C;
       mo.p[q] = w.mix[q];
     }
-    CZ_LAUNCH(ctx, CZ_K_ELEMWISE,
-              (czk::rwkv_ln_mix_kernel<6><<<g4, 128, 0, st>>>(ws.x, v + RV_LN1_W * C, v + RV_LN1_B * C, mu, w.prev_row, w.slot, w.flags,
-                                                             stt.xa[pin] + (size_t)l * cap * C, stt.xa[pout] + (size_t)l * cap * C, mo,
-                                                             n_rows, C, c.norm_eps)));
-    CZ_CHECK_LAUNCH();
+    CZ_TRY(launch_ln_mix<6>(ctx, st, g4, ws.x, v + RV_LN1_W * C, v + RV_LN1_B * C, mu, w.prev_row, w.slot, w.flags,
+                            stt.xa[pin] + (size_t)l * cap * C, stt.xa[pout] + (size_t)l * cap * C, mo, n_rows, C, c.norm_eps));
     // f[0]=r f[1]=k f[2]=v f[3]=w-lora f[4]=a-lora f[5]=v-lora f[6]=g
     auto mm = [&](const __nv_bfloat16 *a, int lda, const __nv_bfloat16 *b, int K, int N, void *out, int ldc, int epi, int bn, int fam) {
       GemmArgs g{};
@@ -500,11 +611,8 @@ int rwkv_forward(cz_model *m, int n_rows, int n_streams, RwkvState &stt, bool in
     czk::MixOut mo1{};
     mu1.p[0] = v + (size_t)RV_FXK * C;
     mo1.p[0] = w.mix[0];
-    CZ_LAUNCH(ctx, CZ_K_ELEMWISE,
-              (czk::rwkv_ln_mix_kernel<1><<<g4, 128, 0, st>>>(ws.x, v + RV_LN2_W * C, v + RV_LN2_B * C, mu1, w.prev_row, w.slot, w.flags,
-                                                             stt.xf[pin] + (size_t)l * cap * C, stt.xf[pout] + (size_t)l * cap * C, mo1,
-                                                             n_rows, C, c.norm_eps)));
-    CZ_CHECK_LAUNCH();
+    CZ_TRY(launch_ln_mix<1>(ctx, st, g4, ws.x, v + RV_LN2_W * C, v + RV_LN2_B * C, mu1, w.prev_row, w.slot, w.flags,
+                            stt.xf[pin] + (size_t)l * cap * C, stt.xf[pout] + (size_t)l * cap * C, mo1, n_rows, C, c.norm_eps));
     CZ_TRY(mm(w.mix[0], C, W.fk, C, F, w.act, F, EPI_RELUSQ_BF16, 256, CZ_K_GEMM_GU));
     CZ_TRY(mm(w.act, F, W.fv, F, C, ws.x, C, EPI_ADD_F32, 192, CZ_K_GEMM_DOWN));
   }
