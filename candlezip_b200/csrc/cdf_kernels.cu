@@ -437,12 +437,17 @@ __global__ void __launch_bounds__(ST_COLS + 32, 2) cdf_stats_tma_kernel(const __
   double norm = 1.0, sum2 = 1.0;
   if (kNorm) {
     pass_barrier();
-    const bool fast = cz_div_rcp_ok(S);
+    // The reciprocal-based divisions are decided per WARP and outside the loops (the same values either way; a per-element
+    // `fast ? ... : __ddiv_rn` left a branch and the IEEE division's code in every group: 14% `branch_resolving` and 6% instruction-
+    // fetch stalls in the RWKV alphabet's passes, profiles/ncu_summary_r02.md).  Every consumer warp is whole, so the vote is safe.
+    const bool fast = __all_sync(0xffffffffu, cz_div_rcp_ok(S));
     const double yS = __drcp_rn(S);
-    auto e_of = [&](const float(&x)[8], double(&d)[8]) {
+    // e_v of the 8 rows: the cached f32 (RWKV alphabet; WIDEN: exact integer widening, values below 2^-126 are floored either way)
+    // or expf again (SmolLM's XE pass)
+    auto e_of = [&](const float(&x)[8], double(&d)[8], auto widen) {
       if (kLit) {
 #pragma unroll
-        for (int k = 0; k < 8; k++) d[k] = fast ? cz_widen_pos(x[k]) : (double)x[k];  // (values below 2^-126 are floored either way)
+        for (int k = 0; k < 8; k++) d[k] = decltype(widen)::value ? cz_widen_pos(x[k]) : (double)x[k];
       } else {
         float a[8], ef[8];
 #pragma unroll
@@ -450,34 +455,40 @@ __global__ void __launch_bounds__(ST_COLS + 32, 2) cdf_stats_tma_kernel(const __
         exp_group<8, false>(a, tab, d, ef);
       }
     };
-    auto div_S = [&](double e) { return fast ? cz_div_rcp(e, S, yS) : __ddiv_rn(e, S); };
     // ---- pass 2: norm ----
-    double acc = 0.0;
-    run_pass([&](int, const float(&x)[8], int cnt) {
-      double d[8];
-      e_of(x, d);
+    auto pass2 = [&](auto rcp) {
+      double acc = 0.0;
+      run_pass([&](int, const float(&x)[8], int cnt) {
+        double d[8];
+        e_of(x, d, rcp);
 #pragma unroll
-      for (int k = 0; k < 8; k++)
-        if (k < cnt) acc = __dadd_rn(acc, fmax(div_S(d[k]), CZ_P_FLOOR));
-    });
-    norm = acc;
+        for (int k = 0; k < 8; k++)
+          if (k < cnt) acc = __dadd_rn(acc, fmax(decltype(rcp)::value ? cz_div_rcp(d[k], S, yS) : __ddiv_rn(d[k], S), CZ_P_FLOOR));
+      });
+      return acc;
+    };
+    norm = fast ? pass2(std::true_type{}) : pass2(std::false_type{});
     if (kLit) {
       // ---- pass 3: sum2 ----  (no stores since pass 1: no barrier needed, the producer may already be ahead)
       const double scale = 1.0 - 256.0 * CZ_P_FLOOR;
-      const bool fastn = fast && cz_div_rcp_ok(norm);
+      const bool fastn = __all_sync(0xffffffffu, fast && cz_div_rcp_ok(norm));
       const double yN = __drcp_rn(norm);
-      acc = 0.0;
-      run_pass([&](int, const float(&x)[8], int cnt) {
-        double d[8];
-        e_of(x, d);
+      auto pass3 = [&](auto rcp) {
+        double acc = 0.0;
+        run_pass([&](int, const float(&x)[8], int cnt) {
+          double d[8];
+          e_of(x, d, rcp);
 #pragma unroll
-        for (int k = 0; k < 8; k++)
-          if (k < cnt) {
-            const double q = fmax(div_S(d[k]), CZ_P_FLOOR);
-            const double q2 = fastn ? cz_div_rcp(q, norm, yN) : __ddiv_rn(q, norm);
-            acc = __dadd_rn(acc, __dmul_rn(q2, scale));
-          }
-      });
+          for (int k = 0; k < 8; k++)
+            if (k < cnt) {
+              const double q = fmax(decltype(rcp)::value ? cz_div_rcp(d[k], S, yS) : __ddiv_rn(d[k], S), CZ_P_FLOOR);
+              const double q2 = decltype(rcp)::value ? cz_div_rcp(q, norm, yN) : __ddiv_rn(q, norm);
+              acc = __dadd_rn(acc, __dmul_rn(q2, scale));
+            }
+        });
+        return acc;
+      };
+      double acc = fastn ? pass3(std::true_type{}) : pass3(std::false_type{});
       for (int j = 0; j < 256; j++) acc = __dadd_rn(acc, CZ_P_FLOOR);
       sum2 = acc;
     }
@@ -522,6 +533,20 @@ struct PdfOf {
     } else {
       return uniform ? uni : dv(e, S, yS);
     }
+  }
+  // the same value with the division mode fixed at compile time (the walk decides once per column, outside its loop): F => every
+  // constant is inside the reciprocal's proven range, in particular S > 0 (not the uniform case) and sum2 > 0
+  template <bool F>
+  __device__ __forceinline__ double get(double e) const {
+    if (!F) {
+      PdfOf t = *this;
+      t.fast = false;
+      return t(e);
+    }
+    if (MODE == CZ_CDF_RWKV_LITERALS)
+      return cz_div_rcp(__dmul_rn(cz_div_rcp(fmax(cz_div_rcp(e, S, yS), CZ_P_FLOOR), norm, yN), 1.0 - 256.0 * CZ_P_FLOOR), sum2, y2);
+    if (FLOORED) return cz_div_rcp(fmax(cz_div_rcp(e, S, yS), CZ_P_FLOOR), norm, yN);
+    return cz_div_rcp(e, S, yS);
   }
   __device__ __forceinline__ double literal() const { return has2 ? __ddiv_rn(CZ_P_FLOOR, sum2) : CZ_P_FLOOR; }
 };
@@ -592,52 +617,58 @@ __global__ void __launch_bounds__(256) cdf_bounds_warp_kernel(const float *__res
       if (CACHED) return v < n ? __ldg(pe + v) : 0.0;
       return v < n ? (kLit ? p[(size_t)v * ld] : __ldg(p + (size_t)v * ld)) : 0.f;
     };
-    auto q_of = [&](X x) -> double {
-      double d;
-      if (CACHED) {
-        d = (double)x;
-      } else if (kLit) {
-        d = pdf.fast ? cz_widen_pos(x) : (double)x;  // (values below 2^-126 are floored either way)
-      } else {
-        const float a1[1] = {__fsub_rn(mx, x)};
-        double d1[1];
-        float e1[1];
-        exp_group<1, false>(a1, tab, d1, e1);
-        d = d1[0];
-      }
-      return pdf(d);
-    };
     double acc = 0.0;
     uint32_t lo = 0, hi = 0;
-    X xr[DEPTH];
-#pragma unroll
-    for (int k = 0; k < DEPTH; k++) xr[k] = ld_x(k);
-    for (int g = 0; g < n_grp; g++) {
-      const X x = xr[0];
-#pragma unroll
-      for (int k = 0; k + 1 < DEPTH; k++) xr[k] = xr[k + 1];
-      xr[DEPTH - 1] = ld_x(g + DEPTH);
-      double *line = xch + (g & 1) * 32;
-      line[lane] = q_of(x);
-      __syncwarp();
-      const int v0 = g * 32;
-      if (v0 + 32 < (int)sym && v0 + 32 <= n) {  // (warp-uniform) a full group that ends before cdf[sym]'s last term: 32 plain adds
-#pragma unroll
-        for (int k = 0; k < 32; k += 2) {
-          const double2 t = *reinterpret_cast<const double2 *>(line + k);
-          acc = __dadd_rn(acc, t.x);
-          acc = __dadd_rn(acc, t.y);
+    // the walk, with the division mode (reciprocal-based or IEEE: same values) fixed per column outside the loop
+    auto walk = [&](auto fast_tag) {
+      constexpr bool kFast = decltype(fast_tag)::value;
+      auto q_of = [&](X x) -> double {
+        double d;
+        if (CACHED) {
+          d = (double)x;
+        } else if (kLit) {
+          d = kFast ? cz_widen_pos(x) : (double)x;  // (values below 2^-126 are floored either way)
+        } else {
+          const float a1[1] = {__fsub_rn(mx, x)};
+          double d1[1];
+          float e1[1];
+          exp_group<1, false>(a1, tab, d1, e1);
+          d = d1[0];
         }
-      } else {  // at most the last two groups of a column
-        const int cnt = n - v0 < 32 ? n - v0 : 32;
-        for (int k = 0; k < cnt; k++) {
-          acc = __dadd_rn(acc, line[k]);
-          const uint32_t v = (uint32_t)(v0 + k);
-          if (v + 1 == sym) lo = quant(acc);
-          if (v == sym) hi = quant(acc);
+        return pdf.template get<kFast>(d);
+      };
+      X xr[DEPTH];
+#pragma unroll
+      for (int k = 0; k < DEPTH; k++) xr[k] = ld_x(k);
+      for (int g = 0; g < n_grp; g++) {
+        const X x = xr[0];
+#pragma unroll
+        for (int k = 0; k + 1 < DEPTH; k++) xr[k] = xr[k + 1];
+        xr[DEPTH - 1] = ld_x(g + DEPTH);
+        double *line = xch + (g & 1) * 32;
+        line[lane] = q_of(x);
+        __syncwarp();
+        const int v0 = g * 32;
+        if (v0 + 32 < (int)sym && v0 + 32 <= n) {  // (warp-uniform) a full group that ends before cdf[sym]'s last term: 32 plain adds
+#pragma unroll
+          for (int k = 0; k < 32; k += 2) {
+            const double2 t = *reinterpret_cast<const double2 *>(line + k);
+            acc = __dadd_rn(acc, t.x);
+            acc = __dadd_rn(acc, t.y);
+          }
+        } else {  // at most the last two groups of a column
+          const int cnt = n - v0 < 32 ? n - v0 : 32;
+          for (int k = 0; k < cnt; k++) {
+            acc = __dadd_rn(acc, line[k]);
+            const uint32_t v = (uint32_t)(v0 + k);
+            if (v + 1 == sym) lo = quant(acc);
+            if (v == sym) hi = quant(acc);
+          }
         }
       }
-    }
+    };
+    if (pdf.fast) walk(std::true_type{});
+    else walk(std::false_type{});
     __syncwarp();  // (the next column's first group reuses line 0)
     if (kLit && (int)sym >= V) {  // literal symbols follow the vocabulary
       const double pl = pdf.literal();
