@@ -16,6 +16,7 @@
 // and the instruction shape are fixed per (BN, K), there is no split-K and no atomics, so the same activation
 // row gives bit-identical results whatever the batch size, tile position or GPU count.
 #include <cuda.h>
+#include <stdlib.h>
 #include <limits.h>
 
 #include "cz_common.cuh"
@@ -194,6 +195,11 @@ __global__ void __launch_bounds__((GemmCfg<BN, EPI, 1>::kThreads), 1)
   }
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // Programmatic dependent launch (the launcher sets cudaLaunchAttributeProgrammaticStreamSerialization): everything above touched no
+  // global data, so it may run while the previous kernel of the stream drains; its results are only read from here on.  The next
+  // kernel's prologue may start as soon as this CTA is past this point and resources free up.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   if (warp == kProdWarp) {
     // ===================== TMA producer =====================
@@ -967,13 +973,16 @@ static int launch_tc_cl(cz_ctx *ctx, const CUtensorMap &ta, const CUtensorMap &t
   cfg.blockDim = dim3(Cfg::kThreads);
   cfg.dynamicSmemBytes = Cfg::kSmemBytes;
   cfg.stream = stream;
-  cudaLaunchAttribute at[1];
+  cudaLaunchAttribute at[2];
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = CL;
   at[0].val.clusterDim.y = 1;
   at[0].val.clusterDim.z = 1;
+  static const bool pdl = getenv("CZ_GEMM_NO_PDL") == nullptr;  // bisecting aid
+  at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl ? 2 : 1;
   CZ_LAUNCH(ctx, g_fam, (cudaLaunchKernelEx(&cfg, kern, ta, tb, tc, td, c, M, N, K, ldc, aux, rx, nx, raster_gw)));
   CZ_CHECK_LAUNCH();
   return CZ_OK;
