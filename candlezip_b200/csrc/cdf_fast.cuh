@@ -13,11 +13,13 @@
 //     FMA-pipe operations:  q0 = RN(a y);  r0 = RN(a - b q0);  q1 = RN(q0 + r0 y);  r1 = a - b q1 (exact);  q = RN(q1 + r1 y).
 //     q1 is a faithful quotient (error < 1 ulp), and Markstein's theorem (Handbook of Floating-Point Arithmetic, thm 4.10: y within
 //     1/2 ulp of 1/b, q1 faithful  =>  RN(q1 + r1 y) = RN(a / b)) makes q the correctly rounded quotient, i.e. __ddiv_rn(a, b).
-//     cz_test_div_random compares the two on 2^36 random operand pairs of the shapes that occur here.
-//   * the encode-side prefix walk stops at the coded symbol, but a warp walks until its LAST lane stops: with real token ids (mean
-//     id / V = 0.1, heavy tail) some lane of 32 nearly always needs most of the vocabulary.  The prefix kernel therefore sorts the
-//     256 columns of a CTA by symbol and hands each warp 32 columns of similar walk length (any column -> any lane: the columns
-//     are independent, results unchanged).
+//     cz_test_div_random compares the two on random operand pairs of the shapes that occur here (2^34 in the test suite).
+//   * the encode-side prefix walk stops at the coded symbol, but with a thread per column a warp walks until its LAST lane stops:
+//     with real token ids (mean id / V = 0.1, heavy tail) some lane of 32 nearly always needs most of the vocabulary.  The prefix
+//     kernel is therefore warp-per-column (cdf_bounds_warp_kernel: the lanes evaluate 32 consecutive pdf entries, only the in-order
+//     accumulation is serial), and it reads the e_v the stats pass left for it in a compact per-column cache instead of the
+//     vocab-major logits (cdf_kernels.cu, "e-cache").
+// The decode-side search (cdf_search_warp_n, below) uses the same fast paths.
 #pragma once
 #include "cdf_device.cuh"
 
