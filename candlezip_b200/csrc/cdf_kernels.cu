@@ -561,12 +561,12 @@ struct PdfOf {
 // divisions: the expensive part) and only the order-dependent accumulation is serial -- every lane performs it redundantly on the
 // shared-memory line the values were exchanged through (cdf_search_warp's scheme), so all lanes hold the same acc and every branch
 // is warp-uniform.  Columns are independent warps of very different lengths, thousands per SM over the kernel's life: the machine
-// stays full until the end, and the longest column costs V / 32 short iterations.  The 8 warps of a CTA take 8 adjacent columns =
-// one 32-byte sector per vocab row, so a row's sector is fetched from DRAM once and the other seven warps find it in L1 / L2.
+// stays full until the end, and the longest column costs V / 32 short iterations.
 // Same operations in the same order as cdf_col's OP_BOUNDS: bit-identical results.
 // Columns are handed out one at a time from a global counter (persistent warps): a warp that finishes a short column takes the
-// next one instead of idling until the longest column of its CTA is done, and columns c .. c + 7 -- which share a 32-byte sector
-// per vocab row -- are in flight at about the same time, so the sector is fetched from DRAM once and found in L2 by the others.
+// next one instead of idling until the longest column of its CTA is done.  (Reading the vocab-major logits this way was meant to
+// share a row's 32-byte sector between the warps of adjacent columns through L1 / L2; ncu showed it does not -- the walks drift
+// apart at once: 38 GB of DRAM reads per 131,072 columns for 2.6 GB used.  Hence the e-cache.)
 // CACHED: the e_v come from the e-cache the stats pass filled (f64, contiguous per column: 256 coalesced bytes per 32 rows, no
 // expf); the kernel is a no-op when the batch did not fit the cache (*eflag == 0).  !CACHED: from the vocab-major logits; a no-op
 // when eflag is given and set.  The launcher issues both, exactly one of them works.
