@@ -10,8 +10,10 @@
 //
 // expf: identical operation sequence to glibc 2.39 x86_64 expf (the FMA ifunc variant), which is what Rust's
 // f32::exp lowers to on Linux; every mul/add/fma is an explicit round-to-nearest intrinsic so nvcc cannot
-// re-contract.  HBM-bound by design: algorithmic bytes = 4*V per column (one read); this implementation
-// reads the column up to 3 times (max / sum / prefix), the 2nd and 3rd mostly from L2 for decode-sized M.
+// re-contract.  Algorithmic bytes = 4*V per column (one read).  Encode (OP_BOUNDS / OP_XE): the max comes from the LM-head
+// GEMM's epilogue, cdf_stats_tma_kernel reads the column once per pass (one pass for SmolLM coding) and leaves the few e_v the
+// prefix walk needs in a compact cache, cdf_bounds_warp_kernel walks that cache; cdf_cols_kernel is the round-1 single kernel,
+// kept for unaligned / tiny batches and bisecting.  Decode (OP_SEARCH): cdf_search_warp_n (cdf_fast.cuh), a warp per stream.
 #include <stdlib.h>
 
 #include <algorithm>
