@@ -131,3 +131,47 @@ def test_reference_arm_does_not_load_the_product_library():
             "print('LOADED', sorted({l.split()[-1].split('/')[-1] for l in open('/proc/self/maps') if 'libcandlezip' in l or 'libcz_oracle' in l}))")
     r = subprocess.run([sys.executable, "-c", code], cwd=ROOT, capture_output=True, text=True, timeout=600)
     assert "LOADED ['libcz_oracle.so']" in r.stdout, (r.stdout[-300:], r.stderr[-300:])
+
+
+def test_built_library_is_made_of_tcgen05_tma_and_fp64_kernels():
+    """The hot kernels are what DESIGN.md says they are, checked on the built sm_100a SASS (cuobjdump needs no GPU): the GEMM and the
+    attention kernel issue tcgen05.mma (UTCHMMA) with tensor-memory loads / stores (LDTM / STTM) and TMA (UTMALDG / UTMASTG); the
+    attention kernel writes P to tensor memory (STTM); the CDF stats kernel is fed by TMA and does its arithmetic in FP64 without
+    F2F conversions in the hot variants; nothing on the default path is an mma.sync (HMMA) kernel except the bisecting fallback."""
+    import collections
+    import re
+    import shutil
+    import subprocess
+
+    if not shutil.which("cuobjdump") or not shutil.which("c++filt"):
+        pytest.skip("cuobjdump / c++filt not available")
+    so = os.path.join(ROOT, "candlezip_b200", "libcandlezip_b200.so")
+    sass = subprocess.run(["cuobjdump", "-sass", so], capture_output=True, text=True, timeout=300).stdout
+    counts, cur = {}, None
+    for line in sass.split("\n"):
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            cur = m.group(1)
+            counts[cur] = collections.Counter()
+            continue
+        m = re.match(r"\s+/\*[0-9a-f]{4,5}\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_]+)", line)
+        if m and cur:
+            counts[cur][m.group(1)] += 1
+    names = list(counts)
+    dm = dict(zip(names, subprocess.run(["c++filt"], input="\n".join(names), capture_output=True, text=True).stdout.split("\n")))
+
+    def kernels(sub):
+        return [counts[n] for n in names if sub in dm[n]]
+
+    gemm, attn = kernels("gemm_tc_kernel<"), kernels("attn_tc_kernel<")
+    assert gemm and attn
+    for c in gemm:
+        assert c["UTCHMMA"] > 0 and c["LDTM"] > 0 and c["UTMALDG"] > 0 and c["HMMA"] == 0
+    assert any(c["UTMASTG"] > 0 for c in gemm) and any(c["UTMAREDG"] > 0 for c in gemm)
+    for c in attn:
+        assert c["UTCHMMA"] > 0 and c["LDTM"] > 0 and c["STTM"] > 0 and c["UTMALDG"] > 0 and c["HMMA"] == 0
+    stats = kernels("cdf_stats_tma_kernel<")
+    assert stats and all(c["UTMALDG"] > 0 and c["DFMA"] > 0 and c["DADD"] > 0 for c in stats)
+    prefix = kernels("cdf_bounds_warp_kernel<")
+    assert prefix and all(c["DADD"] >= 32 for c in prefix)
+    assert kernels("attn_mma_kernel<") and all(c["HMMA"] > 0 for c in kernels("attn_mma_kernel<"))  # the bisecting fallback, and only it
