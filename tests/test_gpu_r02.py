@@ -451,3 +451,27 @@ def test_cli_twin_gate_scan_replay_self_test(gpu_ctx, tmp_path):
     rows = open(out_dir / "proof.csv").read().strip().split("\n")
     assert len(rows) == 6 and rows[0].startswith("file,chunk_index,start_token,end_token,agent_text_len")
     assert [x.split(",")[1:4] for x in rows[1:]] == [[str(k), str(max(0, 512 * k - 1 - 512)), str(512 * k - 1)] for k in range(1, 6)]
+
+
+@pytest.mark.parametrize("arch", ["smollm", "rwkv7"])
+def test_empty_and_one_byte_files_round_trip_through_the_codec(gpu_ctx, arch):
+    """Edge cases of the file-level path (src/main.rs:1979-2358 / 2485-2654): an empty file is a header plus the coder's
+    finish byte 0x40 (the reference's `finish()` on an untouched encoder, src/main.rs:300-318), a one-byte file is one coded token;
+    both come back byte-exact, also when more segments are asked for than there are tokens."""
+    from candlezip_b200 import codec, container
+
+    if arch == "smollm":
+        model = _tiny(gpu_ctx)
+    else:
+        from rwkv7_weights import RWKV7_TINY, make_weights
+
+        model = cz.Model(gpu_ctx, RWKV7_TINY)
+        for name, arr in make_weights(RWKV7_TINY, 7).items():
+            model.set_tensor(name, arr)
+    for data, nseg in ((b"", 1), (b"", 4), (b"a", 1), (b"a", 4), (b"ab", 2)):
+        blob = codec.compress(model, data, n_segments=nseg)
+        f, _, _, _, _, pays = container.read_container(blob)
+        assert f["token_count"] == len(data) and f["orig_len_bytes"] == len(data)
+        if not data:
+            assert b"".join(pays) == b"\x40"
+        assert codec.decompress(model, blob) == data, (data, nseg)
